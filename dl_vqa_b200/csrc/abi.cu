@@ -1,0 +1,15 @@
+// ABI bookkeeping: version and per-thread error string.
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void vqa_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* vqa_last_error_string(void) { return g_err; }
+extern "C" int vqa_abi_version(void) { return VQA_ABI_VERSION; }

@@ -1,0 +1,48 @@
+// Multi-tensor Adam (train.py:55,76-80: torch.optim.Adam defaults; lr supplied per step by the
+// reference's update_learning_rate schedule).  One launch for all parameter tensors; bandwidth-bound:
+// reads p,g,m,v and writes p,m,v (+ optional bf16 shadow of p for the tensor-core arm).
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(float* const* __restrict__ params, const float* const* __restrict__ grads,
+                  float* const* __restrict__ exp_avg, float* const* __restrict__ exp_avg_sq,
+                  void* const* __restrict__ bf16_copy, const int64_t* __restrict__ sizes,
+                  float lr_over_bc1, float beta1, float beta2, float eps, float inv_sqrt_bc2, float grad_scale) {
+    const int t = blockIdx.y;
+    const int64_t n = sizes[t];
+    float* p = params[t];
+    const float* g = grads[t];
+    float* m = exp_avg[t];
+    float* v = exp_avg_sq[t];
+    bf16* sh = bf16_copy ? (bf16*)bf16_copy[t] : nullptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        const float pi = p[i] - lr_over_bc1 * (mi / denom);
+        m[i] = mi; v[i] = vi; p[i] = pi;
+        if (sh) sh[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+}  // namespace
+
+extern "C" int vqa_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, void* const* bf16_copy, const int64_t* sizes, int n,
+                              int64_t max_size, float lr, float beta1, float beta2, float eps, int step,
+                              float grad_scale, void* stream) {
+    VQA_REQUIRE(n > 0 && step >= 1 && max_size > 0, "adam: bad arguments n=%d step=%d", n, step);
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    int64_t gx = ceil_div64(max_size, 256 * 4);
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid((unsigned)gx, (unsigned)n);
+    adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, bf16_copy, sizes,
+                                                             (float)(lr / bc1), beta1, beta2, eps,
+                                                             (float)(1.0 / sqrt(bc2)), grad_scale);
+    VQA_CHECK_LAUNCH("adam_multi");
+    return 0;
+}

@@ -1,0 +1,150 @@
+// Shared device/host helpers for libvqa_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vqa_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: every extern "C" entry returns 0 or an error code; message kept per thread
+// ------------------------------------------------------------------------------------------
+void vqa_set_error(const char* fmt, ...);
+
+#define VQA_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            vqa_set_error(__VA_ARGS__);                \
+            return VQA_ERR_INVALID_ARGUMENT;           \
+        }                                              \
+    } while (0)
+
+#define VQA_CHECK_LAUNCH(name)                                                        \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) {                                                     \
+            vqa_set_error("%s: %s", name, cudaGetErrorString(e__));                   \
+            return (int)e__;                                                          \
+        }                                                                             \
+    } while (0)
+
+#define VQA_CUDA(call)                                                                \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            vqa_set_error("%s: %s", #call, cudaGetErrorString(e__));                  \
+            return (int)e__;                                                          \
+        }                                                                             \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------
+// type helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum; `red` is >= 32 floats of shared memory; result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------
+// counter-based dropout.  Element i of dropout site `site` is kept iff a 16-bit word derived from
+// hash32(key(seed, site) ^ (i >> 1)) is >= threshold (p quantised to 1/65536).  Stateless, so the
+// backward pass regenerates the same mask and no mask tensor ever touches HBM.  One hash (2 IMUL +
+// 3 shift-xor) serves two elements, which keeps the fused attention kernel HBM-bound in train mode
+// (a Philox4x32-10 stream would make it ALU-bound).  The mask cannot match torch's RNG stream bit for
+// bit, so parity runs use eval() / dropout 0 (SURVEY.md section 7 "Dropout parity").
+// ------------------------------------------------------------------------------------------
+struct Dropout {
+    uint64_t seed;
+    uint32_t threshold;   // 16-bit threshold: keep iff word >= threshold; 0 disables dropout
+    float scale;          // 1/(1-p)
+};
+
+static inline Dropout make_dropout(uint64_t seed, float p) {
+    Dropout d;
+    d.seed = seed;
+    if (p <= 0.f) { d.threshold = 0; d.scale = 1.f; }
+    else {
+        double t = (double)p * 65536.0 + 0.5;
+        d.threshold = (t >= 65535.0) ? 65535u : (uint32_t)t;
+        d.scale = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+    return x;
+}
+__device__ __forceinline__ uint32_t dropout_key(const Dropout& d, uint32_t site) {
+    return hash32((uint32_t)d.seed ^ hash32((uint32_t)(d.seed >> 32) + site * 0x9E3779B9u + 0x85ebca6bu));
+}
+// 32 random bits covering elements 2*pair and 2*pair+1
+__device__ __forceinline__ uint32_t dropout_word(uint32_t key, uint64_t pair) {
+    return hash32(((uint32_t)pair ^ key) + (uint32_t)(pair >> 32) * 0xc2b2ae35u);
+}
+// multiplier (0 or scale) for one element
+__device__ __forceinline__ float dropout_mult(const Dropout& d, uint32_t site, uint64_t idx) {
+    if (d.threshold == 0) return 1.f;
+    const uint32_t w = dropout_word(dropout_key(d, site), idx >> 1);
+    const uint32_t h = (idx & 1) ? (w >> 16) : (w & 0xffffu);
+    return h >= d.threshold ? d.scale : 0.f;
+}
+// multipliers for 2 consecutive elements starting at even idx, with a precomputed key
+__device__ __forceinline__ void dropout_mult2(const Dropout& d, uint32_t key, uint64_t idx, float& m0, float& m1) {
+    const uint32_t w = dropout_word(key, idx >> 1);
+    m0 = (w & 0xffffu) >= d.threshold ? d.scale : 0.f;
+    m1 = (w >> 16) >= d.threshold ? d.scale : 0.f;
+}
+
+// dropout sites (one independent mask stream per nn.Dropout call site of models/model.py)
+enum : uint32_t {
+    SITE_IMAGE = 0,      // models/model.py:84   image.drop
+    SITE_ATT_V = 1,      // models/model.py:185  attention.drop(v)
+    SITE_EMBED = 2,      // models/model.py:156  text.drop
+    SITE_ATT_Q = 3,      // models/model.py:186  attention.drop(q)
+    SITE_ATT_X = 4,      // models/model.py:194  attention.drop(x)
+    SITE_CLS_IN = 5,     // models/model.py:201  classifier.drop1
+    SITE_CLS_HID = 6,    // models/model.py:204  classifier.drop2
+};

@@ -1,0 +1,360 @@
+// Bandwidth-bound helpers of the VQA step: dropout + L2 normalisation, embedding + tanh, LSTM backward
+// pointwise, column sums (bias gradients), casts, dropout application.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// image.drop + channel L2 norm (models/model.py:84, :56).  One warp per spatial row of C channels.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn, T* __restrict__ vnd,
+                                    float* __restrict__ nrm, int64_t R, int C, Dropout d_img, Dropout d_att) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const T* xr = x + r * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = to_f32(xr[c]) * dropout_mult(d_img, SITE_IMAGE, (uint64_t)r * C + c);
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float n = sqrtf(ss);
+    const float inv = 1.f / (n + 1e-12f);
+    if (lane == 0) nrm[r] = n;
+    for (int c = lane; c < C; c += 32) {
+        const uint64_t idx = (uint64_t)r * C + c;
+        const float y = to_f32(xr[c]) * dropout_mult(d_img, SITE_IMAGE, idx) * inv;
+        vn[idx] = from_f32<T>(y);
+        if (vnd) vnd[idx] = from_f32<T>(y * dropout_mult(d_att, SITE_ATT_V, idx));
+    }
+}
+
+template <typename T>
+__global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restrict__ dvnd, const T* __restrict__ vn,
+                                    const float* __restrict__ nrm, T* __restrict__ dx, int64_t R, int C,
+                                    Dropout d_img, Dropout d_att) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const uint64_t idx = (uint64_t)r * C + c;
+        float dy = dvn ? to_f32(dvn[idx]) : 0.f;
+        if (dvnd) dy += to_f32(dvnd[idx]) * dropout_mult(d_att, SITE_ATT_V, idx);
+        s += dy * to_f32(vn[idx]);
+    }
+    s = warp_sum(s);
+    const float n = nrm[r];
+    const float inv = 1.f / (n + 1e-12f);
+    const float k = n > 0.f ? s / n : 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const uint64_t idx = (uint64_t)r * C + c;
+        float dy = dvn ? to_f32(dvn[idx]) : 0.f;
+        if (dvnd) dy += to_f32(dvnd[idx]) * dropout_mult(d_att, SITE_ATT_V, idx);
+        const float g = inv * dy - k * to_f32(vn[idx]);
+        dx[idx] = from_f32<T>(g * dropout_mult(d_img, SITE_IMAGE, idx));
+    }
+}
+
+extern "C" int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, int act_dtype, int64_t R, int C,
+                                float p_img, float p_att, uint64_t seed, void* stream) {
+    VQA_REQUIRE(R > 0 && C > 0 && x && vn && nrm, "dropnorm_fwd: bad arguments");
+    const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
+    const int wpb = 8;
+    const unsigned grid = (unsigned)ceil_div64(R, wpb);
+    if (act_dtype == VQA_F32)
+        dropnorm_fwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
+    else if (act_dtype == VQA_BF16)
+        dropnorm_fwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
+    else VQA_REQUIRE(false, "dropnorm_fwd: bad dtype");
+    VQA_CHECK_LAUNCH("dropnorm_fwd");
+    return 0;
+}
+
+extern "C" int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* vn, const float* nrm, void* dx,
+                                int act_dtype, int64_t R, int C, float p_img, float p_att, uint64_t seed, void* stream) {
+    VQA_REQUIRE(R > 0 && C > 0 && vn && nrm && dx && (dvn || dvnd), "dropnorm_bwd: bad arguments");
+    const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
+    const int wpb = 8;
+    const unsigned grid = (unsigned)ceil_div64(R, wpb);
+    if (act_dtype == VQA_F32)
+        dropnorm_bwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
+    else if (act_dtype == VQA_BF16)
+        dropnorm_bwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
+    else VQA_REQUIRE(false, "dropnorm_bwd: bad dtype");
+    VQA_CHECK_LAUNCH("dropnorm_bwd");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding -> dropout -> tanh, written step-indexed for both LSTM directions (models/model.py:155-162)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int step_token_pos(int dir, int s, int len) { return dir == 0 ? s : len - 1 - s; }
+
+template <typename T>
+__global__ void embed_tanh_fwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
+                                      const float* __restrict__ emb, T* __restrict__ xs,
+                                      int B, int T_, int E, int ldx, int dirs, Dropout d) {
+    const int64_t row = blockIdx.x;                 // (dir, s, b)
+    const int b = (int)(row % B);
+    const int s = (int)((row / B) % T_);
+    const int dir = (int)(row / ((int64_t)B * T_));
+    const int len = (int)q_len[b];
+    T* o = xs + row * ldx;
+    const bool active = s < len;
+    int t = 0; int64_t tok = 0;
+    if (active) { t = step_token_pos(dir, s, len); tok = q[(int64_t)b * T_ + t]; }
+    for (int e = threadIdx.x; e < ldx; e += blockDim.x) {
+        float v = 0.f;
+        if (active && e < E) {
+            const float m = dropout_mult(d, SITE_EMBED, ((uint64_t)b * T_ + t) * E + e);
+            v = tanhf(emb[tok * E + e] * m);
+        }
+        o[e] = from_f32<T>(v);
+    }
+}
+
+template <typename T>
+__global__ void embed_tanh_bwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
+                                      const T* __restrict__ xs, const T* __restrict__ dxs, float* __restrict__ demb,
+                                      int B, int T_, int E, int ldx, int dirs, Dropout d) {
+    const int64_t row = blockIdx.x;
+    const int b = (int)(row % B);
+    const int s = (int)((row / B) % T_);
+    const int dir = (int)(row / ((int64_t)B * T_));
+    const int len = (int)q_len[b];
+    if (s >= len) return;
+    const int t = step_token_pos(dir, s, len);
+    const int64_t tok = q[(int64_t)b * T_ + t];
+    if (tok == 0) return;                            // padding_idx: no gradient
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float y = to_f32(xs[row * ldx + e]);
+        const float m = dropout_mult(d, SITE_EMBED, ((uint64_t)b * T_ + t) * E + e);
+        const float g = to_f32(dxs[row * ldx + e]) * (1.f - y * y) * m;
+        atomicAdd(demb + tok * E + e, g);
+    }
+}
+
+extern "C" int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb, void* xs, int act_dtype,
+                                  int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream) {
+    VQA_REQUIRE(B > 0 && T > 0 && E > 0 && ldx >= E && (dirs == 1 || dirs == 2), "embed_fwd: bad dims");
+    const Dropout d = make_dropout(seed, p);
+    const unsigned grid = (unsigned)((int64_t)dirs * T * B);
+    if (act_dtype == VQA_F32)
+        embed_tanh_fwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, emb, (float*)xs, B, T, E, ldx, dirs, d);
+    else if (act_dtype == VQA_BF16)
+        embed_tanh_fwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, emb, (bf16*)xs, B, T, E, ldx, dirs, d);
+    else VQA_REQUIRE(false, "embed_fwd: bad dtype");
+    VQA_CHECK_LAUNCH("embed_tanh_fwd");
+    return 0;
+}
+
+extern "C" int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, const void* dxs, float* demb,
+                                  int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed,
+                                  void* stream) {
+    VQA_REQUIRE(B > 0 && T > 0 && E > 0 && ldx >= E && (dirs == 1 || dirs == 2), "embed_bwd: bad dims");
+    const Dropout d = make_dropout(seed, p);
+    const unsigned grid = (unsigned)((int64_t)dirs * T * B);
+    if (act_dtype == VQA_F32)
+        embed_tanh_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, (const float*)xs, (const float*)dxs, demb, B, T, E, ldx, dirs, d);
+    else if (act_dtype == VQA_BF16)
+        embed_tanh_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, (const bf16*)xs, (const bf16*)dxs, demb, B, T, E, ldx, dirs, d);
+    else VQA_REQUIRE(false, "embed_bwd: bad dtype");
+    VQA_CHECK_LAUNCH("embed_tanh_bwd");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM backward, pointwise part of step s (BPTT through the cell of models/model.py:164)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const float* __restrict__ cs,
+                                          const float* __restrict__ dh, float* __restrict__ dc,
+                                          const T* __restrict__ dc_init, T* __restrict__ dg,
+                                          const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over dirs*B*H
+    if (i >= (int64_t)dirs * B * H) return;
+    const int j = (int)(i % H);
+    const int b = (int)((i / H) % B);
+    const int dir = (int)(i / ((int64_t)B * H));
+    const int64_t row = ((int64_t)dir * T_ + s) * B + b;
+    T* o = dg + row * 4 * H;
+    // gradient w.r.t. the final cell state enters at the first processed step (s == T-1)
+    const float dc_in = dc_init ? to_f32(dc_init[(int64_t)b * dirs * H + (int64_t)dir * H + j]) : dc[i];
+    if (s >= (int)q_len[b]) {
+        o[j] = o[H + j] = o[2 * H + j] = o[3 * H + j] = from_f32<T>(0.f);
+        dc[i] = dc_in;                              // frozen step: dc passes through unchanged
+        return;
+    }
+    const T* g = gates + row * 4 * H;
+    const float gi = to_f32(g[j]), gf = to_f32(g[H + j]), gg = to_f32(g[2 * H + j]), go = to_f32(g[3 * H + j]);
+    const float c = cs[row * H + j];
+    const float c_prev = s > 0 ? cs[(row - B) * H + j] : 0.f;
+    const float tc = tanhf(c);
+    const float dhv = dh[i];
+    float dcv = dc_in + dhv * go * (1.f - tc * tc);
+    const float d_o = dhv * tc;
+    const float d_i = dcv * gg, d_g = dcv * gi, d_f = dcv * c_prev;
+    dc[i] = dcv * gf;
+    o[j] = from_f32<T>(d_i * gi * (1.f - gi));
+    o[H + j] = from_f32<T>(d_f * gf * (1.f - gf));
+    o[2 * H + j] = from_f32<T>(d_g * (1.f - gg * gg));
+    o[3 * H + j] = from_f32<T>(d_o * go * (1.f - go));
+}
+
+extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float* dh, float* dc,
+                                           const void* dc_init, void* dg, const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs,
+                                           void* stream) {
+    VQA_REQUIRE(s >= 0 && s < T && B > 0 && H > 0 && (dirs == 1 || dirs == 2), "lstm bwd pointwise: bad dims");
+    const int64_t n = (int64_t)dirs * B * H;
+    const unsigned grid = (unsigned)ceil_div64(n, 256);
+    if (act_dtype == VQA_F32)
+        lstm_bwd_pointwise_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)gates, cs, dh, dc, (const float*)dc_init, (float*)dg, q_len, s, T, B, H, dirs);
+    else if (act_dtype == VQA_BF16)
+        lstm_bwd_pointwise_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
+    else VQA_REQUIRE(false, "lstm bwd pointwise: bad dtype");
+    VQA_CHECK_LAUNCH("lstm_step_bwd_pointwise");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dropout application / gradient merges / casts / column sums
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dropout_apply_kernel(const T* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out,
+                                     int64_t rows, int cols, Dropout d, uint32_t site) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols; const int c = (int)(i - r * cols);
+    out[r * ld_out + c] = from_f32<T>(to_f32(in[r * ld_in + c]) * dropout_mult(d, site, (uint64_t)i));
+}
+
+extern "C" int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64_t ld_out, int dtype, int64_t rows,
+                                 int cols, float p, uint64_t seed, uint32_t site, void* stream) {
+    VQA_REQUIRE(rows >= 0 && cols > 0 && ld_in >= cols && ld_out >= cols, "dropout_apply: bad dims");
+    if (rows == 0) return 0;
+    const Dropout d = make_dropout(seed, p);
+    const unsigned grid = (unsigned)ceil_div64(rows * cols, 256);
+    if (dtype == VQA_F32)
+        dropout_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, (float*)out, ld_out, rows, cols, d, site);
+    else if (dtype == VQA_BF16)
+        dropout_apply_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols, d, site);
+    else VQA_REQUIRE(false, "dropout_apply: bad dtype");
+    VQA_CHECK_LAUNCH("dropout_apply");
+    return 0;
+}
+
+template <typename T>
+__global__ void add_dropped_kernel(const T* __restrict__ a, int64_t lda, const T* __restrict__ b, int64_t ldb,
+                                   T* __restrict__ dst, int64_t ldd, int64_t rows, int cols, Dropout d, uint32_t site) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols; const int c = (int)(i - r * cols);
+    float v = to_f32(a[r * lda + c]);
+    if (b) v += to_f32(b[r * ldb + c]) * dropout_mult(d, site, (uint64_t)i);
+    dst[r * ldd + c] = from_f32<T>(v);
+}
+
+extern "C" int vqa_add_dropped(const void* a, int64_t lda, const void* b, int64_t ldb, void* dst, int64_t ldd, int dtype,
+                               int64_t rows, int cols, float p, uint64_t seed, uint32_t site, void* stream) {
+    VQA_REQUIRE(rows >= 0 && cols > 0 && a && dst, "add_dropped: bad arguments");
+    if (rows == 0) return 0;
+    const Dropout d = make_dropout(seed, p);
+    const unsigned grid = (unsigned)ceil_div64(rows * cols, 256);
+    if (dtype == VQA_F32)
+        add_dropped_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, (float*)dst, ldd, rows, cols, d, site);
+    else if (dtype == VQA_BF16)
+        add_dropped_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)dst, ldd, rows, cols, d, site);
+    else VQA_REQUIRE(false, "add_dropped: bad dtype");
+    VQA_CHECK_LAUNCH("add_dropped");
+    return 0;
+}
+
+template <typename T>
+__global__ void relu_drop_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz, int64_t n,
+                                     float scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dz[i] = from_f32<T>(to_f32(y[i]) > 0.f ? to_f32(dy[i]) * scale : 0.f);
+}
+
+extern "C" int vqa_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float p, void* stream) {
+    VQA_REQUIRE(n >= 0 && p >= 0.f && p < 1.f, "relu_drop_bwd: bad arguments");
+    if (n == 0) return 0;
+    const float scale = 1.f / (1.f - p);
+    const unsigned grid = (unsigned)ceil_div64(n, 256);
+    if (dtype == VQA_F32)
+        relu_drop_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (float*)dz, n, scale);
+    else if (dtype == VQA_BF16)
+        relu_drop_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)y, (bf16*)dz, n, scale);
+    else VQA_REQUIRE(false, "relu_drop_bwd: bad dtype");
+    VQA_CHECK_LAUNCH("relu_drop_bwd");
+    return 0;
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = from_f32<TD>(to_f32(s[i]));
+}
+
+extern "C" int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+    VQA_REQUIRE(n >= 0, "cast: bad size");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)ceil_div64(n, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+    else VQA_REQUIRE(false, "cast: bad dtypes");
+    VQA_CHECK_LAUNCH("cast");
+    return 0;
+}
+
+// column sums: block = 32 columns x 8 row lanes; rows split over gridDim.y, combined with atomics
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ in, int64_t ld, const uint8_t* __restrict__ mask,
+                              float* __restrict__ out, int64_t rows, int cols, int64_t rows_per_block) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < cols)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            const int64_t idx = r * ld + c;
+            if (!mask || mask[idx] < 4) s += to_f32(in[idx]);
+        }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+int vqa_colsum_impl(const void* in, int dtype, int64_t ld, const uint8_t* mask, float* out, int64_t rows, int cols,
+                    cudaStream_t st) {
+    VQA_REQUIRE(rows >= 0 && cols > 0 && ld >= cols, "colsum: bad dims");
+    if (rows == 0) return 0;
+    const int gx = ceil_div(cols, 32);
+    int64_t gy = ceil_div64(148 * 8, gx);
+    const int64_t max_gy = ceil_div64(rows, 64);
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    const int64_t rpb = ceil_div64(rows, gy);
+    dim3 grid(gx, (unsigned)ceil_div64(rows, rpb)), block(32, 8);
+    if (dtype == VQA_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)in, ld, mask, out, rows, cols, rpb);
+    else if (dtype == VQA_BF16) colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, ld, mask, out, rows, cols, rpb);
+    else VQA_REQUIRE(false, "colsum: bad dtype");
+    VQA_CHECK_LAUNCH("colsum");
+    return 0;
+}
+
+extern "C" int vqa_colsum(const void* in, int dtype, int64_t ld, const uint8_t* mask, float* out, int64_t rows, int cols,
+                          void* stream) {
+    return vqa_colsum_impl(in, dtype, ld, mask, out, rows, cols, (cudaStream_t)stream);
+}

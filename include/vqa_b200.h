@@ -1,0 +1,182 @@
+/* libvqa_b200 -- C ABI of the B200-native DL_VQA training / inference step.
+ *
+ * The reference (OmerShubi/DL_VQA) has no native boundary: its hot path is torch.nn modules called
+ * from models/model.py:53-67 and the loss/score tail of train.py:190-207.  Each entry point below
+ * replaces the torch/cuDNN/cuBLAS call(s) named in its comment (reference file:line).  The Python
+ * host code in dl_vqa_b200/ binds these with ctypes; INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); nothing here
+ *     allocates, frees or synchronises; `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, VQA_ERR_INVALID_ARGUMENT (<0) = rejected arguments, >0 = cudaError_t;
+ *     vqa_last_error_string() describes the last failure on the calling thread;
+ *   - dtype codes: VQA_F32 / VQA_BF16 describe ACTIVATION tensors; parameters are always fp32 in
+ *     the PyTorch layouts of the reference's state_dict (OIHW conv, [out,in] linear, gate-stacked
+ *     i,f,g,o LSTM) unless the entry says "packed";
+ *   - image activations are NHWC ([B, H, W, C], channel contiguous); the network input is the
+ *     reference's NCHW fp32 tensor;
+ *   - dropout is a stateless counter-based mask keyed by (seed, site, element index): forward and
+ *     backward entries take the same (p, seed) and regenerate the same mask.
+ */
+#ifndef VQA_B200_H
+#define VQA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_ABI_VERSION 1
+#define VQA_F32 0
+#define VQA_BF16 1
+#define VQA_ERR_INVALID_ARGUMENT (-1)
+#define VQA_ERR_UNSUPPORTED (-2)
+
+/* attention fusion operator, config.yaml train.attention.do_option (models/model.py:188-193) */
+#define VQA_ATT_ADD 0
+#define VQA_ATT_MUL 1
+
+const char* vqa_last_error_string(void);
+int vqa_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Image encoder -- models/model.py:72-84 (ImageNet2): Conv2d(k, stride, pad 0) -> ReLU -> MaxPool2d(2,2)
+ * One fused kernel per layer; the un-pooled conv output never reaches HBM.
+ *   x      : [B,IH,IW,Cin] NHWC (x_nchw=0) or [B,Cin,IH,IW] NCHW (x_nchw=1, the network input)
+ *   w,bias : fp32 OIHW [Cout,Cin,KS,KS], [Cout]
+ *   out    : [B,PH,PW,Cout] NHWC act_dtype, PH = ((IH-KS)/stride+1)/2 (floor, as MaxPool2d)
+ *   mask   : [B,PH,PW,Cout] uint8: 0..3 = (dy*2+dx) of the window maximum, 4 = ReLU-dead
+ * --------------------------------------------------------------------------------------------- */
+int vqa_conv_relu_pool_fwd(const void* x, int x_dtype, int x_nchw, const float* w, const float* bias,
+                           void* out, uint8_t* mask, int act_dtype,
+                           int B, int IH, int IW, int Cin, int Cout, int KS, int stride, void* stream);
+/* gradient w.r.t. the layer input (autograd of the three modules above):
+ *   dpool [B,PH,PW,Cout] act_dtype, mask from forward -> dx [B,IH,IW,Cin] NHWC act_dtype */
+int vqa_conv_bwd_data(const void* dpool, const uint8_t* mask, const float* w, void* dx, int act_dtype,
+                      int B, int IH, int IW, int Cin, int Cout, int KS, int stride, void* stream);
+/* gradient w.r.t. weight (OIHW fp32, overwritten) and bias (fp32, overwritten) */
+int vqa_conv_bwd_weight(const void* x, int x_dtype, int x_nchw, const void* dpool, const uint8_t* mask,
+                        float* dw, float* db, int act_dtype,
+                        int B, int IH, int IW, int Cin, int Cout, int KS, int stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * image.drop + channel L2 normalisation -- models/model.py:84 and :56
+ *   x [R,C] (R = B*H*W rows, NHWC) -> vn = drop_img(x) / (||drop_img(x)||_2 + 1e-12)   [R,C]
+ *   vnd = drop_att(vn) (the input of attention.v_conv, models/model.py:185); may be NULL when p_att == 0
+ *   nrm [R] fp32 = the norms, saved for backward
+ * backward: dvn (may be NULL) and dvnd (may be NULL) are the gradients w.r.t. vn and vnd -> dx
+ * --------------------------------------------------------------------------------------------- */
+int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, int act_dtype, int64_t R, int C,
+                     float p_img, float p_att, uint64_t seed, void* stream);
+int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* vn, const float* nrm, void* dx,
+                     int act_dtype, int64_t R, int C, float p_img, float p_att, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Question encoder -- models/model.py:151-166
+ * Sequence buffers are STEP-indexed: [dirs][T][B][...]; step s of direction 0 consumes token t=s,
+ * step s of direction 1 consumes t=len-1-s (what pack_padded_sequence + a reverse LSTM does);
+ * steps s >= len[b] are inactive (state frozen).
+ *
+ * embed: xs[dir][s][b][0:E] = tanh(drop(embedding[q[b,t]]))  (models/model.py:155-157); pad columns
+ *        E..ldx-1 are zero-filled; inactive rows are zero.
+ * --------------------------------------------------------------------------------------------- */
+int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb, void* xs, int act_dtype,
+                       int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream);
+/* demb (fp32 [V,E], ACCUMULATED into; caller zeroes) += scatter of dxs * (1-xs^2) * mask; token 0
+ * (padding_idx, models/model.py:138-140) receives nothing */
+int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, const void* dxs, float* demb,
+                       int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream);
+
+/* one LSTM time step for all directions (nn.LSTM, models/model.py:164): gates = gx[:,s] + h_{s-1} W_hh^T,
+ * i,f,g,o nonlinearities, c/h update fused in the GEMM epilogue.
+ *   gx [dirs][T][B][4H] act_dtype: in = x W_ih^T + b_ih + b_hh, out = activated gates (kept for backward)
+ *   cs [dirs][T][B][H] fp32, hs [dirs][T][B][H] act_dtype; qf [B][dirs*H] act_dtype gets c at s == T-1
+ *   w_hh fp32 [dirs][4H][H] */
+int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, const int64_t* q_len,
+                      int act_dtype, int s, int T, int B, int H, int dirs, void* stream);
+/* backward pointwise part of step s: consumes dh (fp32 [dirs][B][H], gradient w.r.t. h_s), updates the
+ * running dc (fp32 [dirs][B][H]) in place, writes pre-activation gate gradients dg[dirs][s][B][4H].
+ * dc_init (act_dtype [B][dirs*H], gradient w.r.t. the final cell state) is non-NULL on the first
+ * processed step (s == T-1) and replaces the running dc there */
+int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float* dh, float* dc,
+                                const void* dc_init, void* dg, const int64_t* q_len, int act_dtype,
+                                int s, int T, int B, int H, int dirs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * General dense contraction (nn.Linear / 1x1 Conv2d / their autograd): for z in [0,nbatch)
+ *   C[z][m, n] (op)= act( sum_k A[z](m,k) * B[z](n,k) + bias[z][n] ) * dropout
+ * A(m,k) = A[m*a_sr + k*a_sk], B(n,k) = B[n*b_sr + k*b_sk] (element strides), C row-major with ldc.
+ *   flags: VQA_GEMM_RELU, VQA_GEMM_ACCUMULATE (C += ...), VQA_GEMM_SPLITK (fp32 C only: atomically
+ *   accumulates K-slices into C, which the caller has zeroed; bias/relu/dropout not allowed)
+ * --------------------------------------------------------------------------------------------- */
+#define VQA_GEMM_RELU 1
+#define VQA_GEMM_ACCUMULATE 2
+#define VQA_GEMM_SPLITK 4
+int vqa_gemm(const void* A, int a_dtype, int64_t a_sr, int64_t a_sk, int64_t a_sb,
+             const void* B, int b_dtype, int64_t b_sr, int64_t b_sk, int64_t b_sb,
+             void* C, int c_dtype, int64_t ldc, int64_t c_sb,
+             const float* bias, const float* bias2, int64_t bias_sb,
+             int M, int N, int K, int nbatch, int flags,
+             float p_drop, uint64_t seed, uint32_t site, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention -- models/model.py:187-195 (tile, +/*, ReLU, dropout, x_conv 1x1) and
+ * models/model.py:208-221 (spatial softmax per glimpse, weighted pooling).  One memory-bound kernel.
+ *   vp [B,P,A] act_dtype = v_conv output; qp [B,A] fp32 = q_lin output; vn [B,P,C] act_dtype (normalised,
+ *   un-dropped features); wx [G,A], bx [G] fp32 = x_conv; prob [B,G,P] fp32 (softmax, saved);
+ *   out: row b at out + b*ldo, [G*C] act_dtype, glimpse-major (the first G*C columns of `combined`)
+ * --------------------------------------------------------------------------------------------- */
+int vqa_attention_fwd(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx,
+                      float* prob, void* out, int64_t ldo, int act_dtype, int op,
+                      int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream);
+/* dout: row b at dout + b*ldd, [G*C] act_dtype.  Writes dvp [B,P,A], dvn [B,P,C] (act_dtype),
+ * dqp [B,A] fp32, and per-sample partials dwx_part [B,G,A], dbx_part [B,G] fp32 (column-sum them) */
+int vqa_attention_bwd(const void* dout, int64_t ldd, const void* vp, const float* qp, const void* vn,
+                      const float* wx, const float* prob, void* dvp, void* dvn, float* dqp,
+                      float* dwx_part, float* dbx_part, int act_dtype, int op,
+                      int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft-target loss + VQA score -- train.py:190-206 and utils/train_utils.py:12-25, one pass:
+ *   loss = (1/B) sum_b sum_j [a_idx[b,j] != 0] * (a_val[b,j]/10) * (-log_softmax(logits[b]))[a_idx[b,j]-1]
+ *   score = sum_b min(0.3 * count_b(argmax logits[b]), 1)
+ *   dlogits (may be NULL) = d loss / d logits
+ *   loss_rows/score_rows: [B] fp32 scratch; loss_out/score_out: 1 fp32 each
+ * --------------------------------------------------------------------------------------------- */
+int vqa_softloss_fwd_bwd(const float* logits, const int64_t* a_idx, const int64_t* a_val, float* dlogits,
+                         float* loss_rows, float* score_rows, float* loss_out, float* score_out,
+                         int B, int N, int A, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * small fused helpers
+ * --------------------------------------------------------------------------------------------- */
+/* out[r, c] = in[r, c] * dropout(site, r*cols + c); in/out row pitches ld_in/ld_out (elements) */
+int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64_t ld_out, int dtype, int64_t rows,
+                      int cols, float p, uint64_t seed, uint32_t site, void* stream);
+/* out[c] += sum_r in[r*ld + c]   (fp32 out, caller zeroes); mask != NULL: only rows where mask[r*ld+c] < 4 */
+int vqa_colsum(const void* in, int dtype, int64_t ld, const uint8_t* mask, float* out, int64_t rows, int cols,
+               void* stream);
+/* dst = (dtype) src, n elements */
+int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* ReLU + dropout backward for classifier.lin1: dz = dy * [y > 0] * scale, y = dropped ReLU output */
+int vqa_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float p, void* stream);
+/* dst[r, 0:cols] = a[r,:] + b[r,:] * dropout(site, r*cols+c)  (b may be NULL) -- gradient merges */
+int vqa_add_dropped(const void* a, int64_t lda, const void* b, int64_t ldb, void* dst, int64_t ldd, int dtype,
+                    int64_t rows, int cols, float p, uint64_t seed, uint32_t site, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Adam -- train.py:55,76-80 (torch.optim.Adam defaults, lr set per step by update_learning_rate).
+ * Multi-tensor: n tensors described by device pointer tables (each [n] of device pointers / sizes
+ * resident in DEVICE memory).  bf16_copy[i] may be NULL; otherwise receives the updated parameter.
+ * --------------------------------------------------------------------------------------------- */
+int vqa_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, void* const* bf16_copy, const int64_t* sizes, int n,
+                   int64_t max_size, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H */

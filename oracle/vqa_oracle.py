@@ -1,0 +1,310 @@
+"""CPU fp32 oracle for the DL_VQA training / inference step.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain functional PyTorch (CPU, fp32), the arithmetic of the reference's
+hot path.  It is imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product path (dl_vqa_b200/) never imports it.
+
+Every function cites the reference file:line it follows (paths relative to the reference repo).
+
+Parity pin: the reference has no golden vectors or tests, so this oracle is pinned
+against OUTPUTS OF THE REFERENCE ITSELF: oracle/make_golden.py imports the unmodified
+models/model.py, runs it on seeded inputs and commits the results under tests/golden/;
+tests/test_oracle.py checks this restatement against those fixtures.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+DEFAULT_CFG = {
+    # config/config.yaml:51-74 (the `train:` block; only the keys models/model.py reads)
+    "text": {"question_features": 1024, "embedding_features": 300, "dropout": 0.3,
+             "num_lstm_layers": 1, "bidirectional": True},
+    "image": {"kernel_size": 3, "dropout": 0.3, "num_channels": [3, 64, 128, 256], "stride": 1,
+              "do_skip_connection": False},
+    "attention": {"hidden_dim": 1024, "glimpses": 2, "do_option": "+", "dropout": 0.3},
+    "classifier": {"hidden_dim": 1024, "dropout": 0.3},
+    "max_answers": 3000,
+    "image_size": 224,
+}
+
+
+def cfg_with(base: Optional[dict] = None, **overrides) -> dict:
+    """Deep-copy a config and apply 'section.key'=value overrides (e.g. **{'image.stride': 2})."""
+    import copy
+    cfg = copy.deepcopy(base if base is not None else DEFAULT_CFG)
+    for k, val in overrides.items():
+        parts = k.split(".")
+        d = cfg
+        for p in parts[:-1]:
+            d = d[p]
+        d[parts[-1]] = val
+    return cfg
+
+
+def zero_dropout(cfg: dict) -> dict:
+    return cfg_with(cfg, **{"text.dropout": 0.0, "image.dropout": 0.0,
+                            "attention.dropout": 0.0, "classifier.dropout": 0.0})
+
+
+# ----------------------------------------------------------------------------------------------
+# model forward, restated stage by stage
+# ----------------------------------------------------------------------------------------------
+def image_encoder(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor) -> torch.Tensor:
+    """models/model.py:72-84 (ImageNet2): per layer Conv2d(k, stride, pad 0) -> ReLU -> MaxPool2d(2,2)
+    floor mode.  The trailing Dropout is identity here (oracle = eval / dropout 0)."""
+    n_layers = len(cfg["image"]["num_channels"]) - 1
+    x = v
+    for i in range(n_layers):
+        x = F.conv2d(x, sd[f"image.conv{i}.weight"], sd[f"image.conv{i}.bias"],
+                     stride=cfg["image"]["stride"])
+        x = torch.clamp_min(x, 0.0)
+        x = F.max_pool2d(x, kernel_size=2, stride=2)
+    return x
+
+
+def l2_normalise(v: torch.Tensor) -> torch.Tensor:
+    """models/model.py:56: v / (||v||_2 over channels + 1e-12)."""
+    n = torch.sqrt((v * v).sum(dim=1, keepdim=True))
+    return v / (n + 1e-12)
+
+
+def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
+                    bidirectional: bool) -> torch.Tensor:
+    """models/model.py:159-166: pack_padded_sequence + nn.LSTM, keep the final CELL state of every
+    direction, laid out [B, dirs*H] as (c_fwd | c_bwd).  Explicit loop; gate order i,f,g,o
+    (torch.nn.LSTM); forward direction consumes t=0..len-1, reverse consumes t=len-1..0."""
+    B, T, _ = x.shape
+    outs = []
+    for suffix, reverse in (("", False), ("_reverse", True)):
+        if reverse and not bidirectional:
+            break
+        w_ih = sd[f"text.lstm.weight_ih_l0{suffix}"]
+        w_hh = sd[f"text.lstm.weight_hh_l0{suffix}"]
+        bias = sd[f"text.lstm.bias_ih_l0{suffix}"] + sd[f"text.lstm.bias_hh_l0{suffix}"]
+        h = x.new_zeros(B, hidden)
+        c = x.new_zeros(B, hidden)
+        for s in range(T):
+            active = (s < lengths)                                   # [B]
+            t_idx = (lengths - 1 - s).clamp_min(0) if reverse else torch.full_like(lengths, s)
+            xt = x[torch.arange(B), t_idx]                           # [B, E]
+            gates = xt @ w_ih.t() + h @ w_hh.t() + bias
+            gi, gf, gg, go = gates.chunk(4, dim=1)
+            c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h_new = torch.sigmoid(go) * torch.tanh(c_new)
+            m = active.unsqueeze(1)
+            c = torch.where(m, c_new, c)
+            h = torch.where(m, h_new, h)
+        outs.append(c)
+    return torch.cat(outs, dim=1)
+
+
+def question_encoder(sd, cfg: dict, q: torch.Tensor, q_len: torch.Tensor) -> torch.Tensor:
+    """models/model.py:151-166: embedding (padding_idx 0) -> dropout(identity) -> tanh -> LSTM c_n."""
+    emb = sd["text.embedding.weight"][q]                             # [B,T,E]
+    x = torch.tanh(emb)
+    return lstm_final_cell(sd, x, q_len.to(torch.long).cpu(), cfg["text"]["question_features"],
+                           cfg["text"]["bidirectional"])
+
+
+def attention_logits(sd, cfg: dict, v: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """models/model.py:183-195 (Attention.forward), dropout = identity."""
+    vp = F.conv2d(v, sd["attention.v_conv.weight"])                  # 1x1, no bias
+    qp = q @ sd["attention.q_lin.weight"].t() + sd["attention.q_lin.bias"]
+    qt = qp[:, :, None, None].expand_as(vp)                          # models/model.py:224-231
+    opt = cfg["attention"]["do_option"]
+    if opt == "+":
+        x = torch.clamp_min(vp + qt, 0.0)
+    elif opt == "*":
+        x = torch.clamp_min(vp * qt, 0.0)
+    elif opt == "|":
+        x = torch.clamp_min(torch.cat([vp, qt], dim=1), 0.0)
+    else:
+        raise ValueError(f"do_option {opt!r}")
+    return F.conv2d(x, sd["attention.x_conv.weight"], sd["attention.x_conv.bias"])
+
+
+def glimpse_pool(v: torch.Tensor, att: torch.Tensor) -> torch.Tensor:
+    """models/model.py:208-221: softmax over the spatial positions per glimpse, weighted sum of the
+    (normalised) image features, flattened glimpse-major."""
+    B, C = v.shape[:2]
+    vf = v.reshape(B, C, -1)                                         # [B,C,S]
+    p = torch.softmax(att.reshape(B, att.shape[1], -1), dim=-1)      # [B,G,S]
+    return torch.einsum("bgs,bcs->bgc", p, vf).reshape(B, -1)
+
+
+def classifier(sd, x: torch.Tensor) -> torch.Tensor:
+    """models/model.py:198-205: drop -> lin1 -> relu -> drop -> lin2 (dropout identity)."""
+    h = torch.clamp_min(x @ sd["classifier.lin1.weight"].t() + sd["classifier.lin1.bias"], 0.0)
+    return h @ sd["classifier.lin2.weight"].t() + sd["classifier.lin2.bias"]
+
+
+def forward(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor, q: torch.Tensor,
+            q_len: torch.Tensor, intermediates: Optional[dict] = None) -> torch.Tensor:
+    """models/model.py:53-67 (VqaNet.forward) in eval mode / dropout 0."""
+    img = image_encoder(sd, cfg, v)
+    vn = l2_normalise(img)
+    qf = question_encoder(sd, cfg, q, q_len)
+    att = attention_logits(sd, cfg, vn, qf)
+    pooled = glimpse_pool(vn, att)
+    comb = torch.cat([pooled, qf], dim=1)
+    logits = classifier(sd, comb)
+    if intermediates is not None:
+        intermediates.update(img=img, vn=vn, qf=qf, att=att, pooled=pooled, comb=comb)
+    return logits
+
+
+# ----------------------------------------------------------------------------------------------
+# loss / score / optimizer (train.py, utils/train_utils.py)
+# ----------------------------------------------------------------------------------------------
+def soft_target_loss(logits: torch.Tensor, a_indices: torch.Tensor, a_values: torch.Tensor) -> torch.Tensor:
+    """train.py:190-206.  nll = -log_softmax(y); for every non-padding answer slot (a_indices != 0)
+    take nll[b, a_indices-1] * a_values/10; sum everything; divide by the batch size."""
+    nll = -torch.log_softmax(logits, dim=1)
+    B = logits.shape[0]
+    total = logits.new_zeros(())
+    for b in range(B):
+        for j in range(a_indices.shape[1]):
+            idx = int(a_indices[b, j])
+            if idx != 0:
+                total = total + nll[b, idx - 1] * (float(a_values[b, j]) / 10.0)
+    return total / B
+
+
+def soft_target_loss_dense(logits, a_indices, a_values) -> torch.Tensor:
+    """Dense cross-check of soft_target_loss."""
+    B, N = logits.shape
+    tgt = torch.zeros(B, N + 1, dtype=logits.dtype)
+    tgt.scatter_add_(1, a_indices.to(torch.long), a_values.to(logits.dtype) / 10.0)
+    tgt = tgt[:, 1:]
+    return (-torch.log_softmax(logits, dim=1) * tgt).sum() / B
+
+
+def vqa_score(logits: torch.Tensor, a_indices: torch.Tensor, a_values: torch.Tensor) -> torch.Tensor:
+    """utils/train_utils.py:12-25 (batch_accuracy): argmax per sample (first max), number of
+    annotators that gave that answer, sum_b min(0.3*count, 1)."""
+    pred = logits.argmax(dim=1)
+    total = 0.0
+    for b in range(logits.shape[0]):
+        cnt = 0.0
+        for j in range(a_indices.shape[1]):
+            idx = int(a_indices[b, j])
+            if idx != 0 and idx - 1 == int(pred[b]):
+                cnt = float(a_values[b, j])
+        total += min(0.3 * cnt, 1.0)
+    return torch.tensor(total, dtype=torch.float32)
+
+
+def learning_rate(initial_lr: float, iteration: int) -> float:
+    """train.py:31-35."""
+    return initial_lr * 0.5 ** (float(iteration) / 50000)
+
+
+def adam_step(p, g, m, v, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
+    """train.py:55,80: torch.optim.Adam defaults (no weight decay, no amsgrad).  In-place on m, v;
+    returns the new parameter."""
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    return p - (lr / bc1) * (m / denom)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameters and synthetic batches
+# ----------------------------------------------------------------------------------------------
+def param_shapes(cfg: dict, embedding_tokens: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict keys and shapes, in the reference's registration order (models/model.py:26-51)."""
+    t, im, at, cl = cfg["text"], cfg["image"], cfg["attention"], cfg["classifier"]
+    H, E = t["question_features"], t["embedding_features"]
+    out = [("text.embedding.weight", (embedding_tokens, E))]
+    for suf in ("", "_reverse") if t["bidirectional"] else ("",):
+        out += [(f"text.lstm.weight_ih_l0{suf}", (4 * H, E)), (f"text.lstm.weight_hh_l0{suf}", (4 * H, H)),
+                (f"text.lstm.bias_ih_l0{suf}", (4 * H,)), (f"text.lstm.bias_hh_l0{suf}", (4 * H,))]
+    ch, k = im["num_channels"], im["kernel_size"]
+    for i in range(len(ch) - 1):
+        out += [(f"image.conv{i}.weight", (ch[i + 1], ch[i], k, k)), (f"image.conv{i}.bias", (ch[i + 1],))]
+    qf = H * (2 if t["bidirectional"] else 1)
+    mid, G = at["hidden_dim"], at["glimpses"]
+    xin = 2 * mid if at["do_option"] == "|" else mid
+    out += [("attention.v_conv.weight", (mid, ch[-1], 1, 1)), ("attention.q_lin.weight", (mid, qf)),
+            ("attention.q_lin.bias", (mid,)), ("attention.x_conv.weight", (G, xin, 1, 1)),
+            ("attention.x_conv.bias", (G,))]
+    out += [("classifier.lin1.weight", (cl["hidden_dim"], G * ch[-1] + qf)),
+            ("classifier.lin1.bias", (cl["hidden_dim"],)),
+            ("classifier.lin2.weight", (cfg["max_answers"], cl["hidden_dim"])),
+            ("classifier.lin2.bias", (cfg["max_answers"],))]
+    return out
+
+
+def random_params(cfg: dict, embedding_tokens: int, seed: int = 1, scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Seeded parameters with fan-in scaling (not the reference's init; used where the test only
+    needs *some* identical weights on both sides).  Row 0 of the embedding is zero (padding_idx)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in param_shapes(cfg, embedding_tokens):
+        if name.endswith("bias") or ".bias_" in name:
+            sd[name] = (torch.rand(shape, generator=g) - 0.5) * 0.2
+        elif name == "text.embedding.weight":
+            w = torch.randn(shape, generator=g)
+            w[0].zero_()
+            sd[name] = w
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            sd[name] = torch.randn(shape, generator=g) * (scale / math.sqrt(fan_in))
+    return sd
+
+
+def synthetic_batch(B: int, cfg: dict, embedding_tokens: int, seed: int = 1, T: int = 23, A: int = 10,
+                    full_first: bool = True):
+    """fp16-rounded N(0,1) images, random-length zero-padded questions with
+    q_len[0] = T, sorted unique 1-based answer ids with counts summing to <= 10."""
+    g = torch.Generator().manual_seed(seed)
+    S = cfg.get("image_size", 224)
+    v = torch.randn(B, cfg["image"]["num_channels"][0], S, S, generator=g).half().float()
+    q_len = torch.randint(1, T + 1, (B,), generator=g)
+    if full_first:
+        q_len[0] = T
+    q = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        q[b, : int(q_len[b])] = torch.randint(1, embedding_tokens, (int(q_len[b]),), generator=g)
+    a_len = torch.randint(1, 5, (B,), generator=g)
+    a_idx = torch.zeros(B, A, dtype=torch.long)
+    a_val = torch.zeros(B, A, dtype=torch.long)
+    for b in range(B):
+        n = int(a_len[b])
+        ids = torch.randperm(cfg["max_answers"], generator=g)[:n].sort().values + 1
+        a_idx[b, :n] = ids
+        cuts = torch.randint(1, 4, (n,), generator=g)
+        while int(cuts.sum()) > 10:
+            cuts = torch.clamp(cuts - 1, min=1)
+        a_val[b, :n] = cuts
+    return v, q, q_len, a_idx, a_val, a_len
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-12) -> float:
+    """Parity metric fixed by SURVEY.md section 8d: ||a-b||_inf / (||b||_inf + eps), per tensor."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + eps))
+
+
+def step_with_grads(sd, cfg, batch, requires=None):
+    """forward + loss + backward by autograd on the restated forward.  Returns
+    (logits, loss, score, grads dict)."""
+    v, q, q_len, a_idx, a_val, _ = batch
+    leaves = {k: t.detach().clone().requires_grad_(True) for k, t in sd.items()}
+    inter = {}
+    logits = forward(leaves, cfg, v, q, q_len, inter)
+    loss = soft_target_loss_dense(logits, a_idx, a_val)
+    loss.backward()
+    grads = {k: (t.grad if t.grad is not None else torch.zeros_like(t)) for k, t in leaves.items()}
+    grads["text.embedding.weight"][0].zero_()       # padding_idx=0 row never receives gradient
+    score = vqa_score(logits.detach(), a_idx, a_val)
+    return logits.detach(), loss.detach(), score, grads, {k: t.detach() for k, t in inter.items()}

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_small():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "vqa_small.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_full():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "vqa_full_seed1.pt"), weights_only=False)
