@@ -11,5 +11,9 @@ void vqa_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void vqa_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" uint64_t vqa_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char* vqa_last_error_string(void) { return g_err; }
 extern "C" int vqa_abi_version(void) { return VQA_ABI_VERSION; }

@@ -13,6 +13,7 @@ typedef __nv_bfloat16 bf16;
 // error plumbing: every extern "C" entry returns 0 or an error code; message kept per thread
 // ------------------------------------------------------------------------------------------
 void vqa_set_error(const char* fmt, ...);
+void vqa_count_launch();
 
 #define VQA_REQUIRE(cond, ...)                         \
     do {                                               \
@@ -24,6 +25,7 @@ void vqa_set_error(const char* fmt, ...);
 
 #define VQA_CHECK_LAUNCH(name)                                                        \
     do {                                                                              \
+        vqa_count_launch();                                                           \
         cudaError_t e__ = cudaGetLastError();                                         \
         if (e__ != cudaSuccess) {                                                     \
             vqa_set_error("%s: %s", name, cudaGetErrorString(e__));                   \

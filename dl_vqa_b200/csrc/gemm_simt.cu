@@ -75,22 +75,23 @@ extern "C" int vqa_gemm(const void* A, int a_dtype, int64_t a_sr, int64_t a_sk, 
 
 // LSTM forward step: A = h_{s-1} [B,H] (row-major), B = W_hh gate-interleaved view, epilogue = cell
 template <typename T>
-static int lstm_step_t(void* gx, float* cs, void* hs, void* qf, const float* w_hh, const int64_t* q_len,
-                       int s, int T_, int B, int H, int dirs, cudaStream_t st) {
+static int lstm_step_t(void* gx, float* cs, void* hs, void* qf, const float* w_hh, int64_t w_sb,
+                       const int64_t* q_len, int s, int T_, int B, int H, int dirs, cudaStream_t st) {
     // h_{s-1} for direction z lives at hs + ((z*T + s-1)*B)*H  -> batch stride T*B*H
     const T* hprev = s > 0 ? (const T*)hs + (int64_t)(s - 1) * B * H : (const T*)hs;
     DenseLoader<T> al{hprev, B, s > 0 ? H : 0, H, 1, (int64_t)T_ * B * H, 0};
-    DenseLoader<float> bl{w_hh, 4 * H, s > 0 ? H : 0, H, 1, (int64_t)4 * H * H, H};
+    DenseLoader<float> bl{w_hh, 4 * H, s > 0 ? H : 0, H, 1, w_sb, H};
     EpLstmCell<T> ep{(T*)gx, cs, (T*)hs, (T*)qf, q_len, s, T_, B, H, dirs, 0};
     return launch(al, bl, ep, B, 4 * H, s > 0 ? H : 0, dirs, 1, st, "lstm_step_fwd");
 }
 
-extern "C" int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, const int64_t* q_len,
-                                 int act_dtype, int s, int T, int B, int H, int dirs, void* stream) {
+extern "C" int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, int64_t w_hh_dir_stride,
+                                 const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs,
+                                 void* stream) {
     VQA_REQUIRE(s >= 0 && s < T && B > 0 && H > 0 && (dirs == 1 || dirs == 2), "lstm step: bad dims");
     cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_F32) return lstm_step_t<float>(gx, cs, hs, qf, w_hh, q_len, s, T, B, H, dirs, st);
-    if (act_dtype == VQA_BF16) return lstm_step_t<bf16>(gx, cs, hs, qf, w_hh, q_len, s, T, B, H, dirs, st);
+    if (act_dtype == VQA_F32) return lstm_step_t<float>(gx, cs, hs, qf, w_hh, w_hh_dir_stride, q_len, s, T, B, H, dirs, st);
+    if (act_dtype == VQA_BF16) return lstm_step_t<bf16>(gx, cs, hs, qf, w_hh, w_hh_dir_stride, q_len, s, T, B, H, dirs, st);
     VQA_REQUIRE(false, "lstm step: bad dtype");
     return 0;
 }

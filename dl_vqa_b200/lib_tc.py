@@ -1,0 +1,6 @@
+"""Prototypes of the tcgen05 / TMA (tensor-core) entry points of libvqa_b200.so."""
+import ctypes as C
+
+_vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
+
+PROTOTYPES = {}

@@ -1,0 +1,478 @@
+"""Drop-in `VqaNet` for OmerShubi/DL_VQA (reference models/model.py:7-67), B200-native.
+
+Same constructor `VqaNet(cfg, embedding_tokens)`, same `forward(v, q, q_len)`, same sub-module attribute
+names (`text`, `image`, `attention`, `classifier`) and the same 24 `state_dict` keys / shapes / layouts,
+so `train.py`, `main.py` and existing `model.pth` checkpoints work unchanged.  The arithmetic runs in
+hand-written CUDA (libvqa_b200.so, include/vqa_b200.h) through ONE autograd node: forward saves the
+activations it needs, backward computes every parameter gradient in a fixed order (classifier ->
+attention -> question encoder -> image encoder) so that a data-parallel wrapper can start reducing the
+large text-side gradients while the convolution backward is still running (dl_vqa_b200/dp.py).
+
+The torch.nn layer classes below are used ONLY as parameter containers (identical default init and
+state_dict names to the reference); their forward() is never called.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import lib
+from .lib import call, ptr
+
+
+class _QuestionParams(nn.Module):
+    """Parameters of reference questionNet (models/model.py:134-149)."""
+
+    def __init__(self, embedding_tokens, embedding_features, lstm_features, num_lstm_layers, drop, bidirectional):
+        super().__init__()
+        if num_lstm_layers != 1:
+            raise NotImplementedError("num_lstm_layers != 1 (the reference itself notes it needs code changes)")
+        self.embedding = nn.Embedding(embedding_tokens, embedding_features, padding_idx=0)
+        self.drop = nn.Dropout(drop)
+        self.tanh = nn.Tanh()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.lstm = nn.LSTM(input_size=embedding_features, hidden_size=lstm_features, num_layers=num_lstm_layers,
+                                dropout=drop, bidirectional=bidirectional)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only; the fused step in VqaNet.forward computes this stage")
+
+
+class _ImageParams(nn.Module):
+    """Parameters of reference ImageNet2 (models/model.py:72-84)."""
+
+    def __init__(self, image_cfg):
+        super().__init__()
+        ch = image_cfg["num_channels"]
+        for i in range(len(ch) - 1):
+            self.add_module(f"conv{i}", nn.Conv2d(ch[i], ch[i + 1], kernel_size=image_cfg["kernel_size"],
+                                                  stride=image_cfg["stride"]))
+            self.add_module(f"relu{i}", nn.ReLU())
+            self.add_module(f"maxpool{i}", nn.MaxPool2d(2, 2))
+        self.add_module("drop", nn.Dropout(image_cfg["dropout"]))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only")
+
+
+class _AttentionParams(nn.Module):
+    """Parameters of reference Attention (models/model.py:169-181)."""
+
+    def __init__(self, v_features, q_features, mid_features, glimpses, do_option, drop):
+        super().__init__()
+        self.do_option = do_option
+        self.v_conv = nn.Conv2d(v_features, mid_features, kernel_size=1, bias=False)
+        self.q_lin = nn.Linear(q_features, mid_features)
+        self.x_conv = nn.Conv2d(2 * mid_features if do_option == "|" else mid_features, glimpses, kernel_size=1)
+        self.drop = nn.Dropout(drop)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only")
+
+
+class _ClassifierParams(nn.Module):
+    """Parameters of reference Classifier (models/model.py:198-205)."""
+
+    def __init__(self, in_features, mid_features, out_features, drop):
+        super().__init__()
+        self.add_module("drop1", nn.Dropout(drop))
+        self.add_module("lin1", nn.Linear(in_features, mid_features))
+        self.add_module("relu", nn.ReLU())
+        self.add_module("drop2", nn.Dropout(drop))
+        self.add_module("lin2", nn.Linear(mid_features, out_features))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only")
+
+
+def _elem_stride(t0: torch.Tensor, t1: torch.Tensor) -> int:
+    d = t1.data_ptr() - t0.data_ptr()
+    assert d % t0.element_size() == 0
+    return d // t0.element_size()
+
+
+class VqaNet(nn.Module):
+    """Show, Ask, Attend and Answer -- B200-native drop-in for reference models/model.py:VqaNet."""
+
+    def __init__(self, cfg, embedding_tokens, compute_dtype: Optional[str] = None):
+        super().__init__()
+        text_cfg, image_cfg = cfg["text"], cfg["image"]
+        attention_cfg, classifier_cfg = cfg["attention"], cfg["classifier"]
+        self.H = int(text_cfg["question_features"])
+        self.E = int(text_cfg["embedding_features"])
+        self.dirs = 2 if text_cfg["bidirectional"] else 1
+        self.G = int(attention_cfg["glimpses"])
+        self.A = int(attention_cfg["hidden_dim"])
+        self.channels = [int(c) for c in image_cfg["num_channels"]]
+        self.KS = int(image_cfg["kernel_size"])
+        self.stride = int(image_cfg["stride"])
+        self.do_option = attention_cfg["do_option"]
+        if self.do_option not in ("+", "*", "|"):
+            raise ValueError(f"attention.do_option {self.do_option!r}")
+        self.hidden = int(classifier_cfg["hidden_dim"])
+        self.max_answers = int(cfg["max_answers"])
+        self.p_text = float(text_cfg["dropout"])
+        self.p_img = float(image_cfg["dropout"])
+        self.p_att = float(attention_cfg["dropout"])
+        self.p_cls = float(classifier_cfg["dropout"])
+        lstm_out = self.H * self.dirs
+
+        # registration order = reference order (models/model.py:26-51): identical init under a seed
+        self.text = _QuestionParams(embedding_tokens, self.E, self.H, text_cfg["num_lstm_layers"],
+                                    text_cfg["dropout"], text_cfg["bidirectional"])
+        self.image = _ImageParams(image_cfg)
+        self.attention = _AttentionParams(self.channels[-1], lstm_out, self.A, self.G, self.do_option, self.p_att)
+        self.classifier = _ClassifierParams(self.G * self.channels[-1] + lstm_out, self.hidden, self.max_answers,
+                                            self.p_cls)
+        self.compute_dtype = torch.float32
+        if compute_dtype is not None:
+            self.set_compute_dtype(compute_dtype)
+        self._seed_counter = 0
+        self.grad_ready_hook = None      # callable(list[(name, grad)]) fired as each stage's grads complete
+
+    # ------------------------------------------------------------------ configuration
+    def set_compute_dtype(self, dt) -> "VqaNet":
+        """'float32' (exact arm, SIMT fp32) or 'bfloat16' (tensor-core arm, fp32 accumulate)."""
+        if isinstance(dt, str):
+            dt = {"float32": torch.float32, "fp32": torch.float32, "bfloat16": torch.bfloat16,
+                  "bf16": torch.bfloat16}[dt]
+        if dt not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"compute dtype {dt}")
+        self.compute_dtype = dt
+        return self
+
+    def _params(self) -> List[nn.Parameter]:
+        return list(self.parameters())
+
+    def _next_seed(self) -> int:
+        # host-side only (CPU generator): respects torch.manual_seed, never synchronises the device
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, v, q, q_len):
+        if self.do_option == "|":
+            raise NotImplementedError("attention.do_option '|' is not implemented in the CUDA path yet")
+        if not v.is_cuda:
+            raise lib.VqaLibraryError("VqaNet.forward: inputs must be CUDA tensors (no CPU fallback); call model.cuda()")
+        if v.requires_grad:
+            raise NotImplementedError("gradient w.r.t. the input image is not produced (the reference never needs it)")
+        dev = v.device
+        if isinstance(q_len, (list, tuple)):
+            q_len = torch.as_tensor([int(x) for x in q_len], dtype=torch.int64)
+        q_len = q_len.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        q = q.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        v = v.to(torch.float32).contiguous()
+        params = self._params()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        seed = self._next_seed() if self.training else 0
+        if need_grad:
+            return _VqaFunction.apply(self, seed, v, q, q_len, *params)
+        logits, _ = self._run_forward(v, q, q_len, seed, save=False)
+        return logits
+
+    # dropout probabilities in effect
+    def _p(self, p: float) -> float:
+        return p if self.training else 0.0
+
+    def _run_forward(self, v, q, q_len, seed: int, save: bool):
+        adt = self.compute_dtype
+        dt = lib.dtype_code(adt)
+        dev = v.device
+        st = lib.stream()
+        B = v.shape[0]
+        f32 = torch.float32
+        ctx = {} if save else None
+        p_text, p_img, p_att, p_cls = self._p(self.p_text), self._p(self.p_img), self._p(self.p_att), self._p(self.p_cls)
+
+        def empty(*shape, dtype=adt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        # ---------------- image encoder: fused conv+ReLU+pool per layer (models/model.py:72-84)
+        assert v.shape[1] == self.channels[0], "image channel count"
+        x, x_dt, nchw = v, lib.F32, 1
+        IH, IW = int(v.shape[2]), int(v.shape[3])
+        conv_saved = []
+        nl = len(self.channels) - 1
+        for i in range(nl):
+            conv = getattr(self.image, f"conv{i}")
+            Cin, Cout = self.channels[i], self.channels[i + 1]
+            OH, OW = (IH - self.KS) // self.stride + 1, (IW - self.KS) // self.stride + 1
+            PH, PW = OH // 2, OW // 2
+            if PH <= 0 or PW <= 0:
+                raise ValueError(f"image too small: layer {i} conv output {OH}x{OW}")
+            out = empty(B, PH, PW, Cout)
+            mask = empty(B, PH, PW, Cout, dtype=torch.uint8)
+            call("vqa_conv_relu_pool_fwd", ptr(x), x_dt, nchw, ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
+                 dt, B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+            conv_saved.append((x, x_dt, nchw, mask, IH, IW, Cin, Cout))
+            x, x_dt, nchw, IH, IW = out, dt, 0, PH, PW
+        P, Cimg = IH * IW, self.channels[-1]
+
+        # ---------------- image.drop + channel L2 norm (models/model.py:84, :56)
+        vn = empty(B * P, Cimg)
+        vnd = empty(B * P, Cimg) if p_att > 0 else None
+        nrm = empty(B * P, dtype=f32)
+        call("vqa_dropnorm_fwd", ptr(x), ptr(vn), ptr(vnd), ptr(nrm), dt, B * P, Cimg, p_img, p_att, seed, st)
+        v_in = vnd if vnd is not None else vn
+
+        # ---------------- question encoder (models/model.py:151-166)
+        T, E, H, dirs = int(q.shape[1]), self.E, self.H, self.dirs
+        lstm = self.text.lstm
+        sfx = ["", "_reverse"][:dirs]
+        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
+        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
+        b_ih = [getattr(lstm, f"bias_ih_l0{s}") for s in sfx]
+        b_hh = [getattr(lstm, f"bias_hh_l0{s}") for s in sfx]
+        ldx = E
+        xs = empty(dirs, T, B, ldx)
+        call("vqa_embed_tanh_fwd", ptr(q), ptr(q_len), ptr(self.text.embedding.weight), ptr(xs), dt,
+             B, T, E, ldx, dirs, p_text, seed, st)
+        gx = empty(dirs, T, B, 4 * H)
+        for d in range(dirs):   # hoisted input projection: x W_ih^T + b_ih + b_hh for all steps at once
+            call("vqa_gemm", ptr(xs[d]), dt, ldx, 1, 0, ptr(w_ih[d]), lib.F32, E, 1, 0,
+                 ptr(gx[d]), dt, 4 * H, 0, ptr(b_ih[d]), ptr(b_hh[d]), 0,
+                 T * B, 4 * H, E, 1, 0, 0.0, 0, 0, st)
+        cs = empty(dirs, T, B, H, dtype=f32)
+        hs = empty(dirs, T, B, H)
+        qf = empty(B, dirs * H)
+        if dirs == 2:
+            whh_stride = _elem_stride(w_hh[0], w_hh[1])
+            whh_joint = True
+        else:
+            whh_stride, whh_joint = 0, True
+        for s in range(T):
+            call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
+                 dt, s, T, B, H, dirs, st)
+
+        # ---------------- attention (models/model.py:183-195, :208-221)
+        att = self.attention
+        QF = dirs * H
+        qd = qf
+        if p_att > 0:
+            qd = empty(B, QF)
+            call("vqa_dropout_apply", ptr(qf), QF, ptr(qd), QF, dt, B, QF, p_att, seed, lib.SITE_ATT_Q, st)
+        qp = empty(B, self.A, dtype=f32)
+        call("vqa_gemm", ptr(qd), dt, QF, 1, 0, ptr(att.q_lin.weight), lib.F32, QF, 1, 0,
+             ptr(qp), lib.F32, self.A, 0, ptr(att.q_lin.bias), None, 0, B, self.A, QF, 1, 0, 0.0, 0, 0, st)
+        vp = empty(B * P, self.A)
+        call("vqa_gemm", ptr(v_in), dt, Cimg, 1, 0, ptr(att.v_conv.weight), lib.F32, Cimg, 1, 0,
+             ptr(vp), dt, self.A, 0, None, None, 0, B * P, self.A, Cimg, 1, 0, 0.0, 0, 0, st)
+        G = self.G
+        KC = G * Cimg + QF
+        comb = empty(B, KC)
+        prob = empty(B, G, P, dtype=f32)
+        op = lib.ATT_ADD if self.do_option == "+" else lib.ATT_MUL
+        call("vqa_attention_fwd", ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
+             ptr(prob), ptr(comb), KC, dt, op, B, P, self.A, Cimg, G, p_att, seed, st)
+        # combined = cat([pooled, q])  (models/model.py:64)
+        esz = comb.element_size()
+        call("vqa_dropout_apply", ptr(qf), QF, comb.data_ptr() + G * Cimg * esz, KC, dt, B, QF, 0.0, 0, 0, st)
+
+        # ---------------- classifier (models/model.py:198-205)
+        cl = self.classifier
+        combd = comb
+        if p_cls > 0:
+            combd = empty(B, KC)
+            call("vqa_dropout_apply", ptr(comb), KC, ptr(combd), KC, dt, B, KC, p_cls, seed, lib.SITE_CLS_IN, st)
+        h1d = empty(B, self.hidden)
+        call("vqa_gemm", ptr(combd), dt, KC, 1, 0, ptr(cl.lin1.weight), lib.F32, KC, 1, 0,
+             ptr(h1d), dt, self.hidden, 0, ptr(cl.lin1.bias), None, 0, B, self.hidden, KC, 1, lib.GEMM_RELU,
+             p_cls, seed, lib.SITE_CLS_HID, st)
+        logits = empty(B, self.max_answers, dtype=f32)
+        call("vqa_gemm", ptr(h1d), dt, self.hidden, 1, 0, ptr(cl.lin2.weight), lib.F32, self.hidden, 1, 0,
+             ptr(logits), lib.F32, self.max_answers, 0, ptr(cl.lin2.bias), None, 0,
+             B, self.max_answers, self.hidden, 1, 0, 0.0, 0, 0, st)
+
+        if save:
+            ctx.update(B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
+                       xs=xs, gx=gx, cs=cs, hs=hs, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
+                       q=q, q_len=q_len, ldx=ldx, whh_stride=whh_stride,
+                       p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
+        return logits, ctx
+
+    # ------------------------------------------------------------------ backward
+    def _run_backward(self, ctx, dlogits: torch.Tensor):
+        """Returns {state_dict key: gradient}.  Order: classifier, attention, text, image."""
+        B, P, T, seed = ctx["B"], ctx["P"], ctx["T"], ctx["seed"]
+        p_text, p_img, p_att, p_cls = ctx["p"]
+        dt, adt = ctx["dt"], ctx["adt"]
+        dev = dlogits.device
+        st = lib.stream()
+        f32 = torch.float32
+        H, E, dirs, G, A = self.H, self.E, self.dirs, self.G, self.A
+        Cimg = self.channels[-1]
+        QF = dirs * H
+        KC = G * Cimg + QF
+        N = self.max_answers
+        hid = self.hidden
+        grads = {}
+
+        def empty(*shape, dtype=adt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        def zeros(*shape, dtype=f32):
+            return torch.zeros(shape, dtype=dtype, device=dev)
+
+        def fire(names):
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook([(n, grads[n]) for n in names])
+
+        def gemm(Aq, a_dt, a_sr, a_sk, Bq, b_dt, b_sr, b_sk, Cq, c_dt, ldc, M, Nn, K, flags=0, a_sb=0, b_sb=0, c_sb=0, nb=1):
+            call("vqa_gemm", Aq, a_dt, a_sr, a_sk, a_sb, Bq, b_dt, b_sr, b_sk, b_sb, Cq, c_dt, ldc, c_sb,
+                 None, None, 0, M, Nn, K, nb, flags, 0.0, 0, 0, st)
+
+        def colsum(src, src_dt, ld, rows, cols):
+            out = zeros(cols)
+            call("vqa_colsum", ptr(src), src_dt, ld, None, ptr(out), rows, cols, st)
+            return out
+
+        dlogits = dlogits.to(f32).contiguous()
+        cl, att = self.classifier, self.attention
+        h1d, combd = ctx["h1d"], ctx["combd"]
+
+        # ---- classifier.lin2
+        dh1d = empty(B, hid)
+        gemm(ptr(dlogits), lib.F32, N, 1, ptr(cl.lin2.weight), lib.F32, 1, hid, ptr(dh1d), dt, hid, B, hid, N)
+        dW2 = empty(N, hid, dtype=f32)
+        gemm(ptr(dlogits), lib.F32, 1, N, ptr(h1d), dt, 1, hid, ptr(dW2), lib.F32, hid, N, hid, B)
+        grads["classifier.lin2.weight"] = dW2
+        grads["classifier.lin2.bias"] = colsum(dlogits, lib.F32, N, B, N)
+        # ---- classifier.lin1 (ReLU + drop2 folded: h1d > 0 <=> unit alive and kept)
+        dz1 = empty(B, hid)
+        call("vqa_relu_drop_bwd", ptr(dh1d), ptr(h1d), ptr(dz1), dt, B * hid, p_cls, st)
+        dcomb = empty(B, KC)
+        gemm(ptr(dz1), dt, hid, 1, ptr(cl.lin1.weight), lib.F32, 1, KC, ptr(dcomb), dt, KC, B, KC, hid)
+        dW1 = empty(hid, KC, dtype=f32)
+        gemm(ptr(dz1), dt, 1, hid, ptr(combd), dt, 1, KC, ptr(dW1), lib.F32, KC, hid, KC, B)
+        grads["classifier.lin1.weight"] = dW1
+        grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid)
+        fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"])
+        if p_cls > 0:   # through classifier.drop1 (in place)
+            call("vqa_dropout_apply", ptr(dcomb), KC, ptr(dcomb), KC, dt, B, KC, p_cls, seed, lib.SITE_CLS_IN, st)
+
+        # ---- fused attention backward
+        vp, qp, vn, v_in, prob, qd = ctx["vp"], ctx["qp"], ctx["vn"], ctx["v_in"], ctx["prob"], ctx["qd"]
+        dvp = empty(B * P, A)
+        dvn_pool = empty(B * P, Cimg)
+        dqp = empty(B, A, dtype=f32)
+        dwx_part = empty(B, G * A, dtype=f32)
+        dbx_part = empty(B, G, dtype=f32)
+        op = lib.ATT_ADD if self.do_option == "+" else lib.ATT_MUL
+        call("vqa_attention_bwd", ptr(dcomb), KC, ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(prob),
+             ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op, B, P, A, Cimg, G,
+             p_att, seed, st)
+        grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * A, B, G * A).view(G, A, 1, 1)
+        grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G)
+        # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)
+        dvnd = empty(B * P, Cimg)
+        gemm(ptr(dvp), dt, A, 1, ptr(att.v_conv.weight), lib.F32, 1, Cimg, ptr(dvnd), dt, Cimg, B * P, Cimg, A)
+        dWv = zeros(A, Cimg)
+        gemm(ptr(dvp), dt, 1, A, ptr(v_in), dt, 1, Cimg, ptr(dWv), lib.F32, Cimg, A, Cimg, B * P, flags=lib.GEMM_SPLITK)
+        grads["attention.v_conv.weight"] = dWv.view(A, Cimg, 1, 1)
+        # ---- attention.q_lin
+        dqd = empty(B, QF)
+        gemm(ptr(dqp), lib.F32, A, 1, ptr(att.q_lin.weight), lib.F32, 1, QF, ptr(dqd), dt, QF, B, QF, A)
+        dWq = empty(A, QF, dtype=f32)
+        gemm(ptr(dqp), lib.F32, 1, A, ptr(qd), dt, 1, QF, ptr(dWq), lib.F32, QF, A, QF, B)
+        grads["attention.q_lin.weight"] = dWq
+        grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A)
+        fire(["attention.v_conv.weight", "attention.q_lin.weight", "attention.q_lin.bias",
+              "attention.x_conv.weight", "attention.x_conv.bias"])
+        # gradient w.r.t. the question feature: concat branch + (dropped) q_lin branch
+        dqf = empty(B, QF)
+        esz = dcomb.element_size()
+        call("vqa_add_dropped", dcomb.data_ptr() + G * Cimg * esz, KC, ptr(dqd), QF, ptr(dqf), QF, dt, B, QF,
+             p_att, seed, lib.SITE_ATT_Q, st)
+
+        # ---- question encoder: BPTT (only c_n feeds the model, models/model.py:164-166)
+        lstm = self.text.lstm
+        sfx = ["", "_reverse"][:dirs]
+        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
+        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
+        gx, cs, hs, xs, ldx = ctx["gx"], ctx["cs"], ctx["hs"], ctx["xs"], ctx["ldx"]
+        q, q_len = ctx["q"], ctx["q_len"]
+        dh = zeros(dirs, B, H)
+        dc = empty(dirs, B, H, dtype=f32)
+        dg = empty(dirs, T, B, 4 * H)
+        gsz = dg.element_size()
+        for s in range(T - 1, -1, -1):
+            call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
+                 ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st)
+            if s > 0:   # dh_{s-1} = dgates_s W_hh
+                gemm(dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, ptr(w_hh[0]), lib.F32, 1, H,
+                     ptr(dh), lib.F32, H, B, H, 4 * H, a_sb=T * B * 4 * H, b_sb=ctx["whh_stride"], c_sb=B * H, nb=dirs)
+        for d in range(dirs):
+            dWhh = empty(4 * H, H, dtype=f32)
+            gemm(dg[d].data_ptr() + B * 4 * H * gsz, dt, 1, 4 * H, ptr(hs[d]), dt, 1, H, ptr(dWhh), lib.F32, H,
+                 4 * H, H, (T - 1) * B)
+            dWih = empty(4 * H, E, dtype=f32)
+            gemm(ptr(dg[d]), dt, 1, 4 * H, ptr(xs[d]), dt, 1, ldx, ptr(dWih), lib.F32, E, 4 * H, E, T * B)
+            db = colsum(dg[d], dt, 4 * H, T * B, 4 * H)
+            grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
+            grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
+            grads[f"text.lstm.bias_ih_l0{sfx[d]}"] = db
+            grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db.clone() if self.grad_ready_hook is not None else db
+        dxs = empty(dirs, T, B, ldx)
+        for d in range(dirs):
+            gemm(ptr(dg[d]), dt, 4 * H, 1, ptr(w_ih[d]), lib.F32, 1, E, ptr(dxs[d]), dt, ldx, T * B, E, 4 * H)
+        demb = zeros(*self.text.embedding.weight.shape)
+        call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
+             p_text, seed, st)
+        grads["text.embedding.weight"] = demb
+        names = ["text.embedding.weight"]
+        for s_ in sfx:
+            names += [f"text.lstm.weight_ih_l0{s_}", f"text.lstm.weight_hh_l0{s_}", f"text.lstm.bias_ih_l0{s_}",
+                      f"text.lstm.bias_hh_l0{s_}"]
+        fire(names)
+
+        # ---- image encoder
+        da = empty(B * P, Cimg)
+        call("vqa_dropnorm_bwd", ptr(dvn_pool), ptr(dvnd), ptr(vn), ptr(ctx["nrm"]), ptr(da), dt, B * P, Cimg,
+             p_img, p_att, seed, st)
+        nl = len(self.channels) - 1
+        names = []
+        for i in range(nl - 1, -1, -1):
+            conv = getattr(self.image, f"conv{i}")
+            x, x_dt, nchw, mask, IH, IW, Cin, Cout = ctx["conv_saved"][i]
+            dW = empty(*conv.weight.shape, dtype=f32)
+            db = empty(Cout, dtype=f32)
+            call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
+                 B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+            grads[f"image.conv{i}.weight"] = dW
+            grads[f"image.conv{i}.bias"] = db
+            names += [f"image.conv{i}.weight", f"image.conv{i}.bias"]
+            if i > 0:
+                dx = empty(B, IH, IW, Cin)
+                call("vqa_conv_bwd_data", ptr(da), ptr(mask), ptr(conv.weight), ptr(dx), dt,
+                     B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+                da = dx
+        fire(names)
+        return grads
+
+
+class _VqaFunction(torch.autograd.Function):
+    """One autograd node for the whole network (forward saves, backward = VqaNet._run_backward)."""
+
+    @staticmethod
+    def forward(ctx, model: VqaNet, seed: int, v, q, q_len, *params):
+        logits, saved = model._run_forward(v, q, q_len, seed, save=True)
+        ctx.model = model
+        ctx.saved = saved
+        ctx.names = [n for n, _ in model.named_parameters()]
+        ctx.param_versions = [p._version for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model = ctx.model
+        grads = model._run_backward(ctx.saved, dlogits)
+        ctx.saved = None
+        out = []
+        for n, need in zip(ctx.names, ctx.needs_input_grad[5:]):
+            out.append(grads[n] if need else None)
+        return (None, None, None, None, None, *out)

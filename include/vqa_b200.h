@@ -40,6 +40,8 @@ extern "C" {
 
 const char* vqa_last_error_string(void);
 int vqa_abi_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t vqa_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Image encoder -- models/model.py:72-84 (ImageNet2): Conv2d(k, stride, pad 0) -> ReLU -> MaxPool2d(2,2)
@@ -93,9 +95,9 @@ int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, c
  * i,f,g,o nonlinearities, c/h update fused in the GEMM epilogue.
  *   gx [dirs][T][B][4H] act_dtype: in = x W_ih^T + b_ih + b_hh, out = activated gates (kept for backward)
  *   cs [dirs][T][B][H] fp32, hs [dirs][T][B][H] act_dtype; qf [B][dirs*H] act_dtype gets c at s == T-1
- *   w_hh fp32 [dirs][4H][H] */
-int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, const int64_t* q_len,
-                      int act_dtype, int s, int T, int B, int H, int dirs, void* stream);
+ *   w_hh fp32 [4H][H] per direction; direction d at w_hh + d*w_hh_dir_stride (elements) */
+int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, int64_t w_hh_dir_stride,
+                      const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs, void* stream);
 /* backward pointwise part of step s: consumes dh (fp32 [dirs][B][H], gradient w.r.t. h_s), updates the
  * running dc (fp32 [dirs][B][H]) in place, writes pre-activation gate gradients dg[dirs][s][B][4H].
  * dc_init (act_dtype [B][dirs*H], gradient w.r.t. the final cell state) is non-NULL on the first

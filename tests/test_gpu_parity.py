@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA path (through the C ABI, via dl_vqa_b200.VqaNet / run_batch) against the CPU oracle
+and against the committed reference outputs (tests/golden).  Bars (BASELINE.json north_star):
+fp32 <= 1e-4 relative error (||a-b||_inf / ||b||_inf) for logits and every gradient; bf16 <= 2e-2."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"parity_{name}.json"), "w") as f:
+        json.dump(obj, f, indent=1)
+
+
+def _err(a, b):
+    """relative error with an absolute floor for gradients that are exactly zero in exact arithmetic"""
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-7))
+
+
+def _cuda_step(cfg, V, sd, batch, dtype, train=True):
+    import dl_vqa_b200 as D
+    v, q, q_len, a_idx, a_val, a_len = batch
+    m = D.VqaNet(cfg, V, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    m.cuda().train(train)
+    loss, score = D.run_batch(m, None, (v, q, a_idx, a_val, a_len, None, q_len), cfg["max_answers"])
+    logits = m(v.cuda(), q.cuda(), q_len.cuda()).detach()
+    grads = {}
+    if train:
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    torch.cuda.synchronize()
+    return logits, loss.detach(), score.detach(), grads
+
+
+def _compare(name, got, want, tol):
+    logits, loss, score, grads = got
+    wl, wloss, wscore, wgrads = want
+    rep = {"logits": _err(logits, wl), "loss": abs(float(loss) - float(wloss)) / max(1e-6, abs(float(wloss))),
+           "score": abs(float(score) - float(wscore)),
+           "top1": float((logits.argmax(1).cpu() == wl.argmax(1)).float().mean())}
+    for k, g in wgrads.items():
+        rep["grad/" + k] = _err(grads[k], g)
+    _dump(name, rep)
+    bad = {k: v for k, v in rep.items() if k not in ("top1", "score") and v > tol}
+    assert not bad, f"{name}: over tolerance {tol}: {bad}"
+    return rep
+
+
+@pytest.mark.parametrize("name", ["plus", "mul", "stride2", "unidir", "g3"])
+def test_small_configs_fp32_vs_reference_golden(golden_small, name):
+    fx = golden_small[name]
+    batch = (fx["batch"][0].float(),) + tuple(fx["batch"][1:])
+    got = _cuda_step(fx["cfg"], fx["V"], fx["sd"], batch, "float32")
+    score = O.vqa_score(fx["logits"], batch[3], batch[4])
+    _compare(f"small_{name}_fp32", got, (fx["logits"], fx["loss"], score, fx["grads"]), FP32_TOL)
+
+
+def test_cat_option_raises(golden_small):
+    fx = golden_small["cat"]
+    batch = (fx["batch"][0].float(),) + tuple(fx["batch"][1:])
+    with pytest.raises(NotImplementedError):
+        _cuda_step(fx["cfg"], fx["V"], fx["sd"], batch, "float32")
+
+
+def _full_case(B, seed):
+    import dl_vqa_b200 as D
+    cfg = O.zero_dropout(O.DEFAULT_CFG)
+    V = 15000
+    torch.manual_seed(1)
+    sd = {k: t.detach().clone() for k, t in D.VqaNet(cfg, V).state_dict().items()}
+    batch = O.synthetic_batch(B, cfg, V, seed=seed)
+    return cfg, V, sd, batch
+
+
+def test_full_config_fp32_vs_golden_and_oracle(golden_full):
+    cfg, V, sd, batch = _full_case(4, 1)
+    got = _cuda_step(cfg, V, sd, batch, "float32")
+    # (1) the reference's own outputs
+    assert _err(got[0], golden_full["logits"]) < FP32_TOL
+    assert abs(float(got[1]) - float(golden_full["loss"])) < 1e-4
+    for k, d in golden_full["grad_digest"].items():
+        assert abs(float(got[3][k].abs().max()) - d["absmax"]) <= 2e-4 * d["absmax"] + 1e-8, k
+    # (2) the oracle on the same inputs, every gradient element
+    logits, loss, score, grads, _ = O.step_with_grads(sd, cfg, batch)
+    _compare("full_fp32", got, (logits, loss, score, grads), FP32_TOL)
+
+
+def test_full_config_bf16_vs_oracle():
+    cfg, V, sd, batch = _full_case(4, 2)
+    got = _cuda_step(cfg, V, sd, batch, "bfloat16")
+    logits, loss, score, grads, _ = O.step_with_grads(sd, cfg, batch)
+    _compare("full_bf16", got, (logits, loss, score, grads), BF16_TOL)
+
+
+def test_eval_mode_matches_train_mode_with_zero_dropout():
+    cfg, V, sd, batch = _full_case(2, 3)
+    a = _cuda_step(cfg, V, sd, batch, "float32", train=False)
+    b = _cuda_step(cfg, V, sd, batch, "float32", train=True)
+    assert torch.equal(a[0], b[0])
+
+
+def test_loss_and_score_kernel_edge_cases():
+    import dl_vqa_b200 as D
+    torch.manual_seed(0)
+    B, N, A = 7, 3000, 10
+    logits = (torch.randn(B, N) * 3).requires_grad_(True)
+    a_idx = torch.zeros(B, A, dtype=torch.long)
+    a_val = torch.zeros(B, A, dtype=torch.long)
+    a_idx[0, :3] = torch.tensor([1, 1500, 3000]); a_val[0, :3] = torch.tensor([1, 2, 7])
+    a_idx[1, :1] = torch.tensor([int(logits[1].argmax()) + 1]); a_val[1, :1] = 10      # predicted, 10 votes
+    a_idx[2, :2] = torch.tensor([int(logits[2].argmax()) + 1, 5]); a_val[2, :2] = torch.tensor([2, 3])
+    # row 3: no answers at all (validation set can have those, main.py:100)
+    a_idx[4, :10] = torch.arange(1, 11); a_val[4, :10] = 1                               # all 10 slots used
+    a_idx[5, :1] = 7; a_val[5, :1] = 3
+    a_idx[6, :2] = torch.tensor([2999, 3000]); a_val[6, :2] = torch.tensor([5, 5])
+    want = O.soft_target_loss(logits, a_idx, a_val)
+    want.backward()
+    wscore = O.vqa_score(logits.detach(), a_idx, a_val)
+    lg = logits.detach().cuda().requires_grad_(True)
+    loss, score = D.soft_target_loss_and_score(lg, a_idx, a_val)
+    loss.backward()
+    assert abs(float(loss) - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+    assert abs(float(score) - float(wscore)) < 1e-6
+    assert _err(lg.grad, logits.grad) < 1e-5
+    # ties -> first maximum, like torch.max
+    t = torch.zeros(2, 50); t[0, 7] = 1; t[0, 30] = 1
+    ai = torch.tensor([[8, 31], [1, 0]]); av = torch.tensor([[4, 9], [2, 0]])
+    _, s2 = D.soft_target_loss_and_score(t.cuda(), ai, av)
+    assert abs(float(s2) - float(O.vqa_score(t, ai, av))) < 1e-6
+
+
+def test_dropout_train_mode_statistics_and_determinism():
+    """Dropout cannot match torch's RNG stream bit for bit; check the mask
+    statistics, that eval ignores it, and that forward/backward are consistent for a fixed seed."""
+    from dl_vqa_b200 import lib
+    x = torch.ones(1000, 1024, device="cuda")
+    y = torch.empty_like(x)
+    lib.call("vqa_dropout_apply", lib.ptr(x), 1024, lib.ptr(y), 1024, lib.F32, 1000, 1024, 0.3, 1234, 5, lib.stream())
+    keep = float((y > 0).float().mean())
+    assert abs(keep - 0.7) < 0.003
+    assert abs(float(y.mean()) - 1.0) < 0.005
+    assert abs(float(y.max()) - 1 / 0.7) < 1e-5
+    y2 = torch.empty_like(x)
+    lib.call("vqa_dropout_apply", lib.ptr(x), 1024, lib.ptr(y2), 1024, lib.F32, 1000, 1024, 0.3, 1234, 5, lib.stream())
+    assert torch.equal(y, y2)
+    lib.call("vqa_dropout_apply", lib.ptr(x), 1024, lib.ptr(y2), 1024, lib.F32, 1000, 1024, 0.3, 1235, 5, lib.stream())
+    assert not torch.equal(y, y2)
+    # column/row correlations of the mask should be tiny
+    m = (y > 0).float()
+    assert float((m[:, ::2] * m[:, 1::2]).mean()) - 0.49 < 0.005
+
+
+def test_train_mode_with_dropout_gradient_check():
+    """With dropout 0.3 the step must still be a consistent function: finite-difference check of the
+    loss w.r.t. one bias vector under a fixed seed."""
+    import dl_vqa_b200 as D
+    fx_cfg = O.cfg_with(O.DEFAULT_CFG, **{"image_size": 64})
+    cfg = O.cfg_with(fx_cfg, **{"text.question_features": 64, "attention.hidden_dim": 64, "classifier.hidden_dim": 64,
+                                 "max_answers": 100, "image.num_channels": [3, 8, 16, 32]})
+    V = 50
+    sd = O.random_params(cfg, V, seed=3, scale=1.5)
+    batch = O.synthetic_batch(6, cfg, V, seed=5, T=9)
+    v, q, q_len, a_idx, a_val, a_len = batch
+    m = D.VqaNet(cfg, V).cuda().train(True)
+    m.load_state_dict(sd)
+
+    def loss_at(delta=None):
+        torch.manual_seed(77)            # same dropout seed every call
+        if delta is not None:
+            with torch.no_grad():
+                m.classifier.lin2.bias.add_(delta)
+        l, _ = D.run_batch(m, None, (v, q, a_idx, a_val, a_len, None, q_len), cfg["max_answers"])
+        if delta is not None:
+            with torch.no_grad():
+                m.classifier.lin2.bias.sub_(delta)
+        return l
+
+    l0 = loss_at()
+    l0.backward()
+    g = m.classifier.lin2.bias.grad.clone()
+    d = torch.zeros_like(g); d[3] = 1e-2
+    fd = (float(loss_at(d)) - float(loss_at(-d))) / 2e-2
+    assert abs(fd - float(g[3])) < 5e-3 * max(1.0, abs(fd))
+    assert float(loss_at()) == float(l0)      # deterministic under a fixed seed
+
+
+def test_fused_adam_matches_torch_adam():
+    import dl_vqa_b200 as D
+    torch.manual_seed(0)
+    ps = [torch.randn(s, device="cuda").requires_grad_(True) for s in [(300, 17), (4096,), (5, 3, 3, 3)]]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    oa, ob = D.FusedAdam(ps, lr=5e-4), torch.optim.Adam(qs, lr=5e-4)
+    for it in range(5):
+        lr = D.update_learning_rate(oa, it * 10000, 5e-4)
+        for gp in ob.param_groups:
+            gp["lr"] = lr
+        for p, q_ in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = g.clone(); q_.grad = g.clone()
+        oa.step(); ob.step()
+    for p, q_ in zip(ps, qs):
+        assert _err(p, q_) < 1e-6
+
+
+def test_cpu_tensors_are_rejected():
+    import dl_vqa_b200 as D
+    cfg = O.cfg_with(O.DEFAULT_CFG, **{"image_size": 64})
+    m = D.VqaNet(cfg, 100)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64), torch.ones(1, 5, dtype=torch.long), torch.tensor([5]))

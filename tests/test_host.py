@@ -1,0 +1,87 @@
+"""CPU-side checks: drop-in boundary (constructor, state_dict keys, init parity with the reference's
+construction order), C-ABI library loads and exports every declared symbol, host helpers."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_keys_shapes_match_reference_contract():
+    import dl_vqa_b200 as D
+    m = D.VqaNet(O.DEFAULT_CFG, 15000)
+    want = O.param_shapes(O.DEFAULT_CFG, 15000)
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == want
+    assert sum(p.numel() for p in m.parameters()) == 23793242
+    for name in ("text", "image", "attention", "classifier"):          # utils/main_utils.py:33-36
+        assert sum(p.numel() for p in getattr(m, name).parameters()) > 0
+
+
+def test_same_seed_init_equals_reference_init(golden_full):
+    import dl_vqa_b200 as D
+    torch.manual_seed(golden_full["seed"])
+    sd = D.VqaNet(golden_full["cfg"], golden_full["V"]).state_dict()
+    for k, d in golden_full["weight_digest"].items():
+        assert torch.equal(sd[k].flatten()[:8], d["head"]), k
+        assert abs(float(sd[k].double().sum()) - d["sum"]) < 1e-6 * max(1.0, abs(d["sum"])), k
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dl_vqa_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
+    declared = set(re.findall(r"\b(vqa_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    dll = ctypes.CDLL(lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(dll, name), f"{name} declared in include/vqa_b200.h but not exported"
+    dll.vqa_abi_version.restype = ctypes.c_int
+    assert dll.vqa_abi_version() == 1
+    lib.load()
+    bound = set(lib.PROTOTYPES) | set(lib._optional_prototypes()) | {"vqa_last_error_string", "vqa_abi_version", "vqa_launch_count"}
+    assert declared <= bound, f"declared but not bound in lib.py: {declared - bound}"
+
+
+def test_no_cpu_fallback():
+    import dl_vqa_b200 as D
+    from dl_vqa_b200 import lib
+    m = D.VqaNet(O.cfg_with(O.DEFAULT_CFG, image_size=64), 50)
+    with pytest.raises(lib.VqaLibraryError):
+        m(torch.zeros(1, 3, 64, 64), torch.ones(1, 4, dtype=torch.long), torch.tensor([4]))
+    with pytest.raises(lib.VqaLibraryError):
+        D.soft_target_loss_and_score(torch.zeros(2, 10), torch.zeros(2, 3, dtype=torch.long),
+                                     torch.zeros(2, 3, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dl_vqa_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU or PyTorch fallback", ""), fn
+
+
+def test_learning_rate_schedule():
+    import dl_vqa_b200 as D
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = torch.optim.Adam([p], lr=5e-4)
+    for it in (0, 1, 50000, 123456):
+        lr = D.update_learning_rate(opt, it, 5e-4)
+        assert lr == O.learning_rate(5e-4, it) == opt.param_groups[0]["lr"]
+
+
+def test_synthetic_batch_shapes():
+    from dl_vqa_b200 import synth
+    v, q, ai, av, al, idx, ql = synth.make_batch(8)
+    assert v.shape == (8, 3, 224, 224) and v.dtype == torch.float32 and torch.equal(v.half().float(), v)
+    assert q.shape == (8, 23) and q.dtype == torch.int64 and int(ql[0]) == 23
+    for b in range(8):
+        assert (q[b, : int(ql[b])] > 0).all() and (q[b, int(ql[b]):] == 0).all()
+        n = int(al[b])
+        assert (ai[b, :n] > 0).all() and (ai[b, n:] == 0).all() and (av[b, n:] == 0).all()
+        assert (ai[b, :n].diff() > 0).all() and int(av[b].sum()) <= 10
