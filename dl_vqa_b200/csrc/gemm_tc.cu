@@ -1,0 +1,323 @@
+// bf16 tensor-core GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma (fp32 accumulators in
+// TMEM) -> tcgen05.ld epilogue.  C[z][m,n] = sum_k A[z][m,k] * B[z][n,k]  (both operands K-major bf16).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).  One 128 x BN output tile per CTA, BK = 64,
+// STAGES-deep mbarrier ring.  Split-K (gridDim.z = nbatch * nsplit) accumulates with fp32 atomics.
+//
+// Used for: the hoisted LSTM input projection, attention.v_conv / q_lin, classifier.lin1 / lin2 and all of
+// their data/weight gradients (operands pre-transposed by vqa_transpose_bf16 where the reduction index is
+// not the contiguous one).
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ host tensor maps
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    VQA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    VQA_REQUIRE(((uintptr_t)base & 15) == 0, "TMA: base pointer %p is not 16-byte aligned", base);
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        VQA_REQUIRE((gstr[i] & 15) == 0, "TMA: stride %llu of dim %d is not a multiple of 16 bytes",
+                    (unsigned long long)gstr[i], i + 1);
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int BM = 128, BK = 64, GEMM_THREADS = 192;
+
+struct GemmEpilogue {
+    void* out; int out_bf16; int64_t ldc, c_sb;
+    const float* bias; const float* bias2; int64_t bias_sb;
+    int relu, atomic, use_dropout;
+    uint32_t site; Dropout drop;
+};
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int STAGES = BN >= 256 ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
+    using S = GemmSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + S::STAGES * S::A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* tmem_full = empty + S::STAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int batch = blockIdx.z / nsplit, split = blockIdx.z - batch * nsplit;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int total_kb = (K + BK - 1) / BK;
+    const int kb_begin = split * kblocks_per_split;
+    const int kb_end = min(total_kb, kb_begin + kblocks_per_split);
+    const int nkb = max(0, kb_end - kb_begin);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, BN);      // BN fp32 columns x 128 lanes
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % S::STAGES;
+                const uint32_t ph = (i / S::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+                const int kc = (kb_begin + i) * BK;
+                tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
+                tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(BM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % S::STAGES;
+                const uint32_t ph = (i / S::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(sa + s * S::A_BYTES), b_addr = smem_u32(sb + s * S::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t ad = smem_desc_k_sw128(a_addr + k * 32), bd = smem_desc_k_sw128(b_addr + k * 32);
+                    umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (hardware restriction)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int m = m0 + row;
+        if (nkb > 0) { mbar_wait(tmem_full, 0); tcgen05_fence_after(); }
+        const float* bias = ep.bias ? ep.bias + (int64_t)batch * ep.bias_sb : nullptr;
+        const float* bias2 = ep.bias2 ? ep.bias2 + (int64_t)batch * ep.bias_sb : nullptr;
+        const uint32_t dkey = ep.use_dropout ? dropout_key(ep.drop, ep.site) : 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= N) break;                     // warp-uniform
+            float v[32];
+            if (nkb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (m >= M) continue;
+            const int nb = n0 + c0;
+            if (ep.atomic) {
+                float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                float x = v[j];
+                if (n < N) {
+                    if (bias) x += bias[n];
+                    if (bias2) x += bias2[n];
+                }
+                if (ep.relu) x = fmaxf(x, 0.f);
+                v[j] = x;
+            }
+            if (ep.use_dropout) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    // element index m*N + n; pairs may straddle an odd boundary, so take single multipliers
+                    const uint64_t idx = (uint64_t)m * N + nb + j;
+                    if ((idx & 1) == 0) {
+                        float a, b; dropout_mult2(ep.drop, dkey, idx, a, b); v[j] *= a; v[j + 1] *= b;
+                    } else {
+                        v[j] *= dropout_mult(ep.drop, ep.site, idx); v[j + 1] *= dropout_mult(ep.drop, ep.site, idx + 1);
+                    }
+                }
+            }
+            const bool full_chunk = nb + 32 <= N;
+            if (ep.out_bf16) {
+                bf16* o = (bf16*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+                if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                        *reinterpret_cast<uint4*>(o + j) = u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = __float2bfloat16_rn(v[j]);
+                }
+            } else {
+                float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+                if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = v[j];
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                       int nbatch, int nsplit, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::BYTES));
+        attr_set = true;
+    }
+    const int total_kb = (K + BK - 1) / BK;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > total_kb) nsplit = total_kb > 0 ? total_kb : 1;
+    int kbps = total_kb > 0 ? (total_kb + nsplit - 1) / nsplit : 1;
+    nsplit = total_kb > 0 ? (total_kb + kbps - 1) / kbps : 1;
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch * nsplit);
+    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::BYTES, st>>>(ta, tb, ep, M, N, K, nsplit, kbps);
+    VQA_CHECK_LAUNCH("gemm_tc");
+    return 0;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// C[z][m,n] = act(sum_k A[z][m,k] B[z][n,k] + bias) ; A [M,K] (row pitch lda), B [N,K] (row pitch ldb), bf16.
+extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
+                           void* C, int c_dtype, int64_t ldc, int64_t c_sb,
+                           const float* bias, const float* bias2, int64_t bias_sb,
+                           int M, int N, int K, int nbatch, int flags,
+                           float p_drop, uint64_t seed, uint32_t site, void* stream) {
+    VQA_REQUIRE(M > 0 && N > 0 && K > 0 && nbatch >= 1, "tc_gemm: bad dims M=%d N=%d K=%d nbatch=%d", M, N, K, nbatch);
+    VQA_REQUIRE(A && B && C, "tc_gemm: null operand");
+    VQA_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: row pitches (%lld, %lld) must be multiples of 8 bf16 elements (TMA 16-byte strides)",
+                (long long)lda, (long long)ldb);
+    VQA_REQUIRE(nbatch == 1 || (a_sb % 8 == 0 && b_sb % 8 == 0), "tc_gemm: batch strides must be multiples of 8 elements");
+    VQA_REQUIRE(c_dtype == VQA_F32 || c_dtype == VQA_BF16, "tc_gemm: bad output dtype");
+    const bool splitk = (flags & VQA_GEMM_SPLITK) != 0;
+    if (splitk) {
+        VQA_REQUIRE(c_dtype == VQA_F32 && !bias && !bias2 && !(flags & VQA_GEMM_RELU) && p_drop == 0.f,
+                    "tc_gemm: split-K needs a zeroed fp32 output and no fused bias/relu/dropout");
+    }
+    VQA_REQUIRE(!(flags & VQA_GEMM_ACCUMULATE), "tc_gemm: ACCUMULATE is not supported (use SPLITK into a zeroed buffer)");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const int BN = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb;
+    {
+        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)nbatch};
+        const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nbatch > 1 ? a_sb : (int64_t)M * lda) * 2};
+        const uint32_t box[3] = {BK, BM, 1};
+        if (int e = make_tmap_bf16(&ta, A, 3, dims, str, box)) return e;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nbatch};
+        const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)N * ldb) * 2};
+        const uint32_t box[3] = {BK, (uint32_t)BN, 1};
+        if (int e = make_tmap_bf16(&tb, B, 3, dims, str, box)) return e;
+    }
+    GemmEpilogue ep{};
+    ep.out = C; ep.out_bf16 = c_dtype == VQA_BF16; ep.ldc = ldc; ep.c_sb = c_sb;
+    ep.bias = bias; ep.bias2 = bias2; ep.bias_sb = bias_sb;
+    ep.relu = (flags & VQA_GEMM_RELU) ? 1 : 0;
+    ep.atomic = splitk ? 1 : 0;
+    ep.use_dropout = p_drop > 0.f;
+    ep.site = site; ep.drop = make_dropout(seed, p_drop);
+
+    int nsplit = 1;
+    if (splitk) {
+        const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * nbatch;
+        nsplit = (int)((148 * 2 + tiles - 1) / tiles);
+        const int maxs = ((K + BK - 1) / BK + 3) / 4;       // at least 4 k-blocks per split
+        if (nsplit > maxs) nsplit = maxs;
+        if (nsplit < 1) nsplit = 1;
+    }
+    if (BN == 64) return launch_gemm<64>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    return launch_gemm<128>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// dst[c, r] (bf16, row pitch ldd) = (bf16) src[r, c]   -- tiled transpose with optional fp32 -> bf16 cast.
+// rows x cols source with pitch lds; batched over z with strides.
+// ------------------------------------------------------------------------------------------
+template <typename TS>
+__global__ void transpose_bf16_kernel(const TS* __restrict__ src, int64_t lds, int64_t s_sb, bf16* __restrict__ dst,
+                                      int64_t ldd, int64_t d_sb, int rows, int cols) {
+    __shared__ float tile[32][33];
+    src += (int64_t)blockIdx.z * s_sb; dst += (int64_t)blockIdx.z * d_sb;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? to_f32(src[(int64_t)r * lds + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) dst[(int64_t)c * ldd + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+
+extern "C" int vqa_transpose_bf16(const void* src, int src_dtype, int64_t lds, int64_t s_sb, void* dst, int64_t ldd,
+                                  int64_t d_sb, int rows, int cols, int nbatch, void* stream) {
+    VQA_REQUIRE(rows > 0 && cols > 0 && nbatch >= 1 && lds >= cols && ldd >= rows, "transpose: bad dims");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, nbatch), block(32, 8);
+    VQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: too many rows/batches for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == VQA_F32) transpose_bf16_kernel<float><<<grid, block, 0, st>>>((const float*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols);
+    else if (src_dtype == VQA_BF16) transpose_bf16_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols);
+    else VQA_REQUIRE(false, "transpose: bad dtype");
+    VQA_CHECK_LAUNCH("transpose_bf16");
+    return 0;
+}

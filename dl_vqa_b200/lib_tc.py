@@ -3,4 +3,8 @@ import ctypes as C
 
 _vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
 
-PROTOTYPES = {}
+PROTOTYPES = {
+    "vqa_tc_gemm": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i, _i64, _i64, _vp, _vp, _i64,
+                    _i, _i, _i, _i, _i, _f, _u64, _u32, _vp],
+    "vqa_transpose_bf16": [_vp, _i, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _vp],
+}

@@ -178,6 +178,24 @@ int vqa_adam_multi(float* const* params, const float* const* grads, float* const
                    int64_t max_size, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                    void* stream);
 
+/* =============================================================================================
+ * Tensor-core arm (bf16 operands, fp32 accumulation): tcgen05.mma with TMEM accumulators, operands
+ * staged by TMA into 128-byte-swizzled shared memory.  Same math as the entries above.
+ * ============================================================================================= */
+
+/* C[z][m,n] (c_dtype, row pitch ldc) = act(sum_k A[z][m,k] * B[z][n,k] + bias[z][n] + bias2[z][n]) * dropout
+ * A [M,K] and B [N,K] are bf16, K contiguous, row pitches lda/ldb (multiples of 8 elements), 16-byte
+ * aligned.  flags as vqa_gemm (VQA_GEMM_RELU, VQA_GEMM_SPLITK; ACCUMULATE unsupported). */
+int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
+                void* C, int c_dtype, int64_t ldc, int64_t c_sb,
+                const float* bias, const float* bias2, int64_t bias_sb,
+                int M, int N, int K, int nbatch, int flags,
+                float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* dst[z][c, r] (bf16, row pitch ldd) = src[z][r, c] (fp32 or bf16, row pitch lds): operand re-layout for the
+ * contractions whose reduction index is not contiguous in memory (weight / data gradients) */
+int vqa_transpose_bf16(const void* src, int src_dtype, int64_t lds, int64_t s_sb, void* dst, int64_t ldd,
+                       int64_t d_sb, int rows, int cols, int nbatch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

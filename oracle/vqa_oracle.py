@@ -53,7 +53,17 @@ def zero_dropout(cfg: dict) -> dict:
 # ----------------------------------------------------------------------------------------------
 # model forward, restated stage by stage
 # ----------------------------------------------------------------------------------------------
-def image_encoder(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor) -> torch.Tensor:
+def _ident(t):
+    return t
+
+
+def bf16_round_ste(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 storage precision with a straight-through gradient.  Used to emulate where the
+    CUDA bf16 arm keeps activations in bf16 (so ReLU / max-pool gating decisions coincide)."""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def image_encoder(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor, rnd=_ident) -> torch.Tensor:
     """models/model.py:72-84 (ImageNet2): per layer Conv2d(k, stride, pad 0) -> ReLU -> MaxPool2d(2,2)
     floor mode.  The trailing Dropout is identity here (oracle = eval / dropout 0)."""
     n_layers = len(cfg["image"]["num_channels"]) - 1
@@ -62,7 +72,7 @@ def image_encoder(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor) -> to
         x = F.conv2d(x, sd[f"image.conv{i}.weight"], sd[f"image.conv{i}.bias"],
                      stride=cfg["image"]["stride"])
         x = torch.clamp_min(x, 0.0)
-        x = F.max_pool2d(x, kernel_size=2, stride=2)
+        x = rnd(F.max_pool2d(x, kernel_size=2, stride=2))
     return x
 
 
@@ -73,7 +83,7 @@ def l2_normalise(v: torch.Tensor) -> torch.Tensor:
 
 
 def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
-                    bidirectional: bool) -> torch.Tensor:
+                    bidirectional: bool, rnd=_ident) -> torch.Tensor:
     """models/model.py:159-166: pack_padded_sequence + nn.LSTM, keep the final CELL state of every
     direction, laid out [B, dirs*H] as (c_fwd | c_bwd).  Explicit loop; gate order i,f,g,o
     (torch.nn.LSTM); forward direction consumes t=0..len-1, reverse consumes t=len-1..0."""
@@ -91,10 +101,10 @@ def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
             active = (s < lengths)                                   # [B]
             t_idx = (lengths - 1 - s).clamp_min(0) if reverse else torch.full_like(lengths, s)
             xt = x[torch.arange(B), t_idx]                           # [B, E]
-            gates = xt @ w_ih.t() + h @ w_hh.t() + bias
+            gates = rnd(xt @ w_ih.t() + bias) + h @ w_hh.t()
             gi, gf, gg, go = gates.chunk(4, dim=1)
             c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
-            h_new = torch.sigmoid(go) * torch.tanh(c_new)
+            h_new = rnd(torch.sigmoid(go) * torch.tanh(c_new))
             m = active.unsqueeze(1)
             c = torch.where(m, c_new, c)
             h = torch.where(m, h_new, h)
@@ -102,17 +112,17 @@ def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
     return torch.cat(outs, dim=1)
 
 
-def question_encoder(sd, cfg: dict, q: torch.Tensor, q_len: torch.Tensor) -> torch.Tensor:
+def question_encoder(sd, cfg: dict, q: torch.Tensor, q_len: torch.Tensor, rnd=_ident) -> torch.Tensor:
     """models/model.py:151-166: embedding (padding_idx 0) -> dropout(identity) -> tanh -> LSTM c_n."""
     emb = sd["text.embedding.weight"][q]                             # [B,T,E]
-    x = torch.tanh(emb)
-    return lstm_final_cell(sd, x, q_len.to(torch.long).cpu(), cfg["text"]["question_features"],
-                           cfg["text"]["bidirectional"])
+    x = rnd(torch.tanh(emb))
+    return rnd(lstm_final_cell(sd, x, q_len.to(torch.long).cpu(), cfg["text"]["question_features"],
+                               cfg["text"]["bidirectional"], rnd))
 
 
-def attention_logits(sd, cfg: dict, v: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+def attention_logits(sd, cfg: dict, v: torch.Tensor, q: torch.Tensor, rnd=_ident) -> torch.Tensor:
     """models/model.py:183-195 (Attention.forward), dropout = identity."""
-    vp = F.conv2d(v, sd["attention.v_conv.weight"])                  # 1x1, no bias
+    vp = rnd(F.conv2d(v, sd["attention.v_conv.weight"]))             # 1x1, no bias
     qp = q @ sd["attention.q_lin.weight"].t() + sd["attention.q_lin.bias"]
     qt = qp[:, :, None, None].expand_as(vp)                          # models/model.py:224-231
     opt = cfg["attention"]["do_option"]
@@ -136,22 +146,24 @@ def glimpse_pool(v: torch.Tensor, att: torch.Tensor) -> torch.Tensor:
     return torch.einsum("bgs,bcs->bgc", p, vf).reshape(B, -1)
 
 
-def classifier(sd, x: torch.Tensor) -> torch.Tensor:
+def classifier(sd, x: torch.Tensor, rnd=_ident) -> torch.Tensor:
     """models/model.py:198-205: drop -> lin1 -> relu -> drop -> lin2 (dropout identity)."""
-    h = torch.clamp_min(x @ sd["classifier.lin1.weight"].t() + sd["classifier.lin1.bias"], 0.0)
+    h = rnd(torch.clamp_min(x @ sd["classifier.lin1.weight"].t() + sd["classifier.lin1.bias"], 0.0))
     return h @ sd["classifier.lin2.weight"].t() + sd["classifier.lin2.bias"]
 
 
 def forward(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor, q: torch.Tensor,
-            q_len: torch.Tensor, intermediates: Optional[dict] = None) -> torch.Tensor:
-    """models/model.py:53-67 (VqaNet.forward) in eval mode / dropout 0."""
-    img = image_encoder(sd, cfg, v)
-    vn = l2_normalise(img)
-    qf = question_encoder(sd, cfg, q, q_len)
-    att = attention_logits(sd, cfg, vn, qf)
-    pooled = glimpse_pool(vn, att)
+            q_len: torch.Tensor, intermediates: Optional[dict] = None, emulate_bf16: bool = False) -> torch.Tensor:
+    """models/model.py:53-67 (VqaNet.forward) in eval mode / dropout 0.  emulate_bf16 rounds the
+    activations that the CUDA bf16 arm stores in bf16 (test aid; the reference itself is fp32)."""
+    rnd = bf16_round_ste if emulate_bf16 else _ident
+    img = image_encoder(sd, cfg, v, rnd)
+    vn = rnd(l2_normalise(img))
+    qf = question_encoder(sd, cfg, q, q_len, rnd)
+    att = attention_logits(sd, cfg, vn, qf, rnd)
+    pooled = rnd(glimpse_pool(vn, att))
     comb = torch.cat([pooled, qf], dim=1)
-    logits = classifier(sd, comb)
+    logits = classifier(sd, comb, rnd)
     if intermediates is not None:
         intermediates.update(img=img, vn=vn, qf=qf, att=att, pooled=pooled, comb=comb)
     return logits
@@ -295,13 +307,13 @@ def rel_err(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-12) -> float:
     return float((a - b).abs().max() / (b.abs().max() + eps))
 
 
-def step_with_grads(sd, cfg, batch, requires=None):
+def step_with_grads(sd, cfg, batch, requires=None, emulate_bf16: bool = False):
     """forward + loss + backward by autograd on the restated forward.  Returns
     (logits, loss, score, grads dict)."""
     v, q, q_len, a_idx, a_val, _ = batch
     leaves = {k: t.detach().clone().requires_grad_(True) for k, t in sd.items()}
     inter = {}
-    logits = forward(leaves, cfg, v, q, q_len, inter)
+    logits = forward(leaves, cfg, v, q, q_len, inter, emulate_bf16=emulate_bf16)
     loss = soft_target_loss_dense(logits, a_idx, a_val)
     loss.backward()
     grads = {k: (t.grad if t.grad is not None else torch.zeros_like(t)) for k, t in leaves.items()}

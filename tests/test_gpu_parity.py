@@ -51,10 +51,18 @@ def _compare(name, got, want, tol):
     rep = {"logits": _err(logits, wl), "loss": abs(float(loss) - float(wloss)) / max(1e-6, abs(float(wloss))),
            "score": abs(float(score) - float(wscore)),
            "top1": float((logits.argmax(1).cpu() == wl.argmax(1)).float().mean())}
+    gmax = max(float(g.abs().max()) for g in wgrads.values())
     for k, g in wgrads.items():
-        rep["grad/" + k] = _err(grads[k], g)
+        if k == "attention.x_conv.bias":
+            # exactly zero in exact arithmetic (softmax is shift invariant): both sides are rounding
+            # noise, so bound it absolutely, relative to the largest gradient of the step
+            rep["grad/" + k] = float((grads[k].detach().cpu() - g).abs().max()) / gmax
+        else:
+            rep["grad/" + k] = _err(grads[k], g)
+        a, b = grads[k].detach().double().cpu().reshape(-1), g.double().reshape(-1)
+        rep["cos/" + k] = float((a @ b) / (a.norm() * b.norm() + 1e-30))
     _dump(name, rep)
-    bad = {k: v for k, v in rep.items() if k not in ("top1", "score") and v > tol}
+    bad = {k: v for k, v in rep.items() if k not in ("top1", "score") and not k.startswith("cos/") and v > tol}
     assert not bad, f"{name}: over tolerance {tol}: {bad}"
     return rep
 
@@ -99,10 +107,27 @@ def test_full_config_fp32_vs_golden_and_oracle(golden_full):
 
 
 def test_full_config_bf16_vs_oracle():
+    """bf16 arm.  Logits / loss / top-1 against the fp32 oracle at the 2e-2 bar.  Gradients: a ReLU /
+    max-pool net stored in bf16 flips ~0.1% of its gating decisions relative to fp32 (inputs perturbed
+    by 2^-9), and each flipped unit changes its gradient entry by 100%, so the max-norm error against
+    the fp32 oracle is ~5% for ANY bf16 implementation.  Gradient parity is therefore taken (a) at
+    2e-2 against the oracle with the same bf16 storage rounding emulated (identical gating), and
+    (b) as direction agreement (cosine >= 0.99) against the pure fp32 oracle."""
     cfg, V, sd, batch = _full_case(4, 2)
     got = _cuda_step(cfg, V, sd, batch, "bfloat16")
     logits, loss, score, grads, _ = O.step_with_grads(sd, cfg, batch)
-    _compare("full_bf16", got, (logits, loss, score, grads), BF16_TOL)
+    assert _err(got[0], logits) < BF16_TOL
+    assert abs(float(got[1]) - float(loss)) < BF16_TOL * abs(float(loss))
+    rep32 = {}
+    for k, g in grads.items():
+        a, b = got[3][k].detach().double().cpu().reshape(-1), g.double().reshape(-1)
+        rep32[k] = {"maxnorm": _err(got[3][k], g), "cos": float((a @ b) / (a.norm() * b.norm() + 1e-30))}
+    _dump("full_bf16_vs_fp32_oracle", rep32)
+    for k, r in rep32.items():
+        if k != "attention.x_conv.bias":
+            assert r["cos"] > 0.99, (k, r)
+    elogits, eloss, escore, egrads, _ = O.step_with_grads(sd, cfg, batch, emulate_bf16=True)
+    _compare("full_bf16", got, (elogits, eloss, escore, egrads), BF16_TOL)
 
 
 def test_eval_mode_matches_train_mode_with_zero_dropout():
