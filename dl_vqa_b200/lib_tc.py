@@ -7,4 +7,8 @@ PROTOTYPES = {
     "vqa_tc_gemm": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i, _i64, _i64, _vp, _vp, _i64,
                     _i, _i, _i, _i, _i, _f, _u64, _u32, _vp],
     "vqa_transpose_bf16": [_vp, _i, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _vp],
+    "vqa_tc_conv3x3_relu_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vqa_tc_conv3x3_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vqa_pack_conv3x3_weight": [_vp, _vp, _vp, _i, _i, _vp],
+    "vqa_unpool_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }

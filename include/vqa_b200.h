@@ -196,6 +196,21 @@ int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t
 int vqa_transpose_bf16(const void* src, int src_dtype, int64_t lds, int64_t s_sb, void* dst, int64_t ldd,
                        int64_t d_sb, int rows, int cols, int nbatch, void* stream);
 
+/* 3x3 stride-1 conv + bias + ReLU + 2x2 max-pool as an implicit GEMM on tcgen05 (replaces the cuDNN conv +
+ * ATen relu + max_pool2d of models/model.py:80-82 for layers with Cin % 64 == 0, Cout in {64,128,256}).
+ *   x [B,IH,IW,Cin] bf16 NHWC; wp [Cout][9*Cin] bf16 packed by vqa_pack_conv3x3_weight; bias fp32
+ *   out / mask [B,PH,PW,Cout] as vqa_conv_relu_pool_fwd */
+int vqa_tc_conv3x3_relu_pool_fwd(const void* x, const void* wp, const float* bias, void* out, uint8_t* mask,
+                                 int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* data gradient: dy [B,2PH,2PW,Cout] bf16 = un-pooled gradient (vqa_unpool_bf16), wd [Cin][9*Cout] bf16 packed,
+ * dx [B,IH,IW,Cin] bf16 */
+int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
+                            int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* w fp32 OIHW [Cout,Cin,3,3] -> wp[co][tap][ci] and/or wd[ci][tap][co] (bf16; either may be NULL) */
+int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream);
+/* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0) */
+int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int PH, int PW, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

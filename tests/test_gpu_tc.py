@@ -60,3 +60,73 @@ def test_transpose_bf16():
     torch.cuda.synchronize()
     assert torch.equal(dst[:, :, :70], src.transpose(1, 2).bfloat16())
     assert float(dst[:, :, 70:].float().min()) == 7.0
+
+
+def _conv_case(B, IH, IW, Cin, Cout, seed):
+    torch.manual_seed(seed)
+    x = torch.randn(B, IH, IW, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cin ** 0.5))
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    return x, w, bias
+
+
+@pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (3, 111, 111, 64, 128), (2, 54, 54, 128, 256),
+                                              (1, 11, 9, 64, 64), (5, 30, 31, 128, 64)])
+def test_tc_conv_fwd_matches_torch(B, IH, IW, Cin, Cout):
+    import torch.nn.functional as F
+    from dl_vqa_b200 import lib
+    x, w, bias = _conv_case(B, IH, IW, Cin, Cout, IH + Cin)
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    wp = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_pack_conv3x3_weight", lib.ptr(w), lib.ptr(wp), None, Cout, Cin, lib.stream())
+    out = torch.empty(B, PH, PW, Cout, dtype=torch.bfloat16, device="cuda")
+    mask = torch.empty(B, PH, PW, Cout, dtype=torch.uint8, device="cuda")
+    lib.call("vqa_tc_conv3x3_relu_pool_fwd", lib.ptr(x), lib.ptr(wp), lib.ptr(bias), lib.ptr(out), lib.ptr(mask),
+             B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    pre = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), bias)
+    want, idx = F.max_pool2d(torch.relu(pre), 2, 2, return_indices=True)
+    want = want.permute(0, 2, 3, 1)
+    err = float((out.float() - want).abs().max() / want.abs().max())
+    assert err < 1e-2, err
+    # arg-max agreement where the maximum is positive and unambiguous
+    OW = IW - 2
+    idx = idx.permute(0, 2, 3, 1)
+    oh, ow = idx // OW, idx % OW
+    e = (oh % 2) * 2 + (ow % 2)
+    alive = want > 1e-3
+    agree = float(((mask.long() == e) | ~alive).float().mean())
+    assert agree > 0.999, agree
+    assert bool(((mask == 4) == (out == 0)).all())
+
+
+@pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (2, 111, 111, 64, 128), (2, 54, 54, 128, 256),
+                                              (1, 13, 10, 64, 64)])
+def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout):
+    import torch.nn.functional as F
+    from dl_vqa_b200 import lib
+    torch.manual_seed(IH)
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cout ** 0.5))
+    dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
+    mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
+    dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
+    # reference un-pool
+    ref = torch.zeros(B, 2 * PH, 2 * PW, Cout, device="cuda")
+    for e in range(4):
+        ref[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
+    torch.cuda.synchronize()
+    assert torch.equal(dy.float(), ref)
+    wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_pack_conv3x3_weight", lib.ptr(w), None, lib.ptr(wd), Cout, Cin, lib.stream())
+    dx = torch.empty(B, IH, IW, Cin, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_tc_conv3x3_bwd_data", lib.ptr(dy), lib.ptr(wd), lib.ptr(dx), B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
+    full[:, :2 * PH, :2 * PW] = ref
+    want = F.conv_transpose2d(full.permute(0, 3, 1, 2), w.bfloat16().float()).permute(0, 2, 3, 1)
+    err = float((dx.float() - want).abs().max() / want.abs().max())
+    assert err < 1e-2, err
