@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the DL_VQA training step (BASELINE.json: "train samples/sec at 1/2/4/8 B200").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+One step = forward + soft-target loss + backward + Adam on one synthetic batch of 256 samples per GPU at the
+config.yaml shapes (BASELINE.json configs[1]), dropout 0.3 active (train mode).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic FLOP per sample of the contraction kernels, forward; dgrad/wgrad equal
+CONV_FLOP = {0: 0.170e9, 1: 1.752e9, 2: 1.595e9}
+STEP_FLOP_PER_SAMPLE = 13.00e9          # fwd + bwd at T = 23
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference step, timed on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=32):
+    import torch
+    from oracle import vqa_oracle as O
+    cfg = O.DEFAULT_CFG
+    V = 15000
+    sd = O.random_params(cfg, V, seed=1)
+    leaves = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+    opt = torch.optim.Adam(list(leaves.values()), lr=5e-4)          # reference train.py:55
+    v, q, q_len, a_idx, a_val, _ = O.synthetic_batch(batch, cfg, V, seed=1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        logits = O.forward(leaves, cfg, v, q, q_len)
+        loss = O.soft_target_loss_dense(logits, a_idx, a_val)
+        opt.zero_grad()
+        for g in opt.param_groups:
+            g["lr"] = O.learning_rate(5e-4, it)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, batch, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    # bounded sample: B=32 per step (about 3 s of CPU work each); cap the total at a few minutes
+    steps_eff = min(steps, 40)
+    warm = min(args.warmup, 3)
+    times, batch, threads = cpu_reference_steps(steps_eff, warm, batch=32)
+    ms = 1000.0 * sum(times) / len(times)
+    val = batch / (ms / 1000.0)
+    sample = (f"oracle port of models/model.py fwd + train.py loss + bwd + torch Adam, fp32, batch {batch} per step "
+              f"(bounded sample of the 256-sample step), {steps_eff} timed steps, {threads} torch threads")
+    line = {"impl": "reference", "metric": "train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps_eff, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single-B200 training step of BASELINE.json configs[1]: full VqaNet fwd+loss+bwd+Adam "
+                                   "at config.yaml shapes, timed here on the host CPU", "batch_per_step": batch},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dl_vqa_b200 as D
+    from dl_vqa_b200 import lib, synth
+    from dl_vqa_b200.dp import GradientAllReduce
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    B = args.batch
+    cfg = synth.default_cfg()                       # config.yaml defaults, dropout 0.3
+    torch.manual_seed(1)
+    model = D.VqaNet(cfg, synth.DEFAULT_TOKENS, compute_dtype=args.dtype).to(dev).train(True)
+    opt = D.FusedAdam(model.parameters(), lr=5e-4)
+    ddp = GradientAllReduce(model)
+    ddp.broadcast_parameters()
+
+    host = synth.make_batch(B, cfg, seed=1 + rank, pin=True)
+    hv, hq, hai, hav, hal, _, hql = host
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (hv, hq, hai, hav, hql))
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def to_dev():
+        return tuple(t.to(dev, non_blocking=True) for t in (hv, hq, hai, hav, hal, hql))
+
+    state = {"it": 0}
+
+    def step(dbatch):
+        dv, dq, dai, dav, dal, dql = dbatch
+        loss, score = D.run_batch(model, None, (dv, dq, dai, dav, dal, None, dql), cfg["max_answers"])
+        opt.zero_grad(set_to_none=True)
+        D.update_learning_rate(opt, state["it"], 5e-4)
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        state["it"] += 1
+        return loss, score
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    dbatch = to_dev()
+    for _ in range(max(3, args.warmup)):
+        step(dbatch)
+    torch.cuda.synchronize()
+
+    # ---- (1) device-resident throughput, with per-kernel CUDA-event timing of the contraction kernels
+    tags = [f"conv{i}_{k}" for i in range(3) for k in ("fwd", "dgrad", "wgrad")] + \
+           ["v_conv", "v_conv_dgrad", "v_conv_wgrad", "vqa_attention_fwd", "vqa_attention_bwd", "lstm_step_fwd",
+            "lstm_step_bwd", "lstm_inproj", "vqa_adam_multi", "act_transpose", "unpool", "w_cast", "w_transpose"]
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = lib.launch_count()
+    lib.enable_kernel_timing(tags)
+    ms_dev = timed(lambda: step(dbatch), args.steps)
+    ktimes = lib.collect_kernel_timing()
+    launches = lib.launch_count() - n0
+    clk = clocks.stop()
+
+    # ---- (2) end to end: pinned host -> device copy of the inputs and device -> host read of the loss every step
+    def e2e_step():
+        loss, score = step(to_dev())
+        loss_host[0].copy_(loss.detach(), non_blocking=True)
+        loss_host[1].copy_(score.detach(), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    per_step = ms_dev / args.steps
+    value = world * B / (per_step / 1000.0)
+    e2e_val = world * B / (ms_e2e / args.steps / 1000.0)
+
+    # dominant kernel: the tag with the largest device time inside the timed region
+    breakdown = {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps} for k, (n, ms) in ktimes.items()}
+    conv_tags = {k: v for k, v in breakdown.items() if k.startswith("conv")}
+    roofline = None
+    if conv_tags:
+        top = max(conv_tags, key=lambda k: conv_tags[k]["ms_per_step"])
+        layer = int(top[4])
+        flop = CONV_FLOP[layer] * B
+        dur_ms = conv_tags[top]["ms_per_step"] / max(1.0, conv_tags[top]["calls_per_step"])
+        achieved = flop / (dur_ms / 1000.0) / 1e12
+        roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"] + " sustained bf16",
+                    "flop_per_launch": flop, "ms_per_launch": dur_ms}
+    att = breakdown.get("vqa_attention_fwd")
+    att_roof = None
+    if att:
+        esz = 2 if args.dtype in ("bf16", "bfloat16") else 4
+        byt = B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4)
+        gbs = byt / (att["ms_per_step"] / 1000.0) / 1e9
+        att_roof = {"kernel": "vqa_attention_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": byt}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, cb, threads = cpu_reference_steps(3, 1, batch=32)
+        cms = sum(times) / len(times)
+        cpu = {"value": cb / cms, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port, fp32, batch {cb}, 1 warm-up + 3 timed steps of fwd+loss+bwd+Adam "
+                         f"({cms:.2f} s/step), os.cpu_count()={os.cpu_count()}"}
+
+    line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.dtype in ("bf16", "bfloat16") else "f32", "data": "synthetic",
+            "config": {"workload": "single-B200 training step (BASELINE.json configs[1]): full VqaNet fwd + soft-target loss "
+                                   "+ bwd + Adam, config.yaml shapes, dropout 0.3, random init, V=15000, T=23",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs + activations per step (>2 GB) far exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "clocks": clk, "roofline": roofline, "attention_roofline": att_roof,
+            "step_tensor_frac": (STEP_FLOP_PER_SAMPLE * B / (per_step / 1000.0) / 1e12) / peaks["tflops"],
+            "kernels": breakdown, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bfloat16", "float32"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.dtype == "fp32":
+        args.dtype = "float32"
+    if args.dtype == "bf16":
+        args.dtype = "bfloat16"
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

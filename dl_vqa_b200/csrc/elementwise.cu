@@ -312,6 +312,31 @@ extern "C" int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype
     return 0;
 }
 
+// 2-D cast with row pitches; destination columns cols..dst_cols-1 are zero filled (TMA-friendly padding)
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ s, int64_t lds, TD* __restrict__ d, int64_t ldd, int64_t rows,
+                              int cols, int dst_cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * dst_cols) return;
+    const int64_t r = i / dst_cols; const int c = (int)(i - r * dst_cols);
+    d[r * ldd + c] = from_f32<TD>(c < cols ? to_f32(s[r * lds + c]) : 0.f);
+}
+
+extern "C" int vqa_cast_2d(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+                           int64_t rows, int cols, int dst_cols, void* stream) {
+    VQA_REQUIRE(rows >= 0 && cols > 0 && dst_cols >= cols && lds >= cols && ldd >= dst_cols, "cast_2d: bad dims");
+    if (rows == 0) return 0;
+    const unsigned grid = (unsigned)ceil_div64(rows * dst_cols, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols);
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, dst_cols);
+    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, dst_cols);
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols);
+    else VQA_REQUIRE(false, "cast_2d: bad dtypes");
+    VQA_CHECK_LAUNCH("cast_2d");
+    return 0;
+}
+
 // column sums: block = 32 columns x 8 row lanes; rows split over gridDim.y, combined with atomics
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ in, int64_t ld, const uint8_t* __restrict__ mask,

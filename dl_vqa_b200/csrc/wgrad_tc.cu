@@ -1,0 +1,246 @@
+// Weight gradient of the 3x3 convolutions on tcgen05 (autograd of models/model.py:80):
+//   dW[co][ci][kh][kw] = sum_{b,oh,ow} dY[b,oh,ow,co] * X[b,oh+kh,ow+kw,ci]
+// The reduction index is the spatial position, so both operands are consumed position-contiguous
+// (channel-major "NCHW" copies with the row pitch padded to a multiple of 8 for TMA):
+//   A tile = dYT[b, co0:co0+128, oh, w0:w0+64]          -> [128 co][64 positions]   (K-major)
+//   B tile = XT [b, 0:CIN,       oh+kh, w0+kw:w0+kw+64] -> [CIN ci][64 positions]   one per tap of a filter row
+// One CTA owns (128 output channels, one filter row kh = 3 taps) and a slice of the positions (split-K);
+// the three taps accumulate in three TMEM column ranges and are flushed once with fp32 atomics.
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int WG_THREADS = 192;
+
+template <int CIN>
+struct WgSmem {
+    static constexpr int STAGES = CIN >= 128 ? 3 : 4;
+    static constexpr int A_BYTES = 128 * 64 * 2, B_BYTES = CIN * 64 * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;
+    static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct WgParams {
+    int B, OHp, wchunks;      // positions: (b, oh in [0,OHp), 64-wide chunk of the output row)
+    int chunks_per_split;
+    int Cin, Cout;
+    float* dw;                // fp32 OIHW, pre-zeroed
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constant__ CUtensorMap tma_x, WgParams p) {
+    using S = WgSmem<CIN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* tmem_full = empty + S::STAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    constexpr uint32_t TMEM_COLS = CIN >= 128 ? 512 : 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kh = blockIdx.x % 3, co0 = (blockIdx.x / 3) * 128;
+    const int total = p.B * p.OHp * p.wchunks;
+    const int c_begin = blockIdx.y * p.chunks_per_split;
+    const int c_end = min(total, c_begin + p.chunks_per_split);
+    const int nch = max(0, c_end - c_begin);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_dy); tma_prefetch_desc(&tma_x);
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int wc = c_begin % p.wchunks, t = c_begin / p.wchunks;
+            int oh = t % p.OHp, b = t / p.OHp;
+            for (int i = 0; i < nch; ++i) {
+                const int s = i % S::STAGES;
+                const uint32_t ph = (i / S::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                uint8_t* st = smem + s * S::STAGE_BYTES;
+                tma_load_4d(st, &tma_dy, &full[s], wc * 64, oh, co0, b);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                    tma_load_4d(st + S::A_BYTES + kw * S::B_BYTES, &tma_x, &full[s], wc * 64 + kw, oh + kh, 0, b);
+                if (++wc == p.wchunks) { wc = 0; if (++oh == p.OHp) { oh = 0; ++b; } }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(128, CIN);
+            for (int i = 0; i < nch; ++i) {
+                const int s = i % S::STAGES;
+                const uint32_t ph = (i / S::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t b_addr = a_addr + S::A_BYTES + kw * S::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem_base + kw * CIN, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(b_addr + k * 32),
+                                 idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else if (nch > 0) {
+        const int quarter = warp & 3;
+        const int co = co0 + quarter * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int kw = 0; kw < 3; ++kw) {
+            const int tap = kh * 3 + kw;
+#pragma unroll 1
+            for (int c0 = 0; c0 < CIN; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kw * CIN + c0, v);
+                if (co < p.Cout) {
+                    float* o = p.dw + ((int64_t)co * p.Cin + c0) * 9 + tap;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(o + j * 9, v[j]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// channel-major tensor map: [B, C, H, Wp] bf16, box [64 w, 1 h, boxC c, 1 b]
+static int chw_tmap(CUtensorMap* m, const void* base, int B, int C, int H, int Wp, int boxC) {
+    const uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)C * H * Wp * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)boxC, 1};
+    return make_tmap_bf16(m, base, 4, dims, str, box);
+}
+
+template <int CIN>
+static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cudaStream_t st) {
+    auto kern = wgrad_tc_kernel<CIN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<CIN>::BYTES));
+        attr_set = true;
+    }
+    const int units = (p.Cout / 128) * 3;
+    const int total = p.B * p.OHp * p.wchunks;
+    int nsplit = (148 + units - 1) / units;
+    if (nsplit > total) nsplit = total;
+    p.chunks_per_split = (total + nsplit - 1) / nsplit;
+    nsplit = (total + p.chunks_per_split - 1) / p.chunks_per_split;
+    dim3 grid(units, nsplit);
+    kern<<<grid, WG_THREADS, WgSmem<CIN>::BYTES, st>>>(tdy, tx, p);
+    VQA_CHECK_LAUNCH("wgrad_tc");
+    return 0;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// xT [B,Cin,IH,IWp] bf16 (IWp = IW rounded up to 8, zero padded); dyT [B,Cout,OHp,OWpp] bf16 (un-pooled gradient,
+// OHp = 2PH rows, row pitch OWpp = 2PW rounded up to 8, zero padded); dw fp32 OIHW (overwritten).
+extern "C" int vqa_tc_conv3x3_bwd_weight(const void* xT, const void* dyT, float* dw,
+                                         int B, int IH, int IWp, int OHp, int OWpp, int Cin, int Cout, void* stream) {
+    VQA_REQUIRE(B > 0 && IH > 2 && OHp > 0 && OHp + 2 <= IH, "tc conv wgrad: bad dims");
+    VQA_REQUIRE(IWp % 8 == 0 && OWpp % 8 == 0, "tc conv wgrad: row pitches must be multiples of 8 (TMA 16-byte strides)");
+    VQA_REQUIRE(Cin == 64 || Cin == 128, "tc conv wgrad: Cin=%d must be 64 or 128", Cin);
+    VQA_REQUIRE(Cout % 128 == 0, "tc conv wgrad: Cout=%d must be a multiple of 128", Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    VQA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
+    CUtensorMap tdy, tx;
+    if (int e = chw_tmap(&tdy, dyT, B, Cout, OHp, OWpp, 128)) return e;
+    if (int e = chw_tmap(&tx, xT, B, Cin, IH, IWp, Cin)) return e;
+    WgParams p{};
+    p.B = B; p.OHp = OHp; p.wchunks = (OWpp + 63) / 64; p.Cin = Cin; p.Cout = Cout; p.dw = dw;
+    if (Cin == 64) return launch_wgrad<64>(tdy, tx, p, st);
+    return launch_wgrad<128>(tdy, tx, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout kernels feeding the weight gradient
+// ------------------------------------------------------------------------------------------
+// x [B,H,W,C] bf16 NHWC -> xT [B,C,H,Wp] (zero padded columns W..Wp-1)
+__global__ void nhwc_to_nchw_pad_kernel(const bf16* __restrict__ x, bf16* __restrict__ xT, int H, int W, int C, int Wp) {
+    __shared__ bf16 tile[32][34];
+    const int bh = blockIdx.z;                       // b*H + h
+    const int b = bh / H, h = bh - b * H;
+    const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {      // i = w offset, threadIdx.x = c offset
+        const int w = w0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (w < W && c < C) ? x[((int64_t)bh * W + w) * C + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {      // i = c offset, threadIdx.x = w offset
+        const int c = c0 + i, w = w0 + threadIdx.x;
+        if (c < C && w < Wp) xT[(((int64_t)b * C + c) * H + h) * Wp + w] = tile[threadIdx.x][i];
+    }
+}
+
+extern "C" int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream) {
+    VQA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Wp >= W, "nhwc_to_nchw: bad dims");
+    VQA_REQUIRE((int64_t)B * H <= 65535 * 32ll, "nhwc_to_nchw: too many rows");
+    dim3 grid((Wp + 31) / 32, (C + 31) / 32, B * H), block(32, 8);
+    VQA_REQUIRE(grid.z <= 65535u * 1024u, "nhwc_to_nchw: grid too large");
+    nhwc_to_nchw_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)xT, H, W, C, Wp);
+    VQA_CHECK_LAUNCH("nhwc_to_nchw_pad");
+    return 0;
+}
+
+// (dpool, mask) [B,PH,PW,C] -> dyT [B,C,2PH,OWpp]: un-pooled gradient, channel-major, zero padded
+__global__ void unpool_nchw_kernel(const bf16* __restrict__ dpool, const uint8_t* __restrict__ mask, bf16* __restrict__ dyT,
+                                   int PH, int PW, int C, int OWpp) {
+    __shared__ bf16 g[32][34];
+    __shared__ uint8_t m[32][36];
+    const int bp = blockIdx.z;                       // b*PH + ph
+    const int b = bp / PH, ph = bp - b * PH;
+    const int pw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {      // i = pw offset, x = c offset
+        const int pw = pw0 + i, c = c0 + threadIdx.x;
+        const bool ok = pw < PW && c < C;
+        const int64_t idx = ((int64_t)bp * PW + pw) * C + c;
+        g[i][threadIdx.x] = ok ? dpool[idx] : __float2bfloat16_rn(0.f);
+        m[i][threadIdx.x] = ok ? mask[idx] : (uint8_t)4;
+    }
+    __syncthreads();
+    // each thread writes 2 consecutive output columns (one pool window wide) for both rows
+    for (int i = threadIdx.y; i < 32; i += 8) {      // i = c offset, x = pw offset
+        const int c = c0 + i, pw = pw0 + threadIdx.x;
+        if (c >= C) continue;
+        const bf16 gv = g[threadIdx.x][i];
+        const int mv = m[threadIdx.x][i];
+        const bf16 z = __float2bfloat16_rn(0.f);
+        const int ow = 2 * pw;
+        if (ow + 1 < OWpp || ow < OWpp) {
+            bf16* r0 = dyT + (((int64_t)b * C + c) * (2 * PH) + 2 * ph) * OWpp;
+            bf16* r1 = r0 + OWpp;
+            if (ow < OWpp) { r0[ow] = mv == 0 ? gv : z; r1[ow] = mv == 2 ? gv : z; }
+            if (ow + 1 < OWpp) { r0[ow + 1] = mv == 1 ? gv : z; r1[ow + 1] = mv == 3 ? gv : z; }
+        }
+    }
+}
+
+extern "C" int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void* dyT, int B, int PH, int PW, int C,
+                                    int OWpp, void* stream) {
+    VQA_REQUIRE(B > 0 && PH > 0 && PW > 0 && C > 0 && OWpp >= 2 * PW, "unpool_nchw: bad dims");
+    // columns [2PW, OWpp) are covered because the pw range is rounded up to OWpp/2
+    dim3 grid(((OWpp + 1) / 2 + 31) / 32, (C + 31) / 32, B * PH), block(32, 8);
+    unpool_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)dpool, mask, (bf16*)dyT, PH, PW, C, OWpp);
+    VQA_CHECK_LAUNCH("unpool_nchw");
+    return 0;
+}

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "vqa_dropout_apply": [_vp, _i64, _vp, _i64, _i, _i64, _i, _f, _u64, _u32, _vp],
     "vqa_colsum": [_vp, _i, _i64, _vp, _vp, _i64, _i, _vp],
     "vqa_cast": [_vp, _i, _vp, _i, _i64, _vp],
+    "vqa_cast_2d": [_vp, _i, _i64, _vp, _i, _i64, _i64, _i, _i, _vp],
     "vqa_relu_drop_bwd": [_vp, _vp, _vp, _i, _i64, _f, _vp],
     "vqa_add_dropped": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i64, _i, _f, _u64, _u32, _vp],
     "vqa_adam_multi": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _i, _f, _vp],

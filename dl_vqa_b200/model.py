@@ -96,6 +96,110 @@ def _elem_stride(t0: torch.Tensor, t1: torch.Tensor) -> int:
     return d // t0.element_size()
 
 
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Math:
+    """The three dense contractions of the step, on either arm.
+
+    fp32 arm  : vqa_gemm (SIMT fp32, exact), operands addressed in place through strides.
+    bf16 arm  : vqa_tc_gemm (tcgen05 / TMEM / TMA).  Tensor-core operands must be bf16 with the reduction
+                index contiguous, so weights get per-step bf16 (transposed) shadows and weight-gradient
+                operands are transposed by vqa_transpose_bf16.
+    """
+
+    def __init__(self, tc: bool, dev, st):
+        self.tc, self.dev, self.st = tc, dev, st
+        self._w = {}
+
+    # ---- bf16 shadows of fp32 parameters (cached for the duration of one forward/backward)
+    def wbf(self, W: torch.Tensor):
+        """[N,K] fp32 -> bf16 [N,Kp], Kp = K rounded up to 8 (zero padded)."""
+        key = ("n", W.data_ptr())
+        if key not in self._w:
+            N, K = W.shape[0], W[0].numel()
+            Kp = _rup(K, 8)
+            out = torch.empty(N, Kp, dtype=torch.bfloat16, device=self.dev)
+            call("vqa_cast_2d", ptr(W), lib.F32, K, ptr(out), lib.BF16, Kp, N, K, Kp, self.st, tag="w_cast")
+            self._w[key] = (out, Kp)
+        return self._w[key]
+
+    def wT(self, W: torch.Tensor):
+        """[N,K] fp32 -> bf16 [K,Np] (transposed), Np = N rounded up to 8."""
+        key = ("t", W.data_ptr())
+        if key not in self._w:
+            N, K = W.shape[0], W[0].numel()
+            Np = _rup(N, 8)
+            out = torch.empty(K, Np, dtype=torch.bfloat16, device=self.dev)
+            call("vqa_transpose_bf16", ptr(W), lib.F32, K, 0, ptr(out), Np, 0, N, K, 1, self.st, tag="w_transpose")
+            self._w[key] = (out, Np)
+        return self._w[key]
+
+    def _as_bf16(self, x_ptr, x_dt, ld, rows, cols):
+        if x_dt == lib.BF16:
+            return x_ptr, ld, None
+        cp = _rup(cols, 8)
+        buf = torch.empty(rows, cp, dtype=torch.bfloat16, device=self.dev)
+        call("vqa_cast_2d", x_ptr, x_dt, ld, ptr(buf), lib.BF16, cp, rows, cols, cp, self.st, tag="act_cast")
+        return buf.data_ptr(), cp, buf
+
+    def _transposed(self, x_ptr, x_dt, ld, rows, cols):
+        rp = _rup(rows, 8)
+        buf = torch.empty(cols, rp, dtype=torch.bfloat16, device=self.dev)
+        r0 = 0
+        while r0 < rows:            # grid.y limit of the transpose kernel: 65535 * 32 rows per launch
+            n = min(rows - r0, 65535 * 32)
+            esz = 4 if x_dt == lib.F32 else 2
+            call("vqa_transpose_bf16", x_ptr + r0 * ld * esz, x_dt, ld, 0, buf.data_ptr() + r0 * 2, rp, 0, n, cols, 1,
+                 self.st, tag="act_transpose")
+            r0 += n
+        return buf, rp
+
+    # ---- out[M,N] = act(x[M,K] W[N,K]^T + bias (+ bias2)) * dropout
+    def lin_fwd(self, x_ptr, x_dt, ldx, W, out_ptr, out_dt, ldo, M, N, K, bias=None, bias2=None, relu=False,
+                p=0.0, seed=0, site=0, tag=None):
+        flags = lib.GEMM_RELU if relu else 0
+        if self.tc:
+            Wb, Kp = self.wbf(W)
+            xp, ldx2, keep = self._as_bf16(x_ptr, x_dt, ldx, M, K)
+            call("vqa_tc_gemm", xp, ldx2, 0, ptr(Wb), Kp, 0, out_ptr, out_dt, ldo, 0, ptr(bias), ptr(bias2), 0,
+                 M, N, K, 1, flags, p, seed, site, self.st, tag=tag)
+        else:
+            call("vqa_gemm", x_ptr, x_dt, ldx, 1, 0, ptr(W), lib.F32, K, 1, 0, out_ptr, out_dt, ldo, 0,
+                 ptr(bias), ptr(bias2), 0, M, N, K, 1, flags, p, seed, site, self.st, tag=tag)
+
+    # ---- dx[M,K] = dy[M,N] W[N,K]
+    def lin_bwd_data(self, dy_ptr, dy_dt, ldy, W, dx_ptr, dx_dt, ldd, M, N, K, tag=None):
+        if self.tc:
+            WT, Np = self.wT(W)
+            yp, ldy2, keep = self._as_bf16(dy_ptr, dy_dt, ldy, M, N)
+            call("vqa_tc_gemm", yp, ldy2, 0, ptr(WT), Np, 0, dx_ptr, dx_dt, ldd, 0, None, None, 0,
+                 M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
+        else:
+            call("vqa_gemm", dy_ptr, dy_dt, ldy, 1, 0, ptr(W), lib.F32, 1, K, 0, dx_ptr, dx_dt, ldd, 0,
+                 None, None, 0, M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
+
+    # ---- dW[N,K] (fp32) = dy[M,N]^T x[M,K]      (reduction over the M rows)
+    def lin_bwd_weight(self, dy_ptr, dy_dt, ldy, x_ptr, x_dt, ldx, dW, M, N, K, tag=None):
+        big = M >= 4096
+        if self.tc:
+            if M == 0:
+                dW.zero_()
+                return
+            yT, mp = self._transposed(dy_ptr, dy_dt, ldy, M, N)
+            xT, mp2 = self._transposed(x_ptr, x_dt, ldx, M, K)
+            if big:
+                dW.zero_()
+            call("vqa_tc_gemm", ptr(yT), mp, 0, ptr(xT), mp2, 0, ptr(dW), lib.F32, K, 0, None, None, 0,
+                 N, K, M, 1, lib.GEMM_SPLITK if big else 0, 0.0, 0, 0, self.st, tag=tag)
+        else:
+            if big:
+                dW.zero_()
+            call("vqa_gemm", dy_ptr, dy_dt, 1, ldy, 0, x_ptr, x_dt, 1, ldx, 0, ptr(dW), lib.F32, K, 0,
+                 None, None, 0, N, K, M, 1, lib.GEMM_SPLITK if big else 0, 0.0, 0, 0, self.st, tag=tag)
+
+
 class VqaNet(nn.Module):
     """Show, Ask, Attend and Answer -- B200-native drop-in for reference models/model.py:VqaNet."""
 
@@ -179,11 +283,19 @@ class VqaNet(nn.Module):
     def _p(self, p: float) -> float:
         return p if self.training else 0.0
 
+    def _tc_conv_ok(self, i: int) -> bool:
+        """tcgen05 implicit-GEMM conv is used for the bf16 arm when the layer shape allows it."""
+        Cin, Cout = self.channels[i], self.channels[i + 1]
+        return (self.compute_dtype == torch.bfloat16 and self.KS == 3 and self.stride == 1 and Cin % 64 == 0
+                and Cout in (64, 128, 256))
+
     def _run_forward(self, v, q, q_len, seed: int, save: bool):
         adt = self.compute_dtype
         dt = lib.dtype_code(adt)
+        tc = adt == torch.bfloat16
         dev = v.device
         st = lib.stream()
+        mm = _Math(tc, dev, st)
         B = v.shape[0]
         f32 = torch.float32
         ctx = {} if save else None
@@ -207,8 +319,14 @@ class VqaNet(nn.Module):
                 raise ValueError(f"image too small: layer {i} conv output {OH}x{OW}")
             out = empty(B, PH, PW, Cout)
             mask = empty(B, PH, PW, Cout, dtype=torch.uint8)
-            call("vqa_conv_relu_pool_fwd", ptr(x), x_dt, nchw, ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
-                 dt, B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+            if self._tc_conv_ok(i) and nchw == 0:
+                wp = empty(Cout, 9 * Cin)
+                call("vqa_pack_conv3x3_weight", ptr(conv.weight), ptr(wp), None, Cout, Cin, st, tag="w_cast")
+                call("vqa_tc_conv3x3_relu_pool_fwd", ptr(x), ptr(wp), ptr(conv.bias), ptr(out), ptr(mask),
+                     B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
+            else:
+                call("vqa_conv_relu_pool_fwd", ptr(x), x_dt, nchw, ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
+                     dt, B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_fwd")
             conv_saved.append((x, x_dt, nchw, mask, IH, IW, Cin, Cout))
             x, x_dt, nchw, IH, IW = out, dt, 0, PH, PW
         P, Cimg = IH * IW, self.channels[-1]
@@ -228,47 +346,41 @@ class VqaNet(nn.Module):
         w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
         b_ih = [getattr(lstm, f"bias_ih_l0{s}") for s in sfx]
         b_hh = [getattr(lstm, f"bias_hh_l0{s}") for s in sfx]
-        ldx = E
+        ldx = _rup(E, 8) if tc else E
         xs = empty(dirs, T, B, ldx)
         call("vqa_embed_tanh_fwd", ptr(q), ptr(q_len), ptr(self.text.embedding.weight), ptr(xs), dt,
              B, T, E, ldx, dirs, p_text, seed, st)
         gx = empty(dirs, T, B, 4 * H)
         for d in range(dirs):   # hoisted input projection: x W_ih^T + b_ih + b_hh for all steps at once
-            call("vqa_gemm", ptr(xs[d]), dt, ldx, 1, 0, ptr(w_ih[d]), lib.F32, E, 1, 0,
-                 ptr(gx[d]), dt, 4 * H, 0, ptr(b_ih[d]), ptr(b_hh[d]), 0,
-                 T * B, 4 * H, E, 1, 0, 0.0, 0, 0, st)
+            mm.lin_fwd(ptr(xs[d]), dt, ldx, w_ih[d], ptr(gx[d]), dt, 4 * H, T * B, 4 * H, E,
+                       bias=b_ih[d], bias2=b_hh[d], tag="lstm_inproj")
         cs = empty(dirs, T, B, H, dtype=f32)
         hs = empty(dirs, T, B, H)
         qf = empty(B, dirs * H)
-        if dirs == 2:
-            whh_stride = _elem_stride(w_hh[0], w_hh[1])
-            whh_joint = True
-        else:
-            whh_stride, whh_joint = 0, True
+        whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
         for s in range(T):
             call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
-                 dt, s, T, B, H, dirs, st)
+                 dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
 
         # ---------------- attention (models/model.py:183-195, :208-221)
         att = self.attention
         QF = dirs * H
+        A = self.A
         qd = qf
         if p_att > 0:
             qd = empty(B, QF)
             call("vqa_dropout_apply", ptr(qf), QF, ptr(qd), QF, dt, B, QF, p_att, seed, lib.SITE_ATT_Q, st)
-        qp = empty(B, self.A, dtype=f32)
-        call("vqa_gemm", ptr(qd), dt, QF, 1, 0, ptr(att.q_lin.weight), lib.F32, QF, 1, 0,
-             ptr(qp), lib.F32, self.A, 0, ptr(att.q_lin.bias), None, 0, B, self.A, QF, 1, 0, 0.0, 0, 0, st)
-        vp = empty(B * P, self.A)
-        call("vqa_gemm", ptr(v_in), dt, Cimg, 1, 0, ptr(att.v_conv.weight), lib.F32, Cimg, 1, 0,
-             ptr(vp), dt, self.A, 0, None, None, 0, B * P, self.A, Cimg, 1, 0, 0.0, 0, 0, st)
+        qp = empty(B, A, dtype=f32)
+        mm.lin_fwd(ptr(qd), dt, QF, att.q_lin.weight, ptr(qp), lib.F32, A, B, A, QF, bias=att.q_lin.bias, tag="q_lin")
+        vp = empty(B * P, A)
+        mm.lin_fwd(ptr(v_in), dt, Cimg, att.v_conv.weight, ptr(vp), dt, A, B * P, A, Cimg, tag="v_conv")
         G = self.G
         KC = G * Cimg + QF
         comb = empty(B, KC)
         prob = empty(B, G, P, dtype=f32)
         op = lib.ATT_ADD if self.do_option == "+" else lib.ATT_MUL
         call("vqa_attention_fwd", ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
-             ptr(prob), ptr(comb), KC, dt, op, B, P, self.A, Cimg, G, p_att, seed, st)
+             ptr(prob), ptr(comb), KC, dt, op, B, P, A, Cimg, G, p_att, seed, st)
         # combined = cat([pooled, q])  (models/model.py:64)
         esz = comb.element_size()
         call("vqa_dropout_apply", ptr(qf), QF, comb.data_ptr() + G * Cimg * esz, KC, dt, B, QF, 0.0, 0, 0, st)
@@ -280,13 +392,11 @@ class VqaNet(nn.Module):
             combd = empty(B, KC)
             call("vqa_dropout_apply", ptr(comb), KC, ptr(combd), KC, dt, B, KC, p_cls, seed, lib.SITE_CLS_IN, st)
         h1d = empty(B, self.hidden)
-        call("vqa_gemm", ptr(combd), dt, KC, 1, 0, ptr(cl.lin1.weight), lib.F32, KC, 1, 0,
-             ptr(h1d), dt, self.hidden, 0, ptr(cl.lin1.bias), None, 0, B, self.hidden, KC, 1, lib.GEMM_RELU,
-             p_cls, seed, lib.SITE_CLS_HID, st)
+        mm.lin_fwd(ptr(combd), dt, KC, cl.lin1.weight, ptr(h1d), dt, self.hidden, B, self.hidden, KC,
+                   bias=cl.lin1.bias, relu=True, p=p_cls, seed=seed, site=lib.SITE_CLS_HID, tag="lin1")
         logits = empty(B, self.max_answers, dtype=f32)
-        call("vqa_gemm", ptr(h1d), dt, self.hidden, 1, 0, ptr(cl.lin2.weight), lib.F32, self.hidden, 1, 0,
-             ptr(logits), lib.F32, self.max_answers, 0, ptr(cl.lin2.bias), None, 0,
-             B, self.max_answers, self.hidden, 1, 0, 0.0, 0, 0, st)
+        mm.lin_fwd(ptr(h1d), dt, self.hidden, cl.lin2.weight, ptr(logits), lib.F32, self.max_answers,
+                   B, self.max_answers, self.hidden, bias=cl.lin2.bias, tag="lin2")
 
         if save:
             ctx.update(B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
@@ -301,8 +411,10 @@ class VqaNet(nn.Module):
         B, P, T, seed = ctx["B"], ctx["P"], ctx["T"], ctx["seed"]
         p_text, p_img, p_att, p_cls = ctx["p"]
         dt, adt = ctx["dt"], ctx["adt"]
+        tc = adt == torch.bfloat16
         dev = dlogits.device
         st = lib.stream()
+        mm = _Math(tc, dev, st)
         f32 = torch.float32
         H, E, dirs, G, A = self.H, self.E, self.dirs, self.G, self.A
         Cimg = self.channels[-1]
@@ -322,10 +434,6 @@ class VqaNet(nn.Module):
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook([(n, grads[n]) for n in names])
 
-        def gemm(Aq, a_dt, a_sr, a_sk, Bq, b_dt, b_sr, b_sk, Cq, c_dt, ldc, M, Nn, K, flags=0, a_sb=0, b_sb=0, c_sb=0, nb=1):
-            call("vqa_gemm", Aq, a_dt, a_sr, a_sk, a_sb, Bq, b_dt, b_sr, b_sk, b_sb, Cq, c_dt, ldc, c_sb,
-                 None, None, 0, M, Nn, K, nb, flags, 0.0, 0, 0, st)
-
         def colsum(src, src_dt, ld, rows, cols):
             out = zeros(cols)
             call("vqa_colsum", ptr(src), src_dt, ld, None, ptr(out), rows, cols, st)
@@ -337,18 +445,18 @@ class VqaNet(nn.Module):
 
         # ---- classifier.lin2
         dh1d = empty(B, hid)
-        gemm(ptr(dlogits), lib.F32, N, 1, ptr(cl.lin2.weight), lib.F32, 1, hid, ptr(dh1d), dt, hid, B, hid, N)
+        mm.lin_bwd_data(ptr(dlogits), lib.F32, N, cl.lin2.weight, ptr(dh1d), dt, hid, B, N, hid, tag="lin2_dgrad")
         dW2 = empty(N, hid, dtype=f32)
-        gemm(ptr(dlogits), lib.F32, 1, N, ptr(h1d), dt, 1, hid, ptr(dW2), lib.F32, hid, N, hid, B)
+        mm.lin_bwd_weight(ptr(dlogits), lib.F32, N, ptr(h1d), dt, hid, dW2, B, N, hid, tag="lin2_wgrad")
         grads["classifier.lin2.weight"] = dW2
         grads["classifier.lin2.bias"] = colsum(dlogits, lib.F32, N, B, N)
         # ---- classifier.lin1 (ReLU + drop2 folded: h1d > 0 <=> unit alive and kept)
         dz1 = empty(B, hid)
         call("vqa_relu_drop_bwd", ptr(dh1d), ptr(h1d), ptr(dz1), dt, B * hid, p_cls, st)
         dcomb = empty(B, KC)
-        gemm(ptr(dz1), dt, hid, 1, ptr(cl.lin1.weight), lib.F32, 1, KC, ptr(dcomb), dt, KC, B, KC, hid)
+        mm.lin_bwd_data(ptr(dz1), dt, hid, cl.lin1.weight, ptr(dcomb), dt, KC, B, hid, KC, tag="lin1_dgrad")
         dW1 = empty(hid, KC, dtype=f32)
-        gemm(ptr(dz1), dt, 1, hid, ptr(combd), dt, 1, KC, ptr(dW1), lib.F32, KC, hid, KC, B)
+        mm.lin_bwd_weight(ptr(dz1), dt, hid, ptr(combd), dt, KC, dW1, B, hid, KC, tag="lin1_wgrad")
         grads["classifier.lin1.weight"] = dW1
         grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid)
         fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"])
@@ -370,15 +478,15 @@ class VqaNet(nn.Module):
         grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G)
         # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)
         dvnd = empty(B * P, Cimg)
-        gemm(ptr(dvp), dt, A, 1, ptr(att.v_conv.weight), lib.F32, 1, Cimg, ptr(dvnd), dt, Cimg, B * P, Cimg, A)
-        dWv = zeros(A, Cimg)
-        gemm(ptr(dvp), dt, 1, A, ptr(v_in), dt, 1, Cimg, ptr(dWv), lib.F32, Cimg, A, Cimg, B * P, flags=lib.GEMM_SPLITK)
+        mm.lin_bwd_data(ptr(dvp), dt, A, att.v_conv.weight, ptr(dvnd), dt, Cimg, B * P, A, Cimg, tag="v_conv_dgrad")
+        dWv = empty(A, Cimg, dtype=f32)
+        mm.lin_bwd_weight(ptr(dvp), dt, A, ptr(v_in), dt, Cimg, dWv, B * P, A, Cimg, tag="v_conv_wgrad")
         grads["attention.v_conv.weight"] = dWv.view(A, Cimg, 1, 1)
         # ---- attention.q_lin
         dqd = empty(B, QF)
-        gemm(ptr(dqp), lib.F32, A, 1, ptr(att.q_lin.weight), lib.F32, 1, QF, ptr(dqd), dt, QF, B, QF, A)
+        mm.lin_bwd_data(ptr(dqp), lib.F32, A, att.q_lin.weight, ptr(dqd), dt, QF, B, A, QF, tag="q_lin_dgrad")
         dWq = empty(A, QF, dtype=f32)
-        gemm(ptr(dqp), lib.F32, 1, A, ptr(qd), dt, 1, QF, ptr(dWq), lib.F32, QF, A, QF, B)
+        mm.lin_bwd_weight(ptr(dqp), lib.F32, A, ptr(qd), dt, QF, dWq, B, A, QF, tag="q_lin_wgrad")
         grads["attention.q_lin.weight"] = dWq
         grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A)
         fire(["attention.v_conv.weight", "attention.q_lin.weight", "attention.q_lin.bias",
@@ -400,18 +508,29 @@ class VqaNet(nn.Module):
         dc = empty(dirs, B, H, dtype=f32)
         dg = empty(dirs, T, B, 4 * H)
         gsz = dg.element_size()
+        if tc and T > 1:
+            whhT = empty(dirs, H, 4 * H)          # bf16 [H, 4H] per direction: B operand of dh = dg W_hh
+            for d in range(dirs):
+                call("vqa_transpose_bf16", ptr(w_hh[d]), lib.F32, H, 0, ptr(whhT[d]), 4 * H, 0, 4 * H, H, 1, st,
+                     tag="w_transpose")
         for s in range(T - 1, -1, -1):
             call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
-                 ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st)
+                 ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
             if s > 0:   # dh_{s-1} = dgates_s W_hh
-                gemm(dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, ptr(w_hh[0]), lib.F32, 1, H,
-                     ptr(dh), lib.F32, H, B, H, 4 * H, a_sb=T * B * 4 * H, b_sb=ctx["whh_stride"], c_sb=B * H, nb=dirs)
+                if tc:
+                    call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhT), 4 * H,
+                         H * 4 * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st,
+                         tag="lstm_step_bwd")
+                else:
+                    call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,
+                         ptr(w_hh[0]), lib.F32, 1, H, ctx["whh_stride"], ptr(dh), lib.F32, H, B * H,
+                         None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
         for d in range(dirs):
             dWhh = empty(4 * H, H, dtype=f32)
-            gemm(dg[d].data_ptr() + B * 4 * H * gsz, dt, 1, 4 * H, ptr(hs[d]), dt, 1, H, ptr(dWhh), lib.F32, H,
-                 4 * H, H, (T - 1) * B)
+            mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(hs[d]), dt, H, dWhh,
+                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad")
             dWih = empty(4 * H, E, dtype=f32)
-            gemm(ptr(dg[d]), dt, 1, 4 * H, ptr(xs[d]), dt, 1, ldx, ptr(dWih), lib.F32, E, 4 * H, E, T * B)
+            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad")
             db = colsum(dg[d], dt, 4 * H, T * B, 4 * H)
             grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
             grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
@@ -419,7 +538,7 @@ class VqaNet(nn.Module):
             grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db.clone() if self.grad_ready_hook is not None else db
         dxs = empty(dirs, T, B, ldx)
         for d in range(dirs):
-            gemm(ptr(dg[d]), dt, 4 * H, 1, ptr(w_ih[d]), lib.F32, 1, E, ptr(dxs[d]), dt, ldx, T * B, E, 4 * H)
+            mm.lin_bwd_data(ptr(dg[d]), dt, 4 * H, w_ih[d], ptr(dxs[d]), dt, ldx, T * B, 4 * H, E, tag="lstm_inproj_dgrad")
         demb = zeros(*self.text.embedding.weight.shape)
         call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
              p_text, seed, st)
@@ -439,17 +558,40 @@ class VqaNet(nn.Module):
         for i in range(nl - 1, -1, -1):
             conv = getattr(self.image, f"conv{i}")
             x, x_dt, nchw, mask, IH, IW, Cin, Cout = ctx["conv_saved"][i]
+            PH, PW = ((IH - self.KS) // self.stride + 1) // 2, ((IW - self.KS) // self.stride + 1) // 2
             dW = empty(*conv.weight.shape, dtype=f32)
             db = empty(Cout, dtype=f32)
-            call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
-                 B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+            use_tc = self._tc_conv_ok(i) and nchw == 0
+            if use_tc and Cin in (64, 128) and Cout % 128 == 0:
+                IWp, OWpp = _rup(IW, 8), _rup(2 * PW, 8)
+                xT = empty(B, Cin, IH, IWp)
+                call("vqa_nhwc_to_nchw_pad_bf16", ptr(x), ptr(xT), B, IH, IW, Cin, IWp, st, tag="act_transpose")
+                dyT = empty(B, Cout, 2 * PH, OWpp)
+                call("vqa_unpool_nchw_bf16", ptr(da), ptr(mask), ptr(dyT), B, PH, PW, Cout, OWpp, st, tag="unpool")
+                call("vqa_tc_conv3x3_bwd_weight", ptr(xT), ptr(dyT), ptr(dW), B, IH, IWp, 2 * PH, OWpp, Cin, Cout, st,
+                     tag=f"conv{i}_wgrad")
+                db.zero_()
+                call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
+                del xT, dyT
+            else:
+                call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
+                     B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_wgrad")
             grads[f"image.conv{i}.weight"] = dW
             grads[f"image.conv{i}.bias"] = db
             names += [f"image.conv{i}.weight", f"image.conv{i}.bias"]
             if i > 0:
                 dx = empty(B, IH, IW, Cin)
-                call("vqa_conv_bwd_data", ptr(da), ptr(mask), ptr(conv.weight), ptr(dx), dt,
-                     B, IH, IW, Cin, Cout, self.KS, self.stride, st)
+                if use_tc:
+                    dy = empty(B, 2 * PH, 2 * PW, Cout)
+                    call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
+                    wd = empty(Cin, 9 * Cout)
+                    call("vqa_pack_conv3x3_weight", ptr(conv.weight), None, ptr(wd), Cout, Cin, st, tag="w_cast")
+                    call("vqa_tc_conv3x3_bwd_data", ptr(dy), ptr(wd), ptr(dx), B, IH, IW, Cin, Cout, st,
+                         tag=f"conv{i}_dgrad")
+                    del dy
+                else:
+                    call("vqa_conv_bwd_data", ptr(da), ptr(mask), ptr(conv.weight), ptr(dx), dt,
+                         B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_dgrad")
                 da = dx
         fire(names)
         return grads

@@ -162,6 +162,9 @@ int vqa_colsum(const void* in, int dtype, int64_t ld, const uint8_t* mask, float
                void* stream);
 /* dst = (dtype) src, n elements */
 int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* dst[r, 0:dst_cols] = (dtype) src[r, 0:cols] with zero fill of columns cols..dst_cols-1; row pitches lds/ldd */
+int vqa_cast_2d(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+                int64_t rows, int cols, int dst_cols, void* stream);
 /* ReLU + dropout backward for classifier.lin1: dz = dy * [y > 0] * scale, y = dropped ReLU output */
 int vqa_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float p, void* stream);
 /* dst[r, 0:cols] = a[r,:] + b[r,:] * dropout(site, r*cols+c)  (b may be NULL) -- gradient merges */
@@ -210,6 +213,15 @@ int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
 int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream);
 /* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0) */
 int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int PH, int PW, int C, void* stream);
+
+/* weight gradient of the 3x3 conv on tcgen05.  Operands are channel-major copies (reduction index = spatial
+ * position must be contiguous): xT [B,Cin,IH,IWp] from vqa_nhwc_to_nchw_pad_bf16, dyT [B,Cout,OHp,OWpp] from
+ * vqa_unpool_nchw_bf16 (OHp = 2PH, pitches multiples of 8, zero padded).  dw fp32 OIHW, overwritten. */
+int vqa_tc_conv3x3_bwd_weight(const void* xT, const void* dyT, float* dw,
+                              int B, int IH, int IWp, int OHp, int OWpp, int Cin, int Cout, void* stream);
+int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream);
+int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void* dyT, int B, int PH, int PW, int C,
+                         int OWpp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,3 +130,35 @@ def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout):
     want = F.conv_transpose2d(full.permute(0, 3, 1, 2), w.bfloat16().float()).permute(0, 2, 3, 1)
     err = float((dx.float() - want).abs().max() / want.abs().max())
     assert err < 1e-2, err
+
+
+@pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (3, 111, 111, 64, 128), (2, 54, 54, 128, 256),
+                                              (1, 13, 10, 64, 128)])
+def test_tc_conv_wgrad_matches_torch(B, IH, IW, Cin, Cout):
+    from dl_vqa_b200 import lib
+    torch.manual_seed(IW)
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    x = torch.randn(B, IH, IW, Cin, device="cuda").bfloat16()
+    dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
+    mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
+    IWp, OWpp = (IW + 7) // 8 * 8, (2 * PW + 7) // 8 * 8
+    xT = torch.full((B, Cin, IH, IWp), 9.0, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_nhwc_to_nchw_pad_bf16", lib.ptr(x), lib.ptr(xT), B, IH, IW, Cin, IWp, lib.stream())
+    dyT = torch.full((B, Cout, 2 * PH, OWpp), 9.0, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_unpool_nchw_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dyT), B, PH, PW, Cout, OWpp, lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(xT[..., :IW], x.permute(0, 3, 1, 2)) and float(xT[..., IW:].float().abs().sum()) == 0
+    ref = torch.zeros(B, 2 * PH, 2 * PW, Cout, device="cuda")
+    for e in range(4):
+        ref[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
+    assert torch.equal(dyT[..., :2 * PW].float(), ref.permute(0, 3, 1, 2)) and float(dyT[..., 2 * PW:].float().abs().sum()) == 0
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    lib.call("vqa_tc_conv3x3_bwd_weight", lib.ptr(xT), lib.ptr(dyT), lib.ptr(dw), B, IH, IWp, 2 * PH, OWpp, Cin, Cout,
+             lib.stream())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
+    full[:, :2 * PH, :2 * PW] = ref
+    want = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3), full.permute(0, 3, 1, 2))
+    err = float((dw - want).abs().max() / want.abs().max())
+    assert err < 2e-3, err
