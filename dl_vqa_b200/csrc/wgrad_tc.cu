@@ -1,27 +1,33 @@
 // Weight gradient of the 3x3 convolutions on tcgen05 (autograd of models/model.py:80):
 //   dW[co][ci][kh][kw] = sum_{b,oh,ow} dY[b,oh,ow,co] * X[b,oh+kh,ow+kw,ci]
-// The reduction index is the spatial position, so both operands are consumed position-contiguous
-// (channel-major "NCHW" copies with the row pitch padded to a multiple of 8 for TMA):
-//   A tile = dYT[b, co0:co0+128, oh, w0:w0+64]          -> [128 co][64 positions]   (K-major)
-//   B tile = XT [b, 0:CIN,       oh+kh, w0+kw:w0+kw+64] -> [CIN ci][64 positions]   one per tap of a filter row
-// One CTA owns (128 output channels, one filter row kh = 3 taps) and a slice of the positions (split-K);
-// the three taps accumulate in three TMEM column ranges and are flushed once with fp32 atomics.
+// The reduction index is the spatial position.  With NHWC activations a TMA box [64 ch, 16 w, 4 h] lands in
+// shared memory as 64 position-rows x 128 bytes (128B swizzle) = the canonical MN-MAJOR UMMA operand
+// (K = positions run across rows, 64 channels contiguous inside a row), so both operands are consumed
+// straight from the NHWC tensors with filter-tap shifts on the W/H box coordinates -- no im2col, no
+// transposed copies:
+//   A = dY[b, h0:h0+4, w0:w0+16, co0:co0+128]            two 64-channel blocks (LBO apart)
+//   B = X [b, h0+kh:+4, w0+kw:+16, 0:CIN]   per tap kw   CIN/64 blocks
+// One CTA owns (128 output channels, one filter row kh = 3 taps) and a slice of the position tiles
+// (split-K); the three taps accumulate in three TMEM column ranges and are flushed once with fp32 atomics.
 #include "tc_common.cuh"
 
 namespace tc {
 
 constexpr int WG_THREADS = 192;
+constexpr int WG_TH = 4, WG_TW = 16;               // 64 positions per k-chunk
+constexpr int BLK_BYTES = 64 * 128;                // one 64-position x 64-channel block
 
 template <int CIN>
 struct WgSmem {
+    static constexpr int NB = CIN / 64;            // channel blocks of the B operand
     static constexpr int STAGES = CIN >= 128 ? 3 : 4;
-    static constexpr int A_BYTES = 128 * 64 * 2, B_BYTES = CIN * 64 * 2;
+    static constexpr int A_BYTES = 2 * BLK_BYTES, B_BYTES = NB * BLK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;
     static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
 struct WgParams {
-    int B, OHp, wchunks;      // positions: (b, oh in [0,OHp), 64-wide chunk of the output row)
+    int B, tiles_h, tiles_w;  // position tiles per image over the un-pooled gradient region
     int chunks_per_split;
     int Cin, Cout;
     float* dw;                // fp32 OIHW, pre-zeroed
@@ -41,7 +47,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kh = blockIdx.x % 3, co0 = (blockIdx.x / 3) * 128;
-    const int total = p.B * p.OHp * p.wchunks;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    const int total = p.B * tiles_per_img;
     const int c_begin = blockIdx.y * p.chunks_per_split;
     const int c_end = min(total, c_begin + p.chunks_per_split);
     const int nch = max(0, c_end - c_begin);
@@ -60,24 +67,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            int wc = c_begin % p.wchunks, t = c_begin / p.wchunks;
-            int oh = t % p.OHp, b = t / p.OHp;
             for (int i = 0; i < nch; ++i) {
+                const int c = c_begin + i;
+                const int b = c / tiles_per_img, r = c - b * tiles_per_img;
+                const int h0 = (r / p.tiles_w) * WG_TH, w0 = (r % p.tiles_w) * WG_TW;
                 const int s = i % S::STAGES;
                 const uint32_t ph = (i / S::STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], S::STAGE_BYTES);
                 uint8_t* st = smem + s * S::STAGE_BYTES;
-                tma_load_4d(st, &tma_dy, &full[s], wc * 64, oh, co0, b);
+                tma_load_4d(st, &tma_dy, &full[s], co0, w0, h0, b);
+                tma_load_4d(st + BLK_BYTES, &tma_dy, &full[s], co0 + 64, w0, h0, b);
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw)
-                    tma_load_4d(st + S::A_BYTES + kw * S::B_BYTES, &tma_x, &full[s], wc * 64 + kw, oh + kh, 0, b);
-                if (++wc == p.wchunks) { wc = 0; if (++oh == p.OHp) { oh = 0; ++b; } }
+#pragma unroll
+                    for (int nb = 0; nb < S::NB; ++nb)
+                        tma_load_4d(st + S::A_BYTES + kw * S::B_BYTES + nb * BLK_BYTES, &tma_x, &full[s],
+                                    nb * 64, w0 + kw, h0 + kh, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(128, CIN);
+            constexpr uint32_t idesc = idesc_bf16(128, CIN, /*a_mn_major=*/1, /*b_mn_major=*/1);
             for (int i = 0; i < nch; ++i) {
                 const int s = i % S::STAGES;
                 const uint32_t ph = (i / S::STAGES) & 1;
@@ -88,9 +99,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
                 for (int kw = 0; kw < 3; ++kw) {
                     const uint32_t b_addr = a_addr + S::A_BYTES + kw * S::B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + kw * CIN, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(b_addr + k * 32),
-                                 idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)          // 16 positions (rows) per MMA: 2048 bytes further
+                        umma_f16(tmem_base + kw * CIN, smem_desc_mn_sw128(a_addr + k * 2048, BLK_BYTES),
+                                 smem_desc_mn_sw128(b_addr + k * 2048, BLK_BYTES), idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty[s]);
             }
@@ -121,11 +132,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-// channel-major tensor map: [B, C, H, Wp] bf16, box [64 w, 1 h, boxC c, 1 b]
-static int chw_tmap(CUtensorMap* m, const void* base, int B, int C, int H, int Wp, int boxC) {
-    const uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)C, (uint64_t)B};
-    const uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)C * H * Wp * 2};
-    const uint32_t box[4] = {64, 1, (uint32_t)boxC, 1};
+// NHWC tensor map with the 64-position box [64 ch, 16 w, 4 h, 1]
+static int pos_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4] = {64, WG_TW, WG_TH, 1};
     return make_tmap_bf16(m, base, 4, dims, str, box);
 }
 
@@ -138,7 +149,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams 
         attr_set = true;
     }
     const int units = (p.Cout / 128) * 3;
-    const int total = p.B * p.OHp * p.wchunks;
+    const int total = p.B * p.tiles_h * p.tiles_w;
     int nsplit = (148 + units - 1) / units;
     if (nsplit > total) nsplit = total;
     p.chunks_per_split = (total + nsplit - 1) / nsplit;
@@ -153,21 +164,22 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams 
 
 using namespace tc;
 
-// xT [B,Cin,IH,IWp] bf16 (IWp = IW rounded up to 8, zero padded); dyT [B,Cout,OHp,OWpp] bf16 (un-pooled gradient,
-// OHp = 2PH rows, row pitch OWpp = 2PW rounded up to 8, zero padded); dw fp32 OIHW (overwritten).
-extern "C" int vqa_tc_conv3x3_bwd_weight(const void* xT, const void* dyT, float* dw,
-                                         int B, int IH, int IWp, int OHp, int OWpp, int Cin, int Cout, void* stream) {
-    VQA_REQUIRE(B > 0 && IH > 2 && OHp > 0 && OHp + 2 <= IH, "tc conv wgrad: bad dims");
-    VQA_REQUIRE(IWp % 8 == 0 && OWpp % 8 == 0, "tc conv wgrad: row pitches must be multiples of 8 (TMA 16-byte strides)");
+// x [B,IH,IW,Cin] bf16 NHWC (the layer input); dy [B,2PH,2PW,Cout] bf16 NHWC (un-pooled gradient from
+// vqa_unpool_bf16); dw fp32 OIHW (overwritten).
+extern "C" int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* dw,
+                                         int B, int IH, int IW, int Cin, int Cout, void* stream) {
+    VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4, "tc conv wgrad: bad dims");
     VQA_REQUIRE(Cin == 64 || Cin == 128, "tc conv wgrad: Cin=%d must be 64 or 128", Cin);
     VQA_REQUIRE(Cout % 128 == 0, "tc conv wgrad: Cout=%d must be a multiple of 128", Cout);
+    const int OHp = ((IH - 2) / 2) * 2, OWp = ((IW - 2) / 2) * 2;
     cudaStream_t st = (cudaStream_t)stream;
     VQA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
     CUtensorMap tdy, tx;
-    if (int e = chw_tmap(&tdy, dyT, B, Cout, OHp, OWpp, 128)) return e;
-    if (int e = chw_tmap(&tx, xT, B, Cin, IH, IWp, Cin)) return e;
+    if (int e = pos_tmap(&tdy, dy, B, OHp, OWp, Cout)) return e;
+    if (int e = pos_tmap(&tx, x, B, IH, IW, Cin)) return e;
     WgParams p{};
-    p.B = B; p.OHp = OHp; p.wchunks = (OWpp + 63) / 64; p.Cin = Cin; p.Cout = Cout; p.dw = dw;
+    p.B = B; p.tiles_h = (OHp + WG_TH - 1) / WG_TH; p.tiles_w = (OWp + WG_TW - 1) / WG_TW;
+    p.Cin = Cin; p.Cout = Cout; p.dw = dw;
     if (Cin == 64) return launch_wgrad<64>(tdy, tx, p, st);
     return launch_wgrad<128>(tdy, tx, p, st);
 }

@@ -562,17 +562,15 @@ class VqaNet(nn.Module):
             dW = empty(*conv.weight.shape, dtype=f32)
             db = empty(Cout, dtype=f32)
             use_tc = self._tc_conv_ok(i) and nchw == 0
+            dy = None
+            if use_tc:          # un-pooled gradient, shared by the weight and the data gradient
+                dy = empty(B, 2 * PH, 2 * PW, Cout)
+                call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
             if use_tc and Cin in (64, 128) and Cout % 128 == 0:
-                IWp, OWpp = _rup(IW, 8), _rup(2 * PW, 8)
-                xT = empty(B, Cin, IH, IWp)
-                call("vqa_nhwc_to_nchw_pad_bf16", ptr(x), ptr(xT), B, IH, IW, Cin, IWp, st, tag="act_transpose")
-                dyT = empty(B, Cout, 2 * PH, OWpp)
-                call("vqa_unpool_nchw_bf16", ptr(da), ptr(mask), ptr(dyT), B, PH, PW, Cout, OWpp, st, tag="unpool")
-                call("vqa_tc_conv3x3_bwd_weight", ptr(xT), ptr(dyT), ptr(dW), B, IH, IWp, 2 * PH, OWpp, Cin, Cout, st,
+                call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
                 db.zero_()
                 call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
-                del xT, dyT
             else:
                 call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
                      B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_wgrad")
@@ -582,8 +580,6 @@ class VqaNet(nn.Module):
             if i > 0:
                 dx = empty(B, IH, IW, Cin)
                 if use_tc:
-                    dy = empty(B, 2 * PH, 2 * PW, Cout)
-                    call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
                     wd = empty(Cin, 9 * Cout)
                     call("vqa_pack_conv3x3_weight", ptr(conv.weight), None, ptr(wd), Cout, Cin, st, tag="w_cast")
                     call("vqa_tc_conv3x3_bwd_data", ptr(dy), ptr(wd), ptr(dx), B, IH, IW, Cin, Cout, st,

@@ -214,11 +214,12 @@ int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Ci
 /* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0) */
 int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int PH, int PW, int C, void* stream);
 
-/* weight gradient of the 3x3 conv on tcgen05.  Operands are channel-major copies (reduction index = spatial
- * position must be contiguous): xT [B,Cin,IH,IWp] from vqa_nhwc_to_nchw_pad_bf16, dyT [B,Cout,OHp,OWpp] from
- * vqa_unpool_nchw_bf16 (OHp = 2PH, pitches multiples of 8, zero padded).  dw fp32 OIHW, overwritten. */
-int vqa_tc_conv3x3_bwd_weight(const void* xT, const void* dyT, float* dw,
-                              int B, int IH, int IWp, int OHp, int OWpp, int Cin, int Cout, void* stream);
+/* weight gradient of the 3x3 conv on tcgen05, straight from the NHWC tensors (MN-major UMMA operands):
+ * x [B,IH,IW,Cin] bf16 (layer input), dy [B,2PH,2PW,Cout] bf16 (vqa_unpool_bf16).  dw fp32 OIHW, overwritten.
+ * Cin in {64,128}, Cout % 128 == 0. */
+int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* dw,
+                              int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* channel-major re-layout helpers (NHWC -> [B,C,H,Wp], zero padded pitch) */
 int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream);
 int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void* dyT, int B, int PH, int PW, int C,
                          int OWpp, void* stream);

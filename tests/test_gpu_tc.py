@@ -141,6 +141,26 @@ def test_tc_conv_wgrad_matches_torch(B, IH, IW, Cin, Cout):
     x = torch.randn(B, IH, IW, Cin, device="cuda").bfloat16()
     dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
     mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
+    dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    lib.call("vqa_tc_conv3x3_bwd_weight", lib.ptr(x), lib.ptr(dy), lib.ptr(dw), B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
+    full[:, :2 * PH, :2 * PW] = dy.float()
+    want = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3), full.permute(0, 3, 1, 2))
+    err = float((dw - want).abs().max() / want.abs().max())
+    assert err < 2e-3, err
+
+
+def test_layout_helpers():
+    from dl_vqa_b200 import lib
+    B, IH, IW, Cin, Cout = 2, 20, 36, 64, 128
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    x = torch.randn(B, IH, IW, Cin, device="cuda").bfloat16()
+    dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
+    mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
     IWp, OWpp = (IW + 7) // 8 * 8, (2 * PW + 7) // 8 * 8
     xT = torch.full((B, Cin, IH, IWp), 9.0, dtype=torch.bfloat16, device="cuda")
     lib.call("vqa_nhwc_to_nchw_pad_bf16", lib.ptr(x), lib.ptr(xT), B, IH, IW, Cin, IWp, lib.stream())
@@ -152,13 +172,3 @@ def test_tc_conv_wgrad_matches_torch(B, IH, IW, Cin, Cout):
     for e in range(4):
         ref[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
     assert torch.equal(dyT[..., :2 * PW].float(), ref.permute(0, 3, 1, 2)) and float(dyT[..., 2 * PW:].float().abs().sum()) == 0
-    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
-    lib.call("vqa_tc_conv3x3_bwd_weight", lib.ptr(xT), lib.ptr(dyT), lib.ptr(dw), B, IH, IWp, 2 * PH, OWpp, Cin, Cout,
-             lib.stream())
-    torch.cuda.synchronize()
-    torch.backends.cudnn.allow_tf32 = False
-    full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
-    full[:, :2 * PH, :2 * PW] = ref
-    want = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3), full.permute(0, 3, 1, 2))
-    err = float((dw - want).abs().max() / want.abs().max())
-    assert err < 2e-3, err
