@@ -63,7 +63,10 @@ struct GemmSmem {
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// MN = false: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
+// MN = true : A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
+//             consumed without transposes; one TMA box per 64-wide column block per stage).
+template <int BN, bool MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
@@ -105,13 +108,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
                 const int kc = (kb_begin + i) * BK;
-                tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
-                tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
+                if (!MN) {
+                    tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
+                    tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
+                } else {
+#pragma unroll
+                    for (int blk = 0; blk < BM / 64; ++blk)
+                        tma_load_3d(sa + s * S::A_BYTES + blk * 8192, &tma_a, &full[s], m0 + blk * 64, kc, batch);
+#pragma unroll
+                    for (int blk = 0; blk < BN / 64; ++blk)
+                        tma_load_3d(sb + s * S::B_BYTES + blk * 8192, &tma_b, &full[s], n0 + blk * 64, kc, batch);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % S::STAGES;
                 const uint32_t ph = (i / S::STAGES) & 1;
@@ -120,7 +132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const uint32_t a_addr = smem_u32(sa + s * S::A_BYTES), b_addr = smem_u32(sb + s * S::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ad = smem_desc_k_sw128(a_addr + k * 32), bd = smem_desc_k_sw128(b_addr + k * 32);
+                    const uint64_t ad = MN ? smem_desc_mn_sw128(a_addr + k * 2048, 8192) : smem_desc_k_sw128(a_addr + k * 32);
+                    const uint64_t bd = MN ? smem_desc_mn_sw128(b_addr + k * 2048, 8192) : smem_desc_k_sw128(b_addr + k * 32);
                     umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
@@ -210,10 +223,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
-template <int BN>
+template <int BN, bool MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                        int nbatch, int nsplit, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN>;
+    auto kern = gemm_tc_kernel<BN, MN>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::BYTES));
@@ -234,7 +247,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 
 using namespace tc;
 
-// C[z][m,n] = act(sum_k A[z][m,k] B[z][n,k] + bias) ; A [M,K] (row pitch lda), B [N,K] (row pitch ldb), bf16.
+// C[z][m,n] = act(sum_k A[z][m,k] B[z][n,k] + bias) ; A [M,K] (row pitch lda), B [N,K] (row pitch ldb), bf16;
+// with VQA_GEMM_OPERANDS_MN: A stored [K,M] (row pitch lda), B stored [K,N] (row pitch ldb).
 extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
                            void* C, int c_dtype, int64_t ldc, int64_t c_sb,
                            const float* bias, const float* bias2, int64_t bias_sb,
@@ -247,6 +261,7 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     VQA_REQUIRE(nbatch == 1 || (a_sb % 8 == 0 && b_sb % 8 == 0), "tc_gemm: batch strides must be multiples of 8 elements");
     VQA_REQUIRE(c_dtype == VQA_F32 || c_dtype == VQA_BF16, "tc_gemm: bad output dtype");
     const bool splitk = (flags & VQA_GEMM_SPLITK) != 0;
+    const bool mn = (flags & VQA_GEMM_OPERANDS_MN) != 0;
     if (splitk) {
         VQA_REQUIRE(c_dtype == VQA_F32 && !bias && !bias2 && !(flags & VQA_GEMM_RELU) && p_drop == 0.f,
                     "tc_gemm: split-K needs a zeroed fp32 output and no fused bias/relu/dropout");
@@ -256,17 +271,23 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
 
     const int BN = N <= 64 ? 64 : 128;
     CUtensorMap ta, tb;
-    {
+    if (!mn) {
         const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)nbatch};
         const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nbatch > 1 ? a_sb : (int64_t)M * lda) * 2};
         const uint32_t box[3] = {BK, BM, 1};
         if (int e = make_tmap_bf16(&ta, A, 3, dims, str, box)) return e;
-    }
-    {
-        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nbatch};
-        const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)N * ldb) * 2};
-        const uint32_t box[3] = {BK, (uint32_t)BN, 1};
-        if (int e = make_tmap_bf16(&tb, B, 3, dims, str, box)) return e;
+        const uint64_t dimsb[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nbatch};
+        const uint64_t strb[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)N * ldb) * 2};
+        const uint32_t boxb[3] = {BK, (uint32_t)BN, 1};
+        if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, boxb)) return e;
+    } else {
+        const uint64_t dims[3] = {(uint64_t)M, (uint64_t)K, (uint64_t)nbatch};
+        const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nbatch > 1 ? a_sb : (int64_t)K * lda) * 2};
+        const uint32_t box[3] = {64, BK, 1};
+        if (int e = make_tmap_bf16(&ta, A, 3, dims, str, box)) return e;
+        const uint64_t dimsb[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)nbatch};
+        const uint64_t strb[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)K * ldb) * 2};
+        if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, box)) return e;
     }
     GemmEpilogue ep{};
     ep.out = C; ep.out_bf16 = c_dtype == VQA_BF16; ep.ldc = ldc; ep.c_sb = c_sb;
@@ -284,8 +305,12 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         if (nsplit > maxs) nsplit = maxs;
         if (nsplit < 1) nsplit = 1;
     }
-    if (BN == 64) return launch_gemm<64>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-    return launch_gemm<128>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    if (mn) {
+        if (BN == 64) return launch_gemm<64, true>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        return launch_gemm<128, true>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    }
+    if (BN == 64) return launch_gemm<64, false>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    return launch_gemm<128, false>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
 }
 
 // ------------------------------------------------------------------------------------------

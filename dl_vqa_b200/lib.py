@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
 
 F32, BF16 = 0, 1
 ATT_ADD, ATT_MUL = 0, 1
-GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK = 1, 2, 4
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN = 1, 2, 4, 8
 SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CLS_HID = range(7)
 
 _vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float

@@ -187,12 +187,13 @@ class _Math:
             if M == 0:
                 dW.zero_()
                 return
-            yT, mp = self._transposed(dy_ptr, dy_dt, ldy, M, N)
-            xT, mp2 = self._transposed(x_ptr, x_dt, ldx, M, K)
+            # reduction index = row of both operands: MN-major tcgen05 operands, no transposes
+            yp, ldy2, keep1 = self._as_bf16(dy_ptr, dy_dt, ldy, M, N)
+            xp, ldx2, keep2 = self._as_bf16(x_ptr, x_dt, ldx, M, K)
             if big:
                 dW.zero_()
-            call("vqa_tc_gemm", ptr(yT), mp, 0, ptr(xT), mp2, 0, ptr(dW), lib.F32, K, 0, None, None, 0,
-                 N, K, M, 1, lib.GEMM_SPLITK if big else 0, 0.0, 0, 0, self.st, tag=tag)
+            call("vqa_tc_gemm", yp, ldy2, 0, xp, ldx2, 0, ptr(dW), lib.F32, K, 0, None, None, 0,
+                 N, K, M, 1, lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if big else 0), 0.0, 0, 0, self.st, tag=tag)
         else:
             if big:
                 dW.zero_()
@@ -319,7 +320,10 @@ class VqaNet(nn.Module):
                 raise ValueError(f"image too small: layer {i} conv output {OH}x{OW}")
             out = empty(B, PH, PW, Cout)
             mask = empty(B, PH, PW, Cout, dtype=torch.uint8)
-            if self._tc_conv_ok(i) and nchw == 0:
+            if tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1:
+                call("vqa_tc_conv0_relu_pool_fwd", ptr(x), ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
+                     B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
+            elif self._tc_conv_ok(i) and nchw == 0:
                 wp = empty(Cout, 9 * Cin)
                 call("vqa_pack_conv3x3_weight", ptr(conv.weight), ptr(wp), None, Cout, Cin, st, tag="w_cast")
                 call("vqa_tc_conv3x3_relu_pool_fwd", ptr(x), ptr(wp), ptr(conv.bias), ptr(out), ptr(mask),
@@ -563,10 +567,15 @@ class VqaNet(nn.Module):
             db = empty(Cout, dtype=f32)
             use_tc = self._tc_conv_ok(i) and nchw == 0
             dy = None
-            if use_tc:          # un-pooled gradient, shared by the weight and the data gradient
+            tc0 = tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1
+            if use_tc or tc0:   # un-pooled gradient, shared by the weight and the data gradient
                 dy = empty(B, 2 * PH, 2 * PW, Cout)
                 call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
-            if use_tc and Cin in (64, 128) and Cout % 128 == 0:
+            if tc0:
+                call("vqa_tc_conv0_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st, tag=f"conv{i}_wgrad")
+                db.zero_()
+                call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
+            elif use_tc and Cin in (64, 128) and Cout % 128 == 0:
                 call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
                 db.zero_()

@@ -116,6 +116,7 @@ int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float*
 #define VQA_GEMM_RELU 1
 #define VQA_GEMM_ACCUMULATE 2
 #define VQA_GEMM_SPLITK 4
+#define VQA_GEMM_OPERANDS_MN 8   /* vqa_tc_gemm only: A stored [K,M], B stored [K,N] (reduction index = row) */
 int vqa_gemm(const void* A, int a_dtype, int64_t a_sr, int64_t a_sk, int64_t a_sb,
              const void* B, int b_dtype, int64_t b_sr, int64_t b_sk, int64_t b_sb,
              void* C, int c_dtype, int64_t ldc, int64_t c_sb,
@@ -188,7 +189,9 @@ int vqa_adam_multi(float* const* params, const float* const* grads, float* const
 
 /* C[z][m,n] (c_dtype, row pitch ldc) = act(sum_k A[z][m,k] * B[z][n,k] + bias[z][n] + bias2[z][n]) * dropout
  * A [M,K] and B [N,K] are bf16, K contiguous, row pitches lda/ldb (multiples of 8 elements), 16-byte
- * aligned.  flags as vqa_gemm (VQA_GEMM_RELU, VQA_GEMM_SPLITK; ACCUMULATE unsupported). */
+ * aligned.  flags as vqa_gemm (VQA_GEMM_RELU, VQA_GEMM_SPLITK; ACCUMULATE unsupported).  With
+ * VQA_GEMM_OPERANDS_MN the operands are stored reduction-major: A [K,M], B [K,N] (pitches lda/ldb); this is the
+ * weight-gradient form dW[N,K'] = dY[rows,N]^T X[rows,K'] consumed without transposes. */
 int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
                 void* C, int c_dtype, int64_t ldc, int64_t c_sb,
                 const float* bias, const float* bias2, int64_t bias_sb,
@@ -219,6 +222,13 @@ int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int
  * Cin in {64,128}, Cout % 128 == 0. */
 int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* dw,
                               int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* first layer (Cin = 3, Cout = 64, 3x3, stride 1) on tcgen05 with the im2col tile built in shared memory by the
+ * kernel itself from the NCHW fp32 network input (K = 27 is too small for a TMA pipeline).  out / mask as above;
+ * wgrad: dy [B,2PH,2PW,64] bf16 from vqa_unpool_bf16, dw fp32 [64,3,3,3] overwritten. */
+int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias, void* out, uint8_t* mask,
+                               int B, int IH, int IW, int Cin, int Cout, void* stream);
+int vqa_tc_conv0_bwd_weight(const float* x, const void* dy, float* dw, int B, int IH, int IW, int Cin, int Cout,
+                            void* stream);
 /* channel-major re-layout helpers (NHWC -> [B,C,H,Wp], zero padded pitch) */
 int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream);
 int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void* dyT, int B, int PH, int PW, int C,

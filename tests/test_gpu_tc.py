@@ -172,3 +172,61 @@ def test_layout_helpers():
     for e in range(4):
         ref[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
     assert torch.equal(dyT[..., :2 * PW].float(), ref.permute(0, 3, 1, 2)) and float(dyT[..., 2 * PW:].float().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("B,IH,IW", [(2, 38, 38), (3, 224, 224), (1, 19, 45)])
+def test_tc_conv0_fwd_and_wgrad_match_torch(B, IH, IW):
+    import torch.nn.functional as F
+    from dl_vqa_b200 import lib
+    torch.manual_seed(IH)
+    Cin, Cout = 3, 64
+    x = torch.randn(B, Cin, IH, IW, device="cuda").half().float()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / 5
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    out = torch.empty(B, PH, PW, Cout, dtype=torch.bfloat16, device="cuda")
+    mask = torch.empty(B, PH, PW, Cout, dtype=torch.uint8, device="cuda")
+    lib.call("vqa_tc_conv0_relu_pool_fwd", lib.ptr(x), lib.ptr(w), lib.ptr(bias), lib.ptr(out), lib.ptr(mask),
+             B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    pre = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), bias)
+    want, idx = F.max_pool2d(torch.relu(pre), 2, 2, return_indices=True)
+    want = want.permute(0, 2, 3, 1)
+    err = float((out.float() - want).abs().max() / want.abs().max())
+    assert err < 1e-2, err
+    OW = IW - 2
+    idx = idx.permute(0, 2, 3, 1)
+    e = ((idx // OW) % 2) * 2 + ((idx % OW) % 2)
+    agree = float(((mask.long() == e) | ~(want > 1e-3)).float().mean())
+    assert agree > 0.999, agree
+    # weight gradient
+    dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
+    dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    lib.call("vqa_tc_conv0_bwd_weight", lib.ptr(x), lib.ptr(dy), lib.ptr(dw), B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
+    full[:, :2 * PH, :2 * PW] = dy.float()
+    wantw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (Cout, Cin, 3, 3), full.permute(0, 3, 1, 2))
+    errw = float((dw - wantw).abs().max() / wantw.abs().max())
+    assert errw < 2e-3, errw
+
+
+@pytest.mark.parametrize("R,N,K", [(256, 3000, 1024), (5888, 4096, 304), (1000, 64, 72), (4, 136, 40), (20000, 1024, 256)])
+def test_tc_gemm_mn_major_weight_gradient_form(R, N, K):
+    """dW[N,K] = dY[R,N]^T X[R,K] with both operands consumed row-major (reduction index = row)."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(R)
+    dY = torch.randn(R, N, device="cuda").bfloat16()
+    X = torch.randn(R, K, device="cuda").bfloat16()
+    big = R >= 4096
+    dW = (torch.zeros if big else torch.empty)(N, K, device="cuda")
+    flags = lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if big else 0)
+    lib.call("vqa_tc_gemm", lib.ptr(dY), N, 0, lib.ptr(X), K, 0, lib.ptr(dW), lib.F32, K, 0, None, None, 0,
+             N, K, R, 1, flags, 0.0, 0, 0, lib.stream())
+    torch.cuda.synchronize()
+    want = dY.float().t() @ X.float()
+    err = float((dW - want).abs().max() / want.abs().max())
+    assert err < 1e-4, err
