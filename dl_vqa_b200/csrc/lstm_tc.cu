@@ -1,0 +1,280 @@
+// Persistent LSTM recurrence (forward) for the question encoder (nn.LSTM, models/model.py:164) on tcgen05.
+//
+// One cooperative launch runs ALL time steps of ALL directions.  The recurrent weights never leave the chip:
+// CTA j of direction d owns hidden units [16j, 16j+16), i.e. the 64 rows {gate*H + 16j + u} of W_hh[d]
+// (64 x H bf16 = 128 KB at H = 1024) loaded ONCE by TMA into shared memory as the K-major B operand, rows
+// ordered u*4+gate so that a thread's accumulator row holds the four gates of each of its 16 units.
+// Per step: D[b, 64] = h_{s-1}[b, :] W_slice^T with h streamed from L2 by TMA (4-stage ring), accumulators in
+// TMEM (one 128-row tile per 128 samples), then the fused cell epilogue: + x-projection, sigmoid/tanh,
+// c/h update, variable-length masking, h_s written back (bf16) for the next step.
+// Between steps the 64 CTAs of a direction meet at a global-memory barrier (release: __threadfence + atomicAdd,
+// acquire: ld.acquire.gpu + fence.proxy.async before the next TMA reads h_s).  The two directions never wait
+// for each other.  Co-residency of all CTAs is guaranteed by cudaLaunchCooperativeKernel.
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int LSTM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (8 warps = 2 m-tiles x 4 quarters)
+constexpr int LSTM_STAGES = 4;
+constexpr int LSTM_A_BYTES = 128 * 64 * 2;
+
+struct LstmParams {
+    bf16* gx;            // [dirs][T][B][4H]  in: x W_ih^T + b ; out: activated gates (saved for backward)
+    float* cs;           // [dirs][T][B][H]
+    bf16* hs;            // [dirs][T+1][B][H]  slot 0 = zeros, slot s+1 = h after step s
+    bf16* qf;            // [B][dirs*H]
+    const int64_t* len;  // [B]
+    unsigned int* sync;  // [dirs] zero-initialised counters
+    int T, B, H, dirs, ctas_per_dir, mtiles;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_constant__ CUtensorMap tma_w, LstmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int kblocks = p.H / 64;
+    uint8_t* sw = smem;                                       // kblocks x [64 rows][128 B]
+    uint8_t* sa = smem + kblocks * 8192;                      // LSTM_STAGES x 16 KB
+    uint64_t* full = reinterpret_cast<uint64_t*>(sa + LSTM_STAGES * LSTM_A_BYTES);
+    uint64_t* empty = full + LSTM_STAGES;
+    uint64_t* w_full = empty + LSTM_STAGES;
+    uint64_t* tmem_full = w_full + 1;                          // [2] one per m-tile
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x / p.ctas_per_dir, j = blockIdx.x - dir * p.ctas_per_dir;
+    const int T = p.T, B = p.B, H = p.H;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_h); tma_prefetch_desc(&tma_w);
+        for (int i = 0; i < LSTM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(w_full, 1);
+        mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, 128);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident recurrent weights: rows [64j, 64j+64) of the packed matrix of this direction
+            mbar_expect_tx(w_full, (uint32_t)kblocks * 8192u);
+            for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(sw + kb * 8192, &tma_w, w_full, kb * 64, j * 64, dir);
+            uint32_t it = 0;
+            const unsigned int* cnt = p.sync + dir;
+            const unsigned int per_step = (unsigned int)p.ctas_per_dir * 8u * (unsigned int)1;
+            for (int s = 0; s < T; ++s) {
+                if (s > 0) {                                   // h_{s-1} of every CTA of this direction is in L2
+                    const unsigned int target = per_step * (unsigned int)s;
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(cnt) < target) {
+                        if (++spins > (1u << 24)) { printf("vqa_b200: lstm step barrier timeout (cta %d step %d)\n", blockIdx.x, s); __trap(); }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                for (int mt = 0; mt < p.mtiles; ++mt)
+                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                        const int st = it % LSTM_STAGES;
+                        const uint32_t ph = (it / LSTM_STAGES) & 1;
+                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_expect_tx(&full[st], LSTM_A_BYTES);
+                        tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * B + mt * 128, dir);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(128, 64);
+            mbar_wait(w_full, 0);
+            uint32_t it = 0;
+            for (int s = 0; s < T; ++s)
+                for (int mt = 0; mt < p.mtiles; ++mt) {
+                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                        const int st = it % LSTM_STAGES;
+                        const uint32_t ph = (it / LSTM_STAGES) & 1;
+                        mbar_wait(&full[st], ph);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(sa + st * LSTM_A_BYTES), b_addr = smem_u32(sw + kb * 8192);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + mt * 64, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(b_addr + k * 32),
+                                     idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty[st]);
+                    }
+                    umma_commit(&tmem_full[mt]);
+                }
+        }
+    } else {
+        // ---- epilogue: warp -> (m-tile, lane quarter); thread -> sample b; 16 hidden units x 4 gates in registers
+        const int ew = warp - 2;
+        const int mt = ew >> 2, quarter = warp & 3;
+        const int b = mt * 128 + quarter * 32 + lane;
+        const bool active_tile = mt < p.mtiles;
+        const bool row_ok = active_tile && b < B;
+        const int len = row_ok ? (int)p.len[b] : 0;
+        const int u0 = j * 16;
+        float c_state[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) c_state[u] = 0.f;
+        float h_state[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) h_state[u] = 0.f;
+        for (int s = 0; s < T; ++s) {
+            if (active_tile) {
+                mbar_wait(&tmem_full[mt], s & 1);
+                tcgen05_fence_after();
+                const int64_t row = ((int64_t)dir * T + s) * B + b;
+                const bool step_on = row_ok && s < len;
+                bf16* g = p.gx + row * 4 * H + u0;
+                // x-projection (+biases) of this thread's 16 units, 4 gates: 8 x 16 B
+                uint4 xq[4][2];
+                if (step_on) {
+#pragma unroll
+                    for (int gate = 0; gate < 4; ++gate) {
+                        xq[gate][0] = *reinterpret_cast<const uint4*>(g + (int64_t)gate * H);
+                        xq[gate][1] = *reinterpret_cast<const uint4*>(g + (int64_t)gate * H + 8);
+                    }
+                }
+                uint4 oq[4][2];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {          // units 8*half .. 8*half+7 <-> accumulator columns 32*half ..
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + mt * 64 + half * 32, v);
+                    if (step_on) {
+#pragma unroll
+                        for (int uu = 0; uu < 8; ++uu) {
+                            const int u = half * 8 + uu;
+                            float xg[4];
+#pragma unroll
+                            for (int gate = 0; gate < 4; ++gate)
+                                xg[gate] = __bfloat162float(reinterpret_cast<const bf16*>(&xq[gate][half])[uu]);
+                            const float gi = sigmoidf_(v[uu * 4 + 0] + xg[0]);
+                            const float gf = sigmoidf_(v[uu * 4 + 1] + xg[1]);
+                            const float gg = tanhf(v[uu * 4 + 2] + xg[2]);
+                            const float go = sigmoidf_(v[uu * 4 + 3] + xg[3]);
+                            c_state[u] = gf * c_state[u] + gi * gg;
+                            h_state[u] = go * tanhf(c_state[u]);
+                            reinterpret_cast<bf16*>(&oq[0][half])[uu] = __float2bfloat16_rn(gi);
+                            reinterpret_cast<bf16*>(&oq[1][half])[uu] = __float2bfloat16_rn(gf);
+                            reinterpret_cast<bf16*>(&oq[2][half])[uu] = __float2bfloat16_rn(gg);
+                            reinterpret_cast<bf16*>(&oq[3][half])[uu] = __float2bfloat16_rn(go);
+                        }
+                    }
+                }
+                if (step_on) {
+#pragma unroll
+                    for (int gate = 0; gate < 4; ++gate) {
+                        *reinterpret_cast<uint4*>(g + (int64_t)gate * H) = oq[gate][0];
+                        *reinterpret_cast<uint4*>(g + (int64_t)gate * H + 8) = oq[gate][1];
+                    }
+                }
+                if (row_ok) {
+                    // state after step s (frozen rows copy forward)
+                    float* cdst = p.cs + row * H + u0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        *reinterpret_cast<float4*>(cdst + 4 * t) = make_float4(c_state[4 * t], c_state[4 * t + 1], c_state[4 * t + 2], c_state[4 * t + 3]);
+                    bf16* hdst = p.hs + (((int64_t)dir * (T + 1) + s + 1) * B + b) * H + u0;
+                    uint4 q[2];
+                    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(h_state[2 * t], h_state[2 * t + 1]);
+                    *reinterpret_cast<uint4*>(hdst) = q[0];
+                    *reinterpret_cast<uint4*>(hdst + 8) = q[1];
+                    if (s == T - 1) {
+                        bf16* qdst = p.qf + (int64_t)b * p.dirs * H + (int64_t)dir * H + u0;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(c_state[2 * t], c_state[2 * t + 1]);
+                        *reinterpret_cast<uint4*>(qdst) = q[0];
+                        *reinterpret_cast<uint4*>(qdst + 8) = q[1];
+                    }
+                }
+                tcgen05_fence_before();
+            }
+            // release this warp's h_s stores to the other CTAs of the direction
+            __syncwarp();
+            if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
+// w_hh fp32 [4H][H] (gate-stacked i,f,g,o) -> bf16 [H/16][64][H], row u*4+gate of block j = source row gate*H + 16j + u
+__global__ void pack_lstm_whh_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int H) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)4 * H * H) return;
+    const int k = (int)(i % H);
+    const int r = (int)(i / H);                 // packed row
+    const int jblk = r >> 6, loc = r & 63, u = loc >> 2, gate = loc & 3;
+    wp[i] = __float2bfloat16_rn(w[((int64_t)gate * H + jblk * 16 + u) * H + k]);
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream) {
+    VQA_REQUIRE(w_hh && wp && H > 0 && H % 16 == 0, "pack_lstm_whh: bad arguments");
+    const int64_t n = (int64_t)4 * H * H;
+    pack_lstm_whh_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh, (bf16*)wp, H);
+    VQA_CHECK_LAUNCH("pack_lstm_whh");
+    return 0;
+}
+
+// gx [dirs][T][B][4H] bf16, cs [dirs][T][B][H] fp32, hs [dirs][T+1][B][H] bf16 (slot 0 must be zero),
+// qf [B][dirs*H] bf16, wp [dirs][4H][H] bf16 from vqa_pack_lstm_whh, sync: dirs zeroed uint32 counters.
+extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
+                               unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
+    VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm: bad dims");
+    VQA_REQUIRE(H % 64 == 0 && H >= 64 && H <= 1024, "tc lstm: hidden size %d must be a multiple of 64 and <= 1024 (weights resident in shared memory)", H);
+    VQA_REQUIRE(B <= 256, "tc lstm: at most 256 sequences per launch (got %d); split the batch", B);
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    VQA_REQUIRE(coop, "tc lstm: device does not support cooperative launch");
+    const int ctas_per_dir = H / 16;
+    VQA_REQUIRE(ctas_per_dir * dirs <= sms, "tc lstm: %d CTAs needed but only %d SMs", ctas_per_dir * dirs, sms);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    CUtensorMap th, tw;
+    {
+        const uint64_t dims[3] = {(uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)dirs};
+        const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)(T + 1) * B * H * 2};
+        const uint32_t box[3] = {64, 128, 1};
+        if (int e = make_tmap_bf16(&th, hs, 3, dims, str, box)) return e;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)H, (uint64_t)4 * H, (uint64_t)dirs};
+        const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)4 * H * H * 2};
+        const uint32_t box[3] = {64, 64, 1};
+        if (int e = make_tmap_bf16(&tw, wp, 3, dims, str, box)) return e;
+    }
+    LstmParams p{};
+    p.gx = (bf16*)gx; p.cs = cs; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
+    p.T = T; p.B = B; p.H = H; p.dirs = dirs; p.ctas_per_dir = ctas_per_dir; p.mtiles = (B + 127) / 128;
+    const int smem = (H / 64) * 8192 + LSTM_STAGES * LSTM_A_BYTES + 1024 + 256;
+    static int attr_smem = 0;
+    if (attr_smem < smem) {
+        VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * dirs, st));
+    void* args[] = {(void*)&th, (void*)&tw, (void*)&p};
+    vqa_count_launch();
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_persistent_fwd_kernel, dim3(ctas_per_dir * dirs),
+                                                dim3(LSTM_THREADS), args, (size_t)smem, st);
+    if (e != cudaSuccess) { vqa_set_error("lstm_persistent_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}

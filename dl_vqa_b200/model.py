@@ -359,12 +359,27 @@ class VqaNet(nn.Module):
             mm.lin_fwd(ptr(xs[d]), dt, ldx, w_ih[d], ptr(gx[d]), dt, 4 * H, T * B, 4 * H, E,
                        bias=b_ih[d], bias2=b_hh[d], tag="lstm_inproj")
         cs = empty(dirs, T, B, H, dtype=f32)
-        hs = empty(dirs, T, B, H)
         qf = empty(B, dirs * H)
         whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
-        for s in range(T):
-            call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
-                 dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        persistent = tc and H % 64 == 0 and H <= 1024 and B <= 256 and dirs * (H // 16) <= sms
+        if persistent:
+            # one cooperative launch for all steps and directions; W_hh resident in shared memory
+            wp = empty(dirs, 4 * H, H)
+            for d in range(dirs):
+                call("vqa_pack_lstm_whh", ptr(w_hh[d]), ptr(wp[d]), H, st, tag="w_cast")
+            hs_ext = torch.zeros(dirs, T + 1, B, H, dtype=adt, device=dev)      # slot 0 = h_{-1} = 0
+            sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
+            call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
+                 T, B, H, dirs, st, tag="lstm_recurrence_fwd")
+            h_prev = [hs_ext[d, 1] for d in range(dirs)]     # h_0 .. h_{T-1} of direction d start here
+            hs = hs_ext
+        else:
+            hs = empty(dirs, T, B, H)
+            for s in range(T):
+                call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
+                     dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
+            h_prev = [hs[d, 0] for d in range(dirs)]
 
         # ---------------- attention (models/model.py:183-195, :208-221)
         att = self.attention
@@ -404,7 +419,7 @@ class VqaNet(nn.Module):
 
         if save:
             ctx.update(B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
-                       xs=xs, gx=gx, cs=cs, hs=hs, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
+                       xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
                        q=q, q_len=q_len, ldx=ldx, whh_stride=whh_stride,
                        p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
         return logits, ctx
@@ -531,7 +546,7 @@ class VqaNet(nn.Module):
                          None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
         for d in range(dirs):
             dWhh = empty(4 * H, H, dtype=f32)
-            mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(hs[d]), dt, H, dWhh,
+            mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(ctx["h_prev"][d]), dt, H, dWhh,
                               (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad")
             dWih = empty(4 * H, E, dtype=f32)
             mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad")

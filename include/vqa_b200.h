@@ -229,6 +229,15 @@ int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias
                                int B, int IH, int IW, int Cin, int Cout, void* stream);
 int vqa_tc_conv0_bwd_weight(const float* x, const void* dy, float* dw, int B, int IH, int IW, int Cin, int Cout,
                             void* stream);
+/* Persistent LSTM recurrence, all steps and directions in one cooperative launch (replaces the cuDNN RNN of
+ * models/model.py:164).  W_hh stays resident in shared memory (64 gate rows per CTA), h is exchanged through L2.
+ *   gx [dirs][T][B][4H] bf16 (in: x W_ih^T + b_ih + b_hh, out: activated gates), cs [dirs][T][B][H] fp32,
+ *   hs [dirs][T+1][B][H] bf16 with slot 0 zero-filled by the caller (slot s+1 = h after step s),
+ *   qf [B][dirs*H] bf16 = final cell state, wp [dirs][4H][H] bf16 from vqa_pack_lstm_whh (one call per direction),
+ *   sync: `dirs` uint32 scratch counters.  H % 64 == 0, H <= 1024, B <= 256 per launch. */
+int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
+                    unsigned int* sync, int T, int B, int H, int dirs, void* stream);
+int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);
 /* channel-major re-layout helpers (NHWC -> [B,C,H,Wp], zero padded pitch) */
 int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream);
 int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void* dyT, int B, int PH, int PW, int C,

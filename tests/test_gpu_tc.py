@@ -230,3 +230,43 @@ def test_tc_gemm_mn_major_weight_gradient_form(R, N, K):
     want = dY.float().t() @ X.float()
     err = float((dW - want).abs().max() / want.abs().max())
     assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (5, 4, 64, 1), (130, 7, 256, 2)])
+def test_persistent_lstm_matches_stepwise_kernel(B, T, H, dirs):
+    """The cooperative tcgen05 recurrence against the per-step SIMT kernel (itself parity-checked against the
+    oracle in test_gpu_parity) on identical bf16 inputs."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(B + T)
+    dev = "cuda"
+    gx0 = (torch.randn(dirs, T, B, 4 * H, device=dev) * 0.8).bfloat16()
+    w_hh = torch.randn(dirs, 4 * H, H, device=dev) / H ** 0.5
+    w_hh_b = w_hh.bfloat16().float().contiguous()            # same rounded weights on both sides
+    q_len = torch.randint(1, T + 1, (B,), device=dev)
+    q_len[0] = T
+    st = lib.stream()
+    # reference: step kernel
+    gx_a = gx0.clone(); cs_a = torch.empty(dirs, T, B, H, device=dev); hs_a = torch.empty(dirs, T, B, H, device=dev, dtype=torch.bfloat16)
+    qf_a = torch.empty(B, dirs * H, device=dev, dtype=torch.bfloat16)
+    for s in range(T):
+        lib.call("vqa_lstm_step_fwd", lib.ptr(gx_a), lib.ptr(cs_a), lib.ptr(hs_a), lib.ptr(qf_a), lib.ptr(w_hh_b), 4 * H * H,
+                 lib.ptr(q_len), lib.BF16, s, T, B, H, dirs, st)
+    # persistent kernel
+    gx_b = gx0.clone(); cs_b = torch.empty(dirs, T, B, H, device=dev)
+    hs_b = torch.zeros(dirs, T + 1, B, H, device=dev, dtype=torch.bfloat16)
+    qf_b = torch.empty(B, dirs * H, device=dev, dtype=torch.bfloat16)
+    wp = torch.empty(dirs, 4 * H, H, device=dev, dtype=torch.bfloat16)
+    for d in range(dirs):
+        lib.call("vqa_pack_lstm_whh", lib.ptr(w_hh[d]), lib.ptr(wp[d]), H, st)
+    sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
+    lib.call("vqa_tc_lstm_fwd", lib.ptr(gx_b), lib.ptr(cs_b), lib.ptr(hs_b), lib.ptr(qf_b), lib.ptr(wp), lib.ptr(q_len),
+             lib.ptr(sync), T, B, H, dirs, st)
+    torch.cuda.synchronize()
+    def err(a, b):
+        return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-9))
+    assert err(qf_b, qf_a) < 2e-2
+    assert err(cs_b, cs_a) < 2e-2
+    assert err(hs_b[:, 1:], hs_a) < 2e-2
+    # activated gates only where the step was active
+    act = (torch.arange(T, device=dev)[None, :, None] < q_len[None, None, :]).unsqueeze(-1)
+    assert err(torch.where(act, gx_b.float(), torch.zeros((), device=dev)), torch.where(act, gx_a.float(), torch.zeros((), device=dev))) < 2e-2
