@@ -71,7 +71,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
             for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(sw + kb * 8192, &tma_w, w_full, kb * 64, j * 64, dir);
             uint32_t it = 0;
             const unsigned int* cnt = p.sync + dir;
-            const unsigned int per_step = (unsigned int)p.ctas_per_dir * 8u * (unsigned int)1;
+            const unsigned int per_step = (unsigned int)p.ctas_per_dir * 4u * (unsigned int)p.mtiles;   // arriving warps
             for (int s = 0; s < T; ++s) {
                 if (s > 0) {                                   // h_{s-1} of every CTA of this direction is in L2
                     const unsigned int target = per_step * (unsigned int)s;
@@ -200,7 +200,8 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                 }
                 tcgen05_fence_before();
             }
-            // release this warp's h_s stores to the other CTAs of the direction
+            // release this warp's h_s stores to the other CTAs of the direction (warps of unused m-tiles stay out)
+            if (!active_tile) break;
             __syncwarp();
             if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
         }
