@@ -24,6 +24,19 @@ CONV_FLOP = {0: 0.170e9, 1: 1.752e9, 2: 1.595e9}
 STEP_FLOP_PER_SAMPLE = 13.00e9          # fwd + bwd at T = 23
 
 
+def _ncu_traffic(tag):
+    """DRAM bytes per launch of kernel `tag` from the newest committed ncu capture (profiles/r*_ncu_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    k = d.get("kernels", {}).get(tag)
+    if not k:
+        return None, None
+    return k["dram_bytes_read"] + k["dram_bytes_write"], os.path.basename(files[-1])
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -43,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -208,9 +221,9 @@ def run_ours(args):
     ms_dev = timed(lambda: step(dbatch), args.steps)
     ktimes = lib.collect_kernel_timing()
     launches = lib.launch_count() - n0
-    clk = clocks.stop()
 
     if args.profile_mode:            # under ncu: no second timed region, no CPU leg
+        clocks.stop()
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms_dev / args.steps}), flush=True)
         if world > 1:
@@ -226,6 +239,7 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
 
     if rank != 0:
         if world > 1:
@@ -247,8 +261,10 @@ def run_ours(args):
         flop = CONV_FLOP[layer] * B
         dur_ms = conv_tags[top]["ms_per_step"] / max(1.0, conv_tags[top]["calls_per_step"])
         achieved = flop / (dur_ms / 1000.0) / 1e12
+        traffic, traffic_src = _ncu_traffic(top)
         roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"] + " sustained bf16",
+                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks["src"] + " sustained bf16",
                     "flop_per_launch": flop, "ms_per_launch": dur_ms}
     att = breakdown.get("vqa_attention_fwd")
     att_roof = None
@@ -257,7 +273,8 @@ def run_ours(args):
         byt = B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4)
         gbs = byt / (att["ms_per_step"] / 1000.0) / 1e9
         att_roof = {"kernel": "vqa_attention_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": byt}
+                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": byt,
+                    "traffic": _ncu_traffic("vqa_attention_fwd")[0]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -288,7 +305,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bfloat16", "float32"])
