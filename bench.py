@@ -155,6 +155,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
+    if args.conv_cta_group:
+        lib.call("vqa_tc_conv_set_cta_group", args.conv_cta_group)
 
     B = args.batch
     cfg = synth.default_cfg()                       # config.yaml defaults, dropout 0.3
@@ -311,6 +313,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bfloat16", "float32"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-cta-group", type=int, default=0, help="override the conv kernels' tcgen05 cta_group (1 or 2)")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + timed steps only (for ncu)")
     args = ap.parse_args()
     if args.dtype == "fp32":

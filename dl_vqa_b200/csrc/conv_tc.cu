@@ -1,24 +1,39 @@
 // 3x3 / stride-1 convolutions of the image encoder on tcgen05 tensor cores (models/model.py:72-84).
 //
-// Implicit GEMM without im2col: one CTA tile = 8 x 16 spatial positions (M = 128) x all output channels
-// (N = BN <= 256); for filter tap (kh,kw) and a 64-channel slice the A operand is ONE 4-D TMA box
-// [64 ch, 16 w, 8 h, 1 image] of the NHWC activation shifted by (kh,kw) -- it lands in shared memory as 128
-// rows x 128 bytes with the 128-byte swizzle, exactly the K-major UMMA operand.  Out-of-bounds rows/cols are
-// zero-filled by TMA (no padding copies).  The B operand is the packed weight [N][tap][C] (K-major).
+// Implicit GEMM without im2col and without re-reading the input per filter tap: one CTA tile = 16 x 8 spatial
+// positions (M = 128) x all output channels (N = BN <= 256).  For a 64-channel slice ONE 4-D TMA box
+// [64 ch, 10 w, 18 h, 1 image] brings the tile plus its halo into shared memory as 180 rows x 128 bytes (128-byte
+// swizzle); the A operand of filter tap (kh,kw) is the same buffer with the start address advanced by
+// (kh*10 + kw) rows and an 8-row-group stride of 10 rows (1280 B) -- the swizzle is a function of the absolute
+// shared-memory address (tools/umma_probe.cu), so nine taps cost one load.  Out-of-bounds rows/cols are zero-filled
+// by TMA (no padding copies).  The B operand is the packed weight [N][tap][C] (K-major); when all of it fits in
+// shared memory (conv1: 144 KB) it is loaded once per CTA and stays resident, otherwise its 64-wide k-slabs are
+// streamed through a second mbarrier ring.
 //
-// Persistent kernel: grid = #SMs, tiles round-robin; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 =
-// epilogue.  Two TMEM accumulators (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on two tiles at once; each CTA loads its own halo
+// tile and HALF of the weight rows, the pair's tensor cores share both halves, so per-SM shared-memory traffic of
+// the B operand halves.  The leader CTA's single MMA thread issues for both; mbarrier completions are multicast.
+//
+// Persistent kernel: grid = #SMs, tiles round-robin; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 =
+// epilogue (two warps per TMEM lane quarter, alternating 32-column chunks).  Two TMEM accumulators (2 x BN columns)
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Epilogues:
-//   POOL  (forward)  bias + ReLU + 2x2 max-pool + arg-max mask: window partners are lanes l, l^1, l^16, l^17 of
-//                    one warp (tile rows are 16 wide); a 2-step butterfly leaves each lane 8 of every 32 channels.
+//   POOL  (forward)  bias + ReLU + 2x2 max-pool + arg-max mask: window partners are lanes l, l^1, l^8, l^9 of
+//                    one warp (tile rows are 8 wide); a 2-step butterfly leaves each lane 8 of every 32 channels.
 //   STORE (dgrad)    plain bf16 store of the 128 x BN tile (gradient w.r.t. the layer input).
 #include "tc_common.cuh"
 
 namespace tc {
 
-constexpr int CONV_THREADS = 192;
-constexpr int TILE_H = 8, TILE_W = 16;
+constexpr int TILE_H = 16, TILE_W = 8;
+constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
+constexpr int HALO_BYTES = HALO_H * HALO_W * 128;            // 23040: one 64-channel slice of tile + halo
+constexpr int A_STAGE_BYTES = 23552;                          // padded to a multiple of 1024
+constexpr int EPI_WARPS = 8;
+constexpr int CONV_THREADS = 64 + EPI_WARPS * 32;
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448 - 1024;                     // 227 KB minus alignment slack
 enum { EPI_POOL = 0, EPI_STORE = 1 };
 
 struct ConvParams {
@@ -27,110 +42,161 @@ struct ConvParams {
     int sign;                      // +1: forward taps (h+kh, w+kw);  -1: data-gradient taps (h-kh, w-kw)
     int valid_h, valid_w;          // extent of valid output positions (conv-output for POOL, input for STORE)
     int N;                         // output channels (== BN)
+    int a_stages, b_stages;        // ring depths (b_stages unused when the weights are resident)
     // POOL
     const float* bias; bf16* pooled; uint8_t* mask; int PH, PW;
     // STORE
     bf16* dx;
 };
 
-template <int BN>
-struct ConvSmem {
-    static constexpr int STAGES = BN >= 256 ? 4 : 6;
-    static constexpr int A_BYTES = 128 * 64 * 2, B_BYTES = BN * 64 * 2;
-    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
-};
-
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA, bool RESIDENT>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, ConvParams p) {
-    using S = ConvSmem<BN>;
+    constexpr int BN_CTA = BN / NCTA;                 // weight rows held by this CTA
+    constexpr int B_SLAB = BN_CTA * 128;              // one 64-wide k-slab of them
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nkb = 9 * p.chunks;
     uint8_t* sa = smem;
-    uint8_t* sb = smem + S::STAGES * S::A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));
-    uint64_t* empty = full + S::STAGES;
-    uint64_t* tmem_full = empty + S::STAGES;     // [2]
-    uint64_t* tmem_empty = tmem_full + 2;        // [2]
+    uint8_t* sb = smem + p.a_stages * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sb + (RESIDENT ? nkb : p.b_stages) * B_SLAB);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + MAX_A_STAGES;
+    uint64_t* fullB = emptyA + MAX_A_STAGES;
+    uint64_t* emptyB = fullB + MAX_B_STAGES;
+    uint64_t* tmem_full = emptyB + MAX_B_STAGES;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
     const int ntiles = p.B * tiles_per_img;
-    const int nkb = 9 * p.chunks;
-    constexpr uint32_t TMEM_COLS = 2 * BN;       // 128, 256 or 512: all powers of two
+    const int nrounds = (ntiles + NCTA - 1) / NCTA;                 // one tile per CTA of the pair per round
+    const int nclusters = gridDim.x / NCTA, cluster_id = blockIdx.x / NCTA;
+    constexpr uint32_t TMEM_COLS = 2 * BN;                            // 128, 256 or 512: all powers of two
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
-        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < MAX_B_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS * NCTA); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    if (warp == 1) { if (NCTA == 2) tmem_alloc_pair(tmem_base_smem, TMEM_COLS); else tmem_alloc(tmem_base_smem, TMEM_COLS); }
     tcgen05_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
     if (warp == 0) {
+        // ===== TMA producer (one per CTA; byte counts go to the leader's barriers) =====
         if (lane == 0) {
-            uint32_t it = 0;                     // running k-block counter across tiles (smem ring position)
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-                const int h0 = (r / p.tiles_w) * TILE_H, w0 = (r % p.tiles_w) * TILE_W;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % S::STAGES;
-                    const uint32_t ph = (it / S::STAGES) & 1;
-                    const int tap = kb / p.chunks, cc = kb - tap * p.chunks;
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
-                    tma_load_4d(sa + s * S::A_BYTES, &tma_a, &full[s], cc * 64, w0 + p.sign * kw, h0 + p.sign * kh, b);
-                    tma_load_2d(sb + s * S::B_BYTES, &tma_b, &full[s], kb * 64, 0);
+            if (RESIDENT) {
+                if (leader) mbar_expect_tx(&fullB[0], (uint32_t)(NCTA * nkb * B_SLAB));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (NCTA == 2) tma_load_2d_pair(sb + kb * B_SLAB, &tma_b, &fullB[0], kb * 64, (int)rank * BN_CTA);
+                    else tma_load_2d(sb + kb * B_SLAB, &tma_b, &fullB[0], kb * 64, 0);
+                }
+            }
+            uint32_t ita = 0, itb = 0;
+            for (int round = cluster_id; round < nrounds; round += nclusters) {
+                const int tile = round * NCTA + (int)rank;
+                int b = p.B, h0 = 0, w0 = 0;                       // b == B: everything out of bounds -> zero fill
+                if (tile < ntiles) {
+                    b = tile / tiles_per_img;
+                    const int r = tile - b * tiles_per_img;
+                    h0 = (r / p.tiles_w) * TILE_H; w0 = (r % p.tiles_w) * TILE_W;
+                }
+                const int hh = p.sign > 0 ? h0 : h0 - 2, ww = p.sign > 0 ? w0 : w0 - 2;
+                for (int cc = 0; cc < p.chunks; ++cc, ++ita) {
+                    const int s = ita % p.a_stages;
+                    const uint32_t ph = (ita / p.a_stages) & 1;
+                    mbar_wait(&emptyA[s], ph ^ 1);
+                    if (leader) mbar_expect_tx(&fullA[s], NCTA * HALO_BYTES);
+                    if (NCTA == 2) tma_load_4d_pair(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
+                    else tma_load_4d(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
+                    if (!RESIDENT) {
+                        for (int tap = 0; tap < 9; ++tap, ++itb) {
+                            const int t = itb % p.b_stages;
+                            const uint32_t pb = (itb / p.b_stages) & 1;
+                            const int kb = tap * p.chunks + cc;
+                            mbar_wait(&emptyB[t], pb ^ 1);
+                            if (leader) mbar_expect_tx(&fullB[t], NCTA * B_SLAB);
+                            if (NCTA == 2) tma_load_2d_pair(sb + t * B_SLAB, &tma_b, &fullB[t], kb * 64, (int)rank * BN_CTA);
+                            else tma_load_2d(sb + t * B_SLAB, &tma_b, &fullB[t], kb * 64, 0);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(128, BN);
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        // ===== MMA issuer: one thread of the leader CTA =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = idesc_bf16(128 * NCTA, BN);
+            constexpr uint16_t ALL = NCTA == 2 ? 3 : 1;
+            auto commit = [&](uint64_t* bar) { if (NCTA == 2) umma_commit_pair(bar, ALL); else umma_commit(bar); };
+            if (RESIDENT) { mbar_wait(&fullB[0], 0); tcgen05_fence_after(); }
+            uint32_t ita = 0, itb = 0, tcount = 0;
+            for (int round = cluster_id; round < nrounds; round += nclusters, ++tcount) {
                 const uint32_t acc = tcount & 1, use = tcount >> 1;
-                mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);      // epilogue has drained this accumulator
+                mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);      // both CTAs' epilogues have drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % S::STAGES;
-                    const uint32_t ph = (it / S::STAGES) & 1;
-                    mbar_wait(&full[s], ph);
+                for (int cc = 0; cc < p.chunks; ++cc, ++ita) {
+                    const int s = ita % p.a_stages;
+                    mbar_wait(&fullA[s], (ita / p.a_stages) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(sa + s * S::A_BYTES), b_addr = smem_u32(sb + s * S::B_BYTES);
+                    const uint32_t a_base = smem_u32(sa + s * A_STAGE_BYTES);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const int row = p.sign > 0 ? kh * HALO_W + kw : (2 - kh) * HALO_W + (2 - kw);
+                        uint32_t b_addr;
+                        int t = 0;
+                        if (RESIDENT) b_addr = smem_u32(sb + (tap * p.chunks + cc) * B_SLAB);
+                        else {
+                            t = itb % p.b_stages;
+                            mbar_wait(&fullB[t], (itb / p.b_stages) & 1);
+                            tcgen05_fence_after();
+                            b_addr = smem_u32(sb + t * B_SLAB);
+                            ++itb;
+                        }
+                        const uint32_t a_addr = a_base + row * 128;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(d_tmem, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(b_addr + k * 32), idesc,
-                                 (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty[s]);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = smem_desc_k_sw128_shifted(a_addr + k * 32, HALO_W * 128);
+                            const uint64_t bd = smem_desc_k_sw128(b_addr + k * 32);
+                            const uint32_t accum = (cc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                            if (NCTA == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum); else umma_f16(d_tmem, ad, bd, idesc, accum);
+                        }
+                        if (!RESIDENT) commit(&emptyB[t]);
+                    }
+                    commit(&emptyA[s]);
                 }
-                umma_commit(&tmem_full[acc]);
+                commit(&tmem_full[acc]);
             }
         }
     } else {
-        const int quarter = warp & 3;
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..+31; the two warps of a quarter alternate column chunks =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        for (int round = cluster_id; round < nrounds; round += nclusters, ++tcount) {
             const uint32_t acc = tcount & 1, use = tcount >> 1;
-            const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+            const int tile = round * NCTA + (int)rank;
+            const bool live = tile < ntiles;
+            const int b = live ? tile / tiles_per_img : 0, r = live ? tile - b * tiles_per_img : 0;
             const int h0 = (r / p.tiles_w) * TILE_H, w0 = (r % p.tiles_w) * TILE_W;
             mbar_wait(&tmem_full[acc], use & 1);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-            const int rr = 2 * quarter + (lane >> 4), cc = lane & 15;       // position inside the 8x16 tile
+            const int rr = 4 * quarter + (lane >> 3), cc = lane & 7;         // position inside the 16x8 tile
             if (EPI == EPI_STORE) {
                 const int h = h0 + rr, w = w0 + cc;
-                const bool ok = h < p.valid_h && w < p.valid_w;
+                const bool ok = live && h < p.valid_h && w < p.valid_w;
                 bf16* o = p.dx + (((int64_t)b * p.valid_h + h) * p.valid_w + w) * p.N;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = half * 32; c0 < BN; c0 += 64) {
                     float v[32];
                     tmem_ld_32x32(taddr + c0, v);
                     if (ok) {
@@ -145,13 +211,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
             } else {
-                // window id: pooled row = h0/2 + quarter, pooled col = w0/2 + cc/2; element e = dy*2+dx
-                const int ph_ = (h0 >> 1) + quarter, pw_ = (w0 >> 1) + (cc >> 1);
-                const bool ok = ph_ < p.PH && pw_ < p.PW;
-                const int bit0 = lane & 1, bit4 = (lane >> 4) & 1;
+                // window: pooled row = h0/2 + 2*quarter + (lane>>4), pooled col = w0/2 + cc/2; element e = dy*2+dx
+                const int ph_ = (h0 >> 1) + 2 * quarter + (lane >> 4), pw_ = (w0 >> 1) + (cc >> 1);
+                const bool ok = live && ph_ < p.PH && pw_ < p.PW;
+                const int bit0 = lane & 1, bitY = (lane >> 3) & 1;
                 const int64_t obase = (((int64_t)b * p.PH + ph_) * p.PW + pw_) * p.N;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = half * 32; c0 < BN; c0 += 64) {
                     float v[32];
                     tmem_ld_32x32(taddr + c0, v);
                     // step 1 (partner lane^1, dx): keep 16 channels: [0,16) if bit0==0 else [16,32)
@@ -166,25 +232,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         k1[j] = take_other ? other : mine;
                         i1[j] = take_other ? (bit0 ^ 1) : bit0;
                     }
-                    // step 2 (partner lane^16, dy): keep 8 channels: first 8 if bit4==0 else last 8
+                    // step 2 (partner lane^8, dy): keep 8 channels: first 8 if bitY==0 else last 8
                     float k2[8]; int i2[8];
                     uint32_t pack_send = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pack_send |= (uint32_t)(bit4 ? i1[j] : i1[8 + j]) << (2 * j);
-                    const uint32_t pack_other = __shfl_xor_sync(0xffffffffu, pack_send, 16);
+                    for (int j = 0; j < 8; ++j) pack_send |= (uint32_t)(bitY ? i1[j] : i1[8 + j]) << (2 * j);
+                    const uint32_t pack_other = __shfl_xor_sync(0xffffffffu, pack_send, 8);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float mine = bit4 ? k1[8 + j] : k1[j];
-                        const int mine_i = (bit4 ? i1[8 + j] : i1[j]) + 2 * bit4;
-                        const float send = bit4 ? k1[j] : k1[8 + j];
-                        const float other = __shfl_xor_sync(0xffffffffu, send, 16);
-                        const int other_i = (int)((pack_other >> (2 * j)) & 3u) + 2 * (bit4 ^ 1);
-                        const bool take_other = bit4 ? (other >= mine) : (other > mine);
+                        const float mine = bitY ? k1[8 + j] : k1[j];
+                        const int mine_i = (bitY ? i1[8 + j] : i1[j]) + 2 * bitY;
+                        const float send = bitY ? k1[j] : k1[8 + j];
+                        const float other = __shfl_xor_sync(0xffffffffu, send, 8);
+                        const int other_i = (int)((pack_other >> (2 * j)) & 3u) + 2 * (bitY ^ 1);
+                        const bool take_other = bitY ? (other >= mine) : (other > mine);
                         k2[j] = take_other ? other : mine;
                         i2[j] = take_other ? other_i : mine_i;
                     }
                     if (ok) {
-                        const int nb = c0 + 16 * bit0 + 8 * bit4;
+                        const int nb = c0 + 16 * bit0 + 8 * bitY;
                         const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb);
                         const float4 b1 = *reinterpret_cast<const float4*>(p.bias + nb + 4);
                         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -208,50 +274,99 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (NCTA == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
     }
 
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        if (NCTA == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
-template <int BN, int EPI>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
-    auto kern = conv_tc_kernel<BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::BYTES));
-        attr_set = true;
+// cta_group selection: 1 = single-CTA MMAs, 2 = CTA pairs.  Changed only by vqa_tc_conv_set_cta_group (tests/bench).
+static int g_conv_cta_group = 1;
+
+template <int BN, int EPI, int NCTA, bool RESIDENT>
+static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvParams p, int smem_bytes, cudaStream_t st) {
+    auto kern = conv_tc_kernel<BN, EPI, NCTA, RESIDENT>;
+    static int attr_bytes = 0;
+    if (attr_bytes < smem_bytes) {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_bytes = smem_bytes;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = p.B * p.tiles_h * p.tiles_w;
-    const int grid = ntiles < sms ? ntiles : sms;
-    kern<<<grid, CONV_THREADS, ConvSmem<BN>::BYTES, st>>>(ta, tb, p);
+    const int nrounds = (ntiles + NCTA - 1) / NCTA;
+    int grid = (nrounds < sms / NCTA ? nrounds : sms / NCTA) * NCTA;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = NCTA == 2 ? 1 : 0;
+    VQA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     VQA_CHECK_LAUNCH("conv_tc");
     return 0;
 }
 
-// activation tensor map: NHWC bf16 [B, H, W, C] with box [64, 16, 8, 1]
+// Chooses resident vs streamed weights and the ring depths from the shared-memory budget, then launches.
+template <int BN, int EPI>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, ConvParams p, cudaStream_t st) {
+    const int ncta = g_conv_cta_group;
+    const int nkb = 9 * p.chunks;
+    const int slab = (BN / ncta) * 128;
+    const int bars = 512;
+    const int resident_bytes = nkb * slab;
+    const bool resident = resident_bytes + 2 * A_STAGE_BYTES + bars <= SMEM_LIMIT;
+    int smem;
+    if (resident) {
+        int a = (SMEM_LIMIT - bars - resident_bytes) / A_STAGE_BYTES;
+        p.a_stages = a > 4 ? 4 : a; p.b_stages = 1;
+        smem = resident_bytes + p.a_stages * A_STAGE_BYTES + bars + 1024;
+    } else {
+        p.a_stages = p.chunks >= 2 ? 3 : 2;
+        int bs = (SMEM_LIMIT - bars - p.a_stages * A_STAGE_BYTES) / slab;
+        p.b_stages = bs > MAX_B_STAGES ? MAX_B_STAGES : bs;
+        VQA_REQUIRE(p.b_stages >= 2, "tc conv: weight slab does not fit in shared memory");
+        smem = p.b_stages * slab + p.a_stages * A_STAGE_BYTES + bars + 1024;
+    }
+    if (ncta == 2) {
+        if (resident) return launch_conv_cfg<BN, EPI, 2, true>(ta, tb2, p, smem, st);
+        return launch_conv_cfg<BN, EPI, 2, false>(ta, tb2, p, smem, st);
+    }
+    if (resident) return launch_conv_cfg<BN, EPI, 1, true>(ta, tb1, p, smem, st);
+    return launch_conv_cfg<BN, EPI, 1, false>(ta, tb1, p, smem, st);
+}
+
+// activation tensor map: NHWC bf16 [B, H, W, C] with box [64, 10, 18, 1] (tile + halo)
 static int act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    const uint32_t box[4] = {64, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {64, HALO_W, HALO_H, 1};
     return make_tmap_bf16(m, base, 4, dims, str, box);
 }
-static int weight_tmap(CUtensorMap* m, const void* base, int N, int K) {
+// weight tensor map: [N][K] bf16, box = 64 k-columns x `rows` weight rows (all of them, or one CTA's half)
+static int weight_tmap(CUtensorMap* m, const void* base, int N, int K, int rows) {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {64, (uint32_t)N};
+    const uint32_t box[2] = {64, (uint32_t)rows};
     return make_tmap_bf16(m, base, 2, dims, str, box);
 }
 
 }  // namespace tc
 
 using namespace tc;
+
+extern "C" int vqa_tc_conv_set_cta_group(int cta_group) {
+    VQA_REQUIRE(cta_group == 1 || cta_group == 2, "conv cta_group must be 1 or 2");
+    g_conv_cta_group = cta_group;
+    return 0;
+}
 
 // x [B,IH,IW,Cin] bf16 NHWC; wp [Cout][9*Cin] bf16 (tap-major, channel-minor); out/mask [B,PH,PW,Cout]
 extern "C" int vqa_tc_conv3x3_relu_pool_fwd(const void* x, const void* wp, const float* bias, void* out, uint8_t* mask,
@@ -260,17 +375,18 @@ extern "C" int vqa_tc_conv3x3_relu_pool_fwd(const void* x, const void* wp, const
     VQA_REQUIRE(Cin % 64 == 0, "tc conv fwd: Cin=%d must be a multiple of 64 (use vqa_conv_relu_pool_fwd)", Cin);
     VQA_REQUIRE(Cout == 64 || Cout == 128 || Cout == 256, "tc conv fwd: Cout=%d must be 64, 128 or 256", Cout);
     const int OH = IH - 2, OW = IW - 2, PH = OH / 2, PW = OW / 2;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb1, tb2;
     if (int e = act_tmap(&ta, x, B, IH, IW, Cin)) return e;
-    if (int e = weight_tmap(&tb, wp, Cout, 9 * Cin)) return e;
+    if (int e = weight_tmap(&tb1, wp, Cout, 9 * Cin, Cout)) return e;
+    if (int e = weight_tmap(&tb2, wp, Cout, 9 * Cin, Cout / 2)) return e;
     ConvParams p{};
     p.B = B; p.tiles_h = (2 * PH + TILE_H - 1) / TILE_H; p.tiles_w = (2 * PW + TILE_W - 1) / TILE_W;
     p.chunks = Cin / 64; p.sign = 1; p.valid_h = 2 * PH; p.valid_w = 2 * PW; p.N = Cout;
     p.bias = bias; p.pooled = (bf16*)out; p.mask = mask; p.PH = PH; p.PW = PW;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cout == 64) return launch_conv<64, EPI_POOL>(ta, tb, p, st);
-    if (Cout == 128) return launch_conv<128, EPI_POOL>(ta, tb, p, st);
-    return launch_conv<256, EPI_POOL>(ta, tb, p, st);
+    if (Cout == 64) return launch_conv<64, EPI_POOL>(ta, tb1, tb2, p, st);
+    if (Cout == 128) return launch_conv<128, EPI_POOL>(ta, tb1, tb2, p, st);
+    return launch_conv<256, EPI_POOL>(ta, tb1, tb2, p, st);
 }
 
 // dy [B,OHp,OWp,Cout] bf16: gradient w.r.t. the conv output restricted to the pooled region (OHp = 2PH,
@@ -282,17 +398,18 @@ extern "C" int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
     VQA_REQUIRE(Cout % 64 == 0, "tc conv dgrad: Cout=%d must be a multiple of 64", Cout);
     VQA_REQUIRE(Cin == 64 || Cin == 128 || Cin == 256, "tc conv dgrad: Cin=%d must be 64, 128 or 256", Cin);
     const int OHp = ((IH - 2) / 2) * 2, OWp = ((IW - 2) / 2) * 2;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb1, tb2;
     if (int e = act_tmap(&ta, dy, B, OHp, OWp, Cout)) return e;
-    if (int e = weight_tmap(&tb, wd, Cin, 9 * Cout)) return e;
+    if (int e = weight_tmap(&tb1, wd, Cin, 9 * Cout, Cin)) return e;
+    if (int e = weight_tmap(&tb2, wd, Cin, 9 * Cout, Cin / 2)) return e;
     ConvParams p{};
     p.B = B; p.tiles_h = (IH + TILE_H - 1) / TILE_H; p.tiles_w = (IW + TILE_W - 1) / TILE_W;
     p.chunks = Cout / 64; p.sign = -1; p.valid_h = IH; p.valid_w = IW; p.N = Cin;
     p.dx = (bf16*)dx;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin == 64) return launch_conv<64, EPI_STORE>(ta, tb, p, st);
-    if (Cin == 128) return launch_conv<128, EPI_STORE>(ta, tb, p, st);
-    return launch_conv<256, EPI_STORE>(ta, tb, p, st);
+    if (Cin == 64) return launch_conv<64, EPI_STORE>(ta, tb1, tb2, p, st);
+    if (Cin == 128) return launch_conv<128, EPI_STORE>(ta, tb1, tb2, p, st);
+    return launch_conv<256, EPI_STORE>(ta, tb1, tb2, p, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -212,6 +212,9 @@ int vqa_tc_conv3x3_relu_pool_fwd(const void* x, const void* wp, const float* bia
  * dx [B,IH,IW,Cin] bf16 */
 int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
                             int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* Tuning knob of the two entries above: 1 = single-CTA tcgen05.mma (cta_group::1), 2 = CTA pairs (cluster of 2,
+ * cta_group::2: each CTA stages half of the weight rows).  Process-wide; results are identical either way. */
+int vqa_tc_conv_set_cta_group(int cta_group);
 /* w fp32 OIHW [Cout,Cin,3,3] -> wp[co][tap][ci] and/or wd[ci][tap][co] (bf16; either may be NULL) */
 int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream);
 /* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0) */

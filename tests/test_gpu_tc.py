@@ -70,9 +70,20 @@ def _conv_case(B, IH, IW, Cin, Cout, seed):
     return x, w, bias
 
 
+@pytest.fixture
+def conv_cta_group(request):
+    """Runs a conv test with single-CTA MMAs (1) or CTA pairs (2) and restores the default afterwards."""
+    from dl_vqa_b200 import lib
+    lib.call("vqa_tc_conv_set_cta_group", request.param)
+    yield request.param
+    lib.call("vqa_tc_conv_set_cta_group", lib.DEFAULT_CONV_CTA_GROUP)
+
+
+@pytest.mark.parametrize("conv_cta_group", [1, 2], indirect=True)
 @pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (3, 111, 111, 64, 128), (2, 54, 54, 128, 256),
-                                              (1, 11, 9, 64, 64), (5, 30, 31, 128, 64)])
-def test_tc_conv_fwd_matches_torch(B, IH, IW, Cin, Cout):
+                                              (1, 11, 9, 64, 64), (5, 30, 31, 128, 64), (1, 20, 12, 256, 256),
+                                              (1, 7, 40, 192, 128)])
+def test_tc_conv_fwd_matches_torch(B, IH, IW, Cin, Cout, conv_cta_group):
     import torch.nn.functional as F
     from dl_vqa_b200 import lib
     x, w, bias = _conv_case(B, IH, IW, Cin, Cout, IH + Cin)
@@ -101,9 +112,10 @@ def test_tc_conv_fwd_matches_torch(B, IH, IW, Cin, Cout):
     assert bool(((mask == 4) == (out == 0)).all())
 
 
+@pytest.mark.parametrize("conv_cta_group", [1, 2], indirect=True)
 @pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (2, 111, 111, 64, 128), (2, 54, 54, 128, 256),
-                                              (1, 13, 10, 64, 64)])
-def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout):
+                                              (1, 13, 10, 64, 64), (3, 19, 9, 256, 192), (1, 40, 8, 64, 256)])
+def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout, conv_cta_group):
     import torch.nn.functional as F
     from dl_vqa_b200 import lib
     torch.manual_seed(IH)
