@@ -132,12 +132,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA =====
-        if (lane == 0 && leader) {
+        // ===== MMA issuer: the leader CTA's warp 1, all lanes converged, one elected lane issues =====
+        if (leader) {
             constexpr uint32_t idesc = idesc_bf16(128 * NCTA, BN);
-            constexpr uint16_t ALL = NCTA == 2 ? 3 : 1;
-            auto commit = [&](uint64_t* bar) { if (NCTA == 2) umma_commit_pair(bar, ALL); else umma_commit(bar); };
+            const uint32_t elected = elect_one();
             if (RESIDENT) { mbar_wait(&fullB[0], 0); tcgen05_fence_after(); }
+            const uint64_t b_desc0 = smem_desc_k_sw128(smem_u32(sb));
             uint32_t ita = 0, itb = 0, tcount = 0;
             for (int round = cluster_id; round < nrounds; round += nclusters, ++tcount) {
                 const uint32_t acc = tcount & 1, use = tcount >> 1;
@@ -148,33 +148,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const int s = ita % p.a_stages;
                     mbar_wait(&fullA[s], (ita / p.a_stages) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_base = smem_u32(sa + s * A_STAGE_BYTES);
+                    // tap (kh,kw) = the halo tile advanced by whole rows: +8 descriptor units (128 B) per row
+                    const uint64_t a_desc0 = smem_desc_k_sw128_shifted(smem_u32(sa + s * A_STAGE_BYTES), HALO_W * 128);
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const int row = p.sign > 0 ? kh * HALO_W + kw : (2 - kh) * HALO_W + (2 - kw);
-                        uint32_t b_addr;
-                        int t = 0;
-                        if (RESIDENT) b_addr = smem_u32(sb + (tap * p.chunks + cc) * B_SLAB);
-                        else {
-                            t = itb % p.b_stages;
+                        const uint64_t ad = a_desc0 + (uint64_t)(row * 8);
+                        if (RESIDENT) {
+                            const uint64_t bd = b_desc0 + (uint64_t)((tap * p.chunks + cc) * (B_SLAB >> 4));
+                            umma_issue_k64<NCTA>(d_tmem, ad, bd, idesc, (cc > 0 || tap > 0) ? 1u : 0u, elected);
+                        } else {
+                            const int t = itb % p.b_stages;
                             mbar_wait(&fullB[t], (itb / p.b_stages) & 1);
                             tcgen05_fence_after();
-                            b_addr = smem_u32(sb + t * B_SLAB);
+                            const uint64_t bd = b_desc0 + (uint64_t)(t * (B_SLAB >> 4));
+                            umma_issue_k64<NCTA>(d_tmem, ad, bd, idesc, (cc > 0 || tap > 0) ? 1u : 0u, elected);
+                            umma_commit_issue<NCTA>(&emptyB[t], elected);
                             ++itb;
                         }
-                        const uint32_t a_addr = a_base + row * 128;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = smem_desc_k_sw128_shifted(a_addr + k * 32, HALO_W * 128);
-                            const uint64_t bd = smem_desc_k_sw128(b_addr + k * 32);
-                            const uint32_t accum = (cc > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                            if (NCTA == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum); else umma_f16(d_tmem, ad, bd, idesc, accum);
-                        }
-                        if (!RESIDENT) commit(&emptyB[t]);
                     }
-                    commit(&emptyA[s]);
+                    umma_commit_issue<NCTA>(&emptyA[s], elected);
                 }
-                commit(&tmem_full[acc]);
+                umma_commit_issue<NCTA>(&tmem_full[acc], elected);
             }
         }
     } else {

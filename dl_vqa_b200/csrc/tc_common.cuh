@@ -81,6 +81,54 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- warp-converged MMA issue -------------------------------------------------------------------------------
+// The issuing warp runs its loops with all 32 lanes converged (warp-uniform values stay in uniform registers) and
+// every tcgen05 instruction carries the predicate of ONE elected lane.  An `if (lane == 0) { ... }` region instead
+// makes ptxas wrap each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (about 200 cycles per MMA, measured
+// with ncu on B200), which starves the tensor pipe whenever N < 256.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred;
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                           uint32_t elected) {
+    if (NCTA == 2)
+        asm volatile(
+            "{\n.reg .pred p, q;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "setp.ne.b32 q, %5, 0;\n"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p, q;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "setp.ne.b32 q, %5, 0;\n"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+// four K = 16 steps over one 64-wide (128-byte) K-major swizzled slab: the start-address field advances by 32 B = 2 units
+template <int NCTA>
+__device__ __forceinline__ void umma_issue_k64(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate_first, uint32_t elected) {
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+        umma_issue<NCTA>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : accumulate_first, elected);
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_issue(uint64_t* bar, uint32_t elected) {
+    if (NCTA == 2)
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+                     "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n}"
+                     ::"r"(smem_u32(bar)), "r"(elected), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+                     ::"r"(smem_u32(bar)), "r"(elected) : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = accumulator row)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];

@@ -1,0 +1,55 @@
+"""Micro-benchmark of the tcgen05 3x3 conv kernels at the config.yaml layer shapes (not product code).
+usage: python tools/conv_bench.py [--batch 256] [--iters 10] [--cta-group 1|2] [--only fwd1,dg1,...]"""
+import argparse, os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dl_vqa_b200 import lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--cta-group", type=int, default=1)
+ap.add_argument("--only", default="")
+args = ap.parse_args()
+lib.load()
+lib.call("vqa_tc_conv_set_cta_group", args.cta_group)
+B = args.batch
+st = lib.stream()
+layers = {1: (111, 111, 64, 128), 2: (54, 54, 128, 256)}
+only = set(args.only.split(",")) if args.only else None
+res = {}
+for li, (IH, IW, Cin, Cout) in layers.items():
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    x = torch.randn(B, IH, IW, Cin, device="cuda").bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cin ** 0.5)
+    bias = torch.zeros(Cout, device="cuda")
+    wp = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device="cuda")
+    wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_pack_conv3x3_weight", lib.ptr(w), lib.ptr(wp), lib.ptr(wd), Cout, Cin, st)
+    out = torch.empty(B, PH, PW, Cout, dtype=torch.bfloat16, device="cuda")
+    mask = torch.empty(B, PH, PW, Cout, dtype=torch.uint8, device="cuda")
+    dy = torch.randn(B, 2 * PH, 2 * PW, Cout, device="cuda").bfloat16()
+    dx = torch.empty(B, IH, IW, Cin, dtype=torch.bfloat16, device="cuda")
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    flop = 2.0 * B * (IH - 2) * (IW - 2) * Cout * Cin * 9
+    cases = {
+        f"fwd{li}": lambda: lib.call("vqa_tc_conv3x3_relu_pool_fwd", lib.ptr(x), lib.ptr(wp), lib.ptr(bias), lib.ptr(out),
+                                     lib.ptr(mask), B, IH, IW, Cin, Cout, st),
+        f"dg{li}": lambda: lib.call("vqa_tc_conv3x3_bwd_data", lib.ptr(dy), lib.ptr(wd), lib.ptr(dx), B, IH, IW, Cin, Cout, st),
+        f"wg{li}": lambda: lib.call("vqa_tc_conv3x3_bwd_weight", lib.ptr(x), lib.ptr(dy), lib.ptr(dw), B, IH, IW, Cin, Cout, st),
+    }
+    for name, fn in cases.items():
+        if only and name not in only:
+            continue
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.iters
+        res[name] = {"ms": round(ms, 4), "tflops": round(flop / ms / 1e9, 1)}
+print(json.dumps({"cta_group": args.cta_group, "batch": B, **res}))
