@@ -122,24 +122,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % S::STAGES;
-                const uint32_t ph = (i / S::STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(sa + s * S::A_BYTES), b_addr = smem_u32(sb + s * S::B_BYTES);
+        // all lanes converged, one elected lane issues (see tc_common.cuh)
+        constexpr uint32_t idesc = idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+        const uint32_t elected = elect_one();
+        const uint64_t a_desc0 = MN ? smem_desc_mn_sw128(smem_u32(sa), 8192) : smem_desc_k_sw128(smem_u32(sa));
+        const uint64_t b_desc0 = MN ? smem_desc_mn_sw128(smem_u32(sb), 8192) : smem_desc_k_sw128(smem_u32(sb));
+        constexpr uint32_t KSTEP = MN ? (2048 >> 4) : (32 >> 4);      // 16 reduction elements further, in 16-byte units
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % S::STAGES;
+            mbar_wait(&full[s], (i / S::STAGES) & 1);
+            tcgen05_fence_after();
+            const uint64_t ad = a_desc0 + (uint64_t)(s * (S::A_BYTES >> 4)), bd = b_desc0 + (uint64_t)(s * (S::B_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ad = MN ? smem_desc_mn_sw128(a_addr + k * 2048, 8192) : smem_desc_k_sw128(a_addr + k * 32);
-                    const uint64_t bd = MN ? smem_desc_mn_sw128(b_addr + k * 2048, 8192) : smem_desc_k_sw128(b_addr + k * 32);
-                    umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
-            }
-            umma_commit(tmem_full);              // accumulator complete
+            for (uint32_t k = 0; k < BK / 16; ++k)
+                umma_issue<1>(tmem_base, ad + k * KSTEP, bd + k * KSTEP, idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
+            umma_commit_issue<1>(&empty[s], elected);      // frees the smem stage when these MMAs retire
         }
+        umma_commit_issue<1>(tmem_full, elected);          // accumulator complete
     } else {
         // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (hardware restriction)
         const int quarter = warp & 3;

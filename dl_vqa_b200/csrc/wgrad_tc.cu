@@ -1,28 +1,31 @@
 // Weight gradient of the 3x3 convolutions on tcgen05 (autograd of models/model.py:80):
 //   dW[co][ci][kh][kw] = sum_{b,oh,ow} dY[b,oh,ow,co] * X[b,oh+kh,ow+kw,ci]
-// The reduction index is the spatial position.  With NHWC activations a TMA box [64 ch, 16 w, 4 h] lands in
-// shared memory as 64 position-rows x 128 bytes (128B swizzle) = the canonical MN-MAJOR UMMA operand
+// The reduction index is the spatial position.  With NHWC activations a TMA box [64 ch, w, 4 h] lands in
+// shared memory as position-rows x 128 bytes (128B swizzle) = the canonical MN-MAJOR UMMA operand
 // (K = positions run across rows, 64 channels contiguous inside a row), so both operands are consumed
-// straight from the NHWC tensors with filter-tap shifts on the W/H box coordinates -- no im2col, no
-// transposed copies:
-//   A = dY[b, h0:h0+4, w0:w0+16, co0:co0+128]            two 64-channel blocks (LBO apart)
-//   B = X [b, h0+kh:+4, w0+kw:+16, 0:CIN]   per tap kw   CIN/64 blocks
-// One CTA owns (128 output channels, one filter row kh = 3 taps) and a slice of the position tiles
-// (split-K); the three taps accumulate in three TMEM column ranges and are flushed once with fp32 atomics.
+// straight from the NHWC tensors -- no im2col, no transposed copies:
+//   A = dY[b, h0:h0+4, w0:w0+16, co0:co0+128]            two 64-channel blocks (LBO = 8 KB apart)
+//   B = X [b, h0+kh:+4, w0:w0+18, 64-channel block]      ONE box with a 2-column halo serves the three kw taps:
+//       tap kw is the same tile one position-row (128 B) further, so the three taps are three "N blocks" of one
+//       MMA with LBO = 128 B (the swizzle is a function of the absolute address, tools/umma_probe.cu).
+// One CTA owns (128 output channels, one filter row kh) and a slice of the position tiles (split-K); per 16
+// positions it issues one M=128 x N=192 MMA per 64-channel block of X (A is read once for three taps).  The
+// accumulators (192 TMEM columns per block) are flushed once with fp32 atomics.
 #include "tc_common.cuh"
 
 namespace tc {
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_TH = 4, WG_TW = 16;               // 64 positions per k-chunk
-constexpr int BLK_BYTES = 64 * 128;                // one 64-position x 64-channel block
+constexpr int BLK_BYTES = 64 * 128;                // one 64-position x 64-channel block of dY
+constexpr int XBLK_BYTES = WG_TH * (WG_TW + 2) * 128;   // 72 position-rows (with halo) x 64 channels of X: 9216 B
 
 template <int CIN>
 struct WgSmem {
     static constexpr int NB = CIN / 64;            // channel blocks of the B operand
-    static constexpr int STAGES = CIN >= 128 ? 3 : 4;
-    static constexpr int A_BYTES = 2 * BLK_BYTES, B_BYTES = NB * BLK_BYTES;
-    static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;
+    static constexpr int A_BYTES = 2 * BLK_BYTES, B_BYTES = NB * XBLK_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (232448 - 2048) / STAGE_BYTES > 8 ? 8 : (232448 - 2048) / STAGE_BYTES;
     static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -43,7 +46,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     uint64_t* empty = full + S::STAGES;
     uint64_t* tmem_full = empty + S::STAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    constexpr uint32_t TMEM_COLS = CIN >= 128 ? 512 : 256;
+    constexpr uint32_t TMEM_COLS = S::NB * 192 <= 256 ? 256 : 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kh = blockIdx.x % 3, co0 = (blockIdx.x / 3) * 128;
@@ -79,50 +82,51 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
                 tma_load_4d(st, &tma_dy, &full[s], co0, w0, h0, b);
                 tma_load_4d(st + BLK_BYTES, &tma_dy, &full[s], co0 + 64, w0, h0, b);
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                    for (int nb = 0; nb < S::NB; ++nb)
-                        tma_load_4d(st + S::A_BYTES + kw * S::B_BYTES + nb * BLK_BYTES, &tma_x, &full[s],
-                                    nb * 64, w0 + kw, h0 + kh, b);
+                for (int nb = 0; nb < S::NB; ++nb)
+                    tma_load_4d(st + S::A_BYTES + nb * XBLK_BYTES, &tma_x, &full[s], nb * 64, w0, h0 + kh, b);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(128, CIN, /*a_mn_major=*/1, /*b_mn_major=*/1);
-            for (int i = 0; i < nch; ++i) {
-                const int s = i % S::STAGES;
-                const uint32_t ph = (i / S::STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        // all lanes converged, one elected lane issues (see tc_common.cuh)
+        constexpr uint32_t idesc = idesc_bf16(128, 192, /*a_mn_major=*/1, /*b_mn_major=*/1);
+        const uint32_t elected = elect_one();
+        const uint64_t a_desc0 = smem_desc_mn_sw128(smem_u32(smem), BLK_BYTES);
+        const uint64_t b_desc0 = smem_desc_mn_sw128(smem_u32(smem + S::A_BYTES), 128);     // LBO = one position = one kw tap
+        for (int i = 0; i < nch; ++i) {
+            const int s = i % S::STAGES;
+            mbar_wait(&full[s], (i / S::STAGES) & 1);
+            tcgen05_fence_after();
+            const uint64_t so = (uint64_t)(s * (S::STAGE_BYTES >> 4));
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const uint32_t b_addr = a_addr + S::A_BYTES + kw * S::B_BYTES;
+            for (int h = 0; h < WG_TH; ++h) {            // 16 positions (one tile row) per MMA
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)          // 16 positions (rows) per MMA: 2048 bytes further
-                        umma_f16(tmem_base + kw * CIN, smem_desc_mn_sw128(a_addr + k * 2048, BLK_BYTES),
-                                 smem_desc_mn_sw128(b_addr + k * 2048, BLK_BYTES), idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty[s]);
+                for (int nb = 0; nb < S::NB; ++nb)
+                    umma_issue<1>(tmem_base + nb * 192, a_desc0 + so + (uint64_t)(h * (2048 >> 4)),
+                                  b_desc0 + so + (uint64_t)((nb * XBLK_BYTES + h * (WG_TW + 2) * 128) >> 4), idesc,
+                                  (i > 0 || h > 0) ? 1u : 0u, elected);
             }
-            umma_commit(tmem_full);
+            umma_commit_issue<1>(&empty[s], elected);
         }
+        umma_commit_issue<1>(tmem_full, elected);
     } else if (nch > 0) {
         const int quarter = warp & 3;
         const int co = co0 + quarter * 32 + lane;
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int kw = 0; kw < 3; ++kw) {
-            const int tap = kh * 3 + kw;
+        for (int nb = 0; nb < S::NB; ++nb) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < CIN; c0 += 32) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kw * CIN + c0, v);
-                if (co < p.Cout) {
-                    float* o = p.dw + ((int64_t)co * p.Cin + c0) * 9 + tap;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int tap = kh * 3 + kw;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + nb * 192 + kw * 64 + c0, v);
+                    if (co < p.Cout) {
+                        float* o = p.dw + ((int64_t)co * p.Cin + nb * 64 + c0) * 9 + tap;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(o + j * 9, v[j]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(o + j * 9, v[j]);
+                    }
                 }
             }
         }
@@ -132,11 +136,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-// NHWC tensor map with the 64-position box [64 ch, 16 w, 4 h, 1]
-static int pos_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+// NHWC tensor map with the position box [64 ch, 16 (+halo) w, 4 h, 1]
+static int pos_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, int halo) {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    const uint32_t box[4] = {64, WG_TW, WG_TH, 1};
+    const uint32_t box[4] = {64, (uint32_t)(WG_TW + halo), WG_TH, 1};
     return make_tmap_bf16(m, base, 4, dims, str, box);
 }
 
@@ -150,7 +154,11 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams 
     }
     const int units = (p.Cout / 128) * 3;
     const int total = p.B * p.tiles_h * p.tiles_w;
-    int nsplit = (148 + units - 1) / units;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int nsplit = sms / units;                      // one CTA per SM, a single wave
+    if (nsplit < 1) nsplit = 1;
     if (nsplit > total) nsplit = total;
     p.chunks_per_split = (total + nsplit - 1) / nsplit;
     nsplit = (total + p.chunks_per_split - 1) / p.chunks_per_split;
@@ -175,8 +183,8 @@ extern "C" int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* d
     cudaStream_t st = (cudaStream_t)stream;
     VQA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
     CUtensorMap tdy, tx;
-    if (int e = pos_tmap(&tdy, dy, B, OHp, OWp, Cout)) return e;
-    if (int e = pos_tmap(&tx, x, B, IH, IW, Cin)) return e;
+    if (int e = pos_tmap(&tdy, dy, B, OHp, OWp, Cout, 0)) return e;
+    if (int e = pos_tmap(&tx, x, B, IH, IW, Cin, 2)) return e;
     WgParams p{};
     p.B = B; p.tiles_h = (OHp + WG_TH - 1) / WG_TH; p.tiles_w = (OWp + WG_TW - 1) / WG_TW;
     p.Cin = Cin; p.Cout = Cout; p.dw = dw;
