@@ -232,15 +232,21 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- (2) end to end: pinned host -> device copy of the inputs and device -> host read of the loss every step
-    def e2e_step():
-        loss, score = step(to_dev())
-        loss_host[0].copy_(loss.detach(), non_blocking=True)
-        loss_host[1].copy_(score.detach(), non_blocking=True)
+    # ---- (2) end to end through the public API: every step's inputs come from pinned host memory through
+    # DevicePrefetcher (copy of batch i+1 on a side stream while batch i computes) and the loss / score of every
+    # step are read back to the host.  One H2D copy of the full batch per step happens inside the timed region.
+    def host_batches(n):
+        for _ in range(n):
+            yield (hv, hq, hai, hav, hal, None, hql)
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    def e2e_run(n):
+        for dv, dq, dai, dav, dal, _, dql in D.DevicePrefetcher(host_batches(n), dev):
+            loss, score = step((dv, dq, dai, dav, dal, dql))
+            loss_host[0].copy_(loss.detach(), non_blocking=True)
+            loss_host[1].copy_(score.detach(), non_blocking=True)
+
+    e2e_run(2)
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
 
     if rank != 0:

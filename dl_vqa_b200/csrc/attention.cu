@@ -8,7 +8,7 @@
 //
 // Algorithmic HBM bytes per sample (forward): (P*A + P*C + G*C) * sizeof(T) + A*4 + G*P*4 (prob, saved
 // for backward) -- SURVEY.md section 8d config 3.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -43,16 +43,8 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {      // 
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// dropout multipliers for 8 consecutive elements starting at (even) idx
-__device__ __forceinline__ void drop8(const Dropout& d, uint32_t key, uint64_t idx, float (&m)[8]) {
-    if (d.threshold == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = 1.f;
-        return;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dropout_mult2(d, key, idx + 2 * i, m[2 * i], m[2 * i + 1]);
-}
+// dropout multipliers for the 8 consecutive elements starting at idx (a multiple of 8)
+__device__ __forceinline__ void drop8(const Dropout8& d, uint64_t idx, float (&m)[8]) { dropout_mult8(d, (uint32_t)(idx >> 3), m); }
 
 template <typename T, int G, int OP>
 __global__ void __launch_bounds__(NTHREADS)
@@ -63,7 +55,7 @@ attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, con
     float* logit = sm;                 // [G][P]
     float* red = sm + G * P;           // [NW][G*256]
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t key = dropout_key(drop, SITE_ATT_X);
+    const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
 
     for (int i = tid; i < G * P; i += NTHREADS) logit[i] = bx[i / P];
     __syncthreads();
@@ -91,7 +83,7 @@ attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, con
                 load8(vpb + (int64_t)s0 * A + a0, x0);
                 if (has1) load8(vpb + (int64_t)s1 * A + a0, x1);
                 float m[8];
-                drop8(drop, key, ((uint64_t)b * P + s0) * A + a0, m);
+                drop8(d8, ((uint64_t)b * P + s0) * A + a0, m);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float pre = OP == VQA_ATT_ADD ? x0[i] + qv[i] : x0[i] * qv[i];
@@ -100,7 +92,7 @@ attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, con
                     for (int g = 0; g < G; ++g) acc0[g] = fmaf(r, wv[g][i], acc0[g]);
                 }
                 if (has1) {
-                    drop8(drop, key, ((uint64_t)b * P + s1) * A + a0, m);
+                    drop8(d8, ((uint64_t)b * P + s1) * A + a0, m);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float pre = OP == VQA_ATT_ADD ? x1[i] + qv[i] : x1[i] * qv[i];
@@ -201,7 +193,7 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
     float* dsm = dl + G * P;              // [G][C] upstream gradient
     float* red = dsm + G * C;             // [NW][(1+G)*256]
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t key = dropout_key(drop, SITE_ATT_X);
+    const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
 
     for (int i = tid; i < G * P; i += NTHREADS) { pr[i] = prob[(int64_t)b * G * P + i]; dl[i] = 0.f; }
     for (int i = tid; i < G * C; i += NTHREADS) dsm[i] = to_f32(dout[(int64_t)b * ldd + i]);
@@ -283,7 +275,7 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
             for (int s = warp; s < P; s += NW) {
                 float x[8], m[8], o[8], dls[G];
                 load8(vpb + (int64_t)s * A + a0, x);
-                drop8(drop, key, ((uint64_t)b * P + s) * A + a0, m);
+                drop8(d8, ((uint64_t)b * P + s) * A + a0, m);
 #pragma unroll
                 for (int g = 0; g < G; ++g) dls[g] = dl[g * P + s];
 #pragma unroll
@@ -321,6 +313,277 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
         __syncthreads();
     }
 }
+
+// ================================================================================================================
+// Streaming forward kernel for the tensor-core arm (bf16 activations, A = 1024, C = 256: the config.yaml shape).
+//
+// Persistent grid (one CTA per SM), samples round-robin.  A producer warp streams the sample's v' [P][A] and then
+// its v [P][C] rows through an 11 x 16 KB shared-memory ring with cp.async.bulk + mbarriers and never stops at
+// sample or phase boundaries, so HBM stays busy while the consumers reduce / normalise.  16 consumer warps work as
+// 8 pairs; a pair owns every 8th 16 KB chunk:
+//   phase 1 (chunk = 8 positions x 1024 channels): each warp of the pair takes half a row (lane = 16 channels,
+//           two conflict-free LDS.128 per position), computes relu(v' (+|*) q') & dropout-mask in packed bf16x2,
+//           accumulates the G glimpse dot products in fp32 and folds its 8 x G per-lane partial sums with a
+//           transposing butterfly (16 shuffles instead of 80).
+//   softmax over the P positions per glimpse (warp shuffles), probabilities kept in shared memory and saved.
+//   phase 3 (chunk = 32 positions x 256 channels): lane = 8 channels, fp32 accumulators, one cross-warp reduction.
+// Algorithmic HBM bytes per sample as for the generic kernel; nothing is read twice.
+// ================================================================================================================
+namespace stream {
+
+constexpr int A_ = 1024, C_ = 256;
+constexpr int NCW = 16, NPAIR = 8;
+constexpr int NTHR = (NCW + 1) * 32;
+constexpr int CHUNK = 16384, NST = 11;
+constexpr int POS1 = CHUNK / (A_ * 2);           // 8 positions of v' per chunk
+constexpr int POS3 = CHUNK / (C_ * 2);           // 32 positions of v per chunk
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hrelu2_bf16(uint32_t a) { uint32_t r; asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u)); return r; }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+// fold n = 8*GP per-lane values over the 32 lanes; afterwards v[0] of lane l holds the total of value index
+// l >> (5 - log2 n) (the other lanes of that group hold the same total)
+template <int N>
+__device__ __forceinline__ void transpose_reduce(float (&v)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? v[n / 2 + i] : v[i];
+            const float send = up ? v[i] : v[n / 2 + i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+
+template <int G, int OP, bool TRAIN>
+__global__ void __launch_bounds__(NTHR, 1)
+attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict__ qp, const bf16* __restrict__ vn,
+                            const float* __restrict__ wx, const float* __restrict__ bx, float* __restrict__ prob,
+                            bf16* __restrict__ out, int64_t ldo, int B, int P, Dropout drop) {
+    constexpr int GP = G <= 2 ? G : 4;                 // glimpses padded to a power of two for the butterfly
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* ring = smem;                                                    // NST x CHUNK
+    float* red = reinterpret_cast<float*>(ring + NST * CHUNK);              // [NCW][G][C_]
+    float* lpart = red + NCW * G * C_;                                       // [2 halves][G][P]
+    float* pr = lpart + 2 * G * P;                                           // [G][P] softmax
+    uint64_t* full = reinterpret_cast<uint64_t*>(pr + G * P + ((G * P) & 1));
+    uint64_t* empty = full + NST;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n1 = (P + POS1 - 1) / POS1, n3 = (P + POS3 - 1) / POS3;
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ===== producer: one thread streams every chunk of every sample of this CTA, in consumption order =====
+        if (lane == 0) {
+            uint32_t c = 0;
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                const uint8_t* src1 = reinterpret_cast<const uint8_t*>(vp + (int64_t)b * P * A_);
+                const uint8_t* src3 = reinterpret_cast<const uint8_t*>(vn + (int64_t)b * P * C_);
+                const int64_t bytes1 = (int64_t)P * A_ * 2, bytes3 = (int64_t)P * C_ * 2;
+                for (int i = 0; i < n1 + n3; ++i, ++c) {
+                    const int slot = c % NST;
+                    tc::mbar_wait(&empty[slot], ((c / NST) & 1) ^ 1);
+                    const bool ph1 = i < n1;
+                    const int64_t off = (int64_t)(ph1 ? i : i - n1) * CHUNK;
+                    const int64_t left = (ph1 ? bytes1 : bytes3) - off;
+                    const uint32_t bytes = (uint32_t)(left < CHUNK ? left : CHUNK);
+                    tc::mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(ring + slot * CHUNK, (ph1 ? src1 : src3) + off, bytes, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int pair = warp >> 1, half = warp & 1;
+    const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
+    const float wscale = TRAIN ? d8.scale : 1.f;
+    // lane's channels in phase 1: half*512 + (j*32 + lane)*8 + [0,8), j = 0,1
+    float wv[G][16];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[g][j * 8 + i] = wx[g * A_ + half * 512 + (j * 32 + lane) * 8 + i] * wscale;
+
+    uint32_t c = 0;                                   // global chunk counter (same sequence as the producer)
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        uint32_t q2[8];                               // q' of this sample, rounded to bf16 (packed pairs)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = *reinterpret_cast<const float2*>(qp + (int64_t)b * A_ + half * 512 + (j * 32 + lane) * 8 + 2 * i);
+                q2[j * 4 + i] = pack_bf16x2(f.x, f.y);
+            }
+        // ---- phase 1: per-position glimpse logits
+        for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n1; i += NPAIR) {
+            const uint32_t cc = c + i;
+            const int slot = cc % NST;
+            tc::mbar_wait(&full[slot], (cc / NST) & 1);
+            const uint8_t* base = ring + slot * CHUNK + half * 1024 + lane * 16;
+            const int pos0 = i * POS1;
+            float acc[POS1 * GP];
+#pragma unroll
+            for (int k = 0; k < POS1 * GP; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int ps = 0; ps < POS1; ++ps) {
+                if (pos0 + ps < P) {                 // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(base + ps * (A_ * 2) + j * 512);
+                        uint32_t x[4] = {u.x, u.y, u.z, u.w};
+                        uint32_t t[4];
+                        if (TRAIN) dropout_flags8(d8, (uint32_t)(((int64_t)b * P + pos0 + ps) * (A_ / 8) + half * 64 + j * 32 + lane), t);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t r = OP == VQA_ATT_ADD ? hadd2_bf16(x[e], q2[j * 4 + e]) : hmul2_bf16(x[e], q2[j * 4 + e]);
+                            r = hrelu2_bf16(r);
+                            if (TRAIN) r &= dropout_mask_bf16x2(t[e]);
+                            const float lo = bf_lo(r), hi = bf_hi(r);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                float a = acc[g * POS1 + ps];
+                                a = fmaf(lo, wv[g][j * 8 + 2 * e], a);
+                                a = fmaf(hi, wv[g][j * 8 + 2 * e + 1], a);
+                                acc[g * POS1 + ps] = a;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&empty[slot]);          // this warp is done with the chunk
+            transpose_reduce<POS1 * GP>(acc, lane);
+            // value index k = g*POS1 + ps sits in lanes with (lane >> SH) == k
+            constexpr int SH = GP == 1 ? 2 : (GP == 2 ? 1 : 0);
+            const int k = lane >> SH, g = k / POS1, ps = k % POS1;
+            if ((lane & ((1 << SH) - 1)) == 0 && g < G && pos0 + ps < P) lpart[(half * G + g) * P + pos0 + ps] = acc[0];
+        }
+        c += n1;
+        consumer_sync();
+
+        // ---- phase 2: spatial softmax per glimpse (warp-shuffle reductions)
+        if (warp < G) {
+            const int g = warp;
+            const float bias = bx[g];
+            float mx = -INFINITY;
+            for (int s = lane; s < P; s += 32) {
+                const float l = lpart[g * P + s] + lpart[(G + g) * P + s] + bias;
+                pr[g * P + s] = l;
+                mx = fmaxf(mx, l);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int s = lane; s < P; s += 32) { const float e = __expf(pr[g * P + s] - mx); pr[g * P + s] = e; sum += e; }
+            sum = warp_sum(sum);
+            const float inv = 1.f / sum;
+            for (int s = lane; s < P; s += 32) {
+                const float pv = pr[g * P + s] * inv;
+                pr[g * P + s] = pv;
+                if (prob) prob[((int64_t)b * G + g) * P + s] = pv;
+            }
+        }
+        consumer_sync();
+
+        // ---- phase 3: out[g][c] = sum_s p[g][s] * vn[s][c]; lane = 8 channels, the pair's warps split the rows
+        float o[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[g][e] = 0.f;
+        for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n3; i += NPAIR) {
+            const uint32_t cc = c + i;
+            const int slot = cc % NST;
+            tc::mbar_wait(&full[slot], (cc / NST) & 1);
+            const uint8_t* base = ring + slot * CHUNK + lane * 16;
+            const int pos0 = i * POS3 + half * (POS3 / 2);
+#pragma unroll 4
+            for (int ps = 0; ps < POS3 / 2; ++ps) {
+                const int s = pos0 + ps;
+                if (s < P) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(base + (half * (POS3 / 2) + ps) * (C_ * 2));
+                    const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float pv = pr[g * P + s];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            o[g][2 * e] = fmaf(pv, bf_lo(x[e]), o[g][2 * e]);
+                            o[g][2 * e + 1] = fmaf(pv, bf_hi(x[e]), o[g][2 * e + 1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&empty[slot]);
+        }
+        c += n3;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8) = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
+            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8 + 4) = make_float4(o[g][4], o[g][5], o[g][6], o[g][7]);
+        }
+        consumer_sync();
+        for (int t = tid; t < G * C_; t += NCW * 32) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) sacc += red[w * G * C_ + t];
+            out[(int64_t)b * ldo + t] = __float2bfloat16_rn(sacc);
+        }
+        // `red`, `lpart` and `pr` are next written after the barriers of the next sample's phases 1 / 2 / 3
+    }
+}
+
+template <int G, int OP>
+int launch_fwd_stream(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
+                      void* out, int64_t ldo, int B, int P, Dropout d, cudaStream_t st) {
+    const size_t smem = (size_t)NST * CHUNK + sizeof(float) * ((size_t)NCW * G * C_ + 3 * (size_t)G * P + 2) + 2 * NST * 8 + 256;
+    VQA_REQUIRE(smem <= 232448, "attention (streaming): spatial grid too large for shared memory");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = B < sms ? B : sms;
+    if (d.threshold != 0) {
+        auto kern = attention_fwd_stream_kernel<G, OP, true>;
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHR, smem, st>>>((const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d);
+    } else {
+        auto kern = attention_fwd_stream_kernel<G, OP, false>;
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHR, smem, st>>>((const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d);
+    }
+    VQA_CHECK_LAUNCH("attention_fwd_stream");
+    return 0;
+}
+
+}  // namespace stream
 
 template <typename T, int G, int OP>
 int launch_fwd(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
@@ -388,6 +651,13 @@ extern "C" int vqa_attention_fwd(const void* vp, const float* qp, const void* vn
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldo)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
+    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && P <= 1024) {     // tensor-core arm at the config.yaml shape
+        VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
+        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_fwd_stream<1, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                                             : stream::launch_fwd_stream<1, VQA_ATT_MUL>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
+        return op == VQA_ATT_ADD ? stream::launch_fwd_stream<2, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                                 : stream::launch_fwd_stream<2, VQA_ATT_MUL>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
+    }
     ATT_DISPATCH(launch_fwd, vp, qp, vn, wx, bx, prob, out, ldo, B, P, A, C, d, st);
     VQA_REQUIRE(false, "attention_fwd: no kernel for this configuration");
     return 0;

@@ -140,6 +140,55 @@ __device__ __forceinline__ void dropout_mult2(const Dropout& d, uint32_t key, ui
     m1 = (w >> 16) >= d.threshold ? d.scale : 0.f;
 }
 
+// ---- vector form used by the fused attention kernels (site ATT_X, 0.7 G elements per step) ------------------------
+// One hash32 per group of 8 consecutive elements, three LCG steps for the other three words; each 32-bit word
+// serves two elements through its two 15-bit fields, and the keep test is a carry into bit 15 / bit 31:
+//   t = (w & 0x7FFF7FFF) + (0x8000 - thr15) * 0x10001     =>  bit 15 (31) set  <=>  low (high) field >= thr15
+// (p quantised to 1/32768).  About 3 integer ops per element instead of 8, which is what lets the attention kernels
+// stay memory-bound in train mode.  Forward and backward regenerate the same flags.
+struct Dropout8 {
+    uint32_t key;       // dropout_key(seed, site)
+    uint32_t addk;      // (0x8000 - thr15) * 0x10001; 0 disables dropout
+    float scale;        // 1/(1-p)
+};
+__device__ __forceinline__ Dropout8 make_dropout8(const Dropout& d, uint32_t site) {
+    Dropout8 r;
+    r.key = dropout_key(d, site);
+    const uint32_t thr15 = d.threshold >> 1;              // 16-bit threshold -> 15-bit
+    r.addk = d.threshold == 0 ? 0u : (0x8000u - thr15) * 0x10001u;
+    r.scale = d.scale;
+    return r;
+}
+// flags for elements 8*group .. 8*group+7: element 2j <-> bit 15 of t[j], element 2j+1 <-> bit 31 of t[j]
+__device__ __forceinline__ void dropout_flags8(const Dropout8& d, uint32_t group, uint32_t (&t)[4]) {
+    uint32_t w = hash32(group ^ d.key);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        t[j] = (w & 0x7FFF7FFFu) + d.addk;
+        w = w * 0x9E3779B1u + 0x7F4A7C15u;
+    }
+}
+// 0xFFFF in each 16-bit half whose element is kept (bf16x2 bit mask)
+__device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) {
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(t));      // replicate the sign of byte 1 / byte 3 over each half
+    return m;
+}
+__device__ __forceinline__ void dropout_mult8(const Dropout8& d, uint32_t group, float (&m)[8]) {
+    if (d.addk == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = 1.f;
+        return;
+    }
+    uint32_t t[4];
+    dropout_flags8(d, group, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        m[2 * j] = (t[j] & 0x8000u) ? d.scale : 0.f;
+        m[2 * j + 1] = (t[j] & 0x80000000u) ? d.scale : 0.f;
+    }
+}
+
 // dropout sites (one independent mask stream per nn.Dropout call site of models/model.py)
 enum : uint32_t {
     SITE_IMAGE = 0,      // models/model.py:84   image.drop

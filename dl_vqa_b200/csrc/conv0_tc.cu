@@ -119,25 +119,23 @@ __global__ void __launch_bounds__(C0_THREADS, 2) conv0_fwd_tc_kernel(Conv0Params
             mbar_arrive(&a_full[s]);
         }
     } else if (warp == 8) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(128, BN);
-            const uint32_t w_addr = smem_u32(sw_tile);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, use = it >> 1;
-                const int s = it % C0_STAGES;
-                const uint32_t ph = (it / C0_STAGES) & 1;
-                mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);
-                mbar_wait(&a_full[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(sa + s * C0_TILE_BYTES);
+        // all lanes converged, one elected lane issues (see tc_common.cuh)
+        constexpr uint32_t idesc = idesc_bf16(128, BN);
+        const uint32_t elected = elect_one();
+        const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa)), w_desc = smem_desc_k_sw128(smem_u32(sw_tile));
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, use = it >> 1;
+            const int s = it % C0_STAGES;
+            mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);
+            mbar_wait(&a_full[s], (it / C0_STAGES) & 1);
+            tcgen05_fence_after();
+            const uint64_t ad = a_desc0 + (uint64_t)(s * (C0_TILE_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    umma_f16(tmem_base + acc * BN, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(w_addr + k * 32),
-                             idesc, k > 0 ? 1u : 0u);
-                umma_commit(&a_empty[s]);
-                umma_commit(&tmem_full[acc]);
-            }
+            for (uint32_t k = 0; k < 2; ++k)
+                umma_issue<1>(tmem_base + acc * BN, ad + 2 * k, w_desc + 2 * k, idesc, k, elected);
+            umma_commit_issue<1>(&a_empty[s], elected);
+            umma_commit_issue<1>(&tmem_full[acc], elected);
         }
     } else if (warp < 4) {
         // ---- epilogue: bias + ReLU + 2x2 max-pool + mask (same butterfly as conv_tc.cu)
@@ -280,24 +278,22 @@ conv0_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, Conv0Params p)
             mbar_arrive(&full[s]);
         }
     } else if (warp == 8) {
-        if (lane == 0) {
-            // D[128 (co; rows 64..127 unused)][32 k] ; A = dY tile (MN-major, 64 channels = one block; the second
-            // block address is arbitrary valid shared memory: its rows only feed the unused accumulator rows)
-            constexpr uint32_t idesc = idesc_bf16(128, 32, 1, 1);
-            for (int i = 0; i < nch; ++i) {
-                const int s = i % C0_STAGES;
-                const uint32_t ph = (i / C0_STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * STAGE), b_addr = a_addr + C0_TILE_BYTES;
+        // D[128 (co; rows 64..127 unused)][32 k] ; A = dY tile (MN-major, 64 channels = one block; the second
+        // block address is arbitrary valid shared memory: its rows only feed the unused accumulator rows)
+        constexpr uint32_t idesc = idesc_bf16(128, 32, 1, 1);
+        const uint32_t elected = elect_one();
+        const uint64_t a_desc0 = smem_desc_mn_sw128(smem_u32(smem), 1024);
+        for (int i = 0; i < nch; ++i) {
+            const int s = i % C0_STAGES;
+            mbar_wait(&full[s], (i / C0_STAGES) & 1);
+            tcgen05_fence_after();
+            const uint64_t ad = a_desc0 + (uint64_t)(s * (STAGE >> 4)), bd = ad + (uint64_t)(C0_TILE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_f16(tmem_base, smem_desc_mn_sw128(a_addr + k * 2048, 1024), smem_desc_mn_sw128(b_addr + k * 2048, 1024),
-                             idesc, (i > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty[s]);
-            }
-            umma_commit(tmem_full);
+            for (uint32_t k = 0; k < 8; ++k)
+                umma_issue<1>(tmem_base, ad + k * (2048 >> 4), bd + k * (2048 >> 4), idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
+            umma_commit_issue<1>(&empty[s], elected);
         }
+        umma_commit_issue<1>(tmem_full, elected);
     } else if (warp < 4 && nch > 0) {
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();

@@ -92,27 +92,24 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(128, 64);
-            mbar_wait(w_full, 0);
-            uint32_t it = 0;
-            for (int s = 0; s < T; ++s)
-                for (int mt = 0; mt < p.mtiles; ++mt) {
-                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                        const int st = it % LSTM_STAGES;
-                        const uint32_t ph = (it / LSTM_STAGES) & 1;
-                        mbar_wait(&full[st], ph);
-                        tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(sa + st * LSTM_A_BYTES), b_addr = smem_u32(sw + kb * 8192);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(tmem_base + mt * 64, smem_desc_k_sw128(a_addr + k * 32), smem_desc_k_sw128(b_addr + k * 32),
-                                     idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&empty[st]);
-                    }
-                    umma_commit(&tmem_full[mt]);
+        // all lanes converged, one elected lane issues (see tc_common.cuh)
+        constexpr uint32_t idesc = idesc_bf16(128, 64);
+        const uint32_t elected = elect_one();
+        mbar_wait(w_full, 0);
+        const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa)), b_desc0 = smem_desc_k_sw128(smem_u32(sw));
+        uint32_t it = 0;
+        for (int s = 0; s < T; ++s)
+            for (int mt = 0; mt < p.mtiles; ++mt) {
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int st = it % LSTM_STAGES;
+                    mbar_wait(&full[st], (it / LSTM_STAGES) & 1);
+                    tcgen05_fence_after();
+                    umma_issue_k64<1>(tmem_base + mt * 64, a_desc0 + (uint64_t)(st * (LSTM_A_BYTES >> 4)),
+                                      b_desc0 + (uint64_t)(kb * (8192 >> 4)), idesc, kb > 0 ? 1u : 0u, elected);
+                    umma_commit_issue<1>(&empty[st], elected);
                 }
-        }
+                umma_commit_issue<1>(&tmem_full[mt], elected);
+            }
     } else {
         // ---- epilogue: warp -> (m-tile, lane quarter); thread -> sample b; 16 hidden units x 4 gates in registers
         const int ew = warp - 2;
