@@ -335,12 +335,23 @@ constexpr int A_ = 1024, C_ = 256;
 constexpr int NCW = 16, NPAIR = 8;
 constexpr int NTHR = (NCW + 1) * 32;
 constexpr int CHUNK = 16384, NST = 11;
+static_assert(NPAIR < NST, "wait_chunk relies on the pair stride being shorter than the ring");
 constexpr int POS1 = CHUNK / (A_ * 2);           // 8 positions of v' per chunk
 constexpr int POS3 = CHUNK / (C_ * 2);           // 32 positions of v per chunk
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+// Ring slots are shared by the 8 consumer pairs (slot = chunk % NST, pair = chunk % NPAIR), so a fast pair may ask for
+// chunk cc before the PREVIOUS use of that slot (chunk cc - NST, another pair's) has even landed; a bare parity wait
+// would then alias with the phase before that and fall through.  Having consumed chunk cc - NPAIR, which was issued
+// after chunk cc - NST (NPAIR < NST, in-order producer), the pair knows the barrier is at worst one phase behind:
+// waiting for that phase first makes the wait exact.
+__device__ __forceinline__ void wait_chunk(uint64_t* full, uint32_t cc) {
+    const uint32_t k = cc / NST;
+    if (k > 0) tc::mbar_wait(&full[cc % NST], (k - 1) & 1);
+    tc::mbar_wait(&full[cc % NST], k & 1);
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -446,7 +457,7 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
         for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n1; i += NPAIR) {
             const uint32_t cc = c + i;
             const int slot = cc % NST;
-            tc::mbar_wait(&full[slot], (cc / NST) & 1);
+            wait_chunk(full, cc);
             const uint8_t* base = ring + slot * CHUNK + half * 1024 + lane * 16;
             const int pos0 = i * POS1;
             float acc[POS1 * GP];
@@ -521,7 +532,7 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
         for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n3; i += NPAIR) {
             const uint32_t cc = c + i;
             const int slot = cc % NST;
-            tc::mbar_wait(&full[slot], (cc / NST) & 1);
+            wait_chunk(full, cc);
             const uint8_t* base = ring + slot * CHUNK + lane * 16;
             const int pos0 = i * POS3 + half * (POS3 / 2);
 #pragma unroll 4
@@ -561,11 +572,15 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
     }
 }
 
+// shared memory of the streaming forward kernel; it needs [3][G][P] floats beside the ring
+static size_t fwd_stream_smem(int G, int P) {
+    return (size_t)NST * CHUNK + sizeof(float) * ((size_t)NCW * G * C_ + 3 * (size_t)G * P + 2) + 2 * NST * 8 + 256;
+}
+
 template <int G, int OP>
 int launch_fwd_stream(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
                       void* out, int64_t ldo, int B, int P, Dropout d, cudaStream_t st) {
-    const size_t smem = (size_t)NST * CHUNK + sizeof(float) * ((size_t)NCW * G * C_ + 3 * (size_t)G * P + 2) + 2 * NST * 8 + 256;
-    VQA_REQUIRE(smem <= 232448, "attention (streaming): spatial grid too large for shared memory");
+    const size_t smem = fwd_stream_smem(G, P);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -580,6 +595,278 @@ int launch_fwd_stream(const void* vp, const float* qp, const void* vn, const flo
         kern<<<grid, NTHR, smem, st>>>((const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d);
     }
     VQA_CHECK_LAUNCH("attention_fwd_stream");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Streaming backward kernel (same arm / shape as the forward).  Every consumer warp takes part in every 32 KB chunk,
+// in order (plain parity waits):
+//   phase A (chunk = 64 rows of v): warp w owns rows w, w+16, ...; lane = 8 channels.  dp[g][s] = <dout[g], v[s]>
+//           (transposing butterfly over 4 rows x G) and dv[s] = sum_g p[g][s] dout[g] is written straight to HBM.
+//   phase B: softmax backward, dlogit = p (dp - <p, dp>), and the x_conv bias gradient.
+//   phase C (chunk = 16 rows of v'): warp (cg, pi) owns channels [256 cg, +256) of rows pi, pi+4, ...; lane = 8
+//           channels, so the dq' / dW_x partial sums are 8 + 8 G registers and only 4 copies meet in shared memory.
+//           The fusion, ReLU gate and dropout mask are recomputed exactly as in the forward (packed bf16x2).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int BCHUNK = 32768, BNST = 5;
+constexpr int BPOSA = BCHUNK / (C_ * 2);          // 64 rows of v per chunk
+constexpr int BPOSC = BCHUNK / (A_ * 2);          // 16 rows of v' per chunk
+
+__device__ __forceinline__ uint32_t ne_mask_bf16x2(uint32_t a) {      // 0xFFFF in each half that is non-zero
+    uint32_t r;
+    asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+    return r;
+}
+
+template <int G, int OP, bool TRAIN>
+__global__ void __launch_bounds__(NTHR, 1)
+attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf16* __restrict__ vp, const float* __restrict__ qp,
+                            const bf16* __restrict__ vn, const float* __restrict__ wx, const float* __restrict__ prob,
+                            bf16* __restrict__ dvp, bf16* __restrict__ dvn, float* __restrict__ dqp, float* __restrict__ dwx_part,
+                            float* __restrict__ dbx_part, int B, int P, Dropout drop) {
+    constexpr int GP = G <= 2 ? G : 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* ring = smem;                                                    // BNST x BCHUNK
+    float* red = reinterpret_cast<float*>(ring + BNST * BCHUNK);            // [4 pi][1 + G][A_]
+    float* pr = red + 4 * (1 + G) * A_;                                      // [P][G] softmax (interleaved)
+    float* dl = pr + G * P;                                                  // [P][G] dp, then dlogit
+    float* dsm = dl + G * P;                                                 // [G][C_] upstream gradient
+    uint64_t* full = reinterpret_cast<uint64_t*>(dsm + G * C_);
+    uint64_t* empty = full + BNST;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nA = (P + BPOSA - 1) / BPOSA, nC = (P + BPOSC - 1) / BPOSC;
+
+    if (tid == 0) {
+        for (int i = 0; i < BNST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], NCW); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        if (lane == 0) {
+            uint32_t c = 0;
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                const uint8_t* srcA = reinterpret_cast<const uint8_t*>(vn + (int64_t)b * P * C_);
+                const uint8_t* srcC = reinterpret_cast<const uint8_t*>(vp + (int64_t)b * P * A_);
+                const int64_t bytesA = (int64_t)P * C_ * 2, bytesC = (int64_t)P * A_ * 2;
+                for (int i = 0; i < nA + nC; ++i, ++c) {
+                    const int slot = c % BNST;
+                    tc::mbar_wait(&empty[slot], ((c / BNST) & 1) ^ 1);
+                    const bool phA = i < nA;
+                    const int64_t off = (int64_t)(phA ? i : i - nA) * BCHUNK;
+                    const int64_t left = (phA ? bytesA : bytesC) - off;
+                    const uint32_t bytes = (uint32_t)(left < BCHUNK ? left : BCHUNK);
+                    tc::mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(ring + slot * BCHUNK, (phA ? srcA : srcC) + off, bytes, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
+    const float scale = TRAIN ? d8.scale : 1.f;
+    const int cg = warp & 3, pi = warp >> 2;
+    const int a0 = cg * 256 + lane * 8;               // lane's 8 channels of v' in phase C
+    float wv[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[g][i] = wx[g * A_ + a0 + i] * scale;
+
+    uint32_t c = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        // per-sample inputs: probabilities, upstream gradient
+        for (int i = tid; i < G * P; i += NCW * 32) { const int g = i / P, sidx = i - g * P; pr[sidx * G + g] = prob[(int64_t)b * G * P + i]; }
+        for (int i = tid; i < G * C_; i += NCW * 32) dsm[i] = __bfloat162float(dout[(int64_t)b * ldd + i]);
+        consumer_sync();
+
+        // ---- phase A
+        {
+            float dv[G][8];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dv[g][i] = dsm[g * C_ + lane * 8 + i];
+            bf16* dvnb = dvn + (int64_t)b * P * C_;
+            for (int i = 0; i < nA; ++i, ++c) {
+                const int slot = c % BNST;
+                tc::mbar_wait(&full[slot], (c / BNST) & 1);
+                const uint8_t* base = ring + slot * BCHUNK + lane * 16;
+                float part[4 * GP];
+#pragma unroll
+                for (int k = 0; k < 4 * GP; ++k) part[k] = 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int r = warp + NCW * t, sidx = i * BPOSA + r;
+                    if (sidx < P) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(base + r * (C_ * 2));
+                        const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            const float pg = pr[sidx * G + g];
+                            float a = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                a = fmaf(dv[g][2 * e], bf_lo(x[e]), a);
+                                a = fmaf(dv[g][2 * e + 1], bf_hi(x[e]), a);
+                                o[2 * e] = fmaf(pg, dv[g][2 * e], o[2 * e]);
+                                o[2 * e + 1] = fmaf(pg, dv[g][2 * e + 1], o[2 * e + 1]);
+                            }
+                            part[g * 4 + t] = a;
+                        }
+                        uint4 w4;
+                        w4.x = pack_bf16x2(o[0], o[1]); w4.y = pack_bf16x2(o[2], o[3]);
+                        w4.z = pack_bf16x2(o[4], o[5]); w4.w = pack_bf16x2(o[6], o[7]);
+                        __stcs(reinterpret_cast<uint4*>(dvnb + (int64_t)sidx * C_ + lane * 8), w4);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&empty[slot]);
+                transpose_reduce<4 * GP>(part, lane);
+                constexpr int SH = GP == 1 ? 3 : (GP == 2 ? 2 : 1);      // 4*GP values -> index = lane >> SH
+                const int k = lane >> SH, g = k >> 2, t = k & 3;
+                const int sidx = i * BPOSA + warp + NCW * t;
+                if ((lane & ((1 << SH) - 1)) == 0 && g < G && sidx < P) dl[sidx * G + g] = part[0];
+            }
+        }
+        consumer_sync();
+
+        // ---- phase B: softmax backward per glimpse
+        if (warp < G) {
+            const int g = warp;
+            float dot = 0.f;
+            for (int sidx = lane; sidx < P; sidx += 32) dot += pr[sidx * G + g] * dl[sidx * G + g];
+            dot = warp_sum(dot);
+            float sb = 0.f;
+            for (int sidx = lane; sidx < P; sidx += 32) {
+                const float d = pr[sidx * G + g] * (dl[sidx * G + g] - dot);
+                dl[sidx * G + g] = d;
+                sb += d;
+            }
+            sb = warp_sum(sb);
+            if (lane == 0) dbx_part[(int64_t)b * G + g] = sb;
+        }
+        consumer_sync();
+
+        // ---- phase C
+        {
+            uint32_t q2[4];
+            float qf[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = *reinterpret_cast<const float2*>(qp + (int64_t)b * A_ + a0 + 2 * e);
+                q2[e] = pack_bf16x2(f.x, f.y);
+                qf[2 * e] = bf_lo(q2[e]); qf[2 * e + 1] = bf_hi(q2[e]);
+            }
+            float dq[8], dw[G][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dq[e] = 0.f;
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dw[g][e] = 0.f;
+            bf16* dvpb = dvp + (int64_t)b * P * A_;
+            for (int i = 0; i < nC; ++i, ++c) {
+                const int slot = c % BNST;
+                tc::mbar_wait(&full[slot], (c / BNST) & 1);
+                const uint8_t* base = ring + slot * BCHUNK + cg * 512 + lane * 16;
+#pragma unroll
+                for (int t = 0; t < BPOSC / 4; ++t) {
+                    const int r = pi + 4 * t, sidx = i * BPOSC + r;
+                    if (sidx < P) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(base + r * (A_ * 2));
+                        const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+                        uint32_t fl[4];
+                        if (TRAIN) dropout_flags8(d8, (uint32_t)(((int64_t)b * P + sidx) * (A_ / 8) + cg * 32 + lane), fl);
+                        float dls[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) dls[g] = dl[sidx * G + g];
+                        uint4 o4;
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t xr = OP == VQA_ATT_ADD ? hadd2_bf16(x[e], q2[e]) : hmul2_bf16(x[e], q2[e]);
+                            xr = hrelu2_bf16(xr);
+                            if (TRAIN) xr &= dropout_mask_bf16x2(fl[e]);          // relu(pre) where kept (unscaled), else 0
+                            const float xl = bf_lo(xr), xh = bf_hi(xr);
+                            float dl_lo = 0.f, dl_hi = 0.f;
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                dl_lo = fmaf(dls[g], wv[g][2 * e], dl_lo);
+                                dl_hi = fmaf(dls[g], wv[g][2 * e + 1], dl_hi);
+                                dw[g][2 * e] = fmaf(dls[g], xl, dw[g][2 * e]);
+                                dw[g][2 * e + 1] = fmaf(dls[g], xh, dw[g][2 * e + 1]);
+                            }
+                            // gradient w.r.t. the pre-activation, gated by (alive and kept) <=> xr != 0
+                            const uint32_t dpre = pack_bf16x2(dl_lo, dl_hi) & ne_mask_bf16x2(xr);
+                            const float pl = bf_lo(dpre), phh = bf_hi(dpre);
+                            if (OP == VQA_ATT_ADD) {
+                                o[e] = dpre;
+                                dq[2 * e] += pl; dq[2 * e + 1] += phh;
+                            } else {
+                                o[e] = pack_bf16x2(pl * qf[2 * e], phh * qf[2 * e + 1]);
+                                dq[2 * e] = fmaf(pl, bf_lo(x[e]), dq[2 * e]);
+                                dq[2 * e + 1] = fmaf(phh, bf_hi(x[e]), dq[2 * e + 1]);
+                            }
+                        }
+                        __stcs(reinterpret_cast<uint4*>(dvpb + (int64_t)sidx * A_ + a0), o4);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&empty[slot]);
+            }
+            // four row-interleaved copies of every channel's partial sums meet in shared memory
+            float* rp = red + pi * (1 + G) * A_ + a0;
+            *reinterpret_cast<float4*>(rp) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+            *reinterpret_cast<float4*>(rp + 4) = make_float4(dq[4], dq[5], dq[6], dq[7]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                *reinterpret_cast<float4*>(rp + (1 + g) * A_) = make_float4(dw[g][0], dw[g][1], dw[g][2], dw[g][3]);
+                *reinterpret_cast<float4*>(rp + (1 + g) * A_ + 4) = make_float4(dw[g][4], dw[g][5], dw[g][6], dw[g][7]);
+            }
+        }
+        consumer_sync();
+        for (int t = tid; t < (1 + G) * A_; t += NCW * 32) {
+            const float sacc = red[t] + red[(1 + G) * A_ + t] + red[2 * (1 + G) * A_ + t] + red[3 * (1 + G) * A_ + t];
+            const int k = t / A_, a = t - k * A_;
+            if (k == 0) dqp[(int64_t)b * A_ + a] = sacc;
+            else dwx_part[((int64_t)b * G + (k - 1)) * A_ + a] = sacc * scale;       // dW_x sees the scaled, dropped x
+        }
+        // the next sample's first consumer_sync (after staging pr / dsm) separates these reads from the next writes of `red`
+    }
+}
+
+static size_t bwd_stream_smem(int G, int P) {
+    return (size_t)BNST * BCHUNK + sizeof(float) * ((size_t)4 * (1 + G) * A_ + 2 * (size_t)G * P + (size_t)G * C_) + 2 * BNST * 8 + 256;
+}
+
+template <int G, int OP>
+int launch_bwd_stream(const void* dout, int64_t ldd, const void* vp, const float* qp, const void* vn, const float* wx,
+                      const float* prob, void* dvp, void* dvn, float* dqp, float* dwx_part, float* dbx_part,
+                      int B, int P, Dropout d, cudaStream_t st) {
+    const size_t smem = bwd_stream_smem(G, P);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = B < sms ? B : sms;
+    if (d.threshold != 0) {
+        auto kern = attention_bwd_stream_kernel<G, OP, true>;
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHR, smem, st>>>((const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
+                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d);
+    } else {
+        auto kern = attention_bwd_stream_kernel<G, OP, false>;
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHR, smem, st>>>((const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
+                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d);
+    }
+    VQA_CHECK_LAUNCH("attention_bwd_stream");
     return 0;
 }
 
@@ -651,7 +938,8 @@ extern "C" int vqa_attention_fwd(const void* vp, const float* qp, const void* vn
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldo)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && P <= 1024) {     // tensor-core arm at the config.yaml shape
+    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && stream::fwd_stream_smem(G, P) <= 232448 &&
+        stream::bwd_stream_smem(G, P) <= 232448) {     // tensor-core arm at the config.yaml shape
         VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
         if (G == 1) return op == VQA_ATT_ADD ? stream::launch_fwd_stream<1, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
                                              : stream::launch_fwd_stream<1, VQA_ATT_MUL>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
@@ -670,6 +958,14 @@ extern "C" int vqa_attention_bwd(const void* dout, int64_t ldd, const void* vp, 
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldd)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
+    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && stream::bwd_stream_smem(G, P) <= 232448 &&
+        stream::fwd_stream_smem(G, P) <= 232448) {     // same condition as the forward: both recompute the fusion in bf16
+        VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
+        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_bwd_stream<1, VQA_ATT_ADD>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                                             : stream::launch_bwd_stream<1, VQA_ATT_MUL>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
+        return op == VQA_ATT_ADD ? stream::launch_bwd_stream<2, VQA_ATT_ADD>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                                 : stream::launch_bwd_stream<2, VQA_ATT_MUL>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
+    }
     ATT_DISPATCH(launch_bwd, dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, A, C, d, st);
     VQA_REQUIRE(false, "attention_bwd: no kernel for this configuration");
     return 0;

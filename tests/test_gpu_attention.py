@@ -92,3 +92,24 @@ def test_streaming_bf16_forward_matches_generic(B, P, G, p_drop, op):
         # a different seed must change the result; eval (p = 0) must differ from train
         _, out2 = _call_fwd(vp, qp, vn, wx, bx, op, p_drop, seed + 1)
         assert not torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("op", ["+", "*"])
+@pytest.mark.parametrize("B,P,G,p_drop", [(300, 676, 2, 0.3), (5, 676, 2, 0.0), (3, 41, 1, 0.3), (149, 8, 2, 0.5), (2, 700, 2, 0.3)])
+def test_streaming_bf16_backward_matches_generic(B, P, G, p_drop, op):
+    """Streaming backward (bf16) against the generic fp32 kernel on the same bf16-rounded inputs and dropout seed.
+    q' is pre-rounded to bf16 so that both kernels gate exactly the same elements (the streaming kernels add in bf16)."""
+    A, C = 1024, 256
+    vp, qp, vn, wx, bx = _inputs(B, P, A, C, G, 9 + B, torch.bfloat16)
+    qp = qp.bfloat16().float()
+    seed = 0xBEEF + B
+    prob, _ = _call_fwd(vp.float(), qp, vn.float(), wx, bx, op, p_drop, seed)
+    dout = (torch.randn(B, G * C, device="cuda")).bfloat16()
+    got = _call_bwd(dout, vp, qp, vn, wx, prob, op, p_drop, seed)
+    want = _call_bwd(dout.float(), vp.float(), qp, vn.float(), wx, prob, op, p_drop, seed)
+    names = ["dvp", "dvn", "dqp", "dwx", "dbx"]
+    for n, g_, w_ in zip(names, got, want):
+        err = _rel(g_, w_)
+        assert err < 2e-2, (n, err)
+    # the gate must be identical: dvp is exactly zero in the same places (ReLU-dead or dropped)
+    assert bool(((got[0].float() == 0) == (want[0] == 0)).float().mean() > 0.999)
