@@ -318,15 +318,15 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
 // Streaming forward kernel for the tensor-core arm (bf16 activations, A = 1024, C = 256: the config.yaml shape).
 //
 // Persistent grid (one CTA per SM), samples round-robin.  A producer warp streams the sample's v' [P][A] and then
-// its v [P][C] rows through an 11 x 16 KB shared-memory ring with cp.async.bulk + mbarriers and never stops at
+// its v [P][C] rows through a 16 x 8 KB shared-memory ring with cp.async.bulk + mbarriers and never stops at
 // sample or phase boundaries, so HBM stays busy while the consumers reduce / normalise.  16 consumer warps work as
-// 8 pairs; a pair owns every 8th 16 KB chunk:
-//   phase 1 (chunk = 8 positions x 1024 channels): each warp of the pair takes half a row (lane = 16 channels,
+// 8 pairs; a pair owns every 8th 8 KB chunk (two private ring slots):
+//   phase 1 (chunk = 4 positions x 1024 channels): each warp of the pair takes half a row (lane = 16 channels,
 //           two conflict-free LDS.128 per position), computes relu(v' (+|*) q') & dropout-mask in packed bf16x2,
-//           accumulates the G glimpse dot products in fp32 and folds its 8 x G per-lane partial sums with a
-//           transposing butterfly (16 shuffles instead of 80).
+//           accumulates the G glimpse dot products in fp32 and folds its 4 x G per-lane partial sums with a
+//           transposing butterfly (9 shuffles instead of 40).
 //   softmax over the P positions per glimpse (warp shuffles), probabilities kept in shared memory and saved.
-//   phase 3 (chunk = 32 positions x 256 channels): lane = 8 channels, fp32 accumulators, one cross-warp reduction.
+//   phase 3 (chunk = 16 positions x 256 channels): lane = 8 channels, fp32 accumulators, one cross-warp reduction.
 // Algorithmic HBM bytes per sample as for the generic kernel; nothing is read twice.
 // ================================================================================================================
 namespace stream {
@@ -334,25 +334,21 @@ namespace stream {
 constexpr int A_ = 1024, C_ = 256;
 constexpr int NCW = 16, NPAIR = 8;
 constexpr int NTHR = (NCW + 1) * 32;
-constexpr int CHUNK = 16384, NST = 11;
-static_assert(NPAIR < NST, "wait_chunk relies on the pair stride being shorter than the ring");
-constexpr int POS1 = CHUNK / (A_ * 2);           // 8 positions of v' per chunk
-constexpr int POS3 = CHUNK / (C_ * 2);           // 32 positions of v per chunk
+constexpr int CHUNK = 8192, NST = 16;
+static_assert(NST % NPAIR == 0, "every ring slot must belong to exactly one consumer pair (see wait_chunk)");
+constexpr int POS1 = CHUNK / (A_ * 2);           // 4 positions of v' per chunk
+constexpr int POS3 = CHUNK / (C_ * 2);           // 16 positions of v per chunk
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
-// Ring slots are shared by the 8 consumer pairs (slot = chunk % NST, pair = chunk % NPAIR), so a fast pair may ask for
-// chunk cc before the PREVIOUS use of that slot (chunk cc - NST, another pair's) has even landed; a bare parity wait
-// would then alias with the phase before that and fall through.  Having consumed chunk cc - NPAIR, which was issued
-// after chunk cc - NST (NPAIR < NST, in-order producer), the pair knows the barrier is at worst one phase behind:
-// waiting for that phase first makes the wait exact.
-__device__ __forceinline__ void wait_chunk(uint64_t* full, uint32_t cc) {
-    const uint32_t k = cc / NST;
-    if (k > 0) tc::mbar_wait(&full[cc % NST], (k - 1) & 1);
-    tc::mbar_wait(&full[cc % NST], k & 1);
-}
+// Slot = chunk % NST and pair = chunk % NPAIR with NST a multiple of NPAIR: a slot is only ever used by ONE pair, so
+// when a pair asks for chunk cc it has already consumed the slot's previous chunk and a plain parity wait is exact.
+// (With slots shared between pairs a fast pair could ask before the previous use of the slot has landed, and the
+// 1-bit phase parity would alias with the phase before that.)
+__device__ __forceinline__ void wait_chunk(uint64_t* full, uint32_t cc) { tc::mbar_wait(&full[cc % NST], (cc / NST) & 1); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -493,7 +489,7 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
             if (lane == 0) tc::mbar_arrive(&empty[slot]);          // this warp is done with the chunk
             transpose_reduce<POS1 * GP>(acc, lane);
             // value index k = g*POS1 + ps sits in lanes with (lane >> SH) == k
-            constexpr int SH = GP == 1 ? 2 : (GP == 2 ? 1 : 0);
+            constexpr int SH = 5 - ilog2(POS1 * GP);
             const int k = lane >> SH, g = k / POS1, ps = k % POS1;
             if ((lane & ((1 << SH) - 1)) == 0 && g < G && pos0 + ps < P) lpart[(half * G + g) * P + pos0 + ps] = acc[0];
         }
@@ -729,7 +725,7 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&empty[slot]);
                 transpose_reduce<4 * GP>(part, lane);
-                constexpr int SH = GP == 1 ? 3 : (GP == 2 ? 2 : 1);      // 4*GP values -> index = lane >> SH
+                constexpr int SH = 5 - ilog2(4 * GP);                    // 4*GP values -> index = lane >> SH
                 const int k = lane >> SH, g = k >> 2, t = k & 3;
                 const int sidx = i * BPOSA + warp + NCW * t;
                 if ((lane & ((1 << SH) - 1)) == 0 && g < G && sidx < P) dl[sidx * G + g] = part[0];
