@@ -134,7 +134,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -212,22 +212,20 @@ def run_ours(args):
         step(dbatch)
     torch.cuda.synchronize()
 
-    # ---- (1) device-resident throughput, with per-kernel CUDA-event timing of the contraction kernels
+    # ---- (1) device-resident throughput (no per-kernel events inside this region)
     tags = [f"conv{i}_{k}" for i in range(3) for k in ("fwd", "dgrad", "wgrad")] + \
            ["v_conv", "v_conv_dgrad", "v_conv_wgrad", "vqa_attention_fwd", "vqa_attention_bwd", "lstm_step_fwd",
             "lstm_step_bwd", "lstm_recurrence_fwd", "lstm_bwd_pointwise", "lstm_inproj", "lstm_whh_wgrad", "lstm_wih_wgrad", "lstm_inproj_dgrad", "lin1", "lin2", "q_lin", "lin1_dgrad", "lin2_dgrad", "lin1_wgrad", "lin2_wgrad", "q_lin_dgrad", "q_lin_wgrad", "act_cast", "vqa_adam_multi", "act_transpose", "unpool", "w_cast", "w_transpose"]
     clocks = ClockSampler(local)
     clocks.start()
     n0 = lib.launch_count()
-    lib.enable_kernel_timing(tags)
     ms_dev = timed(lambda: step(dbatch), args.steps)
-    ktimes = lib.collect_kernel_timing()
     launches = lib.launch_count() - n0
 
-    if args.profile_mode:            # under ncu: no second timed region, no CPU leg
+    if args.profile_mode:            # under ncu: no second timed region, no breakdown pass, no CPU leg
         clocks.stop()
         if rank == 0:
-            print(json.dumps({"profile_mode": True, "ms_per_step": ms_dev / args.steps}), flush=True)
+            _emit({"profile_mode": True, "ms_per_step": ms_dev / args.steps})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -249,6 +247,14 @@ def run_ours(args):
     ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
 
+    # ---- (3) per-kernel breakdown: a separate pass with CUDA events around every tagged C-ABI call (the events add
+    # launch gaps, so this pass is not part of `value` / `e2e`)
+    nb = min(args.steps, 5)
+    lib.enable_kernel_timing(tags)
+    for _ in range(nb):
+        step(dbatch)
+    ktimes = lib.collect_kernel_timing()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -260,24 +266,43 @@ def run_ours(args):
     e2e_val = world * B / (ms_e2e / args.steps / 1000.0)
 
     # dominant kernel: the tag with the largest device time inside the timed region
-    breakdown = {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps} for k, (n, ms) in ktimes.items()}
-    conv_tags = {k: v for k, v in breakdown.items() if k.startswith("conv")}
+    breakdown = {k: {"calls_per_step": n / nb, "ms_per_step": ms / nb} for k, (n, ms) in ktimes.items()}
+    # roofline of the dominant kernel: the tagged kernel with the largest device time whose algorithmic work is known
+    esz = 2 if args.dtype in ("bf16", "bfloat16") else 4
+    work = {}
+    for i in (1, 2):
+        for k in ("fwd", "dgrad", "wgrad"):
+            work[f"conv{i}_{k}"] = ("tensor", CONV_FLOP[i] * B)
+    for k in ("v_conv", "v_conv_dgrad", "v_conv_wgrad"):
+        work[k] = ("tensor", 2.0 * B * 676 * 256 * 1024)
+    # conv0 (K = 27): HBM-bound.  fwd reads the fp32 NCHW image and writes pooled bf16 + uint8 mask; wgrad reads the
+    # image and the un-pooled bf16 gradient
+    work["conv0_fwd"] = ("hbm", B * (3 * 224 * 224 * 4 + 110 * 110 * 64 * (esz + 1)))
+    work["conv0_wgrad"] = ("hbm", B * (3 * 224 * 224 * 4 + 220 * 220 * 64 * esz))
+    work["vqa_attention_fwd"] = ("hbm", B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4))
+    work["vqa_attention_bwd"] = ("hbm", B * ((2 * 676 * 1024 + 2 * 676 * 256 + 512) * esz + 2 * 1024 * 4 + 2 * 676 * 4 + 2 * 1024 * 4))
     roofline = None
-    if conv_tags:
-        top = max(conv_tags, key=lambda k: conv_tags[k]["ms_per_step"])
-        layer = int(top[4])
-        flop = CONV_FLOP[layer] * B
-        dur_ms = conv_tags[top]["ms_per_step"] / max(1.0, conv_tags[top]["calls_per_step"])
-        achieved = flop / (dur_ms / 1000.0) / 1e12
+    known = {k: v for k, v in breakdown.items() if k in work and v["calls_per_step"] > 0}
+    if known:
+        top = max(known, key=lambda k: known[k]["ms_per_step"])
+        bound, amount = work[top]
+        dur_ms = known[top]["ms_per_step"] / known[top]["calls_per_step"]
         traffic, traffic_src = _ncu_traffic(top)
-        roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peaks["src"] + " sustained bf16",
-                    "flop_per_launch": flop, "ms_per_launch": dur_ms}
+        if bound == "tensor":
+            achieved, peak, unit, psrc = amount / (dur_ms / 1000.0) / 1e12, peaks["tflops"], "TFLOP/s", peaks["src"] + " sustained bf16"
+        else:
+            achieved, peak, unit, psrc = amount / (dur_ms / 1000.0) / 1e9, peaks["hbm_gbs"], "GB/s", peaks["src"] + " copy bandwidth"
+        roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": psrc,
+                    "work_per_launch": amount, "ms_per_launch": dur_ms}
+    per_kernel_frac = {}
+    for k, v in known.items():
+        bound, amount = work[k]
+        d = v["ms_per_step"] / v["calls_per_step"] / 1000.0
+        per_kernel_frac[k] = round((amount / d / 1e12) / peaks["tflops"] if bound == "tensor" else (amount / d / 1e9) / peaks["hbm_gbs"], 4)
     att = breakdown.get("vqa_attention_fwd")
     att_roof = None
     if att:
-        esz = 2 if args.dtype in ("bf16", "bfloat16") else 4
         byt = B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4)
         gbs = byt / (att["ms_per_step"] / 1000.0) / 1e9
         att_roof = {"kernel": "vqa_attention_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
@@ -304,13 +329,26 @@ def run_ours(args):
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clk, "roofline": roofline, "attention_roofline": att_roof,
             "step_tensor_frac": (STEP_FLOP_PER_SAMPLE * B / (per_step / 1000.0) / 1e12) / peaks["tflops"],
-            "kernels": breakdown, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+            "roofline_frac_by_kernel": per_kernel_frac, "kernels": breakdown, "cpu_baseline": cpu}
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 during the run (NCCL's version
+    banner, library chatter) was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

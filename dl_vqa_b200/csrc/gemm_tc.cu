@@ -56,9 +56,12 @@ struct GemmEpilogue {
     uint32_t site; Dropout drop;
 };
 
-template <int BN>
+// ST = ring depth.  6 stages (one CTA per SM) for few, long tiles; 3 stages (96 KB at BN = 128, two or three CTAs
+// per SM, each with its own TMEM columns) when there are many short tiles, so that one CTA's prologue / epilogue
+// overlaps another CTA's MMAs (attention.v_conv: 10816 tiles of only 4 k-blocks each).
+template <int BN, int ST>
 struct GemmSmem {
-    static constexpr int STAGES = BN >= 256 ? 4 : 6;
+    static constexpr int STAGES = ST;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -66,11 +69,11 @@ struct GemmSmem {
 // MN = false: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
 // MN = true : A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
 //             consumed without transposes; one TMA box per 64-wide column block per stage).
-template <int BN, bool MN>
+template <int BN, bool MN, int ST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sa = smem;
@@ -222,24 +225,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
+template <int BN, bool MN, int ST>
+static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                          dim3 grid, int nsplit, int kbps, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, MN, ST>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, ST>::BYTES));
+        attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, GemmSmem<BN, ST>::BYTES, st>>>(ta, tb, ep, M, N, K, nsplit, kbps);
+    VQA_CHECK_LAUNCH("gemm_tc");
+    return 0;
+}
+
 template <int BN, bool MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                        int nbatch, int nsplit, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, MN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::BYTES));
-        attr_set = true;
-    }
     const int total_kb = (K + BK - 1) / BK;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > total_kb) nsplit = total_kb > 0 ? total_kb : 1;
     int kbps = total_kb > 0 ? (total_kb + nsplit - 1) / nsplit : 1;
     nsplit = total_kb > 0 ? (total_kb + kbps - 1) / kbps : 1;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch * nsplit);
-    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::BYTES, st>>>(ta, tb, ep, M, N, K, nsplit, kbps);
-    VQA_CHECK_LAUNCH("gemm_tc");
-    return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+    if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MN, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+    return launch_gemm_st<BN, MN, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
 }
 
 }  // namespace tc
