@@ -1,86 +1,132 @@
 // First image-encoder layer (3 input channels, models/model.py:80 with num_channels[0] = 3) on tcgen05.
 //
-// K = 3*3*3 = 27 is far too small for a TMA-fed pipeline to pay off and the NCHW fp32 network input is not a
-// UMMA operand, so builder warps write the im2col tile straight into 128-byte-swizzled shared memory:
-// one thread per output position gathers its 27 inputs (L1-cached, each input is reused 9x), converts to
-// bf16 and stores 4 x 16 B at the swizzled chunk positions -> a [128 positions][k] tile with 128-byte rows.
-//   forward : that tile is the K-major A operand (K = 32, two MMAs), weights [64 co][k] are built once per
-//             CTA; epilogue = bias + ReLU + 2x2 max-pool + mask exactly as conv_tc.cu (the 64x222x222 un-pooled
-//             activation, 1.6 GB per 256-sample batch, never exists).
-//   wgrad   : the SAME bytes read as an MN-major B operand (rows = positions = reduction index), the gradient
-//             tile dY[128 positions][64 co] arrives by TMA as the MN-major A operand:
-//             dW[co][k] += sum_pos dY[pos][co] * patch[pos][k]  -- accumulated in TMEM over the CTA's slice of
-//             positions, flushed once with atomics (64 x 27 outputs).
-// Both are bandwidth/epilogue-bound kernels; the tensor core only removes the 27x64 FMAs per position that a
-// SIMT formulation spends.
+// K = 3*3*3 = 27 is far too small for a TMA-fed pipeline and the NCHW fp32 network input is not a UMMA operand, so
+// builder warps write the im2col rows straight into 128-byte-swizzled shared memory.  Both kernels are WINDOW-major:
+// the M / reduction index of a tile is a 2x2 pooling window (8 x 16 windows = 128 per tile) and the four window
+// elements e = (dy,dx) are four separate operand tiles built from the window's 4x4x3 input patch (48 loads per
+// window instead of 4 x 27):
+//   patch_e[window][k] = x[ci][2ph+dy+kh][2pw+dx+kw],  k = ci*9 + kh*3 + kw  (k = 27 holds 1.0, k = 28..31 zero)
+// Two elements share one 128-byte row (k-range 0..31 of e at byte 64*(e&1)), so a stage is two 16 KB tiles.
+//
+//   forward : D[window][e*64 + co] = patch_e W^T -- four N = 64 accumulators side by side in TMEM (256 columns,
+//             double buffered).  The 2x2 max-pool is then a per-thread max over four registers per channel: no
+//             shuffles, no cross-lane traffic; epilogue = max / arg-max + bias + ReLU + mask, written as 128 B of
+//             pooled bf16 and 64 B of mask per window.  The 64x222x222 un-pooled activation never exists.
+//   backward: dW[co][k] = sum_{window,e} [mask[window][co] == e] dpool[window][co] * patch_e[window][k].  The builders
+//             expand (dpool, mask) into the four masked MN-major A tiles in shared memory, so the 1.6 GB un-pooled
+//             gradient never exists either (it used to be written by vqa_unpool_bf16 and re-read twice); the patch
+//             tiles are the MN-major B operand (the same bytes the forward uses K-major).  Column k = 27 of the
+//             patch is 1.0, hence D[co][27] is the bias gradient.  One [128 x 32] fp32 accumulator per CTA, flushed
+//             once with atomics.
+// Both kernels are HBM / issue-bound; the tensor core only removes the 27 x 64 FMAs per position.
 #include "tc_common.cuh"
 
 namespace tc {
 
-constexpr int C0_THREADS = 288;        // warps 0-3 epilogue, 4-7 im2col builders, 8 MMA issuer
-constexpr int C0_TILE_BYTES = 128 * 128;
-constexpr int C0_STAGES = 3;
 constexpr int C0_K = 27;
+constexpr int C0_TILE_BYTES = 128 * 128;           // 128 windows x 128 B
+constexpr int C0_WH = 8, C0_WW = 16;               // windows per tile
 
 struct Conv0Params {
     const float* x;                    // [B,3,IH,IW] NCHW fp32
-    int B, IH, IW, tiles_h, tiles_w;
+    int B, IH, IW, PH, PW, tiles_h, tiles_w;
     // forward
-    const float* w; const float* bias; bf16* pooled; uint8_t* mask; int PH, PW;
-    // wgrad
-    float* dw; int chunks_per_cta;
+    const float* w; const float* bias; bf16* pooled; uint8_t* mask;
+    // backward
+    const bf16* dpool; const uint8_t* bmask; float* dw; float* db; int tiles_per_cta;
 };
 
-// gather the 27 inputs of output position (h,w) of image b (clamped so that out-of-range tile positions read
-// valid memory; their results are discarded) and write one swizzled 64-byte row segment of the tile
-__device__ __forceinline__ void build_im2col_row(const Conv0Params& p, uint8_t* tile, int row, int b, int h, int w) {
-    const int hc = min(h, p.IH - 3), wc = min(w, p.IW - 3);
-    const float* src = p.x + ((int64_t)b * 3 * p.IH + hc) * p.IW + wc;
-    float v[32];
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (no wait: batch several, then tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Builds the four im2col rows of window (ph,pw) of image b (coordinates clamped so that out-of-range tile windows read
+// valid memory; their results are discarded / multiplied by zero) into `tiles` = two 16 KB tiles, row m.
+__device__ __forceinline__ void build_patch_rows(const Conv0Params& p, uint8_t* tiles, int m, int b, int ph, int pw) {
+    const int phc = min(ph, p.PH - 1), pwc = min(pw, p.PW - 1);
+    const float* src = p.x + ((int64_t)b * 3 * p.IH + 2 * phc) * p.IW + 2 * pwc;
+    const bool al8 = (p.IW & 1) == 0;                 // even row pitch: every (row, 2*pw) address is 8-byte aligned
+    float v[3][4][4];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+        for (int r = 0; r < 4; ++r) {
+            const float* q = src + ((int64_t)ci * p.IH + r) * p.IW;
+            if (al8) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(q)), c = __ldg(reinterpret_cast<const float2*>(q) + 1);
+                v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+            } else {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-                v[ci * 9 + kh * 3 + kw] = __ldg(src + ((int64_t)ci * p.IH + kh) * p.IW + kw);
+                for (int c = 0; c < 4; ++c) v[ci][r][c] = __ldg(q + c);
+            }
+        }
+    const int sw = m & 7;
 #pragma unroll
-    for (int k = C0_K; k < 32; ++k) v[k] = 0.f;
-    uint8_t* rowp = tile + row * 128;
-    const int sw = row & 7;
+    for (int e = 0; e < 4; ++e) {
+        const int dy = e >> 1, dx = e & 1;
+        float k[32];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+        for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
-        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = u;
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) k[ci * 9 + kh * 3 + kw] = v[ci][dy + kh][dx + kw];
+        k[27] = 1.f;                                   // bias-gradient column (the forward weights have a zero there)
+#pragma unroll
+        for (int i = 28; i < 32; ++i) k[i] = 0.f;
+        uint8_t* rowp = tiles + (e >> 1) * C0_TILE_BYTES + m * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack2(k[8 * j], k[8 * j + 1]); u.y = pack2(k[8 * j + 2], k[8 * j + 3]);
+            u.z = pack2(k[8 * j + 4], k[8 * j + 5]); u.w = pack2(k[8 * j + 6], k[8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((4 * (e & 1) + j) ^ sw) << 4)) = u;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(C0_THREADS, 2) conv0_fwd_tc_kernel(Conv0Params p) {
+// warps 0-7 epilogue (TMEM lane quarter = w & 3, channel half = w >> 2), warps 8-15 two builder groups, warp 16 MMA
+constexpr int C0F_THREADS = 17 * 32;
+constexpr int C0F_STAGES = 4;                      // two per builder group
+constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
+
+__global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sw_tile = smem;                                   // [64 co][128 B]
-    uint8_t* sa = smem + 64 * 128;                             // C0_STAGES x [128 pos][128 B]
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(sa + C0_STAGES * C0_TILE_BYTES);
-    uint64_t* a_empty = a_full + C0_STAGES;
-    uint64_t* tmem_full = a_empty + C0_STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
+    uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
+    uint8_t* sa = smem + 64 * 128;                             // C0F_STAGES x 32 KB
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(sa + C0F_STAGES * C0F_STAGE_BYTES);
+    uint64_t* a_empty = a_full + C0F_STAGES;
+    uint64_t* tmem_full = a_empty + C0F_STAGES;               // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                      // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    constexpr int BN = 64;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
     const int ntiles = p.B * tiles_per_img;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C0_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < C0F_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
         fence_barrier_init();
     }
-    if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid)
+    if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
         const int co = threadIdx.x;
         float v[32];
 #pragma unroll
@@ -88,121 +134,102 @@ __global__ void __launch_bounds__(C0_THREADS, 2) conv0_fwd_tc_kernel(Conv0Params
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             uint4 u = make_uint4(0, 0, 0, 0);
-            if (j < 4) {
-                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
-            }
+            if (j < 4) { u.x = pack2(v[8 * j], v[8 * j + 1]); u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+                         u.z = pack2(v[8 * j + 4], v[8 * j + 5]); u.w = pack2(v[8 * j + 6], v[8 * j + 7]); }
             *reinterpret_cast<uint4*>(sw_tile + co * 128 + ((j ^ (co & 7)) << 4)) = u;
         }
         fence_proxy_async();
     }
-    if (warp == 8) tmem_alloc(tmem_base_smem, 2 * BN);
+    if (warp == 16) tmem_alloc(tmem_base_smem, 512);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    if (warp >= 4 && warp < 8) {
-        // ---- im2col builders: thread -> tile position
-        const int t = threadIdx.x - 128;
-        const int rr = t >> 4, cc = t & 15;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    if (warp >= 8 && warp < 16) {
+        // ---- builders: group g builds tiles g, g+2, ... of this CTA; thread -> window of the tile
+        const int g = (warp - 8) >> 2, t = (threadIdx.x - 256) & 127;
+        const int wr = t >> 4, wc = t & 15;
+        uint32_t it = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, it += 2) {
             const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-            const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
-            const int s = it % C0_STAGES;
-            const uint32_t ph = (it / C0_STAGES) & 1;
-            mbar_wait(&a_empty[s], ph ^ 1);
-            build_im2col_row(p, sa + s * C0_TILE_BYTES, t, b, h0 + rr, w0 + cc);
+            const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
+            const int s = it % C0F_STAGES;
+            mbar_wait(&a_empty[s], ((it / C0F_STAGES) & 1) ^ 1);
+            build_patch_rows(p, sa + s * C0F_STAGE_BYTES, t, b, ph0 + wr, pw0 + wc);
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
         }
-    } else if (warp == 8) {
-        // all lanes converged, one elected lane issues (see tc_common.cuh)
-        constexpr uint32_t idesc = idesc_bf16(128, BN);
+    } else if (warp == 16) {
+        // ---- MMA issuer: all lanes converged, one elected lane issues (see tc_common.cuh)
+        constexpr uint32_t idesc = idesc_bf16(128, 64);
         const uint32_t elected = elect_one();
         const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa)), w_desc = smem_desc_k_sw128(smem_u32(sw_tile));
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, use = it >> 1;
-            const int s = it % C0_STAGES;
+            const int s = it % C0F_STAGES;
             mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);
-            mbar_wait(&a_full[s], (it / C0_STAGES) & 1);
+            mbar_wait(&a_full[s], (it / C0F_STAGES) & 1);
             tcgen05_fence_after();
-            const uint64_t ad = a_desc0 + (uint64_t)(s * (C0_TILE_BYTES >> 4));
+            const uint64_t ad = a_desc0 + (uint64_t)(s * (C0F_STAGE_BYTES >> 4));
 #pragma unroll
-            for (uint32_t k = 0; k < 2; ++k)
-                umma_issue<1>(tmem_base + acc * BN, ad + 2 * k, w_desc + 2 * k, idesc, k, elected);
+            for (uint32_t e = 0; e < 4; ++e) {
+                const uint64_t ae = ad + (uint64_t)((e >> 1) * (C0_TILE_BYTES >> 4) + (e & 1) * 4);     // +64 B for odd elements
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k)
+                    umma_issue<1>(tmem_base + acc * 256 + e * 64, ae + 2 * k, w_desc + 2 * k, idesc, k, elected);
+            }
             umma_commit_issue<1>(&a_empty[s], elected);
             umma_commit_issue<1>(&tmem_full[acc], elected);
         }
-    } else if (warp < 4) {
-        // ---- epilogue: bias + ReLU + 2x2 max-pool + mask (same butterfly as conv_tc.cu)
-        const int quarter = warp;
-        const int cc = lane & 15;
-        const int bit0 = lane & 1, bit4 = (lane >> 4) & 1;
+    } else {
+        // ---- epilogue: thread = window (TMEM lane), 2x2 max-pool = max over the four element accumulators
+        const int quarter = warp & 3, half = warp >> 2;
+        const int m = quarter * 32 + lane, wr = m >> 4, wc = m & 15;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, use = it >> 1;
             const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-            const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
+            const int ph = (r / p.tiles_w) * C0_WH + wr, pw = (r % p.tiles_w) * C0_WW + wc;
+            const bool ok = ph < p.PH && pw < p.PW;
+            const int64_t obase = (((int64_t)b * p.PH + ph) * p.PW + pw) * 64;
             mbar_wait(&tmem_full[acc], use & 1);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-            const int ph_ = (h0 >> 1) + quarter, pw_ = (w0 >> 1) + (cc >> 1);
-            const bool ok = ph_ < p.PH && pw_ < p.PW;
-            const int64_t obase = (((int64_t)b * p.PH + ph_) * p.PW + pw_) * BN;
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16) + half * 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                float k1[16]; int i1[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float mine = bit0 ? v[16 + j] : v[j];
-                    const float send = bit0 ? v[j] : v[16 + j];
-                    const float other = __shfl_xor_sync(0xffffffffu, send, 1);
-                    const bool take_other = bit0 ? (other >= mine) : (other > mine);
-                    k1[j] = take_other ? other : mine;
-                    i1[j] = take_other ? (bit0 ^ 1) : bit0;
-                }
-                float k2[8]; int i2[8];
-                uint32_t pack_send = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pack_send |= (uint32_t)(bit4 ? i1[j] : i1[8 + j]) << (2 * j);
-                const uint32_t pack_other = __shfl_xor_sync(0xffffffffu, pack_send, 16);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float mine = bit4 ? k1[8 + j] : k1[j];
-                    const int mine_i = (bit4 ? i1[8 + j] : i1[j]) + 2 * bit4;
-                    const float send = bit4 ? k1[j] : k1[8 + j];
-                    const float other = __shfl_xor_sync(0xffffffffu, send, 16);
-                    const int other_i = (int)((pack_other >> (2 * j)) & 3u) + 2 * (bit4 ^ 1);
-                    const bool take_other = bit4 ? (other >= mine) : (other > mine);
-                    k2[j] = take_other ? other : mine;
-                    i2[j] = take_other ? other_i : mine_i;
-                }
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                float v0[16], v1[16], v2[16], v3[16];
+                tmem_ld_32x16(taddr + c0, v0);
+                tmem_ld_32x16(taddr + 64 + c0, v1);
+                tmem_ld_32x16(taddr + 128 + c0, v2);
+                tmem_ld_32x16(taddr + 192 + c0, v3);
+                tmem_ld_wait();
                 if (ok) {
-                    const int nb = c0 + 16 * bit0 + 8 * bit4;
-                    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb);
-                    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + nb + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    uint4 u; uint2 mk;
-                    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-                    uint8_t* mb = reinterpret_cast<uint8_t*>(&mk);
-                    float o[8];
+                    const int nb = half * 32 + c0;
+                    uint32_t ob[8], mb[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float x = k2[j] + bb[j];
-                        int id = i2[j];
-                        if (!(x > 0.f)) { x = 0.f; id = 4; }
-                        o[j] = x; mb[j] = (uint8_t)id;
+                    for (int j = 0; j < 16; j += 2) {
+                        float x[2]; uint32_t id[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float a0 = v0[j + u], a1 = v1[j + u], a2 = v2[j + u], a3 = v3[j + u];
+                            // first maximum in element order (ties go to the lower id, as torch max_pool2d)
+                            const float m01 = fmaxf(a0, a1), m23 = fmaxf(a2, a3);
+                            const uint32_t i01 = a1 > a0 ? 1u : 0u, i23 = a3 > a2 ? 3u : 2u;
+                            float mx = fmaxf(m01, m23);
+                            uint32_t ix = m23 > m01 ? i23 : i01;
+                            mx += __ldg(p.bias + nb + j + u);
+                            if (!(mx > 0.f)) { mx = 0.f; ix = 4u; }
+                            x[u] = mx; id[u] = ix;
+                        }
+                        ob[j >> 1] = pack2(x[0], x[1]);
+                        const uint32_t pair = id[0] | (id[1] << 8);
+                        if ((j & 2) == 0) mb[j >> 2] = pair; else mb[j >> 2] |= pair << 16;
                     }
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(o[2 * t], o[2 * t + 1]);
-                    *reinterpret_cast<uint4*>(p.pooled + obase + nb) = u;
-                    *reinterpret_cast<uint2*>(p.mask + obase + nb) = mk;
+                    *reinterpret_cast<uint4*>(p.pooled + obase + nb) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                    *reinterpret_cast<uint4*>(p.pooled + obase + nb + 8) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+                    *reinterpret_cast<uint4*>(p.mask + obase + nb) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
                 }
             }
             tcgen05_fence_before();
@@ -212,102 +239,131 @@ __global__ void __launch_bounds__(C0_THREADS, 2) conv0_fwd_tc_kernel(Conv0Params
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 8) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+    if (warp == 16) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// ------------------------------------------------------------------------------------------ weight gradient
-// thread roles: warps 0-3 final epilogue, warps 4-7 im2col builders (B operand), warp 8 MMA, warp 9 TMA (A operand)
-constexpr int C0W_THREADS = 320;
+// ------------------------------------------------------------------------------------------ backward (weight + bias)
+// warps 0-3 final epilogue, warps 4-11 two builder groups (group g owns stage g), warp 12 MMA
+constexpr int C0B_THREADS = 13 * 32;
+constexpr int C0B_STAGE_BYTES = 6 * C0_TILE_BYTES;            // 4 masked-gradient tiles (A) + 2 patch tiles (B)
 
-__global__ void __launch_bounds__(C0W_THREADS, 1)
-conv0_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, Conv0Params p) {
+__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // stage = [A: dY tile 128 pos x 64 co][B: im2col tile 128 pos x 64 k]
-    constexpr int STAGE = 2 * C0_TILE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C0_STAGES * STAGE);
-    uint64_t* empty = full + C0_STAGES;
-    uint64_t* tmem_full = empty + C0_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * C0B_STAGE_BYTES);
+    uint64_t* empty = full + 2;
+    uint64_t* tmem_full = empty + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
     constexpr uint32_t TMEM_COLS = 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
     const int total = p.B * tiles_per_img;
-    const int c_begin = blockIdx.x * p.chunks_per_cta;
-    const int c_end = min(total, c_begin + p.chunks_per_cta);
-    const int nch = max(0, c_end - c_begin);
+    const int t_begin = blockIdx.x * p.tiles_per_cta;
+    const int t_end = min(total, t_begin + p.tiles_per_cta);
+    const int nt = max(0, t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tma_dy);
-        for (int i = 0; i < C0_STAGES; ++i) { mbar_init(&full[i], 129); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    if (warp == 12) tmem_alloc(tmem_base_smem, TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    if (warp == 9) {
-        if (lane == 0) {
-            for (int i = 0; i < nch; ++i) {
-                const int c = c_begin + i;
-                const int b = c / tiles_per_img, r = c - b * tiles_per_img;
-                const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
-                const int s = i % C0_STAGES;
-                const uint32_t ph = (i / C0_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], C0_TILE_BYTES);
-                tma_load_4d(smem + s * STAGE, &tma_dy, &full[s], 0, w0, h0, b);
+    if (warp >= 4 && warp < 12) {
+        const int g = (warp - 4) >> 2, t = (threadIdx.x - 128) & 127;
+        const int wr = t >> 4, wc = t & 15, sw = t & 7;
+        uint8_t* stage = smem + g * C0B_STAGE_BYTES;
+        uint32_t use = 0;
+        for (int i = g; i < nt; i += 2, ++use) {
+            const int tile = t_begin + i;
+            const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+            const int ph = (r / p.tiles_w) * C0_WH + wr, pw = (r % p.tiles_w) * C0_WW + wc;
+            const bool ok = ph < p.PH && pw < p.PW;
+            // the window's pooled gradient (64 channels bf16) and arg-max mask (64 bytes); loaded before the wait
+            uint4 d[8], mk[4];
+            if (ok) {
+                const int64_t off = (((int64_t)b * p.PH + ph) * p.PW + pw) * 64;
+                const uint4* dp = reinterpret_cast<const uint4*>(p.dpool + off);
+                const uint4* mp = reinterpret_cast<const uint4*>(p.bmask + off);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = __ldcs(dp + j);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mk[j] = __ldcs(mp + j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mk[j] = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u);
             }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        const int t = threadIdx.x - 128;
-        const int rr = t >> 4, cc = t & 15;
-        for (int i = 0; i < nch; ++i) {
-            const int c = c_begin + i;
-            const int b = c / tiles_per_img, r = c - b * tiles_per_img;
-            const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
-            const int s = i % C0_STAGES;
-            const uint32_t ph = (i / C0_STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            build_im2col_row(p, smem + s * STAGE + C0_TILE_BYTES, t, b, h0 + rr, w0 + cc);
+            mbar_wait(&empty[g], (use & 1) ^ 1);
+            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows, 128B-swizzled)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint8_t* rowp = stage + e * C0_TILE_BYTES + t * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                  // 8 channels per 16-byte chunk; their mask bytes: 2 words
+                    const uint32_t* mw = reinterpret_cast<const uint32_t*>(&mk[j >> 1]) + 2 * (j & 1);
+                    uint4 o;
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+                    const uint32_t* dw_ = reinterpret_cast<const uint32_t*>(&d[j]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // bytes are 0..4: (8 - (byte ^ e)) has bit 3 set iff byte == e; move it to the byte's sign bit
+                        const uint32_t f = (0x08080808u - (mw[h] ^ (0x01010101u * e))) << 4;
+                        uint32_t lo, hi;
+                        asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(lo) : "r"(f));      // bytes 0,1 -> two 16-bit masks
+                        asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(hi) : "r"(f));      // bytes 2,3
+                        ow[2 * h] = dw_[2 * h] & lo;
+                        ow[2 * h + 1] = dw_[2 * h + 1] & hi;
+                    }
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o;
+                }
+            }
+            build_patch_rows(p, stage + 4 * C0_TILE_BYTES, t, b, ph, pw);
             fence_proxy_async();
-            mbar_arrive(&full[s]);
+            mbar_arrive(&full[g]);
         }
-    } else if (warp == 8) {
-        // D[128 (co; rows 64..127 unused)][32 k] ; A = dY tile (MN-major, 64 channels = one block; the second
-        // block address is arbitrary valid shared memory: its rows only feed the unused accumulator rows)
+    } else if (warp == 12) {
+        // D[128 (co; rows 64..127 unused)][32 k] += A_e^T B_e over the 128 windows of the tile, e = 0..3.
+        // A: MN-major, 64 channels = one 128-byte block (the second M block of the instruction reads whatever follows
+        // 1 KB later: those rows only feed accumulator rows 64..127, which are never read).
         constexpr uint32_t idesc = idesc_bf16(128, 32, 1, 1);
         const uint32_t elected = elect_one();
         const uint64_t a_desc0 = smem_desc_mn_sw128(smem_u32(smem), 1024);
-        for (int i = 0; i < nch; ++i) {
-            const int s = i % C0_STAGES;
-            mbar_wait(&full[s], (i / C0_STAGES) & 1);
+        for (int i = 0; i < nt; ++i) {
+            const int g = i & 1;
+            mbar_wait(&full[g], (i >> 1) & 1);
             tcgen05_fence_after();
-            const uint64_t ad = a_desc0 + (uint64_t)(s * (STAGE >> 4)), bd = ad + (uint64_t)(C0_TILE_BYTES >> 4);
+            const uint64_t sd = a_desc0 + (uint64_t)(g * (C0B_STAGE_BYTES >> 4));
 #pragma unroll
-            for (uint32_t k = 0; k < 8; ++k)
-                umma_issue<1>(tmem_base, ad + k * (2048 >> 4), bd + k * (2048 >> 4), idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
-            umma_commit_issue<1>(&empty[s], elected);
+            for (uint32_t e = 0; e < 4; ++e) {
+                const uint64_t ad = sd + (uint64_t)(e * (C0_TILE_BYTES >> 4));
+                const uint64_t bd = sd + (uint64_t)((4 + (e >> 1)) * (C0_TILE_BYTES >> 4) + (e & 1) * 4);
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k)            // 16 windows (rows) per MMA: 2048 bytes further
+                    umma_issue<1>(tmem_base, ad + k * (2048 >> 4), bd + k * (2048 >> 4), idesc, (i > 0 || e > 0 || k > 0) ? 1u : 0u, elected);
+            }
+            umma_commit_issue<1>(&empty[g], elected);
         }
         umma_commit_issue<1>(tmem_full, elected);
-    } else if (warp < 4 && nch > 0) {
+    } else if (warp < 2 && nt > 0) {
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
         const int co = warp * 32 + lane;
-        if (co < 64) {
 #pragma unroll
-            for (int k = 0; k < C0_K; ++k) atomicAdd(p.dw + co * C0_K + k, v[k]);
-        }
+        for (int k = 0; k < C0_K; ++k) atomicAdd(p.dw + co * C0_K + k, v[k]);
+        atomicAdd(p.db + co, v[27]);
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 8) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (warp == 12) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 }  // namespace tc
@@ -329,46 +385,41 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const 
     Conv0Params p{};
     p.x = x; p.B = B; p.IH = IH; p.IW = IW;
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
-    p.tiles_h = (2 * p.PH + 7) / 8; p.tiles_w = (2 * p.PW + 15) / 16;
+    p.tiles_h = (p.PH + C0_WH - 1) / C0_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;
     p.w = w; p.bias = bias; p.pooled = (bf16*)out; p.mask = mask;
-    const int smem = 64 * 128 + C0_STAGES * C0_TILE_BYTES + 1024 + 256;
+    const int smem = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
     const int ntiles = B * p.tiles_h * p.tiles_w;
     const int sms = sm_count();
-    conv0_fwd_tc_kernel<<<ntiles < 2 * sms ? ntiles : 2 * sms, C0_THREADS, smem, (cudaStream_t)stream>>>(p);
+    conv0_fwd_tc_kernel<<<ntiles < sms ? ntiles : sms, C0F_THREADS, smem, (cudaStream_t)stream>>>(p);
     VQA_CHECK_LAUNCH("conv0_fwd_tc");
     return 0;
 }
 
-// x [B,3,IH,IW] fp32 NCHW; dy [B,2PH,2PW,64] bf16 (vqa_unpool_bf16); dw [64,3,3,3] fp32 (overwritten)
-extern "C" int vqa_tc_conv0_bwd_weight(const float* x, const void* dy, float* dw, int B, int IH, int IW, int Cin, int Cout,
-                                       void* stream) {
-    VQA_REQUIRE(Cin == 3 && Cout == 64, "tc conv0 wgrad: only Cin=3, Cout=64 (got %d, %d)", Cin, Cout);
-    VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4, "tc conv0 wgrad: bad dims");
+// x [B,3,IH,IW] fp32 NCHW; dpool [B,PH,PW,64] bf16 = gradient w.r.t. the pooled output; mask [B,PH,PW,64] from the
+// forward; dw [64,3,3,3] and db [64] fp32 (both overwritten)
+extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_t* mask, float* dw, float* db,
+                                            int B, int IH, int IW, int Cin, int Cout, void* stream) {
+    VQA_REQUIRE(Cin == 3 && Cout == 64, "tc conv0 backward: only Cin=3, Cout=64 (got %d, %d)", Cin, Cout);
+    VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4, "tc conv0 backward: bad dims");
     cudaStream_t st = (cudaStream_t)stream;
     VQA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 64 * C0_K, st));
+    VQA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 64, st));
     Conv0Params p{};
     p.x = x; p.B = B; p.IH = IH; p.IW = IW;
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
-    p.tiles_h = (2 * p.PH + 7) / 8; p.tiles_w = (2 * p.PW + 15) / 16;
-    p.dw = dw;
-    CUtensorMap tdy;
-    {
-        const uint64_t dims[4] = {64, (uint64_t)(2 * p.PW), (uint64_t)(2 * p.PH), (uint64_t)B};
-        const uint64_t str[3] = {64 * 2, (uint64_t)(2 * p.PW) * 64 * 2, (uint64_t)(2 * p.PH) * (2 * p.PW) * 64 * 2};
-        const uint32_t box[4] = {64, 16, 8, 1};
-        if (int e = make_tmap_bf16(&tdy, dy, 4, dims, str, box)) return e;
-    }
+    p.tiles_h = (p.PH + C0_WH - 1) / C0_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;
+    p.dpool = (const bf16*)dpool; p.bmask = mask; p.dw = dw; p.db = db;
     const int total = B * p.tiles_h * p.tiles_w;
     const int sms = sm_count();
     int ctas = total < sms ? total : sms;
-    p.chunks_per_cta = (total + ctas - 1) / ctas;
-    ctas = (total + p.chunks_per_cta - 1) / p.chunks_per_cta;
-    const int smem = C0_STAGES * 2 * C0_TILE_BYTES + 1024 + 256;
+    p.tiles_per_cta = (total + ctas - 1) / ctas;
+    ctas = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    const int smem = 2 * C0B_STAGE_BYTES + 1024 + 256;
     static bool attr_set = false;
-    if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-    conv0_wgrad_tc_kernel<<<ctas, C0W_THREADS, smem, st>>>(tdy, p);
-    VQA_CHECK_LAUNCH("conv0_wgrad_tc");
+    if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    conv0_bwd_tc_kernel<<<ctas, C0B_THREADS, smem, st>>>(p);
+    VQA_CHECK_LAUNCH("conv0_bwd_tc");
     return 0;
 }

@@ -14,7 +14,7 @@ PROTOTYPES = {
     "vqa_unpool_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_bwd_weight": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv0_relu_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "vqa_tc_conv0_bwd_weight": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vqa_tc_conv0_bwd_weight_bias": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_pack_lstm_whh": [_vp, _vp, _i, _vp],
     "vqa_nhwc_to_nchw_pad_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

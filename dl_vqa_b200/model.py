@@ -583,13 +583,14 @@ class VqaNet(nn.Module):
             use_tc = self._tc_conv_ok(i) and nchw == 0
             dy = None
             tc0 = tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1
-            if use_tc or tc0:   # un-pooled gradient, shared by the weight and the data gradient
+            if tc0:     # fused un-pool + weight gradient + bias gradient straight from (dpool, mask): no dY tensor
+                call("vqa_tc_conv0_bwd_weight_bias", ptr(x), ptr(da), ptr(mask), ptr(dW), ptr(db), B, IH, IW, Cin, Cout, st,
+                     tag=f"conv{i}_wgrad")
+            elif use_tc:   # un-pooled gradient, shared by the weight and the data gradient
                 dy = empty(B, 2 * PH, 2 * PW, Cout)
                 call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
             if tc0:
-                call("vqa_tc_conv0_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st, tag=f"conv{i}_wgrad")
-                db.zero_()
-                call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
+                pass
             elif use_tc and Cin in (64, 128) and Cout % 128 == 0:
                 call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")

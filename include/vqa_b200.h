@@ -225,13 +225,17 @@ int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int
  * Cin in {64,128}, Cout % 128 == 0. */
 int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* dw,
                               int B, int IH, int IW, int Cin, int Cout, void* stream);
-/* first layer (Cin = 3, Cout = 64, 3x3, stride 1) on tcgen05 with the im2col tile built in shared memory by the
- * kernel itself from the NCHW fp32 network input (K = 27 is too small for a TMA pipeline).  out / mask as above;
- * wgrad: dy [B,2PH,2PW,64] bf16 from vqa_unpool_bf16, dw fp32 [64,3,3,3] overwritten. */
+/* first layer (Cin = 3, Cout = 64, 3x3, stride 1) on tcgen05, window-major: the im2col rows of every 2x2 pooling
+ * window are built in shared memory by the kernel itself from the NCHW fp32 network input (K = 27 is too small for a
+ * TMA pipeline), the four window elements accumulate side by side in TMEM and the max-pool is a per-thread max.
+ * out / mask as vqa_conv_relu_pool_fwd.
+ * backward: weight AND bias gradient straight from the pooled gradient dpool [B,PH,PW,64] bf16 and the forward's mask
+ * (the un-pooled gradient is expanded in shared memory only); dw fp32 [64,3,3,3] and db fp32 [64] are overwritten.
+ * Replaces the autograd of models/model.py:80-82 for layer 0 (cuDNN wgrad + max_pool2d backward + bias reduction). */
 int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias, void* out, uint8_t* mask,
                                int B, int IH, int IW, int Cin, int Cout, void* stream);
-int vqa_tc_conv0_bwd_weight(const float* x, const void* dy, float* dw, int B, int IH, int IW, int Cin, int Cout,
-                            void* stream);
+int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_t* mask, float* dw, float* db,
+                                 int B, int IH, int IW, int Cin, int Cout, void* stream);
 /* Persistent LSTM recurrence, all steps and directions in one cooperative launch (replaces the cuDNN RNN of
  * models/model.py:164).  W_hh stays resident in shared memory (64 gate rows per CTA), h is exchanged through L2.
  *   gx [dirs][T][B][4H] bf16 (in: x W_ih^T + b_ih + b_hh, out: activated gates), cs [dirs][T][B][H] fp32,

@@ -186,7 +186,7 @@ def test_layout_helpers():
     assert torch.equal(dyT[..., :2 * PW].float(), ref.permute(0, 3, 1, 2)) and float(dyT[..., 2 * PW:].float().abs().sum()) == 0
 
 
-@pytest.mark.parametrize("B,IH,IW", [(2, 38, 38), (3, 224, 224), (1, 19, 45)])
+@pytest.mark.parametrize("B,IH,IW", [(2, 38, 38), (3, 224, 224), (1, 19, 45), (150, 36, 70)])
 def test_tc_conv0_fwd_and_wgrad_match_torch(B, IH, IW):
     import torch.nn.functional as F
     from dl_vqa_b200 import lib
@@ -212,18 +212,24 @@ def test_tc_conv0_fwd_and_wgrad_match_torch(B, IH, IW):
     e = ((idx // OW) % 2) * 2 + ((idx % OW) % 2)
     agree = float(((mask.long() == e) | ~(want > 1e-3)).float().mean())
     assert agree > 0.999, agree
-    # weight gradient
+    # weight + bias gradient, fused with the un-pooling (no dY tensor)
     dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
-    dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
-    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
-    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
-    lib.call("vqa_tc_conv0_bwd_weight", lib.ptr(x), lib.ptr(dy), lib.ptr(dw), B, IH, IW, Cin, Cout, lib.stream())
+    dw = torch.full((Cout, Cin, 3, 3), 7.0, device="cuda")
+    db = torch.full((Cout,), 7.0, device="cuda")
+    lib.call("vqa_tc_conv0_bwd_weight_bias", lib.ptr(x), lib.ptr(dpool), lib.ptr(mask), lib.ptr(dw), lib.ptr(db),
+             B, IH, IW, Cin, Cout, lib.stream())
     torch.cuda.synchronize()
+    dy = torch.zeros(B, 2 * PH, 2 * PW, Cout, device="cuda")          # reference un-pool
+    for e in range(4):
+        dy[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
     full = torch.zeros(B, IH - 2, IW - 2, Cout, device="cuda")
-    full[:, :2 * PH, :2 * PW] = dy.float()
+    full[:, :2 * PH, :2 * PW] = dy
     wantw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (Cout, Cin, 3, 3), full.permute(0, 3, 1, 2))
     errw = float((dw - wantw).abs().max() / wantw.abs().max())
     assert errw < 2e-3, errw
+    wantb = dy.sum(dim=(0, 1, 2))
+    errb = float((db - wantb).abs().max() / wantb.abs().max())
+    assert errb < 2e-3, errb
 
 
 @pytest.mark.parametrize("R,N,K", [(256, 3000, 1024), (5888, 4096, 304), (1000, 64, 72), (4, 136, 40), (20000, 1024, 256)])
