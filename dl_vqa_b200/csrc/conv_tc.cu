@@ -432,37 +432,68 @@ extern "C" int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int C
 }
 
 // dy[b, 2ph+dy, 2pw+dx, c] = (mask[b,ph,pw,c] == dy*2+dx) ? dpool[b,ph,pw,c] : 0      (8 channels per thread)
-__global__ void unpool_bf16_kernel(const bf16* __restrict__ dpool, const uint8_t* __restrict__ mask, bf16* __restrict__ dy,
-                                   int64_t npos, int PH, int PW, int C) {
+// and, in the same pass over (dpool, mask), the bias gradient db[c] = sum over positions of dpool where the ReLU was
+// alive (mask < 4).  Grid-stride over positions with a fixed channel chunk per thread, one block reduction + C atomics.
+__global__ void __launch_bounds__(256)
+unpool_bf16_kernel(const bf16* __restrict__ dpool, const uint8_t* __restrict__ mask, bf16* __restrict__ dy,
+                   float* __restrict__ db, int64_t npos, int PH, int PW, int C) {
+    __shared__ float red[256][9];
     const int c8 = C >> 3;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npos * c8) return;
-    const int64_t pos = i / c8;
-    const int c0 = (int)(i - pos * c8) * 8;
-    const int pw = (int)(pos % PW);
-    const int64_t t = pos / PW;
-    const int ph = (int)(t % PH);
-    const int64_t b = t / PH;
-    const uint4 g = *reinterpret_cast<const uint4*>(dpool + pos * C + c0);
-    const uint2 m = *reinterpret_cast<const uint2*>(mask + pos * C + c0);
-    const uint16_t* gs = reinterpret_cast<const uint16_t*>(&g);
-    const uint8_t* ms = reinterpret_cast<const uint8_t*>(&m);
+    const int64_t total = npos * c8;
+    float acc[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        uint4 o;
-        uint16_t* os = reinterpret_cast<uint16_t*>(&o);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = i / c8;
+        const int c0 = (int)(i - pos * c8) * 8;
+        const int pw = (int)(pos % PW);
+        const int64_t t = pos / PW;
+        const int ph = (int)(t % PH);
+        const int64_t b = t / PH;
+        const uint4 g = __ldcs(reinterpret_cast<const uint4*>(dpool + pos * C + c0));
+        const uint2 m = __ldcs(reinterpret_cast<const uint2*>(mask + pos * C + c0));
+        const uint16_t* gs = reinterpret_cast<const uint16_t*>(&g);
+        const uint8_t* ms = reinterpret_cast<const uint8_t*>(&m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) os[j] = ms[j] == e ? gs[j] : (uint16_t)0;
-        const int64_t opos = ((b * 2 * PH + 2 * ph + (e >> 1)) * (2 * PW) + 2 * pw + (e & 1));
-        *reinterpret_cast<uint4*>(dy + opos * C + c0) = o;
+        for (int e = 0; e < 4; ++e) {
+            uint4 o;
+            uint16_t* os = reinterpret_cast<uint16_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) os[j] = ms[j] == e ? gs[j] : (uint16_t)0;
+            const int64_t opos = ((b * 2 * PH + 2 * ph + (e >> 1)) * (2 * PW) + 2 * pw + (e & 1));
+            __stcs(reinterpret_cast<uint4*>(dy + opos * C + c0), o);
+        }
+        if (db) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (ms[j] < 4) acc[j] += __uint_as_float((uint32_t)gs[j] << 16);
+        }
+    }
+    if (db) {
+        // threads with equal (threadIdx.x % c8) own the same 8 channels (blockDim and the grid stride are multiples of c8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+        __syncthreads();
+        if (threadIdx.x < C) {
+            const int chunk = threadIdx.x >> 3, j = threadIdx.x & 7;
+            float s = 0.f;
+            for (int t = chunk; t < 256; t += c8) s += red[t][j];
+            atomicAdd(db + threadIdx.x, s);
+        }
     }
 }
 
-extern "C" int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int PH, int PW, int C, void* stream) {
+extern "C" int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, float* db, int B, int PH, int PW, int C, void* stream) {
     VQA_REQUIRE(B > 0 && PH > 0 && PW > 0 && C % 8 == 0, "unpool: bad dims (C must be a multiple of 8)");
+    VQA_REQUIRE(db == nullptr || (C <= 256 && 256 % (C / 8) == 0), "unpool: the fused bias gradient needs C in {8,16,...,256} with 256 %% (C/8) == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (db) VQA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
     const int64_t npos = (int64_t)B * PH * PW;
-    unpool_bf16_kernel<<<(unsigned)ceil_div64(npos * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dpool, mask, (bf16*)dy, npos, PH, PW, C);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = ceil_div64(npos * (C / 8), 256);
+    const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    unpool_bf16_kernel<<<grid, 256, 0, st>>>((const bf16*)dpool, mask, (bf16*)dy, db, npos, PH, PW, C);
     VQA_CHECK_LAUNCH("unpool_bf16");
     return 0;
 }

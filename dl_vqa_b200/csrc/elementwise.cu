@@ -3,29 +3,76 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
-// image.drop + channel L2 norm (models/model.py:84, :56).  One warp per spatial row of C channels.
+// image.drop + channel L2 norm (models/model.py:84, :56).  One warp per spatial row of C channels; a lane owns
+// groups of 8 consecutive channels (128-bit loads / stores), the row stays in registers between the reduction
+// and the scaling pass, and both dropout sites use the 8-element vector flags of common.cuh (one hash per group).
 // ------------------------------------------------------------------------------------------
+namespace {
+constexpr int DN_MAXK = 4;            // up to 4 groups of 8 channels per lane: C <= 1024
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+}  // namespace
+
 template <typename T>
 __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn, T* __restrict__ vnd,
                                     float* __restrict__ nrm, int64_t R, int C, Dropout d_img, Dropout d_att) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
-    const T* xr = x + r * C;
+    const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
+    const int c8n = C >> 3;
+    float v[DN_MAXK][8];
     float ss = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        const float v = to_f32(xr[c]) * dropout_mult(d_img, SITE_IMAGE, (uint64_t)r * C + c);
-        ss += v * v;
+#pragma unroll
+    for (int k = 0; k < DN_MAXK; ++k) {
+        const int c8 = lane + 32 * k;
+        if (c8 < c8n) {
+            float m[8];
+            ld8(x + r * C + c8 * 8, v[k]);
+            dropout_mult8(di, (uint32_t)(r * c8n + c8), m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[k][i] *= m[i]; ss = fmaf(v[k][i], v[k][i], ss); }
+        }
     }
     ss = warp_sum(ss);
     const float n = sqrtf(ss);
     const float inv = 1.f / (n + 1e-12f);
     if (lane == 0) nrm[r] = n;
-    for (int c = lane; c < C; c += 32) {
-        const uint64_t idx = (uint64_t)r * C + c;
-        const float y = to_f32(xr[c]) * dropout_mult(d_img, SITE_IMAGE, idx) * inv;
-        vn[idx] = from_f32<T>(y);
-        if (vnd) vnd[idx] = from_f32<T>(y * dropout_mult(d_att, SITE_ATT_V, idx));
+#pragma unroll
+    for (int k = 0; k < DN_MAXK; ++k) {
+        const int c8 = lane + 32 * k;
+        if (c8 < c8n) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[k][i] *= inv;
+            st8(vn + r * C + c8 * 8, v[k]);
+            if (vnd) {
+                float m[8];
+                dropout_mult8(da, (uint32_t)(r * c8n + c8), m);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] *= m[i];
+                st8(vnd + r * C + c8 * 8, v[k]);
+            }
+        }
     }
 }
 
@@ -36,29 +83,54 @@ __global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restri
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
+    const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
+    const int c8n = C >> 3;
+    float dy[DN_MAXK][8], y[DN_MAXK][8];
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        const uint64_t idx = (uint64_t)r * C + c;
-        float dy = dvn ? to_f32(dvn[idx]) : 0.f;
-        if (dvnd) dy += to_f32(dvnd[idx]) * dropout_mult(d_att, SITE_ATT_V, idx);
-        s += dy * to_f32(vn[idx]);
+#pragma unroll
+    for (int k = 0; k < DN_MAXK; ++k) {
+        const int c8 = lane + 32 * k;
+        if (c8 < c8n) {
+            const int64_t off = r * C + c8 * 8;
+            if (dvn) ld8(dvn + off, dy[k]);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dy[k][i] = 0.f;
+            }
+            if (dvnd) {
+                float t[8], m[8];
+                ld8(dvnd + off, t);
+                dropout_mult8(da, (uint32_t)(r * c8n + c8), m);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dy[k][i] = fmaf(t[i], m[i], dy[k][i]);
+            }
+            ld8(vn + off, y[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(dy[k][i], y[k][i], s);
+        }
     }
     s = warp_sum(s);
     const float n = nrm[r];
     const float inv = 1.f / (n + 1e-12f);
-    const float k = n > 0.f ? s / n : 0.f;
-    for (int c = lane; c < C; c += 32) {
-        const uint64_t idx = (uint64_t)r * C + c;
-        float dy = dvn ? to_f32(dvn[idx]) : 0.f;
-        if (dvnd) dy += to_f32(dvnd[idx]) * dropout_mult(d_att, SITE_ATT_V, idx);
-        const float g = inv * dy - k * to_f32(vn[idx]);
-        dx[idx] = from_f32<T>(g * dropout_mult(d_img, SITE_IMAGE, idx));
+    const float kk = n > 0.f ? s / n : 0.f;
+#pragma unroll
+    for (int k = 0; k < DN_MAXK; ++k) {
+        const int c8 = lane + 32 * k;
+        if (c8 < c8n) {
+            float m[8], g[8];
+            dropout_mult8(di, (uint32_t)(r * c8n + c8), m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = (inv * dy[k][i] - kk * y[k][i]) * m[i];
+            st8(dx + r * C + c8 * 8, g);
+        }
     }
 }
 
 extern "C" int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, int act_dtype, int64_t R, int C,
                                 float p_img, float p_att, uint64_t seed, void* stream) {
     VQA_REQUIRE(R > 0 && C > 0 && x && vn && nrm, "dropnorm_fwd: bad arguments");
+    VQA_REQUIRE(C % 8 == 0 && C <= 256 * DN_MAXK, "dropnorm_fwd: channel count %d must be a multiple of 8 and <= %d", C, 256 * DN_MAXK);
+    VQA_REQUIRE(R * (C / 8) < (1ll << 32), "dropnorm_fwd: tensor too large for the 32-bit dropout counter");
     const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
     const int wpb = 8;
     const unsigned grid = (unsigned)ceil_div64(R, wpb);
@@ -74,6 +146,7 @@ extern "C" int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, 
 extern "C" int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* vn, const float* nrm, void* dx,
                                 int act_dtype, int64_t R, int C, float p_img, float p_att, uint64_t seed, void* stream) {
     VQA_REQUIRE(R > 0 && C > 0 && vn && nrm && dx && (dvn || dvnd), "dropnorm_bwd: bad arguments");
+    VQA_REQUIRE(C % 8 == 0 && C <= 256 * DN_MAXK, "dropnorm_bwd: channel count %d must be a multiple of 8 and <= %d", C, 256 * DN_MAXK);
     const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
     const int wpb = 8;
     const unsigned grid = (unsigned)ceil_div64(R, wpb);

@@ -282,7 +282,15 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     VQA_REQUIRE(!(flags & VQA_GEMM_ACCUMULATE), "tc_gemm: ACCUMULATE is not supported (use SPLITK into a zeroed buffer)");
     cudaStream_t st = (cudaStream_t)stream;
 
-    const int BN = N <= 64 ? 64 : 128;
+    // 128-wide tiles unless that leaves most SMs idle (e.g. the per-step LSTM data gradient: M = 256): then 64-wide
+    int BN = N <= 64 ? 64 : 128;
+    if (BN == 128 && !splitk) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t tiles128 = (int64_t)((M + BM - 1) / BM) * ((N + 127) / 128) * nbatch;
+        if (tiles128 * 2 <= sms) BN = 64;
+    }
     CUtensorMap ta, tb;
     if (!mn) {
         const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)nbatch};

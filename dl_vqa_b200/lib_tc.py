@@ -11,7 +11,7 @@ PROTOTYPES = {
     "vqa_tc_conv3x3_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv_set_cta_group": [_i],
     "vqa_pack_conv3x3_weight": [_vp, _vp, _vp, _i, _i, _vp],
-    "vqa_unpool_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_unpool_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_bwd_weight": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv0_relu_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv0_bwd_weight_bias": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -588,14 +588,17 @@ class VqaNet(nn.Module):
                      tag=f"conv{i}_wgrad")
             elif use_tc:   # un-pooled gradient, shared by the weight and the data gradient
                 dy = empty(B, 2 * PH, 2 * PW, Cout)
-                call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), B, PH, PW, Cout, st, tag="unpool")
+                fused_db = use_tc and Cin in (64, 128) and Cout % 128 == 0 and Cout <= 256
+                call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), ptr(db) if fused_db else None, B, PH, PW, Cout, st,
+                     tag="unpool")
             if tc0:
                 pass
             elif use_tc and Cin in (64, 128) and Cout % 128 == 0:
                 call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
-                db.zero_()
-                call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
+                if not fused_db:
+                    db.zero_()
+                    call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
             else:
                 call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
                      B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_wgrad")

@@ -217,8 +217,9 @@ int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
 int vqa_tc_conv_set_cta_group(int cta_group);
 /* w fp32 OIHW [Cout,Cin,3,3] -> wp[co][tap][ci] and/or wd[ci][tap][co] (bf16; either may be NULL) */
 int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream);
-/* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0) */
-int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, int B, int PH, int PW, int C, void* stream);
+/* dy[b,2ph+dy,2pw+dx,c] = mask[b,ph,pw,c] == dy*2+dx ? dpool[b,ph,pw,c] : 0  (bf16, C % 8 == 0); when db != NULL
+ * the same pass also produces the conv bias gradient db[c] = sum of dpool over positions with mask < 4 (overwritten) */
+int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy, float* db, int B, int PH, int PW, int C, void* stream);
 
 /* weight gradient of the 3x3 conv on tcgen05, straight from the NHWC tensors (MN-major UMMA operands):
  * x [B,IH,IW,Cin] bf16 (layer input), dy [B,2PH,2PW,Cout] bf16 (vqa_unpool_bf16).  dw fp32 OIHW, overwritten.

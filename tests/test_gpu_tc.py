@@ -124,13 +124,19 @@ def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout, conv_cta_group):
     dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
     mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
     dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
-    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
+    fused_db = 256 % (Cout // 8) == 0
+    db = torch.full((Cout,), 5.0, device="cuda")
+    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), lib.ptr(db) if fused_db else None,
+             B, PH, PW, Cout, lib.stream())
     # reference un-pool
     ref = torch.zeros(B, 2 * PH, 2 * PW, Cout, device="cuda")
     for e in range(4):
         ref[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, dpool.float(), torch.zeros_like(dpool.float()))
     torch.cuda.synchronize()
     assert torch.equal(dy.float(), ref)
+    if fused_db:                                     # fused conv-bias gradient
+        want_db = ref.sum(dim=(0, 1, 2))
+        assert float((db - want_db).abs().max()) < 1e-3 * float(want_db.abs().max() + 1)
     wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device="cuda")
     lib.call("vqa_pack_conv3x3_weight", lib.ptr(w), None, lib.ptr(wd), Cout, Cin, lib.stream())
     dx = torch.empty(B, IH, IW, Cin, dtype=torch.bfloat16, device="cuda")
@@ -154,7 +160,7 @@ def test_tc_conv_wgrad_matches_torch(B, IH, IW, Cin, Cout):
     dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
     mask = torch.randint(0, 5, (B, PH, PW, Cout), device="cuda", dtype=torch.uint8)
     dy = torch.empty(B, 2 * PH, 2 * PW, Cout, dtype=torch.bfloat16, device="cuda")
-    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), B, PH, PW, Cout, lib.stream())
+    lib.call("vqa_unpool_bf16", lib.ptr(dpool), lib.ptr(mask), lib.ptr(dy), None, B, PH, PW, Cout, lib.stream())
     dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
     lib.call("vqa_tc_conv3x3_bwd_weight", lib.ptr(x), lib.ptr(dy), lib.ptr(dw), B, IH, IW, Cin, Cout, lib.stream())
     torch.cuda.synchronize()
