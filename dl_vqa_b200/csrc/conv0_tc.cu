@@ -55,13 +55,12 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Builds the four im2col rows of window (ph,pw) of image b (coordinates clamped so that out-of-range tile windows read
-// valid memory; their results are discarded / multiplied by zero) into `tiles` = two 16 KB tiles, row m.
-__device__ __forceinline__ void build_patch_rows(const Conv0Params& p, uint8_t* tiles, int m, int b, int ph, int pw) {
+// The 4x4x3 input patch of window (ph,pw) of image b, straight from global memory (coordinates clamped so that
+// out-of-range tile windows read valid memory; their results are discarded / multiplied by zero).
+__device__ __forceinline__ void load_patch_global(const Conv0Params& p, int b, int ph, int pw, float (&v)[3][4][4]) {
     const int phc = min(ph, p.PH - 1), pwc = min(pw, p.PW - 1);
     const float* src = p.x + ((int64_t)b * 3 * p.IH + 2 * phc) * p.IW + 2 * pwc;
     const bool al8 = (p.IW & 1) == 0;                 // even row pitch: every (row, 2*pw) address is 8-byte aligned
-    float v[3][4][4];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -75,6 +74,24 @@ __device__ __forceinline__ void build_patch_rows(const Conv0Params& p, uint8_t* 
                 for (int c = 0; c < 4; ++c) v[ci][r][c] = __ldg(q + c);
             }
         }
+}
+// The same patch from the TMA-staged input region of the tile: fp32 [3][18 rows][36 cols], window (wr, wc) of the tile
+constexpr int C0_XROWS = 2 * C0_WH + 2, C0_XCOLS = 2 * C0_WW + 4;      // 18 x 36 (34 used; 36 keeps rows 16-byte multiples)
+constexpr int C0_XBYTES = 3 * C0_XROWS * C0_XCOLS * 4;                 // 7776
+constexpr int C0_XSTAGE = 8192;
+__device__ __forceinline__ void load_patch_staged(const uint8_t* xs, int wr, int wc, float (&v)[3][4][4]) {
+    const float* base = reinterpret_cast<const float*>(xs) + (2 * wr) * C0_XCOLS + 2 * wc;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float2* q = reinterpret_cast<const float2*>(base + (ci * C0_XROWS + r) * C0_XCOLS);
+            const float2 a = q[0], c = q[1];
+            v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+        }
+}
+// Writes the four im2col rows of a window into `tiles` = two 16 KB tiles, row m.
+__device__ __forceinline__ void store_patch_rows(uint8_t* tiles, int m, const float (&v)[3][4][4]) {
     const int sw = m & 7;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -99,23 +116,30 @@ __device__ __forceinline__ void build_patch_rows(const Conv0Params& p, uint8_t* 
         }
     }
 }
-
 // ------------------------------------------------------------------------------------------ forward
-// warps 0-7 epilogue (TMEM lane quarter = w & 3, channel half = w >> 2), warps 8-15 two builder groups, warp 16 MMA
-constexpr int C0F_THREADS = 17 * 32;
+// warps 0-7 epilogue (TMEM lane quarter = w & 3, channel half = w >> 2), warps 8-15 two builder groups, warp 16 MMA,
+// warp 17 TMA producer.  STAGED (image row pitch a multiple of 16 bytes): the producer streams each tile's fp32 input
+// region [3][18][36] through a 6-deep shared-memory ring with TMA (zero fill outside the image), so the builders issue
+// no global loads at all -- with direct loads they stall on the load/store-unit queue (48 scattered loads per window).
+constexpr int C0F_THREADS = 18 * 32;
+constexpr int C0F_XSTAGES = 6;
 constexpr int C0F_STAGES = 4;                      // two per builder group
 constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 
-__global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Params p) {
+template <bool STAGED>
+__global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
     uint8_t* sa = smem + 64 * 128;                             // C0F_STAGES x 32 KB
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(sa + C0F_STAGES * C0F_STAGE_BYTES);
+    uint8_t* xs = sa + C0F_STAGES * C0F_STAGE_BYTES;           // C0F_XSTAGES x 8 KB staged input regions
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(xs + C0F_XSTAGES * C0_XSTAGE);
     uint64_t* a_empty = a_full + C0F_STAGES;
     uint64_t* tmem_full = a_empty + C0F_STAGES;               // [2]
     uint64_t* tmem_empty = tmem_full + 2;                      // [2]
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* x_full = tmem_empty + 2;                         // [C0F_XSTAGES]
+    uint64_t* x_empty = x_full + C0F_XSTAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + C0F_XSTAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -124,6 +148,8 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Param
     if (threadIdx.x == 0) {
         for (int i = 0; i < C0F_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        for (int i = 0; i < C0F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
+        if (STAGED) tma_prefetch_desc(&tma_x);
         fence_barrier_init();
     }
     if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
@@ -146,7 +172,20 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Param
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    if (warp >= 8 && warp < 16) {
+    if (warp == 17) {
+        // ---- TMA producer of the staged input regions (one thread), tiles in consumption order
+        if (STAGED && lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+                const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
+                const int q = it % C0F_XSTAGES;
+                mbar_wait(&x_empty[q], ((it / C0F_XSTAGES) & 1) ^ 1);
+                mbar_expect_tx(&x_full[q], C0_XBYTES);
+                tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * pw0, 2 * ph0, 0, b);
+            }
+        }
+    } else if (warp >= 8 && warp < 16) {
         // ---- builders: group g builds tiles g, g+2, ... of this CTA; thread -> window of the tile
         const int g = (warp - 8) >> 2, t = (threadIdx.x - 256) & 127;
         const int wr = t >> 4, wc = t & 15;
@@ -155,8 +194,17 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Param
             const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
             const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
             const int s = it % C0F_STAGES;
+            float v[3][4][4];
+            if (STAGED) {
+                const int q = it % C0F_XSTAGES;
+                mbar_wait(&x_full[q], (it / C0F_XSTAGES) & 1);
+                load_patch_staged(xs + q * C0_XSTAGE, wr, wc, v);
+                mbar_arrive(&x_empty[q]);                      // the values are in registers: the region can be refilled
+            } else {
+                load_patch_global(p, b, ph0 + wr, pw0 + wc, v);
+            }
             mbar_wait(&a_empty[s], ((it / C0F_STAGES) & 1) ^ 1);
-            build_patch_rows(p, sa + s * C0F_STAGE_BYTES, t, b, ph0 + wr, pw0 + wc);
+            store_patch_rows(sa + s * C0F_STAGE_BYTES, t, v);
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
         }
@@ -243,17 +291,23 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(Conv0Param
 }
 
 // ------------------------------------------------------------------------------------------ backward (weight + bias)
-// warps 0-3 final epilogue, warps 4-11 two builder groups (group g owns stage g), warp 12 MMA
-constexpr int C0B_THREADS = 13 * 32;
+// warps 0-3 final epilogue, warps 4-11 two builder groups (group g owns stage g), warp 12 MMA, warp 13 TMA producer of
+// the staged input regions (STAGED, as in the forward)
+constexpr int C0B_THREADS = 14 * 32;
 constexpr int C0B_STAGE_BYTES = 6 * C0_TILE_BYTES;            // 4 masked-gradient tiles (A) + 2 patch tiles (B)
+constexpr int C0B_XSTAGES = 3;
 
-__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(Conv0Params p) {
+template <bool STAGED>
+__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * C0B_STAGE_BYTES);
+    uint8_t* xs = smem + 2 * C0B_STAGE_BYTES;                  // C0B_XSTAGES x 8 KB staged input regions
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs + C0B_XSTAGES * C0_XSTAGE);
     uint64_t* empty = full + 2;
     uint64_t* tmem_full = empty + 2;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* x_full = tmem_full + 1;                          // [C0B_XSTAGES]
+    uint64_t* x_empty = x_full + C0B_XSTAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + C0B_XSTAGES);
     constexpr uint32_t TMEM_COLS = 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,6 +320,8 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(Conv0Param
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
+        for (int i = 0; i < C0B_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
+        if (STAGED) tma_prefetch_desc(&tma_x);
         fence_barrier_init();
     }
     if (warp == 12) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -274,7 +330,18 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(Conv0Param
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp == 13) {
+        if (STAGED && lane == 0) {
+            for (int i = 0; i < nt; ++i) {
+                const int tile = t_begin + i;
+                const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+                const int q = i % C0B_XSTAGES;
+                mbar_wait(&x_empty[q], ((i / C0B_XSTAGES) & 1) ^ 1);
+                mbar_expect_tx(&x_full[q], C0_XBYTES);
+                tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * (r % p.tiles_w) * C0_WW, 2 * (r / p.tiles_w) * C0_WH, 0, b);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
         const int g = (warp - 4) >> 2, t = (threadIdx.x - 128) & 127;
         const int wr = t >> 4, wc = t & 15, sw = t & 7;
         uint8_t* stage = smem + g * C0B_STAGE_BYTES;
@@ -324,7 +391,17 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(Conv0Param
                     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o;
                 }
             }
-            build_patch_rows(p, stage + 4 * C0_TILE_BYTES, t, b, ph, pw);
+            // the patch rows last: (d, mk) are dead by now, so the 48 patch values do not add to the register peak
+            float v[3][4][4];
+            if (STAGED) {
+                const int q = i % C0B_XSTAGES;
+                mbar_wait(&x_full[q], (i / C0B_XSTAGES) & 1);
+                load_patch_staged(xs + q * C0_XSTAGE, wr, wc, v);
+                mbar_arrive(&x_empty[q]);
+            } else {
+                load_patch_global(p, b, ph, pw, v);
+            }
+            store_patch_rows(stage + 4 * C0_TILE_BYTES, t, v);
             fence_proxy_async();
             mbar_arrive(&full[g]);
         }
@@ -387,12 +464,25 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const 
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
     p.tiles_h = (p.PH + C0_WH - 1) / C0_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;
     p.w = w; p.bias = bias; p.pooled = (bf16*)out; p.mask = mask;
-    const int smem = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    const int smem = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 1024 + 512;
     const int ntiles = B * p.tiles_h * p.tiles_w;
     const int sms = sm_count();
-    conv0_fwd_tc_kernel<<<ntiles < sms ? ntiles : sms, C0F_THREADS, smem, (cudaStream_t)stream>>>(p);
+    const int grid = ntiles < sms ? ntiles : sms;
+    const bool staged = (IW % 4) == 0 && ((uintptr_t)x & 15) == 0;     // TMA needs 16-byte aligned rows
+    CUtensorMap tx{};
+    if (staged) {
+        const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)IW * 4, (uint64_t)IH * IW * 4, (uint64_t)3 * IH * IW * 4};
+        const uint32_t box[4] = {C0_XCOLS, C0_XROWS, 3, 1};
+        if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
+        static bool attr_set = false;
+        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+        conv0_fwd_tc_kernel<true><<<grid, C0F_THREADS, smem, (cudaStream_t)stream>>>(tx, p);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+        conv0_fwd_tc_kernel<false><<<grid, C0F_THREADS, smem, (cudaStream_t)stream>>>(tx, p);
+    }
     VQA_CHECK_LAUNCH("conv0_fwd_tc");
     return 0;
 }
@@ -416,10 +506,22 @@ extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, c
     int ctas = total < sms ? total : sms;
     p.tiles_per_cta = (total + ctas - 1) / ctas;
     ctas = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    const int smem = 2 * C0B_STAGE_BYTES + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-    conv0_bwd_tc_kernel<<<ctas, C0B_THREADS, smem, st>>>(p);
+    const int smem = 2 * C0B_STAGE_BYTES + C0B_XSTAGES * C0_XSTAGE + 1024 + 256;
+    const bool staged = (IW % 4) == 0 && ((uintptr_t)x & 15) == 0;     // TMA needs 16-byte aligned rows
+    CUtensorMap tx{};
+    if (staged) {
+        const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)IW * 4, (uint64_t)IH * IW * 4, (uint64_t)3 * IH * IW * 4};
+        const uint32_t box[4] = {C0_XCOLS, C0_XROWS, 3, 1};
+        if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
+        static bool attr_set = false;
+        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+        conv0_bwd_tc_kernel<true><<<ctas, C0B_THREADS, smem, st>>>(tx, p);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+        conv0_bwd_tc_kernel<false><<<ctas, C0B_THREADS, smem, st>>>(tx, p);
+    }
     VQA_CHECK_LAUNCH("conv0_bwd_tc");
     return 0;
 }

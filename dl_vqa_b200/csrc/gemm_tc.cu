@@ -46,6 +46,23 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return 0;
 }
 
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle, const void* base, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    VQA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    VQA_REQUIRE(((uintptr_t)base & 15) == 0, "TMA: base pointer %p is not 16-byte aligned", base);
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        VQA_REQUIRE((gstr[i] & 15) == 0, "TMA: stride %llu of dim %d is not a multiple of 16 bytes", (unsigned long long)gstr[i], i + 1);
+    }
+    CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int BM = 128, BK = 64, GEMM_THREADS = 192;
 

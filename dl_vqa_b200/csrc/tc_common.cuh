@@ -242,5 +242,8 @@ PFN_encodeTiled get_encode_tiled();
 // Returns 0 or an error code (message set).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides = nullptr);
+// general form: any element type / swizzle mode (box inner extent in bytes must be a multiple of 16)
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle, const void* base, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace tc
