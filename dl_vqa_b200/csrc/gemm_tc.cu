@@ -83,6 +83,67 @@ struct GemmSmem {
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one accumulator row chunk: v[0..31] = columns nb..nb+31 of output row m (batch `batch`): bias / ReLU /
+// dropout / conversion / store (or fp32 atomics for split-K).
+__device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (&v)[32], int batch, int m, int nb, int N,
+                                                 const float* bias, const float* bias2, uint32_t dkey) {
+    if (ep.atomic) {
+        float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = nb + j;
+        float x = v[j];
+        if (n < N) {
+            if (bias) x += bias[n];
+            if (bias2) x += bias2[n];
+        }
+        if (ep.relu) x = fmaxf(x, 0.f);
+        v[j] = x;
+    }
+    if (ep.use_dropout) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            // element index m*N + n; pairs may straddle an odd boundary, so take single multipliers
+            const uint64_t idx = (uint64_t)m * N + nb + j;
+            if ((idx & 1) == 0) {
+                float a, b; dropout_mult2(ep.drop, dkey, idx, a, b); v[j] *= a; v[j + 1] *= b;
+            } else {
+                v[j] *= dropout_mult(ep.drop, ep.site, idx); v[j + 1] *= dropout_mult(ep.drop, ep.site, idx + 1);
+            }
+        }
+    }
+    const bool full_chunk = nb + 32 <= N;
+    if (ep.out_bf16) {
+        bf16* o = (bf16*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = v[j];
+        }
+    }
+}
+
 // MN = false: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
 // MN = true : A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
 //             consumed without transposes; one TMA box per 64-wide column block per stage).
@@ -178,68 +239,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             if (m >= M) continue;
-            const int nb = n0 + c0;
-            if (ep.atomic) {
-                float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
-                continue;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                float x = v[j];
-                if (n < N) {
-                    if (bias) x += bias[n];
-                    if (bias2) x += bias2[n];
-                }
-                if (ep.relu) x = fmaxf(x, 0.f);
-                v[j] = x;
-            }
-            if (ep.use_dropout) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    // element index m*N + n; pairs may straddle an odd boundary, so take single multipliers
-                    const uint64_t idx = (uint64_t)m * N + nb + j;
-                    if ((idx & 1) == 0) {
-                        float a, b; dropout_mult2(ep.drop, dkey, idx, a, b); v[j] *= a; v[j + 1] *= b;
-                    } else {
-                        v[j] *= dropout_mult(ep.drop, ep.site, idx); v[j + 1] *= dropout_mult(ep.drop, ep.site, idx + 1);
-                    }
-                }
-            }
-            const bool full_chunk = nb + 32 <= N;
-            if (ep.out_bf16) {
-                bf16* o = (bf16*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
-                if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                        *reinterpret_cast<uint4*>(o + j) = u;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = __float2bfloat16_rn(v[j]);
-                }
-            } else {
-                float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
-                if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = v[j];
-                }
-            }
+            gemm_store_chunk(ep, v, batch, m, n0 + c0, N, bias, bias2, dkey);
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+// ------------------------------------------------------------------------------------------ persistent variant
+// K-major operands, no split-K: grid = #SMs, output tiles round-robin (n fastest, so concurrently running CTAs share the
+// A rows in L2), one continuous TMA ring across tiles, two TMEM accumulators so that the epilogue of tile i (8 warps)
+// overlaps the MMAs of tile i+1.  Used when a GEMM has many tiles (attention.v_conv: 10816 tiles of 4 k-blocks, the
+// LSTM input projection): per-CTA setup, pipeline fill and the store-heavy epilogue then vanish from the critical path.
+constexpr int PGEMM_THREADS = 64 + 8 * 32;
+template <int BN>
+struct PGemmSmem {
+    static constexpr int STAGES = 6;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(PGEMM_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                          GemmEpilogue ep, int M, int N, int K, int nbatch) {
+    using S = PGemmSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + S::STAGES * S::A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* tmem_full = empty + S::STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
+    const int ntiles = mt * nt * nbatch;
+    const int nkb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, 2 * BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int batch = tile / (mt * nt), r = tile - batch * (mt * nt);
+                const int m0 = (r / nt) * BM, n0 = (r % nt) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % S::STAGES;
+                    mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+                    tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kb * BK, m0, batch);
+                    tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kb * BK, n0, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = idesc_bf16(BM, BN);
+        const uint32_t elected = elect_one();
+        const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa)), b_desc0 = smem_desc_k_sw128(smem_u32(sb));
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1, use = tcount >> 1;
+            mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);
+            tcgen05_fence_after();
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % S::STAGES;
+                mbar_wait(&full[s], (it / S::STAGES) & 1);
+                tcgen05_fence_after();
+                umma_issue_k64<1>(tmem_base + acc * BN, a_desc0 + (uint64_t)(s * (S::A_BYTES >> 4)),
+                                  b_desc0 + (uint64_t)(s * (S::B_BYTES >> 4)), idesc, kb > 0 ? 1u : 0u, elected);
+                umma_commit_issue<1>(&empty[s], elected);
+            }
+            umma_commit_issue<1>(&tmem_full[acc], elected);
+        }
+    } else {
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t dkey = ep.use_dropout ? dropout_key(ep.drop, ep.site) : 0;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1, use = tcount >> 1;
+            const int batch = tile / (mt * nt), r = tile - batch * (mt * nt);
+            const int m0 = (r / nt) * BM, n0 = (r % nt) * BN;
+            const int m = m0 + quarter * 32 + lane;
+            const float* bias = ep.bias ? ep.bias + (int64_t)batch * ep.bias_sb : nullptr;
+            const float* bias2 = ep.bias2 ? ep.bias2 + (int64_t)batch * ep.bias_sb : nullptr;
+            mbar_wait(&tmem_full[acc], use & 1);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                if (n0 + c0 >= N) break;                     // warp-uniform
+                float v[32];
+                tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (m < M) gemm_store_chunk(ep, v, batch, m, n0 + c0, N, bias, bias2, dkey);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+template <int BN>
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                                  int nbatch, int sms, cudaStream_t st) {
+    auto kern = gemm_tc_persistent_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PGemmSmem<BN>::BYTES));
+        attr_set = true;
+    }
+    kern<<<sms, PGEMM_THREADS, PGemmSmem<BN>::BYTES, st>>>(ta, tb, ep, M, N, K, nbatch);
+    VQA_CHECK_LAUNCH("gemm_tc_persistent");
+    return 0;
 }
 
 template <int BN, bool MN, int ST>
@@ -269,6 +398,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+    if (!MN && nsplit == 1 && !ep.atomic && total_kb > 0 && ctas >= 4 * (int64_t)sms)
+        return launch_gemm_persistent<BN>(ta, tb, ep, M, N, K, nbatch, sms, st);
     if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MN, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
     return launch_gemm_st<BN, MN, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
 }
