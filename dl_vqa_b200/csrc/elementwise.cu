@@ -275,6 +275,56 @@ __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const flo
     o[3 * H + j] = from_f32<T>(d_o * go * (1.f - go));
 }
 
+// bf16 tensor-core arm: 8 hidden units per thread, 128-bit accesses (the scalar kernel above is latency-bound: 2-byte
+// accesses to four gate planes)
+__global__ void __launch_bounds__(128)
+lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __restrict__ cs, const float* __restrict__ dh,
+                               float* __restrict__ dc, const bf16* __restrict__ dc_init, bf16* __restrict__ dg,
+                               const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+    const int h8 = H >> 3;
+    const int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over dirs*B*H/8
+    if (i8 >= (int64_t)dirs * B * h8) return;
+    const int j = (int)(i8 % h8) * 8;
+    const int b = (int)((i8 / h8) % B);
+    const int dir = (int)(i8 / ((int64_t)B * h8));
+    const int64_t i = ((int64_t)dir * B + b) * H + j;
+    const int64_t row = ((int64_t)dir * T_ + s) * B + b;
+    bf16* o = dg + row * 4 * H + j;
+    float dc_in[8];
+    if (dc_init) ld8(dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j, dc_in);
+    else ld8(dc + i, dc_in);
+    if (s >= (int)q_len[b]) {                     // frozen step: zero gate gradients, dc passes through unchanged
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o + g * H) = z;
+        st8(dc + i, dc_in);
+        return;
+    }
+    const bf16* g = gates + row * 4 * H + j;
+    float gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
+    ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go);
+    ld8(cs + row * H + j, c);
+    if (s > 0) ld8(cs + (row - B) * H + j, cp);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp[k] = 0.f;
+    }
+    ld8(dh + i, dhv);
+    float di[8], df[8], dgg[8], dox[8], dcn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float tc = tanhf(c[k]);
+        const float dcv = dc_in[k] + dhv[k] * go[k] * (1.f - tc * tc);
+        dcn[k] = dcv * gf[k];
+        di[k] = dcv * gg[k] * gi[k] * (1.f - gi[k]);
+        df[k] = dcv * cp[k] * gf[k] * (1.f - gf[k]);
+        dgg[k] = dcv * gi[k] * (1.f - gg[k] * gg[k]);
+        dox[k] = dhv[k] * tc * go[k] * (1.f - go[k]);
+    }
+    st8(dc + i, dcn);
+    st8(o, di); st8(o + H, df); st8(o + 2 * H, dgg); st8(o + 3 * H, dox);
+}
+
 extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float* dh, float* dc,
                                            const void* dc_init, void* dg, const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs,
                                            void* stream) {
@@ -283,6 +333,8 @@ extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, c
     const unsigned grid = (unsigned)ceil_div64(n, 256);
     if (act_dtype == VQA_F32)
         lstm_bwd_pointwise_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)gates, cs, dh, dc, (const float*)dc_init, (float*)dg, q_len, s, T, B, H, dirs);
+    else if (act_dtype == VQA_BF16 && H % 8 == 0)
+        lstm_bwd_pointwise_vec8_kernel<<<(unsigned)ceil_div64(n / 8, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
     else if (act_dtype == VQA_BF16)
         lstm_bwd_pointwise_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
     else VQA_REQUIRE(false, "lstm bwd pointwise: bad dtype");
