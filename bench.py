@@ -275,10 +275,10 @@ def run_ours(args):
             work[f"conv{i}_{k}"] = ("tensor", CONV_FLOP[i] * B)
     for k in ("v_conv", "v_conv_dgrad", "v_conv_wgrad"):
         work[k] = ("tensor", 2.0 * B * 676 * 256 * 1024)
-    # conv0 (K = 27): HBM-bound.  fwd reads the fp32 NCHW image and writes pooled bf16 + uint8 mask; wgrad reads the
-    # image and the un-pooled bf16 gradient
-    work["conv0_fwd"] = ("hbm", B * (3 * 224 * 224 * 4 + 110 * 110 * 64 * (esz + 1)))
-    work["conv0_wgrad"] = ("hbm", B * (3 * 224 * 224 * 4 + 220 * 220 * 64 * esz))
+    # conv0 (K = 27): HBM-bound.  fwd reads the fp32 NCHW image and writes pooled bf16 + uint8 mask [B,111,111,64]; the
+    # fused backward reads the image, the pooled gradient and the mask (the un-pooled gradient never exists)
+    work["conv0_fwd"] = ("hbm", B * (3 * 224 * 224 * 4 + 111 * 111 * 64 * (esz + 1)))
+    work["conv0_wgrad"] = ("hbm", B * (3 * 224 * 224 * 4 + 111 * 111 * 64 * (esz + 1)))
     work["vqa_attention_fwd"] = ("hbm", B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4))
     work["vqa_attention_bwd"] = ("hbm", B * ((2 * 676 * 1024 + 2 * 676 * 256 + 512) * esz + 2 * 1024 * 4 + 2 * 676 * 4 + 2 * 1024 * 4))
     roofline = None
