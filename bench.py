@@ -192,13 +192,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host = {"enqueue_ms": 0.0}
+
     def timed(fn, n):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         a.record()
         for _ in range(n):
             fn()
         b.record()
+        host["enqueue_ms"] = 1000.0 * (time.perf_counter() - t0)      # host time to enqueue the region (no sync inside)
         barrier()
         ms = a.elapsed_time(b)
         if world > 1:
@@ -220,6 +224,7 @@ def run_ours(args):
     clocks.start()
     n0 = lib.launch_count()
     ms_dev = timed(lambda: step(dbatch), args.steps)
+    host_ms_dev = host["enqueue_ms"] / args.steps
     launches = lib.launch_count() - n0
 
     if args.profile_mode:            # under ncu: no second timed region, no breakdown pass, no CPU leg
@@ -245,6 +250,7 @@ def run_ours(args):
 
     e2e_run(2)
     ms_e2e = timed(lambda: e2e_run(args.steps), 1)
+    host_ms_e2e = host["enqueue_ms"] / args.steps
     clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
 
     # ---- (3) per-kernel breakdown: a separate pass with CUDA events around every tagged C-ABI call (the events add
@@ -327,6 +333,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "host_enqueue_ms_per_step": {"device_resident": host_ms_dev, "e2e": host_ms_e2e},
             "clocks": clk, "roofline": roofline, "attention_roofline": att_roof,
             "step_tensor_frac": (STEP_FLOP_PER_SAMPLE * B / (per_step / 1000.0) / 1e12) / peaks["tflops"],
             "roofline_frac_by_kernel": per_kernel_frac, "kernels": breakdown, "cpu_baseline": cpu}

@@ -17,17 +17,36 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}
 
+    _RING = 4
+
     def _table(self, gi, tensors_key, lists):
-        """Device-resident pointer tables, rebuilt only when a pointer changes."""
+        """Device-resident pointer tables, rebuilt only when a pointer changes (gradient tensors usually do change
+        from step to step).  The upload goes through a small ring of PINNED host buffers with non-blocking copies:
+        a pageable `.to(device)` would block the host until the stream drains, i.e. synchronise host and GPU once
+        per step and expose the launch latency of every following forward pass."""
         cached = self._tables.get(gi)
-        if cached is not None and cached[0] == tensors_key:
-            return cached[1]
+        if cached is not None and cached["key"] == tensors_key:
+            return cached["dev"][cached["slot"]]
         dev = lists["p"][0].device
-        host = torch.tensor([[t.data_ptr() for t in lists[k]] for k in ("p", "g", "m", "v")] +
-                            [[t.numel() for t in lists["p"]]], dtype=torch.int64)
-        table = host.to(dev)
-        self._tables[gi] = (tensors_key, table)
-        return table
+        n = len(lists["p"])
+        if cached is None or cached["n"] != n:
+            cached = {"n": n, "slot": -1, "key": None,
+                      "host": [torch.empty(5, n, dtype=torch.int64).pin_memory() for _ in range(self._RING)],
+                      "dev": [torch.empty(5, n, dtype=torch.int64, device=dev) for _ in range(self._RING)],
+                      "done": [None] * self._RING}
+            self._tables[gi] = cached
+        slot = (cached["slot"] + 1) % self._RING
+        if cached["done"][slot] is not None:
+            cached["done"][slot].synchronize()          # the copy that last used this pinned buffer (4 steps ago)
+        host = cached["host"][slot]
+        host.copy_(torch.tensor([[t.data_ptr() for t in lists[k]] for k in ("p", "g", "m", "v")] +
+                                [[t.numel() for t in lists["p"]]], dtype=torch.int64))
+        cached["dev"][slot].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        cached["done"][slot] = ev
+        cached["slot"], cached["key"] = slot, tensors_key
+        return cached["dev"][slot]
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
