@@ -163,6 +163,7 @@ def run_ours(args):
     torch.manual_seed(1)
     model = D.VqaNet(cfg, synth.DEFAULT_TOKENS, compute_dtype=args.dtype).to(dev).train(True)
     opt = D.FusedAdam(model.parameters(), lr=5e-4)
+    model.use_gradient_arena(True)        # gradients live in persistent per-stage buckets (all-reduced in place for N > 1)
     ddp = GradientAllReduce(model)
     ddp.broadcast_parameters()
 
@@ -183,7 +184,7 @@ def run_ours(args):
         D.update_learning_rate(opt, state["it"], 5e-4)
         loss.backward()
         ddp.finish()
-        opt.step()
+        opt.step(grad_scale=ddp.grad_scale)
         state["it"] += 1
         return loss, score
 

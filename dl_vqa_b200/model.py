@@ -239,6 +239,7 @@ class VqaNet(nn.Module):
             self.set_compute_dtype(compute_dtype)
         self._seed_counter = 0
         self.grad_ready_hook = None      # callable(list[(name, grad)]) fired as each stage's grads complete
+        self._arena = None               # see use_gradient_arena()
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dt) -> "VqaNet":
@@ -253,6 +254,42 @@ class VqaNet(nn.Module):
 
     def _params(self) -> List[nn.Parameter]:
         return list(self.parameters())
+
+    # ------------------------------------------------------------------ gradient arena
+    STAGES = ("classifier", "attention", "text", "image")      # order in which _run_backward finishes them
+
+    def use_gradient_arena(self, enable: bool = True) -> "VqaNet":
+        """Write every parameter gradient into a persistent flat fp32 buffer per stage (classifier / attention /
+        text / image) instead of freshly allocated tensors.  `p.grad` then aliases the arena: gradient pointers are
+        stable from step to step (FusedAdam never re-uploads its pointer table) and a data-parallel wrapper can
+        all-reduce each stage's bucket IN PLACE (`dp.GradientAllReduce`) with no concatenate / scatter copies.
+        Contract: call `optimizer.zero_grad(set_to_none=True)` (or consume the gradients) before the next backward;
+        if a live `.grad` still aliases the arena, that backward falls back to fresh tensors so that autograd's
+        accumulation stays correct."""
+        self._arena = {} if enable else None
+        return self
+
+    def _arena_views(self, dev):
+        """{name: view} and {stage: flat bucket}, (re)built lazily for the current device / parameter shapes."""
+        a = self._arena
+        if a and a.get("dev") == dev:
+            return a
+        named = list(self.named_parameters())
+        buckets, views = {}, {}
+        for stage in self.STAGES:
+            mine = [(n, p) for n, p in named if n.startswith(stage + ".")]
+            flat = torch.zeros(sum(_rup(p.numel(), 4) for _, p in mine), dtype=torch.float32, device=dev)
+            off = 0
+            for n, p in mine:
+                views[n] = flat[off:off + p.numel()].view(p.shape)
+                off += _rup(p.numel(), 4)                      # keep every view 16-byte aligned
+            buckets[stage] = flat
+        self._arena = {"dev": dev, "views": views, "buckets": buckets}
+        return self._arena
+
+    def gradient_buckets(self):
+        """{stage: flat fp32 tensor} of the arena (None when the arena is off or not built yet)."""
+        return self._arena.get("buckets") if self._arena else None
 
     def _next_seed(self) -> int:
         # host-side only (CPU generator): respects torch.manual_seed, never synchronises the device
@@ -453,8 +490,28 @@ class VqaNet(nn.Module):
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook([(n, grads[n]) for n in names])
 
-        def colsum(src, src_dt, ld, rows, cols):
-            out = zeros(cols)
+        arena = None
+        if self._arena is not None:
+            arena = self._arena_views(dev)["views"]
+            owned = {b.untyped_storage().data_ptr() for b in self._arena["buckets"].values()}
+            for p_ in self.parameters():                 # a live .grad still aliasing the arena: accumulate safely
+                if p_.grad is not None and p_.grad.untyped_storage().data_ptr() in owned:
+                    arena = None
+                    break
+
+        def galloc(name, *shape, zero=False):
+            """fp32 gradient tensor of parameter `name`: a view of the stage arena, or a fresh tensor"""
+            if arena is not None:
+                t = arena[name]
+                assert tuple(t.shape) == tuple(shape) or t.numel() == int(torch.Size(shape).numel()), name
+                t = t.view(*shape)
+                if zero:
+                    t.zero_()
+                return t
+            return zeros(*shape) if zero else empty(*shape, dtype=f32)
+
+        def colsum(src, src_dt, ld, rows, cols, name):
+            out = galloc(name, cols, zero=True)
             call("vqa_colsum", ptr(src), src_dt, ld, None, ptr(out), rows, cols, st)
             return out
 
@@ -465,19 +522,19 @@ class VqaNet(nn.Module):
         # ---- classifier.lin2
         dh1d = empty(B, hid)
         mm.lin_bwd_data(ptr(dlogits), lib.F32, N, cl.lin2.weight, ptr(dh1d), dt, hid, B, N, hid, tag="lin2_dgrad")
-        dW2 = empty(N, hid, dtype=f32)
+        dW2 = galloc("classifier.lin2.weight", N, hid)
         mm.lin_bwd_weight(ptr(dlogits), lib.F32, N, ptr(h1d), dt, hid, dW2, B, N, hid, tag="lin2_wgrad")
         grads["classifier.lin2.weight"] = dW2
-        grads["classifier.lin2.bias"] = colsum(dlogits, lib.F32, N, B, N)
+        grads["classifier.lin2.bias"] = colsum(dlogits, lib.F32, N, B, N, "classifier.lin2.bias")
         # ---- classifier.lin1 (ReLU + drop2 folded: h1d > 0 <=> unit alive and kept)
         dz1 = empty(B, hid)
         call("vqa_relu_drop_bwd", ptr(dh1d), ptr(h1d), ptr(dz1), dt, B * hid, p_cls, st)
         dcomb = empty(B, KC)
         mm.lin_bwd_data(ptr(dz1), dt, hid, cl.lin1.weight, ptr(dcomb), dt, KC, B, hid, KC, tag="lin1_dgrad")
-        dW1 = empty(hid, KC, dtype=f32)
+        dW1 = galloc("classifier.lin1.weight", hid, KC)
         mm.lin_bwd_weight(ptr(dz1), dt, hid, ptr(combd), dt, KC, dW1, B, hid, KC, tag="lin1_wgrad")
         grads["classifier.lin1.weight"] = dW1
-        grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid)
+        grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid, "classifier.lin1.bias")
         fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"])
         if p_cls > 0:   # through classifier.drop1 (in place)
             call("vqa_dropout_apply", ptr(dcomb), KC, ptr(dcomb), KC, dt, B, KC, p_cls, seed, lib.SITE_CLS_IN, st)
@@ -493,21 +550,21 @@ class VqaNet(nn.Module):
         call("vqa_attention_bwd", ptr(dcomb), KC, ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(prob),
              ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op, B, P, A, Cimg, G,
              p_att, seed, st)
-        grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * A, B, G * A).view(G, A, 1, 1)
-        grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G)
+        grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * A, B, G * A, "attention.x_conv.weight").view(G, A, 1, 1)
+        grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G, "attention.x_conv.bias")
         # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)
         dvnd = empty(B * P, Cimg)
         mm.lin_bwd_data(ptr(dvp), dt, A, att.v_conv.weight, ptr(dvnd), dt, Cimg, B * P, A, Cimg, tag="v_conv_dgrad")
-        dWv = empty(A, Cimg, dtype=f32)
+        dWv = galloc("attention.v_conv.weight", A, Cimg)
         mm.lin_bwd_weight(ptr(dvp), dt, A, ptr(v_in), dt, Cimg, dWv, B * P, A, Cimg, tag="v_conv_wgrad")
         grads["attention.v_conv.weight"] = dWv.view(A, Cimg, 1, 1)
         # ---- attention.q_lin
         dqd = empty(B, QF)
         mm.lin_bwd_data(ptr(dqp), lib.F32, A, att.q_lin.weight, ptr(dqd), dt, QF, B, A, QF, tag="q_lin_dgrad")
-        dWq = empty(A, QF, dtype=f32)
+        dWq = galloc("attention.q_lin.weight", A, QF)
         mm.lin_bwd_weight(ptr(dqp), lib.F32, A, ptr(qd), dt, QF, dWq, B, A, QF, tag="q_lin_wgrad")
         grads["attention.q_lin.weight"] = dWq
-        grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A)
+        grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A, "attention.q_lin.bias")
         fire(["attention.v_conv.weight", "attention.q_lin.weight", "attention.q_lin.bias",
               "attention.x_conv.weight", "attention.x_conv.bias"])
         # gradient w.r.t. the question feature: concat branch + (dropped) q_lin branch
@@ -545,20 +602,25 @@ class VqaNet(nn.Module):
                          ptr(w_hh[0]), lib.F32, 1, H, ctx["whh_stride"], ptr(dh), lib.F32, H, B * H,
                          None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
         for d in range(dirs):
-            dWhh = empty(4 * H, H, dtype=f32)
+            dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
             mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(ctx["h_prev"][d]), dt, H, dWhh,
                               (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad")
-            dWih = empty(4 * H, E, dtype=f32)
+            dWih = galloc(f"text.lstm.weight_ih_l0{sfx[d]}", 4 * H, E)
             mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad")
-            db = colsum(dg[d], dt, 4 * H, T * B, 4 * H)
+            db = colsum(dg[d], dt, 4 * H, T * B, 4 * H, f"text.lstm.bias_ih_l0{sfx[d]}")
             grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
             grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
             grads[f"text.lstm.bias_ih_l0{sfx[d]}"] = db
-            grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db.clone() if self.grad_ready_hook is not None else db
+            if arena is not None:        # b_ih and b_hh always enter as a sum: identical gradients, separate storage
+                db2 = galloc(f"text.lstm.bias_hh_l0{sfx[d]}", 4 * H)
+                db2.copy_(db)
+            else:
+                db2 = db.clone() if self.grad_ready_hook is not None else db
+            grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db2
         dxs = empty(dirs, T, B, ldx)
         for d in range(dirs):
             mm.lin_bwd_data(ptr(dg[d]), dt, 4 * H, w_ih[d], ptr(dxs[d]), dt, ldx, T * B, 4 * H, E, tag="lstm_inproj_dgrad")
-        demb = zeros(*self.text.embedding.weight.shape)
+        demb = galloc("text.embedding.weight", *self.text.embedding.weight.shape, zero=True)
         call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
              p_text, seed, st)
         grads["text.embedding.weight"] = demb
@@ -578,8 +640,8 @@ class VqaNet(nn.Module):
             conv = getattr(self.image, f"conv{i}")
             x, x_dt, nchw, mask, IH, IW, Cin, Cout = ctx["conv_saved"][i]
             PH, PW = ((IH - self.KS) // self.stride + 1) // 2, ((IW - self.KS) // self.stride + 1) // 2
-            dW = empty(*conv.weight.shape, dtype=f32)
-            db = empty(Cout, dtype=f32)
+            dW = galloc(f"image.conv{i}.weight", *conv.weight.shape)
+            db = galloc(f"image.conv{i}.bias", Cout)
             use_tc = self._tc_conv_ok(i) and nchw == 0
             dy = None
             tc0 = tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1

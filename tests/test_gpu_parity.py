@@ -256,3 +256,51 @@ def test_cpu_tensors_are_rejected():
     m = D.VqaNet(cfg, 100)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64), torch.ones(1, 5, dtype=torch.long), torch.tensor([5]))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_gradient_arena_gives_identical_gradients_and_stays_safe(dtype):
+    """VqaNet.use_gradient_arena(): gradients written into persistent per-stage buckets must equal the freshly
+    allocated ones bit for bit, alias the buckets, keep stable addresses across steps, and a second backward
+    without zero_grad must still ACCUMULATE correctly (fallback to fresh tensors)."""
+    import dl_vqa_b200 as D
+    cfg = O.zero_dropout(O.cfg_with(O.DEFAULT_CFG, image_size=64))
+    V = 300
+    sd = O.random_params(cfg, V, seed=4, scale=1.5)
+    v, q, q_len, a_idx, a_val, a_len = O.synthetic_batch(5, cfg, V, seed=8, T=9)
+    data = (v, q, a_idx, a_val, a_len, None, q_len)
+
+    def grads_of(arena):
+        m = D.VqaNet(cfg, V, compute_dtype=dtype)
+        m.load_state_dict(sd)
+        m.cuda().train(True)
+        m.use_gradient_arena(arena)
+        loss, _ = D.run_batch(m, None, data, cfg["max_answers"])
+        loss.backward()
+        torch.cuda.synchronize()
+        return m, {k: p.grad for k, p in m.named_parameters()}
+
+    _, plain = grads_of(False)
+    m, ar = grads_of(True)
+    buckets = m.gradient_buckets()
+    assert set(buckets) == {"classifier", "attention", "text", "image"}
+    for k, g in ar.items():
+        # split-K weight gradients accumulate with fp32 atomics in a run-dependent order: compare with a tight tolerance
+        assert float((g - plain[k]).abs().max()) <= 1e-5 * float(plain[k].abs().max() + 1e-30), k
+        flat = buckets[k.split(".")[0]]
+        assert flat.data_ptr() <= g.data_ptr() < flat.data_ptr() + flat.numel() * 4, k
+    ptrs = {k: g.data_ptr() for k, g in ar.items()}
+    first = {k: g.clone() for k, g in ar.items()}
+    # next step after zero_grad(set_to_none=True): same addresses
+    for p in m.parameters():
+        p.grad = None
+    loss, _ = D.run_batch(m, None, data, cfg["max_answers"])
+    loss.backward()
+    assert {k: p.grad.data_ptr() for k, p in m.named_parameters()} == ptrs
+    # a further backward WITHOUT clearing the gradients accumulates (2x), it must not alias-add the arena to itself
+    loss, _ = D.run_batch(m, None, data, cfg["max_answers"])
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        ref = 2 * first[k]
+        assert float((p.grad - ref).abs().max()) <= 1e-4 * float(ref.abs().max() + 1e-30), k
