@@ -9,7 +9,11 @@
 // c/h update, variable-length masking, h_s written back (bf16) for the next step.
 // Between steps the 64 CTAs of a direction meet at a global-memory barrier (release: __threadfence + atomicAdd,
 // acquire: ld.acquire.gpu + fence.proxy.async before the next TMA reads h_s).  The two directions never wait
-// for each other.  Co-residency of all CTAs is guaranteed by cudaLaunchCooperativeKernel.
+// for each other.  Co-residency of all CTAs is guaranteed by the cooperative launch.
+// CS = 4: the CTAs run as clusters of four of the same direction.  Every CTA needs ALL of h_{s-1} each step, so
+// without sharing the 64 CTAs of a direction pull 64 x 512 KB through L2 per step (the kernel was L2-bandwidth-bound);
+// in a cluster each CTA fetches a quarter of every h tile and TMA-multicasts it to its three peers, a slot is
+// released to all four producers by a multicast tcgen05.commit.
 #include "tc_common.cuh"
 
 namespace tc {
@@ -34,6 +38,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     return v;
 }
 
+template <int CS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_constant__ CUtensorMap tma_w, LstmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -53,15 +58,18 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_h); tma_prefetch_desc(&tma_w);
-        for (int i = 0; i < LSTM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < LSTM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
         mbar_init(w_full, 1);
         mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, 128);
     tcgen05_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers exist before anything is multicast
     tcgen05_fence_after();
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
+    constexpr int SLICE_ROWS = 128 / CS;
     const uint32_t tmem_base = *tmem_base_smem;
 
     if (warp == 0) {
@@ -85,9 +93,13 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                     for (int kb = 0; kb < kblocks; ++kb, ++it) {
                         const int st = it % LSTM_STAGES;
                         const uint32_t ph = (it / LSTM_STAGES) & 1;
-                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_wait(&empty[st], ph ^ 1);            // all CS consumers have released the slot
                         mbar_expect_tx(&full[st], LSTM_A_BYTES);
-                        tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * B + mt * 128, dir);
+                        if (CS > 1)                               // my quarter of the tile, to every CTA of the cluster
+                            tma_load_3d_mcast(sa + st * LSTM_A_BYTES + crank * SLICE_ROWS * 128, &tma_h, &full[st], kb * 64,
+                                              s * B + mt * 128 + (int)crank * SLICE_ROWS, dir, CMASK);
+                        else
+                            tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * B + mt * 128, dir);
                     }
             }
         }
@@ -106,7 +118,8 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                     tcgen05_fence_after();
                     umma_issue_k64<1>(tmem_base + mt * 64, a_desc0 + (uint64_t)(st * (LSTM_A_BYTES >> 4)),
                                       b_desc0 + (uint64_t)(kb * (8192 >> 4)), idesc, kb > 0 ? 1u : 0u, elected);
-                    umma_commit_issue<1>(&empty[st], elected);
+                    if (CS > 1) umma_commit_mcast_issue(&empty[st], CMASK, elected);
+                    else umma_commit_issue<1>(&empty[st], elected);
                 }
                 umma_commit_issue<1>(&tmem_full[mt], elected);
             }
@@ -204,7 +217,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while peers may still signal its barriers
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
@@ -222,6 +235,10 @@ __global__ void pack_lstm_whh_kernel(const float* __restrict__ w, bf16* __restri
 
 using namespace tc;
 
+static int g_lstm_cluster_ok = -1;
+// 4 if the persistent LSTM runs as clusters of four with TMA multicast, 1 if the driver rejected that launch, 0 if unknown
+extern "C" int vqa_tc_lstm_cluster_size(void) { return g_lstm_cluster_ok < 0 ? 0 : (g_lstm_cluster_ok ? 4 : 1); }
+
 extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream) {
     VQA_REQUIRE(w_hh && wp && H > 0 && H % 16 == 0, "pack_lstm_whh: bad arguments");
     const int64_t n = (int64_t)4 * H * H;
@@ -232,7 +249,7 @@ extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* strea
 
 // gx [dirs][T][B][4H] bf16, cs [dirs][T][B][H] fp32, hs [dirs][T+1][B][H] bf16 (slot 0 must be zero),
 // qf [B][dirs*H] bf16, wp [dirs][4H][H] bf16 from vqa_pack_lstm_whh, sync: dirs zeroed uint32 counters.
-extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
+extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const void* wp, const int64_t* q_len,
                                unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
     VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm: bad dims");
     VQA_REQUIRE(H % 64 == 0 && H >= 64 && H <= 1024, "tc lstm: hidden size %d must be a multiple of 64 and <= 1024 (weights resident in shared memory)", H);
@@ -246,11 +263,14 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const vo
     VQA_REQUIRE(ctas_per_dir * dirs <= sms, "tc lstm: %d CTAs needed but only %d SMs", ctas_per_dir * dirs, sms);
     cudaStream_t st = (cudaStream_t)stream;
 
+    // clusters of 4 (TMA multicast of h) when the driver accepts a cooperative cluster launch; else single CTAs
+    int& cluster_ok = g_lstm_cluster_ok;           // -1 unknown, 0 rejected once, 1 works
+    const int cs = (cluster_ok != 0 && ctas_per_dir % 4 == 0) ? 4 : 1;
     CUtensorMap th, tw;
     {
         const uint64_t dims[3] = {(uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)dirs};
         const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)(T + 1) * B * H * 2};
-        const uint32_t box[3] = {64, 128, 1};
+        const uint32_t box[3] = {64, (uint32_t)(128 / cs), 1};
         if (int e = make_tmap_bf16(&th, hs, 3, dims, str, box)) return e;
     }
     {
@@ -260,19 +280,41 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const vo
         if (int e = make_tmap_bf16(&tw, wp, 3, dims, str, box)) return e;
     }
     LstmParams p{};
-    p.gx = (bf16*)gx; p.cs = cs; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
+    p.gx = (bf16*)gx; p.cs = cs_; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
     p.T = T; p.B = B; p.H = H; p.dirs = dirs; p.ctas_per_dir = ctas_per_dir; p.mtiles = (B + 127) / 128;
     const int smem = (H / 64) * 8192 + LSTM_STAGES * LSTM_A_BYTES + 1024 + 256;
-    static int attr_smem = 0;
-    if (attr_smem < smem) {
-        VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+    static int attr_smem1 = 0, attr_smem4 = 0;
+    if (attr_smem1 < smem) {
+        VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem1 = smem;
+    }
+    if (attr_smem4 < smem) {
+        VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem4 = smem;
     }
     VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * dirs, st));
-    void* args[] = {(void*)&th, (void*)&tw, (void*)&p};
     vqa_count_launch();
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_persistent_fwd_kernel, dim3(ctas_per_dir * dirs),
-                                                dim3(LSTM_THREADS), args, (size_t)smem, st);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ctas_per_dir * dirs); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 4; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    if (cs == 4) {
+        cfg.numAttrs = 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<4>, th, tw, p);
+        if (e == cudaSuccess) { cluster_ok = 1; return 0; }
+        (void)cudaGetLastError();
+        if (cluster_ok == 1) { vqa_set_error("lstm_persistent_fwd (clusters): %s", cudaGetErrorString(e)); return (int)e; }
+        cluster_ok = 0;                            // first attempt rejected: rebuild the h map with full-tile boxes, single CTAs
+        const uint64_t dims[3] = {(uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)dirs};
+        const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)(T + 1) * B * H * 2};
+        const uint32_t box[3] = {64, 128, 1};
+        if (int e2 = make_tmap_bf16(&th, hs, 3, dims, str, box)) return e2;
+    }
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<1>, th, tw, p);
     if (e != cudaSuccess) { vqa_set_error("lstm_persistent_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }

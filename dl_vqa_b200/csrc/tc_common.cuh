@@ -196,6 +196,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// TMA load multicast to the CTAs of `cta_mask` (same shared-memory offset and mbarrier offset in each of them)
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+// cta_group::1 commit whose mbarrier arrive is multicast to the CTAs of `cta_mask` (releases a slot that peers refill)
+__device__ __forceinline__ void umma_commit_mcast_issue(uint64_t* bar, uint16_t cta_mask, uint32_t elected) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n}"
+                 ::"r"(smem_u32(bar)), "r"(elected), "h"(cta_mask) : "memory");
+}
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // clears the CTA-pair peer bit: the address then names the leader CTA
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, bytes are counted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
