@@ -33,7 +33,7 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 }
 }  // namespace
 
-template <typename T>
+template <typename T, int NK>
 __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn, T* __restrict__ vnd,
                                     float* __restrict__ nrm, int64_t R, int C, Dropout d_img, Dropout d_att) {
     const int lane = threadIdx.x & 31;
@@ -41,10 +41,10 @@ __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn,
     if (r >= R) return;
     const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
     const int c8n = C >> 3;
-    float v[DN_MAXK][8];
+    float v[NK][8];
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < DN_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
         const int c8 = lane + 32 * k;
         if (c8 < c8n) {
             float m[8];
@@ -59,7 +59,7 @@ __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn,
     const float inv = 1.f / (n + 1e-12f);
     if (lane == 0) nrm[r] = n;
 #pragma unroll
-    for (int k = 0; k < DN_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
         const int c8 = lane + 32 * k;
         if (c8 < c8n) {
 #pragma unroll
@@ -76,7 +76,7 @@ __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn,
     }
 }
 
-template <typename T>
+template <typename T, int NK>
 __global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restrict__ dvnd, const T* __restrict__ vn,
                                     const float* __restrict__ nrm, T* __restrict__ dx, int64_t R, int C,
                                     Dropout d_img, Dropout d_att) {
@@ -85,10 +85,10 @@ __global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restri
     if (r >= R) return;
     const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
     const int c8n = C >> 3;
-    float dy[DN_MAXK][8], y[DN_MAXK][8];
+    float dy[NK][8], y[NK][8];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < DN_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
         const int c8 = lane + 32 * k;
         if (c8 < c8n) {
             const int64_t off = r * C + c8 * 8;
@@ -114,7 +114,7 @@ __global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restri
     const float inv = 1.f / (n + 1e-12f);
     const float kk = n > 0.f ? s / n : 0.f;
 #pragma unroll
-    for (int k = 0; k < DN_MAXK; ++k) {
+    for (int k = 0; k < NK; ++k) {
         const int c8 = lane + 32 * k;
         if (c8 < c8n) {
             float m[8], g[8];
@@ -134,11 +134,14 @@ extern "C" int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, 
     const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
     const int wpb = 8;
     const unsigned grid = (unsigned)ceil_div64(R, wpb);
-    if (act_dtype == VQA_F32)
-        dropnorm_fwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
-    else if (act_dtype == VQA_BF16)
-        dropnorm_fwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
-    else VQA_REQUIRE(false, "dropnorm_fwd: bad dtype");
+    // NK = groups of 8 channels per lane: 1 covers C <= 256 (the config.yaml shape) with a third of the registers
+    if (act_dtype == VQA_F32) {
+        if (C <= 256) dropnorm_fwd_kernel<float, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
+        else dropnorm_fwd_kernel<float, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
+    } else if (act_dtype == VQA_BF16) {
+        if (C <= 256) dropnorm_fwd_kernel<bf16, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
+        else dropnorm_fwd_kernel<bf16, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
+    } else VQA_REQUIRE(false, "dropnorm_fwd: bad dtype");
     VQA_CHECK_LAUNCH("dropnorm_fwd");
     return 0;
 }
@@ -150,11 +153,13 @@ extern "C" int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* v
     const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
     const int wpb = 8;
     const unsigned grid = (unsigned)ceil_div64(R, wpb);
-    if (act_dtype == VQA_F32)
-        dropnorm_bwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
-    else if (act_dtype == VQA_BF16)
-        dropnorm_bwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
-    else VQA_REQUIRE(false, "dropnorm_bwd: bad dtype");
+    if (act_dtype == VQA_F32) {
+        if (C <= 256) dropnorm_bwd_kernel<float, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
+        else dropnorm_bwd_kernel<float, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
+    } else if (act_dtype == VQA_BF16) {
+        if (C <= 256) dropnorm_bwd_kernel<bf16, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
+        else dropnorm_bwd_kernel<bf16, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
+    } else VQA_REQUIRE(false, "dropnorm_bwd: bad dtype");
     VQA_CHECK_LAUNCH("dropnorm_bwd");
     return 0;
 }
