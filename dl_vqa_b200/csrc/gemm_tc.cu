@@ -472,7 +472,9 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         nsplit = (int)((148 * 2 + tiles - 1) / tiles);
         const int maxs = ((K + BK - 1) / BK + 3) / 4;       // at least 4 k-blocks per split
         if (nsplit > maxs) nsplit = maxs;
+        if (tiles >= 148) nsplit = 1;                       // enough tiles to fill the GPU: no split, no atomics
         if (nsplit < 1) nsplit = 1;
+        if (nsplit == 1) ep.atomic = 0;                     // the output is zeroed, a plain store is equivalent
     }
     if (mn) {
         if (BN == 64) return launch_gemm<64, true>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
