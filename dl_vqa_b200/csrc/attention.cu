@@ -386,7 +386,7 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
                             bf16* __restrict__ out, int64_t ldo, int B, int P, Dropout drop) {
     constexpr int GP = G <= 2 ? G : 4;                 // glimpses padded to a power of two for the butterfly
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* ring = smem;                                                    // NST x CHUNK
     float* red = reinterpret_cast<float*>(ring + NST * CHUNK);              // [NCW][G][C_]
     float* lpart = red + NCW * G * C_;                                       // [2 halves][G][P]
@@ -622,7 +622,7 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                             float* __restrict__ dbx_part, int B, int P, Dropout drop) {
     constexpr int GP = G <= 2 ? G : 4;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* ring = smem;                                                    // BNST x BCHUNK
     float* red = reinterpret_cast<float*>(ring + BNST * BCHUNK);            // [4 pi][1 + G][A_]
     float* pr = red + 4 * (1 + G) * A_;                                      // [P][G] softmax (interleaved)

@@ -129,7 +129,7 @@ constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 template <bool STAGED>
 __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
     uint8_t* sa = smem + 64 * 128;                             // C0F_STAGES x 32 KB
     uint8_t* xs = sa + C0F_STAGES * C0F_STAGE_BYTES;           // C0F_XSTAGES x 8 KB staged input regions
@@ -300,7 +300,7 @@ constexpr int C0B_XSTAGES = 3;
 template <bool STAGED>
 __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* xs = smem + 2 * C0B_STAGE_BYTES;                  // C0B_XSTAGES x 8 KB staged input regions
     uint64_t* full = reinterpret_cast<uint64_t*>(xs + C0B_XSTAGES * C0_XSTAGE);
     uint64_t* empty = full + 2;

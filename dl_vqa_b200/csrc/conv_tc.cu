@@ -55,7 +55,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr int BN_CTA = BN / NCTA;                 // weight rows held by this CTA
     constexpr int B_SLAB = BN_CTA * 128;              // one 64-wide k-slab of them
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int nkb = 9 * p.chunks;
     uint8_t* sa = smem;
     uint8_t* sb = smem + p.a_stages * A_STAGE_BYTES;

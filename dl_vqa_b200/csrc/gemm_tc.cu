@@ -153,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
     using S = GemmSmem<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sa = smem;
     uint8_t* sb = smem + S::STAGES * S::A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));
@@ -267,7 +267,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
                           GemmEpilogue ep, int M, int N, int K, int nbatch) {
     using S = PGemmSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sa = smem;
     uint8_t* sb = smem + S::STAGES * S::A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));

@@ -42,7 +42,7 @@ template <int CS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_constant__ CUtensorMap tma_w, LstmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int kblocks = p.H / 64;
     uint8_t* sw = smem;                                       // kblocks x [64 rows][128 B]
     uint8_t* sa = smem + kblocks * 8192;                      // LSTM_STAGES x 16 KB
