@@ -10,11 +10,12 @@
 // Between steps the 64 CTAs of a direction meet at a global-memory barrier (release: __threadfence + atomicAdd,
 // acquire: ld.acquire.gpu + fence.proxy.async before the next TMA reads h_s).  The two directions never wait
 // for each other.  Co-residency of all CTAs is guaranteed by the cooperative launch.
-// CS = 4: the CTAs run as clusters of four of the same direction.  Every CTA needs ALL of h_{s-1} each step, so
+// CS = 4 (opt-in, see vqa_tc_lstm_fwd): the CTAs run as clusters of four of the same direction.  Every CTA needs ALL of h_{s-1} each step, so
 // without sharing the 64 CTAs of a direction pull 64 x 512 KB through L2 per step (the kernel was L2-bandwidth-bound);
 // in a cluster each CTA fetches a quarter of every h tile and TMA-multicasts it to its three peers, a slot is
 // released to all four producers by a multicast tcgen05.commit.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace tc {
 
@@ -263,8 +264,14 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
     VQA_REQUIRE(ctas_per_dir * dirs <= sms, "tc lstm: %d CTAs needed but only %d SMs", ctas_per_dir * dirs, sms);
     cudaStream_t st = (cudaStream_t)stream;
 
-    // clusters of 4 (TMA multicast of h) when the driver accepts a cooperative cluster launch; else single CTAs
-    int& cluster_ok = g_lstm_cluster_ok;           // -1 unknown, 0 rejected once, 1 works
+    // Clusters of 4 (TMA multicast of h) are OPT-IN (environment VQA_LSTM_CLUSTER=4): they cut the L2 traffic 4x but
+    // measured no faster on B200 (the per-SM ingest of h bounds the step), and Nsight Compute cannot replay a
+    // cooperative cluster launch (LaunchFailed), which would break profiling of the whole step.
+    int& cluster_ok = g_lstm_cluster_ok;           // -1 unknown, 0 rejected / not requested, 1 works
+    if (cluster_ok < 0) {
+        const char* env = getenv("VQA_LSTM_CLUSTER");
+        if (!(env && atoi(env) == 4)) cluster_ok = 0;
+    }
     const int cs = (cluster_ok != 0 && ctas_per_dir % 4 == 0) ? 4 : 1;
     CUtensorMap th, tw;
     {

@@ -246,8 +246,9 @@ int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_
 int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
                     unsigned int* sync, int T, int B, int H, int dirs, void* stream);
 int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);
-/* diagnostic: 4 = vqa_tc_lstm_fwd runs as clusters of four CTAs with TMA multicast of h, 1 = single CTAs (the driver
- * rejected the cooperative cluster launch), 0 = not launched yet */
+/* diagnostic: 4 = vqa_tc_lstm_fwd runs as clusters of four CTAs with TMA multicast of h (opt-in through the
+ * environment variable VQA_LSTM_CLUSTER=4), 1 = single CTAs (default, or the driver rejected the cooperative cluster
+ * launch), 0 = not launched yet */
 int vqa_tc_lstm_cluster_size(void);
 /* channel-major re-layout helpers (NHWC -> [B,C,H,Wp], zero padded pitch) */
 int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, int W, int C, int Wp, void* stream);

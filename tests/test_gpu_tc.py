@@ -294,3 +294,20 @@ def test_persistent_lstm_matches_stepwise_kernel(B, T, H, dirs):
     # activated gates only where the step was active
     act = (torch.arange(T, device=dev)[None, :, None] < q_len[None, None, :]).unsqueeze(-1)
     assert err(torch.where(act, gx_b.float(), torch.zeros((), device=dev)), torch.where(act, gx_a.float(), torch.zeros((), device=dev))) < 2e-2
+
+
+def test_persistent_lstm_cluster_multicast_variant_in_fresh_process():
+    """The opt-in cluster / TMA-multicast form of the persistent LSTM (VQA_LSTM_CLUSTER=4 is read at the first launch,
+    hence a fresh interpreter): same parity test, and the library must report that clusters were really used."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VQA_LSTM_CLUSTER="4")
+    if env.get("VQA_LSTM_CLUSTER_CHILD"):
+        pytest.skip("already inside the child run")
+    env["VQA_LSTM_CLUSTER_CHILD"] = "1"
+    code = ("import sys, pytest; rc = pytest.main(['-q', '-x', 'tests/test_gpu_tc.py', '-k', 'persistent_lstm_matches']);"
+            "from dl_vqa_b200 import lib; cs = lib.load().vqa_tc_lstm_cluster_size(); print('cluster_size', cs);"
+            "sys.exit(int(rc) if int(rc) else (0 if cs == 4 else 7))")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -1,5 +1,5 @@
 """Micro-benchmark of the persistent LSTM recurrence (BASELINE.json configs[3] shape per 256-sequence launch) -- not product code."""
-import argparse, os, sys, json
+import argparse, os, sys, json      # VQA_LSTM_CLUSTER=4 python tools/lstm_bench.py for the cluster / multicast variant
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dl_vqa_b200 import lib
