@@ -87,6 +87,11 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return r;
 }
 
+// fire-and-forget fp32 atomic add of four consecutive elements (REDG.E.ADD.F32x4, sm_90+); p must be 16-byte aligned
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------

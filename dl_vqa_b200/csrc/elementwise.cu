@@ -247,7 +247,7 @@ extern "C" int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const 
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const float* __restrict__ cs,
-                                          const float* __restrict__ dh, float* __restrict__ dc,
+                                          float* __restrict__ dh, float* __restrict__ dc,
                                           const T* __restrict__ dc_init, T* __restrict__ dg,
                                           const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over dirs*B*H
@@ -270,6 +270,7 @@ __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const flo
     const float c_prev = s > 0 ? cs[(row - B) * H + j] : 0.f;
     const float tc = tanhf(c);
     const float dhv = dh[i];
+    dh[i] = 0.f;                                    // read-and-clear: the next step's data gradient ACCUMULATES into dh (split-K)
     float dcv = dc_in + dhv * go * (1.f - tc * tc);
     const float d_o = dhv * tc;
     const float d_i = dcv * gg, d_g = dcv * gi, d_f = dcv * c_prev;
@@ -283,7 +284,7 @@ __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const flo
 // bf16 tensor-core arm: 8 hidden units per thread, 128-bit accesses (the scalar kernel above is latency-bound: 2-byte
 // accesses to four gate planes)
 __global__ void __launch_bounds__(128)
-lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __restrict__ cs, const float* __restrict__ dh,
+lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __restrict__ cs, float* __restrict__ dh,
                                float* __restrict__ dc, const bf16* __restrict__ dc_init, bf16* __restrict__ dg,
                                const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
     const int h8 = H >> 3;
@@ -315,6 +316,10 @@ lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __re
         for (int k = 0; k < 8; ++k) cp[k] = 0.f;
     }
     ld8(dh + i, dhv);
+    {   // read-and-clear: the next step's data gradient ACCUMULATES into dh (split-K with vector reductions)
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        st8(dh + i, z);
+    }
     float di[8], df[8], dgg[8], dox[8], dcn[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -330,7 +335,7 @@ lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __re
     st8(o, di); st8(o + H, df); st8(o + 2 * H, dgg); st8(o + 3 * H, dox);
 }
 
-extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float* dh, float* dc,
+extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, float* dh, float* dc,
                                            const void* dc_init, void* dg, const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs,
                                            void* stream) {
     VQA_REQUIRE(s >= 0 && s < T && B > 0 && H > 0 && (dirs == 1 || dirs == 2), "lstm bwd pointwise: bad dims");

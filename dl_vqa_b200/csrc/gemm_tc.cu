@@ -89,8 +89,13 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
                                                  const float* bias, const float* bias2, uint32_t dkey) {
     if (ep.atomic) {
         float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+        if (nb + 32 <= N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {       // 8 vector reductions instead of 32 scalar ones
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
+            for (int j = 0; j < 32; j += 4) red_add_f32x4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
+        }
         return;
     }
 #pragma unroll
@@ -469,7 +474,7 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     int nsplit = 1;
     if (splitk) {
         const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * nbatch;
-        nsplit = (int)((148 * 2 + tiles - 1) / tiles);
+        nsplit = (int)(148 / tiles);                        // about one CTA per SM: every extra split adds a full tile of atomics
         const int maxs = ((K + BK - 1) / BK + 3) / 4;       // at least 4 k-blocks per split
         if (nsplit > maxs) nsplit = maxs;
         if (tiles >= 148) nsplit = 1;                       // enough tiles to fill the GPU: no split, no atomics

@@ -594,8 +594,10 @@ class VqaNet(nn.Module):
                  ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
             if s > 0:   # dh_{s-1} = dgates_s W_hh
                 if tc:
+                    # split-K with vector reductions into dh, which the pointwise kernel above has just cleared:
+                    # M = B is small, so an unsplit GEMM leaves most SMs idle and each CTA ingests all of K
                     call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhT), 4 * H,
-                         H * 4 * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st,
+                         H * 4 * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs, lib.GEMM_SPLITK, 0.0, 0, 0, st,
                          tag="lstm_step_bwd")
                 else:
                     call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,

@@ -98,11 +98,12 @@ int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, c
  *   w_hh fp32 [4H][H] per direction; direction d at w_hh + d*w_hh_dir_stride (elements) */
 int vqa_lstm_step_fwd(void* gx, float* cs, void* hs, void* qf, const float* w_hh, int64_t w_hh_dir_stride,
                       const int64_t* q_len, int act_dtype, int s, int T, int B, int H, int dirs, void* stream);
-/* backward pointwise part of step s: consumes dh (fp32 [dirs][B][H], gradient w.r.t. h_s), updates the
+/* backward pointwise part of step s: consumes dh (fp32 [dirs][B][H], gradient w.r.t. h_s) and CLEARS the entries it
+ * read (the next step's dh = dg W_hh may then be accumulated by a split-K GEMM), updates the
  * running dc (fp32 [dirs][B][H]) in place, writes pre-activation gate gradients dg[dirs][s][B][4H].
  * dc_init (act_dtype [B][dirs*H], gradient w.r.t. the final cell state) is non-NULL on the first
  * processed step (s == T-1) and replaces the running dc there */
-int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, const float* dh, float* dc,
+int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, float* dh, float* dc,
                                 const void* dc_init, void* dg, const int64_t* q_len, int act_dtype,
                                 int s, int T, int B, int H, int dirs, void* stream);
 

@@ -285,8 +285,10 @@ def test_gradient_arena_gives_identical_gradients_and_stays_safe(dtype):
     buckets = m.gradient_buckets()
     assert set(buckets) == {"classifier", "attention", "text", "image"}
     for k, g in ar.items():
-        # split-K weight gradients accumulate with fp32 atomics in a run-dependent order: compare with a tight tolerance
-        assert float((g - plain[k]).abs().max()) <= 1e-5 * float(plain[k].abs().max() + 1e-30), k
+        # split-K contractions accumulate with fp32 atomics in a run-dependent order; in the bf16 arm the per-step LSTM
+        # data gradient is one of them and its fp32 rounding differences are re-rounded to bf16 every step
+        rtol = 1e-5 if dtype == "float32" else 2e-3
+        assert float((g - plain[k]).abs().max()) <= rtol * float(plain[k].abs().max() + 1e-30), k
         flat = buckets[k.split(".")[0]]
         assert flat.data_ptr() <= g.data_ptr() < flat.data_ptr() + flat.numel() * 4, k
     ptrs = {k: g.data_ptr() for k, g in ar.items()}
@@ -303,4 +305,4 @@ def test_gradient_arena_gives_identical_gradients_and_stays_safe(dtype):
     torch.cuda.synchronize()
     for k, p in m.named_parameters():
         ref = 2 * first[k]
-        assert float((p.grad - ref).abs().max()) <= 1e-4 * float(ref.abs().max() + 1e-30), k
+        assert float((p.grad - ref).abs().max()) <= (1e-4 if dtype == "float32" else 4e-3) * float(ref.abs().max() + 1e-30), k
