@@ -31,6 +31,7 @@ struct LstmParams {
     const int64_t* len;  // [B]
     unsigned int* sync;  // [dirs] zero-initialised counters
     int T, B, H, dirs, ctas_per_dir, mtiles;
+    int Bp, b0;          // batch pitch of the tensors and first sequence of this launch (B = sequences in this launch, <= 256)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -98,9 +99,9 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                         mbar_expect_tx(&full[st], LSTM_A_BYTES);
                         if (CS > 1)                               // my quarter of the tile, to every CTA of the cluster
                             tma_load_3d_mcast(sa + st * LSTM_A_BYTES + crank * SLICE_ROWS * 128, &tma_h, &full[st], kb * 64,
-                                              s * B + mt * 128 + (int)crank * SLICE_ROWS, dir, CMASK);
+                                              s * p.Bp + p.b0 + mt * 128 + (int)crank * SLICE_ROWS, dir, CMASK);
                         else
-                            tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * B + mt * 128, dir);
+                            tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * p.Bp + p.b0 + mt * 128, dir);
                     }
             }
         }
@@ -131,7 +132,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
         const int b = mt * 128 + quarter * 32 + lane;
         const bool active_tile = mt < p.mtiles;
         const bool row_ok = active_tile && b < B;
-        const int len = row_ok ? (int)p.len[b] : 0;
+        const int len = row_ok ? (int)p.len[p.b0 + b] : 0;
         const int u0 = j * 16;
         float c_state[16];
 #pragma unroll
@@ -143,7 +144,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
             if (active_tile) {
                 mbar_wait(&tmem_full[mt], s & 1);
                 tcgen05_fence_after();
-                const int64_t row = ((int64_t)dir * T + s) * B + b;
+                const int64_t row = ((int64_t)dir * T + s) * p.Bp + p.b0 + b;
                 const bool step_on = row_ok && s < len;
                 bf16* g = p.gx + row * 4 * H + u0;
                 // x-projection (+biases) of this thread's 16 units, 4 gates: 8 x 16 B
@@ -194,7 +195,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
                         *reinterpret_cast<float4*>(cdst + 4 * t) = make_float4(c_state[4 * t], c_state[4 * t + 1], c_state[4 * t + 2], c_state[4 * t + 3]);
-                    bf16* hdst = p.hs + (((int64_t)dir * (T + 1) + s + 1) * B + b) * H + u0;
+                    bf16* hdst = p.hs + (((int64_t)dir * (T + 1) + s + 1) * p.Bp + p.b0 + b) * H + u0;
                     uint4 q[2];
                     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
 #pragma unroll
@@ -202,7 +203,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                     *reinterpret_cast<uint4*>(hdst) = q[0];
                     *reinterpret_cast<uint4*>(hdst + 8) = q[1];
                     if (s == T - 1) {
-                        bf16* qdst = p.qf + (int64_t)b * p.dirs * H + (int64_t)dir * H + u0;
+                        bf16* qdst = p.qf + (int64_t)(p.b0 + b) * p.dirs * H + (int64_t)dir * H + u0;
 #pragma unroll
                         for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(c_state[2 * t], c_state[2 * t + 1]);
                         *reinterpret_cast<uint4*>(qdst) = q[0];
@@ -254,7 +255,6 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
                                unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
     VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm: bad dims");
     VQA_REQUIRE(H % 64 == 0 && H >= 64 && H <= 1024, "tc lstm: hidden size %d must be a multiple of 64 and <= 1024 (weights resident in shared memory)", H);
-    VQA_REQUIRE(B <= 256, "tc lstm: at most 256 sequences per launch (got %d); split the batch", B);
     int dev = 0, sms = 148, coop = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -286,9 +286,6 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
         const uint32_t box[3] = {64, 64, 1};
         if (int e = make_tmap_bf16(&tw, wp, 3, dims, str, box)) return e;
     }
-    LstmParams p{};
-    p.gx = (bf16*)gx; p.cs = cs_; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
-    p.T = T; p.B = B; p.H = H; p.dirs = dirs; p.ctas_per_dir = ctas_per_dir; p.mtiles = (B + 127) / 128;
     const int smem = (H / 64) * 8192 + LSTM_STAGES * LSTM_A_BYTES + 1024 + 256;
     static int attr_smem1 = 0, attr_smem4 = 0;
     if (attr_smem1 < smem) {
@@ -299,29 +296,36 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
         VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem4 = smem;
     }
-    VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * dirs, st));
-    vqa_count_launch();
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(ctas_per_dir * dirs); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 4; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    if (cs == 4) {
-        cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<4>, th, tw, p);
-        if (e == cudaSuccess) { cluster_ok = 1; return 0; }
-        (void)cudaGetLastError();
-        if (cluster_ok == 1) { vqa_set_error("lstm_persistent_fwd (clusters): %s", cudaGetErrorString(e)); return (int)e; }
-        cluster_ok = 0;                            // first attempt rejected: rebuild the h map with full-tile boxes, single CTAs
-        const uint64_t dims[3] = {(uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)dirs};
-        const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)(T + 1) * B * H * 2};
-        const uint32_t box[3] = {64, 128, 1};
-        if (int e2 = make_tmap_bf16(&th, hs, 3, dims, str, box)) return e2;
+    // at most 256 sequences (two 128-row accumulator tiles) per cooperative launch: larger batches run chunk by chunk
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        LstmParams p{};
+        p.gx = (bf16*)gx; p.cs = cs_; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
+        p.T = T; p.B = B - b0 < 256 ? B - b0 : 256; p.Bp = B; p.b0 = b0;
+        p.H = H; p.dirs = dirs; p.ctas_per_dir = ctas_per_dir; p.mtiles = (p.B + 127) / 128;
+        VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * dirs, st));
+        vqa_count_launch();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(ctas_per_dir * dirs); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 4; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        if (cluster_ok != 0 && ctas_per_dir % 4 == 0) {
+            cfg.numAttrs = 2;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<4>, th, tw, p);
+            if (e == cudaSuccess) { cluster_ok = 1; continue; }
+            (void)cudaGetLastError();
+            if (cluster_ok == 1) { vqa_set_error("lstm_persistent_fwd (clusters): %s", cudaGetErrorString(e)); return (int)e; }
+            cluster_ok = 0;                        // first attempt rejected: rebuild the h map with full-tile boxes, single CTAs
+            const uint64_t dims[3] = {(uint64_t)H, (uint64_t)(T + 1) * B, (uint64_t)dirs};
+            const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)(T + 1) * B * H * 2};
+            const uint32_t box[3] = {64, 128, 1};
+            if (int e2 = make_tmap_bf16(&th, hs, 3, dims, str, box)) return e2;
+        }
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<1>, th, tw, p);
+        if (e != cudaSuccess) { vqa_set_error("lstm_persistent_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<1>, th, tw, p);
-    if (e != cudaSuccess) { vqa_set_error("lstm_persistent_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }

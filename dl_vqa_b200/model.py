@@ -399,7 +399,7 @@ class VqaNet(nn.Module):
         qf = empty(B, dirs * H)
         whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        persistent = tc and H % 64 == 0 and H <= 1024 and B <= 256 and dirs * (H // 16) <= sms
+        persistent = tc and H % 64 == 0 and H <= 1024 and dirs * (H // 16) <= sms
         if persistent:
             # one cooperative launch for all steps and directions; W_hh resident in shared memory
             wp = empty(dirs, 4 * H, H)

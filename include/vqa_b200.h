@@ -243,7 +243,8 @@ int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_
  *   gx [dirs][T][B][4H] bf16 (in: x W_ih^T + b_ih + b_hh, out: activated gates), cs [dirs][T][B][H] fp32,
  *   hs [dirs][T+1][B][H] bf16 with slot 0 zero-filled by the caller (slot s+1 = h after step s),
  *   qf [B][dirs*H] bf16 = final cell state, wp [dirs][4H][H] bf16 from vqa_pack_lstm_whh (one call per direction),
- *   sync: `dirs` uint32 scratch counters.  H % 64 == 0, H <= 1024, B <= 256 per launch. */
+ *   sync: `dirs` uint32 scratch counters.  H % 64 == 0, H <= 1024; batches above 256 sequences run as consecutive
+ *   cooperative launches of 256 (two 128-row TMEM accumulator tiles per CTA). */
 int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
                     unsigned int* sync, int T, int B, int H, int dirs, void* stream);
 int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);

@@ -256,7 +256,7 @@ def test_tc_gemm_mn_major_weight_gradient_form(R, N, K):
     assert err < 1e-4, err
 
 
-@pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (5, 4, 64, 1), (130, 7, 256, 2)])
+@pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (5, 4, 64, 1), (130, 7, 256, 2), (600, 9, 256, 2)])
 def test_persistent_lstm_matches_stepwise_kernel(B, T, H, dirs):
     """The cooperative tcgen05 recurrence against the per-step SIMT kernel (itself parity-checked against the
     oracle in test_gpu_parity) on identical bf16 inputs."""
