@@ -49,7 +49,9 @@ struct ConvParams {
     bf16* dx;
 };
 
-template <int BN, int EPI, int NCTA, bool RESIDENT>
+// MT = tiles per CTA and round.  MT = 2 (streamed weights, BN <= 128): both tiles' MMAs share every weight slab, which
+// halves the TMA traffic of the B operand into shared memory and the mbarrier waits per MMA.
+template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, ConvParams p) {
     constexpr int BN_CTA = BN / NCTA;                 // weight rows held by this CTA
@@ -73,9 +75,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool leader = rank == 0;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
     const int ntiles = p.B * tiles_per_img;
-    const int nrounds = (ntiles + NCTA - 1) / NCTA;                 // one tile per CTA of the pair per round
+    const int nrounds = (ntiles + NCTA * MT - 1) / (NCTA * MT);     // MT tiles per CTA of the pair per round
     const int nclusters = gridDim.x / NCTA, cluster_id = blockIdx.x / NCTA;
-    constexpr uint32_t TMEM_COLS = 2 * BN;                            // 128, 256 or 512: all powers of two
+    constexpr uint32_t TMEM_COLS = 2 * MT * BN;                       // 128, 256 or 512: all powers of two
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "accumulators must fit the 512 TMEM columns");
+    static_assert(MT == 1 || NCTA == 1, "MT > 1 is implemented for single-CTA MMAs only");
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
@@ -102,21 +106,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             uint32_t ita = 0, itb = 0;
             for (int round = cluster_id; round < nrounds; round += nclusters) {
-                const int tile = round * NCTA + (int)rank;
-                int b = p.B, h0 = 0, w0 = 0;                       // b == B: everything out of bounds -> zero fill
-                if (tile < ntiles) {
-                    b = tile / tiles_per_img;
-                    const int r = tile - b * tiles_per_img;
-                    h0 = (r / p.tiles_w) * TILE_H; w0 = (r % p.tiles_w) * TILE_W;
-                }
-                const int hh = p.sign > 0 ? h0 : h0 - 2, ww = p.sign > 0 ? w0 : w0 - 2;
-                for (int cc = 0; cc < p.chunks; ++cc, ++ita) {
-                    const int s = ita % p.a_stages;
-                    const uint32_t ph = (ita / p.a_stages) & 1;
-                    mbar_wait(&emptyA[s], ph ^ 1);
-                    if (leader) mbar_expect_tx(&fullA[s], NCTA * HALO_BYTES);
-                    if (NCTA == 2) tma_load_4d_pair(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
-                    else tma_load_4d(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
+                for (int cc = 0; cc < p.chunks; ++cc) {
+                    for (int i = 0; i < MT; ++i, ++ita) {
+                        const int tile = (round * MT + i) * NCTA + (int)rank;
+                        int b = p.B, h0 = 0, w0 = 0;                   // b == B: everything out of bounds -> zero fill
+                        if (tile < ntiles) {
+                            b = tile / tiles_per_img;
+                            const int r = tile - b * tiles_per_img;
+                            h0 = (r / p.tiles_w) * TILE_H; w0 = (r % p.tiles_w) * TILE_W;
+                        }
+                        const int hh = p.sign > 0 ? h0 : h0 - 2, ww = p.sign > 0 ? w0 : w0 - 2;
+                        const int s = ita % p.a_stages;
+                        const uint32_t ph = (ita / p.a_stages) & 1;
+                        mbar_wait(&emptyA[s], ph ^ 1);
+                        if (leader) mbar_expect_tx(&fullA[s], NCTA * HALO_BYTES);
+                        if (NCTA == 2) tma_load_4d_pair(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
+                        else tma_load_4d(sa + s * A_STAGE_BYTES, &tma_a, &fullA[s], cc * 64, ww, hh, b);
+                    }
                     if (!RESIDENT) {
                         for (int tap = 0; tap < 9; ++tap, ++itb) {
                             const int t = itb % p.b_stages;
@@ -143,32 +149,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const uint32_t acc = tcount & 1, use = tcount >> 1;
                 mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);      // both CTAs' epilogues have drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int cc = 0; cc < p.chunks; ++cc, ++ita) {
-                    const int s = ita % p.a_stages;
-                    mbar_wait(&fullA[s], (ita / p.a_stages) & 1);
-                    tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+                for (int cc = 0; cc < p.chunks; ++cc, ita += MT) {
                     // tap (kh,kw) = the halo tile advanced by whole rows: +8 descriptor units (128 B) per row
-                    const uint64_t a_desc0 = smem_desc_k_sw128_shifted(smem_u32(sa + s * A_STAGE_BYTES), HALO_W * 128);
+                    uint64_t a_desc0[MT];
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const int s = (ita + i) % p.a_stages;
+                        mbar_wait(&fullA[s], ((ita + i) / p.a_stages) & 1);
+                        a_desc0[i] = smem_desc_k_sw128_shifted(smem_u32(sa + s * A_STAGE_BYTES), HALO_W * 128);
+                    }
+                    tcgen05_fence_after();
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const int row = p.sign > 0 ? kh * HALO_W + kw : (2 - kh) * HALO_W + (2 - kw);
-                        const uint64_t ad = a_desc0 + (uint64_t)(row * 8);
-                        if (RESIDENT) {
-                            const uint64_t bd = b_desc0 + (uint64_t)((tap * p.chunks + cc) * (B_SLAB >> 4));
-                            umma_issue_k64<NCTA>(d_tmem, ad, bd, idesc, (cc > 0 || tap > 0) ? 1u : 0u, elected);
-                        } else {
-                            const int t = itb % p.b_stages;
+                        uint64_t bd;
+                        int t = 0;
+                        if (RESIDENT) bd = b_desc0 + (uint64_t)((tap * p.chunks + cc) * (B_SLAB >> 4));
+                        else {
+                            t = itb % p.b_stages;
                             mbar_wait(&fullB[t], (itb / p.b_stages) & 1);
                             tcgen05_fence_after();
-                            const uint64_t bd = b_desc0 + (uint64_t)(t * (B_SLAB >> 4));
-                            umma_issue_k64<NCTA>(d_tmem, ad, bd, idesc, (cc > 0 || tap > 0) ? 1u : 0u, elected);
-                            umma_commit_issue<NCTA>(&emptyB[t], elected);
+                            bd = b_desc0 + (uint64_t)(t * (B_SLAB >> 4));
                             ++itb;
                         }
+#pragma unroll
+                        for (int i = 0; i < MT; ++i)
+                            umma_issue_k64<NCTA>(d_tmem + i * BN, a_desc0[i] + (uint64_t)(row * 8), bd, idesc,
+                                                 (cc > 0 || tap > 0) ? 1u : 0u, elected);
+                        if (!RESIDENT) umma_commit_issue<NCTA>(&emptyB[t], elected);
                     }
-                    umma_commit_issue<NCTA>(&emptyA[s], elected);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) umma_commit_issue<NCTA>(&emptyA[(ita + i) % p.a_stages], elected);
                 }
                 umma_commit_issue<NCTA>(&tmem_full[acc], elected);
             }
@@ -179,13 +192,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint32_t tcount = 0;
         for (int round = cluster_id; round < nrounds; round += nclusters, ++tcount) {
             const uint32_t acc = tcount & 1, use = tcount >> 1;
-            const int tile = round * NCTA + (int)rank;
+            mbar_wait(&tmem_full[acc], use & 1);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int ti = 0; ti < MT; ++ti) {
+            const int tile = (round * MT + ti) * NCTA + (int)rank;
             const bool live = tile < ntiles;
             const int b = live ? tile / tiles_per_img : 0, r = live ? tile - b * tiles_per_img : 0;
             const int h0 = (r / p.tiles_w) * TILE_H, w0 = (r % p.tiles_w) * TILE_W;
-            mbar_wait(&tmem_full[acc], use & 1);
-            tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr = tmem_base + (acc * MT + ti) * BN + ((uint32_t)(quarter * 32) << 16);
             const int rr = 4 * quarter + (lane >> 3), cc = lane & 7;         // position inside the 16x8 tile
             if (EPI == EPI_STORE) {
                 const int h = h0 + rr, w = w0 + cc;
@@ -268,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
             }
+            }   // tiles of the round
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) { if (NCTA == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
@@ -285,9 +301,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // cta_group selection: 1 = single-CTA MMAs, 2 = CTA pairs.  Changed only by vqa_tc_conv_set_cta_group (tests/bench).
 static int g_conv_cta_group = 1;
 
-template <int BN, int EPI, int NCTA, bool RESIDENT>
+template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
 static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvParams p, int smem_bytes, cudaStream_t st) {
-    auto kern = conv_tc_kernel<BN, EPI, NCTA, RESIDENT>;
+    auto kern = conv_tc_kernel<BN, EPI, NCTA, RESIDENT, MT>;
     static int attr_bytes = 0;
     if (attr_bytes < smem_bytes) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -297,7 +313,7 @@ static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvPar
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = p.B * p.tiles_h * p.tiles_w;
-    const int nrounds = (ntiles + NCTA - 1) / NCTA;
+    const int nrounds = (ntiles + NCTA * MT - 1) / (NCTA * MT);
     int grid = (nrounds < sms / NCTA ? nrounds : sms / NCTA) * NCTA;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -325,7 +341,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
         p.a_stages = a > 4 ? 4 : a; p.b_stages = 1;
         smem = resident_bytes + p.a_stages * A_STAGE_BYTES + bars + 1024;
     } else {
-        p.a_stages = p.chunks >= 2 ? 3 : 2;
+        const bool mt2 = ncta == 1 && BN <= 128 && EPI == EPI_STORE;          // two tiles share every streamed weight slab
+        p.a_stages = mt2 ? 4 : (p.chunks >= 2 ? 3 : 2);
         int bs = (SMEM_LIMIT - bars - p.a_stages * A_STAGE_BYTES) / slab;
         p.b_stages = bs > MAX_B_STAGES ? MAX_B_STAGES : bs;
         VQA_REQUIRE(p.b_stages >= 2, "tc conv: weight slab does not fit in shared memory");
@@ -336,7 +353,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
         return launch_conv_cfg<BN, EPI, 2, false>(ta, tb2, p, smem, st);
     }
     if (resident) return launch_conv_cfg<BN, EPI, 1, true>(ta, tb1, p, smem, st);
-    return launch_conv_cfg<BN, EPI, 1, false>(ta, tb1, p, smem, st);
+    if constexpr (BN <= 128 && EPI == EPI_STORE) return launch_conv_cfg<BN, EPI, 1, false, 2>(ta, tb1, p, smem, st);
+    else return launch_conv_cfg<BN, EPI, 1, false>(ta, tb1, p, smem, st);
 }
 
 // activation tensor map: NHWC bf16 [B, H, W, C] with box [64, 10, 18, 1] (tile + halo)
