@@ -149,14 +149,17 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
     }
 }
 
-// MN = false: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
-// MN = true : A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
-//             consumed without transposes; one TMA box per 64-wide column block per stage).
-template <int BN, bool MN, int ST>
+// MAJ = 0: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
+// MAJ = 1: A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
+//          consumed without transposes; one TMA box per 64-wide column block per stage).
+// MAJ = 2: A [M,K] K-major, B [K,N] MN-major: the data-gradient form dX = dY W with W [N_red, K_out] read as stored
+//          (no transposed weight copy).
+template <int BN, int MAJ, int ST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
     using S = GemmSmem<BN, ST>;
+    constexpr bool AMN = MAJ == 1, BMN = MAJ >= 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sa = smem;
@@ -194,13 +197,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
                 const int kc = (kb_begin + i) * BK;
-                if (!MN) {
-                    tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
-                    tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
-                } else {
+                if (!AMN) tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
+                else {
 #pragma unroll
                     for (int blk = 0; blk < BM / 64; ++blk)
                         tma_load_3d(sa + s * S::A_BYTES + blk * 8192, &tma_a, &full[s], m0 + blk * 64, kc, batch);
+                }
+                if (!BMN) tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
+                else {
 #pragma unroll
                     for (int blk = 0; blk < BN / 64; ++blk)
                         tma_load_3d(sb + s * S::B_BYTES + blk * 8192, &tma_b, &full[s], n0 + blk * 64, kc, batch);
@@ -209,11 +213,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // all lanes converged, one elected lane issues (see tc_common.cuh)
-        constexpr uint32_t idesc = idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+        constexpr uint32_t idesc = idesc_bf16(BM, BN, AMN ? 1 : 0, BMN ? 1 : 0);
         const uint32_t elected = elect_one();
-        const uint64_t a_desc0 = MN ? smem_desc_mn_sw128(smem_u32(sa), 8192) : smem_desc_k_sw128(smem_u32(sa));
-        const uint64_t b_desc0 = MN ? smem_desc_mn_sw128(smem_u32(sb), 8192) : smem_desc_k_sw128(smem_u32(sb));
-        constexpr uint32_t KSTEP = MN ? (2048 >> 4) : (32 >> 4);      // 16 reduction elements further, in 16-byte units
+        const uint64_t a_desc0 = AMN ? smem_desc_mn_sw128(smem_u32(sa), 8192) : smem_desc_k_sw128(smem_u32(sa));
+        const uint64_t b_desc0 = BMN ? smem_desc_mn_sw128(smem_u32(sb), 8192) : smem_desc_k_sw128(smem_u32(sb));
+        constexpr uint32_t KSTEP_A = AMN ? (2048 >> 4) : (32 >> 4);   // 16 reduction elements further, in 16-byte units
+        constexpr uint32_t KSTEP_B = BMN ? (2048 >> 4) : (32 >> 4);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % S::STAGES;
             mbar_wait(&full[s], (i / S::STAGES) & 1);
@@ -221,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t ad = a_desc0 + (uint64_t)(s * (S::A_BYTES >> 4)), bd = b_desc0 + (uint64_t)(s * (S::B_BYTES >> 4));
 #pragma unroll
             for (uint32_t k = 0; k < BK / 16; ++k)
-                umma_issue<1>(tmem_base, ad + k * KSTEP, bd + k * KSTEP, idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
+                umma_issue<1>(tmem_base, ad + k * KSTEP_A, bd + k * KSTEP_B, idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
             umma_commit_issue<1>(&empty[s], elected);      // frees the smem stage when these MMAs retire
         }
         umma_commit_issue<1>(tmem_full, elected);          // accumulator complete
@@ -266,7 +271,7 @@ struct PGemmSmem {
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool BMN>
 __global__ void __launch_bounds__(PGEMM_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           GemmEpilogue ep, int M, int N, int K, int nbatch) {
@@ -309,14 +314,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
                     mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
                     tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kb * BK, m0, batch);
-                    tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kb * BK, n0, batch);
+                    if (!BMN) tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kb * BK, n0, batch);
+                    else {
+#pragma unroll
+                        for (int blk = 0; blk < BN / 64; ++blk)
+                            tma_load_3d(sb + s * S::B_BYTES + blk * 8192, &tma_b, &full[s], n0 + blk * 64, kb * BK, batch);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = idesc_bf16(BM, BN, 0, BMN ? 1 : 0);
+        constexpr uint32_t KSTEP_B = BMN ? (2048 >> 4) : (32 >> 4);
         const uint32_t elected = elect_one();
-        const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa)), b_desc0 = smem_desc_k_sw128(smem_u32(sb));
+        const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa));
+        const uint64_t b_desc0 = BMN ? smem_desc_mn_sw128(smem_u32(sb), 8192) : smem_desc_k_sw128(smem_u32(sb));
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const uint32_t acc = tcount & 1, use = tcount >> 1;
@@ -326,8 +338,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
                 const int s = it % S::STAGES;
                 mbar_wait(&full[s], (it / S::STAGES) & 1);
                 tcgen05_fence_after();
-                umma_issue_k64<1>(tmem_base + acc * BN, a_desc0 + (uint64_t)(s * (S::A_BYTES >> 4)),
-                                  b_desc0 + (uint64_t)(s * (S::B_BYTES >> 4)), idesc, kb > 0 ? 1u : 0u, elected);
+                const uint64_t ad = a_desc0 + (uint64_t)(s * (S::A_BYTES >> 4)), bd = b_desc0 + (uint64_t)(s * (S::B_BYTES >> 4));
+#pragma unroll
+                for (uint32_t k = 0; k < BK / 16; ++k)
+                    umma_issue<1>(tmem_base + acc * BN, ad + 2 * k, bd + k * KSTEP_B, idesc, (kb > 0 || k > 0) ? 1u : 0u, elected);
                 umma_commit_issue<1>(&empty[s], elected);
             }
             umma_commit_issue<1>(&tmem_full[acc], elected);
@@ -362,10 +376,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
-template <int BN>
+template <int BN, bool BMN>
 static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                                   int nbatch, int sms, cudaStream_t st) {
-    auto kern = gemm_tc_persistent_kernel<BN>;
+    auto kern = gemm_tc_persistent_kernel<BN, BMN>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PGemmSmem<BN>::BYTES));
@@ -376,10 +390,10 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
     return 0;
 }
 
-template <int BN, bool MN, int ST>
+template <int BN, int MAJ, int ST>
 static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                           dim3 grid, int nsplit, int kbps, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, MN, ST>;
+    auto kern = gemm_tc_kernel<BN, MAJ, ST>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, ST>::BYTES));
@@ -390,7 +404,7 @@ static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     return 0;
 }
 
-template <int BN, bool MN>
+template <int BN, int MAJ>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                        int nbatch, int nsplit, cudaStream_t st) {
     const int total_kb = (K + BK - 1) / BK;
@@ -403,10 +417,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
-    if (!MN && nsplit == 1 && !ep.atomic && total_kb > 0 && ctas >= 4 * (int64_t)sms)
-        return launch_gemm_persistent<BN>(ta, tb, ep, M, N, K, nbatch, sms, st);
-    if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MN, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
-    return launch_gemm_st<BN, MN, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+    if (MAJ != 1 && nsplit == 1 && !ep.atomic && total_kb > 0 && ctas >= 4 * (int64_t)sms)
+        return launch_gemm_persistent<BN, MAJ == 2>(ta, tb, ep, M, N, K, nbatch, sms, st);
+    if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MAJ, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+    return launch_gemm_st<BN, MAJ, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
 }
 
 }  // namespace tc
@@ -428,6 +442,8 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     VQA_REQUIRE(c_dtype == VQA_F32 || c_dtype == VQA_BF16, "tc_gemm: bad output dtype");
     const bool splitk = (flags & VQA_GEMM_SPLITK) != 0;
     const bool mn = (flags & VQA_GEMM_OPERANDS_MN) != 0;
+    const bool bmn = (flags & VQA_GEMM_B_MN) != 0;          // A [M,K] K-major, B stored [K,N]
+    VQA_REQUIRE(!(mn && bmn), "tc_gemm: OPERANDS_MN and B_MN are mutually exclusive");
     if (splitk) {
         VQA_REQUIRE(c_dtype == VQA_F32 && !bias && !bias2 && !(flags & VQA_GEMM_RELU) && p_drop == 0.f,
                     "tc_gemm: split-K needs a zeroed fp32 output and no fused bias/relu/dropout");
@@ -450,10 +466,17 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nbatch > 1 ? a_sb : (int64_t)M * lda) * 2};
         const uint32_t box[3] = {BK, BM, 1};
         if (int e = make_tmap_bf16(&ta, A, 3, dims, str, box)) return e;
-        const uint64_t dimsb[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nbatch};
-        const uint64_t strb[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)N * ldb) * 2};
-        const uint32_t boxb[3] = {BK, (uint32_t)BN, 1};
-        if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, boxb)) return e;
+        if (!bmn) {
+            const uint64_t dimsb[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nbatch};
+            const uint64_t strb[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)N * ldb) * 2};
+            const uint32_t boxb[3] = {BK, (uint32_t)BN, 1};
+            if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, boxb)) return e;
+        } else {
+            const uint64_t dimsb[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)nbatch};
+            const uint64_t strb[2] = {(uint64_t)ldb * 2, (uint64_t)(nbatch > 1 ? b_sb : (int64_t)K * ldb) * 2};
+            const uint32_t boxb[3] = {64, BK, 1};
+            if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, boxb)) return e;
+        }
     } else {
         const uint64_t dims[3] = {(uint64_t)M, (uint64_t)K, (uint64_t)nbatch};
         const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(nbatch > 1 ? a_sb : (int64_t)K * lda) * 2};
@@ -482,11 +505,15 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         if (nsplit == 1) ep.atomic = 0;                     // the output is zeroed, a plain store is equivalent
     }
     if (mn) {
-        if (BN == 64) return launch_gemm<64, true>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-        return launch_gemm<128, true>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        if (BN == 64) return launch_gemm<64, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        return launch_gemm<128, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
     }
-    if (BN == 64) return launch_gemm<64, false>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-    return launch_gemm<128, false>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    if (bmn) {
+        if (BN == 64) return launch_gemm<64, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        return launch_gemm<128, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    }
+    if (BN == 64) return launch_gemm<64, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    return launch_gemm<128, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
 }
 
 // ------------------------------------------------------------------------------------------

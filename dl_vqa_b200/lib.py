@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
 
 F32, BF16 = 0, 1
 ATT_ADD, ATT_MUL = 0, 1
-GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN = 1, 2, 4, 8
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN, GEMM_B_MN = 1, 2, 4, 8, 16
 SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CLS_HID = range(7)
 
 DEFAULT_CONV_CTA_GROUP = 1      # tcgen05 cta_group used by the 3x3 conv kernels (vqa_tc_conv_set_cta_group)

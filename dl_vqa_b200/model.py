@@ -104,14 +104,14 @@ class _Math:
     """The three dense contractions of the step, on either arm.
 
     fp32 arm  : vqa_gemm (SIMT fp32, exact), operands addressed in place through strides.
-    bf16 arm  : vqa_tc_gemm (tcgen05 / TMEM / TMA).  Tensor-core operands must be bf16 with the reduction
-                index contiguous, so weights get per-step bf16 (transposed) shadows and weight-gradient
-                operands are transposed by vqa_transpose_bf16.
+    bf16 arm  : vqa_tc_gemm (tcgen05 / TMEM / TMA).  Weights get ONE bf16 shadow per step (same [N,K] layout), used
+                K-major by the forward and MN-major (GEMM_B_MN) by the data gradient; weight gradients consume both
+                operands MN-major (GEMM_OPERANDS_MN).  No transposed copies anywhere.
     """
 
-    def __init__(self, tc: bool, dev, st):
+    def __init__(self, tc: bool, dev, st, wcache=None):
         self.tc, self.dev, self.st = tc, dev, st
-        self._w = {}
+        self._w = wcache if wcache is not None else {}     # bf16 weight shadows; the backward pass reuses the forward's
 
     # ---- bf16 shadows of fp32 parameters (cached for the duration of one forward/backward)
     def wbf(self, W: torch.Tensor):
@@ -125,17 +125,6 @@ class _Math:
             self._w[key] = (out, Kp)
         return self._w[key]
 
-    def wT(self, W: torch.Tensor):
-        """[N,K] fp32 -> bf16 [K,Np] (transposed), Np = N rounded up to 8."""
-        key = ("t", W.data_ptr())
-        if key not in self._w:
-            N, K = W.shape[0], W[0].numel()
-            Np = _rup(N, 8)
-            out = torch.empty(K, Np, dtype=torch.bfloat16, device=self.dev)
-            call("vqa_transpose_bf16", ptr(W), lib.F32, K, 0, ptr(out), Np, 0, N, K, 1, self.st, tag="w_transpose")
-            self._w[key] = (out, Np)
-        return self._w[key]
-
     def _as_bf16(self, x_ptr, x_dt, ld, rows, cols):
         if x_dt == lib.BF16:
             return x_ptr, ld, None
@@ -143,18 +132,6 @@ class _Math:
         buf = torch.empty(rows, cp, dtype=torch.bfloat16, device=self.dev)
         call("vqa_cast_2d", x_ptr, x_dt, ld, ptr(buf), lib.BF16, cp, rows, cols, cp, self.st, tag="act_cast")
         return buf.data_ptr(), cp, buf
-
-    def _transposed(self, x_ptr, x_dt, ld, rows, cols):
-        rp = _rup(rows, 8)
-        buf = torch.empty(cols, rp, dtype=torch.bfloat16, device=self.dev)
-        r0 = 0
-        while r0 < rows:            # grid.y limit of the transpose kernel: 65535 * 32 rows per launch
-            n = min(rows - r0, 65535 * 32)
-            esz = 4 if x_dt == lib.F32 else 2
-            call("vqa_transpose_bf16", x_ptr + r0 * ld * esz, x_dt, ld, 0, buf.data_ptr() + r0 * 2, rp, 0, n, cols, 1,
-                 self.st, tag="act_transpose")
-            r0 += n
-        return buf, rp
 
     # ---- out[M,N] = act(x[M,K] W[N,K]^T + bias (+ bias2)) * dropout
     def lin_fwd(self, x_ptr, x_dt, ldx, W, out_ptr, out_dt, ldo, M, N, K, bias=None, bias2=None, relu=False,
@@ -172,10 +149,11 @@ class _Math:
     # ---- dx[M,K] = dy[M,N] W[N,K]
     def lin_bwd_data(self, dy_ptr, dy_dt, ldy, W, dx_ptr, dx_dt, ldd, M, N, K, tag=None):
         if self.tc:
-            WT, Np = self.wT(W)
+            # W [N,K] read as stored (the forward's bf16 shadow): reduction index = its row => MN-major B operand
+            Wb, Kp = self.wbf(W)
             yp, ldy2, keep = self._as_bf16(dy_ptr, dy_dt, ldy, M, N)
-            call("vqa_tc_gemm", yp, ldy2, 0, ptr(WT), Np, 0, dx_ptr, dx_dt, ldd, 0, None, None, 0,
-                 M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
+            call("vqa_tc_gemm", yp, ldy2, 0, ptr(Wb), Kp, 0, dx_ptr, dx_dt, ldd, 0, None, None, 0,
+                 M, K, N, 1, lib.GEMM_B_MN, 0.0, 0, 0, self.st, tag=tag)
         else:
             call("vqa_gemm", dy_ptr, dy_dt, ldy, 1, 0, ptr(W), lib.F32, 1, K, 0, dx_ptr, dx_dt, ldd, 0,
                  None, None, 0, M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
@@ -455,7 +433,7 @@ class VqaNet(nn.Module):
                    B, self.max_answers, self.hidden, bias=cl.lin2.bias, tag="lin2")
 
         if save:
-            ctx.update(B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
+            ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
                        xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
                        q=q, q_len=q_len, ldx=ldx, whh_stride=whh_stride,
                        p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
@@ -470,7 +448,7 @@ class VqaNet(nn.Module):
         tc = adt == torch.bfloat16
         dev = dlogits.device
         st = lib.stream()
-        mm = _Math(tc, dev, st)
+        mm = _Math(tc, dev, st, ctx.get("wcache"))
         f32 = torch.float32
         H, E, dirs, G, A = self.H, self.E, self.dirs, self.G, self.A
         Cimg = self.channels[-1]
@@ -585,10 +563,9 @@ class VqaNet(nn.Module):
         dg = empty(dirs, T, B, 4 * H)
         gsz = dg.element_size()
         if tc and T > 1:
-            whhT = empty(dirs, H, 4 * H)          # bf16 [H, 4H] per direction: B operand of dh = dg W_hh
+            whhb = empty(dirs, 4 * H, H)          # bf16 shadow of W_hh as stored [4H, H]: MN-major B operand of dh = dg W_hh
             for d in range(dirs):
-                call("vqa_transpose_bf16", ptr(w_hh[d]), lib.F32, H, 0, ptr(whhT[d]), 4 * H, 0, 4 * H, H, 1, st,
-                     tag="w_transpose")
+                call("vqa_cast_2d", ptr(w_hh[d]), lib.F32, H, ptr(whhb[d]), lib.BF16, H, 4 * H, H, H, st, tag="w_cast")
         for s in range(T - 1, -1, -1):
             call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
                  ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
@@ -596,9 +573,9 @@ class VqaNet(nn.Module):
                 if tc:
                     # split-K with vector reductions into dh, which the pointwise kernel above has just cleared:
                     # M = B is small, so an unsplit GEMM leaves most SMs idle and each CTA ingests all of K
-                    call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhT), 4 * H,
-                         H * 4 * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs, lib.GEMM_SPLITK, 0.0, 0, 0, st,
-                         tag="lstm_step_bwd")
+                    call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhb), H,
+                         4 * H * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs,
+                         lib.GEMM_SPLITK | lib.GEMM_B_MN, 0.0, 0, 0, st, tag="lstm_step_bwd")
                 else:
                     call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,
                          ptr(w_hh[0]), lib.F32, 1, H, ctx["whh_stride"], ptr(dh), lib.F32, H, B * H,

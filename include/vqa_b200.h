@@ -118,6 +118,7 @@ int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, float* dh, f
 #define VQA_GEMM_ACCUMULATE 2
 #define VQA_GEMM_SPLITK 4
 #define VQA_GEMM_OPERANDS_MN 8   /* vqa_tc_gemm only: A stored [K,M], B stored [K,N] (reduction index = row) */
+#define VQA_GEMM_B_MN 16         /* vqa_tc_gemm only: A stored [M,K], B stored [K,N]: dX = dY W with W as stored */
 int vqa_gemm(const void* A, int a_dtype, int64_t a_sr, int64_t a_sk, int64_t a_sb,
              const void* B, int b_dtype, int64_t b_sr, int64_t b_sk, int64_t b_sb,
              void* C, int c_dtype, int64_t ldc, int64_t c_sb,

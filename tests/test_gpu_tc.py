@@ -256,6 +256,26 @@ def test_tc_gemm_mn_major_weight_gradient_form(R, N, K):
     assert err < 1e-4, err
 
 
+@pytest.mark.parametrize("M,N,K,splitk", [(256, 1024, 4096, True), (256, 2560, 1024, False), (173056, 256, 1024, False),
+                                          (5888, 300, 4096, False), (77, 72, 200, False), (300, 3000, 136, False)])
+def test_tc_gemm_b_mn_major_data_gradient_form(M, N, K, splitk):
+    """dX[M,N] = dY[M,K] W[K,N] with W consumed as stored (GEMM_B_MN): the data-gradient form of nn.Linear."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(M + N)
+    dY = torch.randn(M, K, device="cuda").bfloat16()
+    Np = (N + 7) // 8 * 8
+    W = torch.zeros(K, Np, device="cuda", dtype=torch.bfloat16)
+    W[:, :N] = (torch.randn(K, N, device="cuda") / K ** 0.5).bfloat16()
+    out = (torch.zeros if splitk else torch.empty)(M, Np, device="cuda")
+    flags = lib.GEMM_B_MN | (lib.GEMM_SPLITK if splitk else 0)
+    lib.call("vqa_tc_gemm", lib.ptr(dY), K, 0, lib.ptr(W), Np, 0, lib.ptr(out), lib.F32, Np, 0, None, None, 0,
+             M, N, K, 1, flags, 0.0, 0, 0, lib.stream())
+    torch.cuda.synchronize()
+    want = dY.float() @ W[:, :N].float()
+    err = float((out[:, :N] - want).abs().max() / want.abs().max())
+    assert err < 1e-4, err
+
+
 @pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (5, 4, 64, 1), (130, 7, 256, 2), (600, 9, 256, 2)])
 def test_persistent_lstm_matches_stepwise_kernel(B, T, H, dirs):
     """The cooperative tcgen05 recurrence against the per-step SIMT kernel (itself parity-checked against the
