@@ -189,6 +189,8 @@ def run_ours(args):
     model = D.VqaNet(cfg, synth.DEFAULT_TOKENS, compute_dtype=args.dtype).to(dev).train(True)
     opt = D.FusedAdam(model.parameters(), lr=5e-4)
     model.use_gradient_arena(True)        # gradients live in persistent per-stage buckets (all-reduced in place for N > 1)
+    if args.dtype == "bfloat16":
+        model.use_weight_shadows(opt)     # FusedAdam keeps the bf16 GEMM weight shadows current (no per-step re-casts)
     ddp = GradientAllReduce(model)
     ddp.broadcast_parameters()
 

@@ -109,14 +109,19 @@ class _Math:
                 operands MN-major (GEMM_OPERANDS_MN).  No transposed copies anywhere.
     """
 
-    def __init__(self, tc: bool, dev, st, wcache=None):
+    def __init__(self, tc: bool, dev, st, wcache=None, shadows=None):
         self.tc, self.dev, self.st = tc, dev, st
         self._w = wcache if wcache is not None else {}     # bf16 weight shadows; the backward pass reuses the forward's
+        self._shadows = shadows                            # persistent shadows kept current by FusedAdam (optional)
 
     # ---- bf16 shadows of fp32 parameters (cached for the duration of one forward/backward)
     def wbf(self, W: torch.Tensor):
         """[N,K] fp32 -> bf16 [N,Kp], Kp = K rounded up to 8 (zero padded)."""
         key = ("n", W.data_ptr())
+        if key not in self._w and self._shadows is not None:
+            sh = self._shadows.get(W.data_ptr())           # (bf16 tensor, parameter, version at which it was written)
+            if sh is not None and sh[1]._version == sh[2] and sh[0].device == W.device:
+                self._w[key] = (sh[0], W[0].numel())
         if key not in self._w:
             N, K = W.shape[0], W[0].numel()
             Kp = _rup(K, 8)
@@ -218,6 +223,8 @@ class VqaNet(nn.Module):
         self._seed_counter = 0
         self.grad_ready_hook = None      # callable(list[(name, grad)]) fired as each stage's grads complete
         self._arena = None               # see use_gradient_arena()
+        self._shadows = None             # see use_weight_shadows()
+        self._whh_shadow = None
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dt) -> "VqaNet":
@@ -265,6 +272,32 @@ class VqaNet(nn.Module):
         self._arena = {"dev": dev, "views": views, "buckets": buckets}
         return self._arena
 
+    # ------------------------------------------------------------------ persistent bf16 weight shadows
+    def use_weight_shadows(self, optimizer) -> "VqaNet":
+        """Tensor-core arm: let `optimizer` (a FusedAdam) write the bf16 shadow of every GEMM weight in the same kernel
+        that updates the fp32 master, instead of re-casting the weights every step.  A shadow is used only while the
+        parameter's autograd version equals the version recorded when it was written, so `load_state_dict`, another
+        optimizer or any in-place torch op on the parameter silently falls back to the per-step cast.  Contract:
+        do not modify the parameters through `.data` (that bypasses the version counter)."""
+        if not hasattr(optimizer, "register_bf16_shadow"):
+            raise TypeError("use_weight_shadows needs a dl_vqa_b200.FusedAdam")
+        self._shadows = {}
+        lstm = self.text.lstm
+        weights = [self.classifier.lin1.weight, self.classifier.lin2.weight, self.attention.q_lin.weight, self.attention.v_conv.weight]
+        whh = [getattr(lstm, f"weight_hh_l0{s}") for s in ["", "_reverse"][:self.dirs]]
+        # the recurrent weights of both directions share one [dirs, 4H, H] buffer (the backward GEMM is batched over them)
+        self._whh_shadow = torch.empty(self.dirs, 4 * self.H, self.H, dtype=torch.bfloat16, device=whh[0].device) if whh[0].is_cuda else None
+        pairs = [(W, None) for W in weights] + [(W, self._whh_shadow[d] if self._whh_shadow is not None else None) for d, W in enumerate(whh)]
+        for W, sh in pairs:
+            if W[0].numel() % 8 != 0 or not W.is_cuda:
+                continue                                   # shadows are unpadded [N,K] copies: TMA needs 16-byte row pitches
+            if sh is None:
+                sh = torch.empty(W.shape[0], W[0].numel(), dtype=torch.bfloat16, device=W.device)
+            entry = [sh, W, -1]                            # version -1: not valid until the optimizer has written it
+            self._shadows[W.data_ptr()] = entry
+            optimizer.register_bf16_shadow(W, sh, entry)
+        return self
+
     def gradient_buckets(self):
         """{stage: flat fp32 tensor} of the arena (None when the arena is off or not built yet)."""
         return self._arena.get("buckets") if self._arena else None
@@ -311,7 +344,7 @@ class VqaNet(nn.Module):
         tc = adt == torch.bfloat16
         dev = v.device
         st = lib.stream()
-        mm = _Math(tc, dev, st)
+        mm = _Math(tc, dev, st, shadows=self._shadows if tc else None)
         B = v.shape[0]
         f32 = torch.float32
         ctx = {} if save else None
@@ -448,7 +481,7 @@ class VqaNet(nn.Module):
         tc = adt == torch.bfloat16
         dev = dlogits.device
         st = lib.stream()
-        mm = _Math(tc, dev, st, ctx.get("wcache"))
+        mm = _Math(tc, dev, st, ctx.get("wcache"), shadows=self._shadows if tc else None)
         f32 = torch.float32
         H, E, dirs, G, A = self.H, self.E, self.dirs, self.G, self.A
         Cimg = self.channels[-1]
@@ -563,9 +596,15 @@ class VqaNet(nn.Module):
         dg = empty(dirs, T, B, 4 * H)
         gsz = dg.element_size()
         if tc and T > 1:
-            whhb = empty(dirs, 4 * H, H)          # bf16 shadow of W_hh as stored [4H, H]: MN-major B operand of dh = dg W_hh
-            for d in range(dirs):
-                call("vqa_cast_2d", ptr(w_hh[d]), lib.F32, H, ptr(whhb[d]), lib.BF16, H, 4 * H, H, H, st, tag="w_cast")
+            # bf16 shadow of W_hh as stored [dirs, 4H, H]: MN-major B operand of dh = dg W_hh
+            shs = [mm.wbf(w_hh[d])[0] for d in range(dirs)]          # Adam-maintained shadows when valid, else one cast each
+            base = getattr(self, "_whh_shadow", None)
+            if base is not None and all(shs[d].data_ptr() == base[d].data_ptr() for d in range(dirs)):
+                whhb = base
+            else:
+                whhb = empty(dirs, 4 * H, H)
+                for d in range(dirs):
+                    whhb[d].copy_(shs[d])
         for s in range(T - 1, -1, -1):
             call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
                  ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")

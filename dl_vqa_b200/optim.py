@@ -16,8 +16,16 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps)
         super().__init__(params, defaults)
         self._tables = {}
+        self._shadow = {}          # id(param) -> (bf16 tensor, validity entry [tensor, param, version]) : VqaNet.use_weight_shadows
 
     _RING = 4
+
+    def register_bf16_shadow(self, param, shadow, entry):
+        """`shadow` (bf16, same element order as `param`) receives the updated parameter in every step();
+        `entry[2]` is set to the parameter's version afterwards so that the model can tell a current shadow."""
+        if shadow.numel() != param.numel() or shadow.dtype != torch.bfloat16 or not shadow.is_contiguous():
+            raise ValueError("bf16 shadow must be a contiguous bf16 tensor with the parameter's element count")
+        self._shadow[id(param)] = (shadow, entry)
 
     def _table(self, gi, tensors_key, lists):
         """Device-resident pointer tables, rebuilt only when a pointer changes (gradient tensors usually do change
@@ -31,8 +39,8 @@ class FusedAdam(torch.optim.Optimizer):
         n = len(lists["p"])
         if cached is None or cached["n"] != n:
             cached = {"n": n, "slot": -1, "key": None,
-                      "host": [torch.empty(5, n, dtype=torch.int64).pin_memory() for _ in range(self._RING)],
-                      "dev": [torch.empty(5, n, dtype=torch.int64, device=dev) for _ in range(self._RING)],
+                      "host": [torch.empty(6, n, dtype=torch.int64).pin_memory() for _ in range(self._RING)],
+                      "dev": [torch.empty(6, n, dtype=torch.int64, device=dev) for _ in range(self._RING)],
                       "done": [None] * self._RING}
             self._tables[gi] = cached
         slot = (cached["slot"] + 1) % self._RING
@@ -40,7 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
             cached["done"][slot].synchronize()          # the copy that last used this pinned buffer (4 steps ago)
         host = cached["host"][slot]
         host.copy_(torch.tensor([[t.data_ptr() for t in lists[k]] for k in ("p", "g", "m", "v")] +
-                                [[t.numel() for t in lists["p"]]], dtype=torch.int64))
+                                [[t.numel() for t in lists["p"]], lists["s"]], dtype=torch.int64))
         cached["dev"][slot].copy_(host, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -55,7 +63,8 @@ class FusedAdam(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            lists = {"p": [], "g": [], "m": [], "v": []}
+            lists = {"p": [], "g": [], "m": [], "v": [], "s": []}
+            shadowed = []
             for p in ps:
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise lib.VqaLibraryError("FusedAdam: fp32 CUDA parameters only (no CPU fallback)")
@@ -68,12 +77,19 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 lists["p"].append(p.data); lists["g"].append(g); lists["m"].append(st["exp_avg"])
                 lists["v"].append(st["exp_avg_sq"])
+                sh = self._shadow.get(id(p))
+                lists["s"].append(sh[0].data_ptr() if sh is not None else 0)
+                if sh is not None:
+                    shadowed.append((p, sh[1]))
             step = self.state[ps[0]]["step"]
-            key = tuple(t.data_ptr() for k in ("p", "g", "m", "v") for t in lists[k])
+            key = tuple(t.data_ptr() for k in ("p", "g", "m", "v") for t in lists[k]) + tuple(lists["s"])
             table = self._table(gi, key, lists)
             n = len(ps)
             b1, b2 = group["betas"]
-            call("vqa_adam_multi", ptr(table[0]), ptr(table[1]), ptr(table[2]), ptr(table[3]), None, ptr(table[4]),
+            call("vqa_adam_multi", ptr(table[0]), ptr(table[1]), ptr(table[2]), ptr(table[3]),
+                 ptr(table[5]) if shadowed else None, ptr(table[4]),
                  n, max(t.numel() for t in lists["p"]), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                  int(step), float(grad_scale), lib.stream())
+            for p, entry in shadowed:          # the kernel has just rewritten these shadows from the updated masters
+                entry[2] = p._version
         return loss

@@ -306,3 +306,49 @@ def test_gradient_arena_gives_identical_gradients_and_stays_safe(dtype):
     for k, p in m.named_parameters():
         ref = 2 * first[k]
         assert float((p.grad - ref).abs().max()) <= (1e-4 if dtype == "float32" else 4e-3) * float(ref.abs().max() + 1e-30), k
+
+
+def test_adam_maintained_weight_shadows_match_per_step_casts():
+    """VqaNet.use_weight_shadows(FusedAdam): three training steps with optimizer-maintained bf16 weight shadows must
+    follow the same trajectory as re-casting the weights every step, and a load_state_dict must invalidate them."""
+    import dl_vqa_b200 as D
+    cfg = O.zero_dropout(O.cfg_with(O.DEFAULT_CFG, image_size=64))
+    V = 300
+    sd = O.random_params(cfg, V, seed=6, scale=1.5)
+    v, q, q_len, a_idx, a_val, a_len = O.synthetic_batch(6, cfg, V, seed=12, T=9)
+    data = (v, q, a_idx, a_val, a_len, None, q_len)
+
+    def run(shadows):
+        m = D.VqaNet(cfg, V, compute_dtype="bfloat16")
+        m.load_state_dict(sd)
+        m.cuda().train(True)
+        opt = D.FusedAdam(m.parameters(), lr=1e-3)
+        if shadows:
+            m.use_weight_shadows(opt)
+        losses = []
+        for _ in range(3):
+            loss, _ = D.run_batch(m, None, data, cfg["max_answers"])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return m, opt, losses
+
+    _, _, plain = run(False)
+    m, opt, shadowed = run(True)
+    assert all(e[2] == e[1]._version for e in m._shadows.values())                 # every shadow is current after a step
+    for a, b in zip(plain, shadowed):
+        assert abs(a - b) <= 2e-3 * abs(a), (plain, shadowed)
+    assert shadowed[2] < shadowed[0]                                               # it is actually training
+    # new weights through load_state_dict: the shadows are stale and must not be used
+    m.load_state_dict(sd)
+    assert all(e[2] != e[1]._version for e in m._shadows.values())
+    m.eval()
+    with torch.no_grad():
+        got = m(v.cuda(), q.cuda(), q_len.cuda())
+    ref = D.VqaNet(cfg, V, compute_dtype="bfloat16")
+    ref.load_state_dict(sd)
+    ref.cuda().eval()
+    with torch.no_grad():
+        want = ref(v.cuda(), q.cuda(), q_len.cuda())
+    assert torch.equal(got, want)

@@ -10,6 +10,7 @@ cfg = synth.default_cfg()
 torch.manual_seed(1)
 model = D.VqaNet(cfg, synth.DEFAULT_TOKENS, compute_dtype="bfloat16").to(dev).train(True)
 opt = D.FusedAdam(model.parameters(), lr=5e-4)
+model.use_gradient_arena(True); model.use_weight_shadows(opt)
 hv, hq, hai, hav, hal, _, hql = synth.make_batch(256, cfg, seed=1, pin=True)
 db = tuple(t.to(dev) for t in (hv, hq, hai, hav, hal, hql))
 def step():
