@@ -65,6 +65,27 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Sign bits of the four bytes of z replicated over two 16-bit lanes each: LO -> bytes 0,1; HI -> bytes 2,3
+// (prmt's sign-replicate selector mode, which __byte_perm does not expose).
+__device__ __forceinline__ uint32_t sign_mask16_lo(uint32_t z) { uint32_t m; asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m) : "r"(z)); return m; }
+__device__ __forceinline__ uint32_t sign_mask16_hi(uint32_t z) { uint32_t m; asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m) : "r"(z)); return m; }
+
+// Column sums of a 32 x 32 tile held one ROW per lane (v[j] = element j of this lane's row): afterwards v[0] of lane l is
+// the sum over all 32 lanes of element l.  Transposing butterfly: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = 32; n > 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? v[n / 2 + i] : v[i];
+            const float send = up ? v[i] : v[n / 2 + i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
 // block-wide sum; `red` is >= 32 floats of shared memory; result valid in every thread
 __device__ __forceinline__ float block_sum(float v, float* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -22,6 +22,9 @@
 //   POOL  (forward)  bias + ReLU + 2x2 max-pool + arg-max mask: window partners are lanes l, l^1, l^8, l^9 of
 //                    one warp (tile rows are 8 wide); a 2-step butterfly leaves each lane 8 of every 32 channels.
 //   STORE (dgrad)    plain bf16 store of the 128 x BN tile (gradient w.r.t. the layer input).
+//   UNPOOL (dgrad)   the layer input is the pooled output of the layer below: the tile is written straight into that
+//                    layer's UN-POOLED gradient (value at the arg-max element of each 2x2 window, zeros elsewhere) and
+//                    its bias gradient is reduced with a transposing butterfly -- vqa_unpool_bf16 disappears.
 #include "tc_common.cuh"
 
 namespace tc {
@@ -34,7 +37,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int CONV_THREADS = 64 + EPI_WARPS * 32;
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448 - 1024;                     // 227 KB minus alignment slack
-enum { EPI_POOL = 0, EPI_STORE = 1 };
+enum { EPI_POOL = 0, EPI_STORE = 1, EPI_UNPOOL = 2 };
 
 struct ConvParams {
     int B, tiles_h, tiles_w;       // tile grid per image
@@ -47,6 +50,9 @@ struct ConvParams {
     const float* bias; bf16* pooled; uint8_t* mask; int PH, PW;
     // STORE
     bf16* dx;
+    // UNPOOL: dgrad fused with the max-pool backward (+ bias gradient) of the layer below: instead of dx it writes that
+    // layer's un-pooled gradient udy [B, 2*valid_h, 2*valid_w, N] using its pooling mask umask [B, valid_h, valid_w, N]
+    const uint8_t* umask; bf16* udy; float* udb;
 };
 
 // MT = tiles per CTA and round.  MT = 2 (streamed weights, BN <= 128): both tiles' MMAs share every weight slab, which
@@ -189,6 +195,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..+31; the two warps of a quarter alternate column chunks =====
         const int quarter = warp & 3, half = (warp - 2) >> 2;
+        float dbsum[4] = {0.f, 0.f, 0.f, 0.f};          // UNPOOL: bias-gradient partials, see the epilogue for the lane -> channel map
+        // UNPOOL: the pooling-mask bytes of this lane's position do not depend on the MMAs, so they are fetched one tile
+        // ahead (their DRAM latency would otherwise sit on the epilogue's critical path four times per round)
+        constexpr int NMK = EPI == EPI_UNPOOL ? BN / 64 : 1;
+        uint32_t mnext[NMK][8];
+        auto load_masks = [&](int tile) {
+            const bool live = tile < ntiles;
+            const int b = live ? tile / tiles_per_img : 0, r = live ? tile - b * tiles_per_img : 0;
+            const int h = (r / p.tiles_w) * TILE_H + 4 * quarter + (lane >> 3), w = (r % p.tiles_w) * TILE_W + (lane & 7);
+            const bool ok = live && h < p.valid_h && w < p.valid_w;
+            const uint8_t* mp = p.umask + (((int64_t)b * p.valid_h + h) * p.valid_w + w) * p.N + half * 32;
+#pragma unroll
+            for (int k = 0; k < NMK; ++k) {
+                uint4 m0 = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u), m1 = m0;   // 4 = dead / outside
+                if (ok) {
+                    m0 = __ldcs(reinterpret_cast<const uint4*>(mp + 64 * k));
+                    m1 = __ldcs(reinterpret_cast<const uint4*>(mp + 64 * k) + 1);
+                }
+                mnext[k][0] = m0.x; mnext[k][1] = m0.y; mnext[k][2] = m0.z; mnext[k][3] = m0.w;
+                mnext[k][4] = m1.x; mnext[k][5] = m1.y; mnext[k][6] = m1.z; mnext[k][7] = m1.w;
+            }
+        };
+        if (EPI == EPI_UNPOOL) load_masks((cluster_id * MT) * NCTA + (int)rank);
         uint32_t tcount = 0;
         for (int round = cluster_id; round < nrounds; round += nclusters, ++tcount) {
             const uint32_t acc = tcount & 1, use = tcount >> 1;
@@ -220,6 +249,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             *reinterpret_cast<uint4*>(o + c0 + j) = u;
                         }
                     }
+                }
+            } else if (EPI == EPI_UNPOOL) {
+                // A lane owns one position (TMEM lane) and 32 channels = four 16-byte pieces.  A 4 x 4 transpose inside each
+                // lane quad (positions w..w+3 of one row) leaves lane q with piece q of all four positions, so that one
+                // store instruction writes 64 contiguous bytes per position (8 lines instead of 32 per instruction).
+                const int q = lane & 3;
+                const int h = h0 + rr, wq = w0 + (cc & 4);                 // the quad's row and first column
+                const bool okh = live && h < p.valid_h;
+                uint32_t mcur[NMK][8];
+#pragma unroll
+                for (int k = 0; k < NMK; ++k)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mcur[k][j] = mnext[k][j];
+                load_masks(ti + 1 < MT ? tile + NCTA : ((round + nclusters) * MT) * NCTA + (int)rank);
+                bf16* obase = p.udy + (((int64_t)b * 2 * p.valid_h + 2 * h) * (2 * p.valid_w) + 2 * wq) * p.N + half * 32 + 8 * q;
+#pragma unroll
+                for (int k = 0; k < NMK; ++k) {
+                    const int c0 = half * 32 + 64 * k;
+                    float v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    uint32_t G[4][4], M[4][2];          // [piece -> position after the transpose][words]
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) M[j >> 1][j & 1] = mcur[k][j];
+#pragma unroll
+                    for (int step = 0; step < 2; ++step) {
+                        const int off = 1 << step;
+                        const bool up = (q & off) != 0;
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const int lo = step == 0 ? 2 * m : m, hi = lo + off;   // slot pair exchanged in this step
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const uint32_t r = __shfl_xor_sync(0xffffffffu, up ? G[lo][t] : G[hi][t], off);
+                                if (up) G[lo][t] = r; else G[hi][t] = r;
+                            }
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const uint32_t r = __shfl_xor_sync(0xffffffffu, up ? M[lo][t] : M[hi][t], off);
+                                if (up) M[lo][t] = r; else M[hi][t] = r;
+                            }
+                        }
+                    }
+                    // now G[j] / M[j] = channels c0 + 8q .. + 7 of position (h, wq + j)
+                    float bs[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bs[i] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (okh && wq + j < p.valid_w) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // bytes equal to e -> 0x08 -> sign bit; prmt replicates the sign over each bf16
+                                const uint32_t z0 = (0x08080808u - (M[j][0] ^ (0x01010101u * e))) << 4;
+                                const uint32_t z1 = (0x08080808u - (M[j][1] ^ (0x01010101u * e))) << 4;
+                                uint4 u;
+                                u.x = G[j][0] & sign_mask16_lo(z0); u.y = G[j][1] & sign_mask16_hi(z0);
+                                u.z = G[j][2] & sign_mask16_lo(z1); u.w = G[j][3] & sign_mask16_hi(z1);
+                                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * p.valid_w) + 2 * j + (e & 1)) * p.N + 64 * k), u);
+                            }
+                        }
+                        // bias gradient of the layer below: (bf16) gradients whose ReLU was alive (mask byte != 4; the
+                        // prefetch fills 4 for positions outside the image)
+                        const uint32_t z0 = M[j][0] << 5, z1 = M[j][1] << 5;          // bit 2 -> sign bit of each byte
+                        const uint32_t a0 = G[j][0] & ~sign_mask16_lo(z0), a1 = G[j][1] & ~sign_mask16_hi(z0);
+                        const uint32_t a2 = G[j][2] & ~sign_mask16_lo(z1), a3 = G[j][3] & ~sign_mask16_hi(z1);
+                        bs[0] += __uint_as_float(a0 << 16); bs[1] += __uint_as_float(a0 & 0xffff0000u);
+                        bs[2] += __uint_as_float(a1 << 16); bs[3] += __uint_as_float(a1 & 0xffff0000u);
+                        bs[4] += __uint_as_float(a2 << 16); bs[5] += __uint_as_float(a2 & 0xffff0000u);
+                        bs[6] += __uint_as_float(a3 << 16); bs[7] += __uint_as_float(a3 & 0xffff0000u);
+                    }
+                    // transposing reduction over the 8 lanes that share q: lane ends with channel 8q + 4*b4 + 2*b3 + b2
+                    {
+                        int n = 8;
+#pragma unroll
+                        for (int off = 16; off >= 4; off >>= 1, n >>= 1) {
+                            const bool up = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < n / 2; ++i) {
+                                const float keep = up ? bs[n / 2 + i] : bs[i];
+                                const float send = up ? bs[i] : bs[n / 2 + i];
+                                bs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                    }
+                    dbsum[k] += bs[0];
                 }
             } else {
                 // window: pooled row = h0/2 + 2*quarter + (lane>>4), pooled col = w0/2 + cc/2; element e = dy*2+dx
@@ -288,6 +407,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) { if (NCTA == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
+        if (EPI == EPI_UNPOOL) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (half * 32 + 64 * k < BN)
+                    atomicAdd(p.udb + half * 32 + 64 * k + 8 * (lane & 3) + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1),
+                              dbsum[k]);
+        }
     }
 
     tcgen05_fence_before();
@@ -341,7 +467,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
         p.a_stages = a > 4 ? 4 : a; p.b_stages = 1;
         smem = resident_bytes + p.a_stages * A_STAGE_BYTES + bars + 1024;
     } else {
-        const bool mt2 = ncta == 1 && BN <= 128 && EPI == EPI_STORE;          // two tiles share every streamed weight slab
+        const bool mt2 = ncta == 1 && BN <= 128 && EPI != EPI_POOL;          // two tiles share every streamed weight slab
         p.a_stages = mt2 ? 4 : (p.chunks >= 2 ? 3 : 2);
         int bs = (SMEM_LIMIT - bars - p.a_stages * A_STAGE_BYTES) / slab;
         p.b_stages = bs > MAX_B_STAGES ? MAX_B_STAGES : bs;
@@ -353,7 +479,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
         return launch_conv_cfg<BN, EPI, 2, false>(ta, tb2, p, smem, st);
     }
     if (resident) return launch_conv_cfg<BN, EPI, 1, true>(ta, tb1, p, smem, st);
-    if constexpr (BN <= 128 && EPI == EPI_STORE) return launch_conv_cfg<BN, EPI, 1, false, 2>(ta, tb1, p, smem, st);
+    if constexpr (BN <= 128 && EPI != EPI_POOL) return launch_conv_cfg<BN, EPI, 1, false, 2>(ta, tb1, p, smem, st);
     else return launch_conv_cfg<BN, EPI, 1, false>(ta, tb1, p, smem, st);
 }
 
@@ -424,6 +550,30 @@ extern "C" int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
     if (Cin == 64) return launch_conv<64, EPI_STORE>(ta, tb1, tb2, p, st);
     if (Cin == 128) return launch_conv<128, EPI_STORE>(ta, tb1, tb2, p, st);
     return launch_conv<256, EPI_STORE>(ta, tb1, tb2, p, st);
+}
+
+// Data gradient fused with the max-pool backward and bias gradient of the layer BELOW (whose pooled output is this
+// layer's input): mask_below [B,IH,IW,Cin] is that layer's arg-max mask; dy_below [B,2IH,2IW,Cin] receives its un-pooled
+// gradient and db_below [Cin] its bias gradient (overwritten).  Replaces vqa_tc_conv3x3_bwd_data + vqa_unpool_bf16.
+extern "C" int vqa_tc_conv3x3_bwd_data_unpool(const void* dy, const void* wd, const uint8_t* mask_below, void* dy_below,
+                                              float* db_below, int B, int IH, int IW, int Cin, int Cout, void* stream) {
+    VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4 && mask_below && dy_below && db_below, "tc conv dgrad+unpool: bad arguments");
+    VQA_REQUIRE(Cout % 64 == 0, "tc conv dgrad+unpool: Cout=%d must be a multiple of 64", Cout);
+    VQA_REQUIRE(Cin == 64 || Cin == 128 || Cin == 256, "tc conv dgrad+unpool: Cin=%d must be 64, 128 or 256", Cin);
+    const int OHp = ((IH - 2) / 2) * 2, OWp = ((IW - 2) / 2) * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    VQA_CUDA(cudaMemsetAsync(db_below, 0, sizeof(float) * Cin, st));
+    CUtensorMap ta, tb1, tb2;
+    if (int e = act_tmap(&ta, dy, B, OHp, OWp, Cout)) return e;
+    if (int e = weight_tmap(&tb1, wd, Cin, 9 * Cout, Cin)) return e;
+    if (int e = weight_tmap(&tb2, wd, Cin, 9 * Cout, Cin / 2)) return e;
+    ConvParams p{};
+    p.B = B; p.tiles_h = (IH + TILE_H - 1) / TILE_H; p.tiles_w = (IW + TILE_W - 1) / TILE_W;
+    p.chunks = Cout / 64; p.sign = -1; p.valid_h = IH; p.valid_w = IW; p.N = Cin;
+    p.umask = mask_below; p.udy = (bf16*)dy_below; p.udb = db_below;
+    if (Cin == 64) return launch_conv<64, EPI_UNPOOL>(ta, tb1, tb2, p, st);
+    if (Cin == 128) return launch_conv<128, EPI_UNPOOL>(ta, tb1, tb2, p, st);
+    return launch_conv<256, EPI_UNPOOL>(ta, tb1, tb2, p, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,6 +16,11 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {       // 8 packed bf16 -> fp32
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -161,6 +166,129 @@ extern "C" int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* v
         else dropnorm_bwd_kernel<bf16, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
     } else VQA_REQUIRE(false, "dropnorm_bwd: bad dtype");
     VQA_CHECK_LAUNCH("dropnorm_bwd");
+    return 0;
+}
+
+// Same backward, fused with the max-pool backward of the last conv layer and its bias gradient (tensor-core arm):
+// instead of the compact gradient w.r.t. the pooled activation it writes the UN-POOLED gradient
+//   dy[b, 2ph+dy, 2pw+dx, c] = mask[b,ph,pw,c] == dy*2+dx ? g : 0
+// that the conv dgrad / wgrad kernels consume, and db[c] = sum of g where the ReLU was alive (mask < 4).
+// One pass instead of dropnorm_bwd + unpool (saves writing and re-reading the compact gradient and re-reading the mask).
+__global__ void __launch_bounds__(256, 3)
+dropnorm_bwd_unpool_kernel(const bf16* __restrict__ dvn, const bf16* __restrict__ dvnd, const bf16* __restrict__ vn,
+                           const float* __restrict__ nrm, const uint8_t* __restrict__ mask, bf16* __restrict__ dy,
+                           float* __restrict__ db, int64_t R, int C, int PH, int PW, Dropout d_img, Dropout d_att) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
+    const int c8n = C >> 3;
+    const bool act = lane < c8n;
+    float bsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+    // software pipeline: the five loads of the NEXT row are issued before the current row's reduction / stores
+    struct Row { uint4 g, gd, y; uint2 mk; float n; };
+    auto fetch = [&](int64_t r, Row& x) {
+        x.g = x.gd = x.y = make_uint4(0u, 0u, 0u, 0u);
+        x.mk = make_uint2(0x04040404u, 0x04040404u);
+        x.n = 0.f;
+        if (act && r < R) {
+            const int64_t off = r * C + lane * 8;
+            if (dvn) x.g = __ldcs(reinterpret_cast<const uint4*>(dvn + off));
+            if (dvnd) x.gd = __ldcs(reinterpret_cast<const uint4*>(dvnd + off));
+            x.y = __ldcs(reinterpret_cast<const uint4*>(vn + off));
+            x.mk = __ldcs(reinterpret_cast<const uint2*>(mask + off));
+            x.n = nrm[r];
+        }
+    };
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    Row nxt;
+    fetch((int64_t)blockIdx.x * 8 + warp, nxt);
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < R; r += stride) {
+        const Row cur = nxt;
+        fetch(r + stride, nxt);
+        float dyv[8], y[8], t[8];
+        unpack8(cur.g, dyv);
+        unpack8(cur.gd, t);
+        unpack8(cur.y, y);
+        if (dvnd) {
+            float m[8];
+            dropout_mult8(da, (uint32_t)(r * c8n + lane), m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dyv[i] = fmaf(t[i], m[i], dyv[i]);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(dyv[i], y[i], s);
+        s = warp_sum(s);
+        if (act) {
+            const float n = cur.n;
+            const float inv = 1.f / (n + 1e-12f);
+            const float kk = n > 0.f ? s / n : 0.f;
+            float m[8];
+            dropout_mult8(di, (uint32_t)(r * c8n + lane), m);
+            uint32_t gq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn((inv * dyv[2 * i] - kk * y[2 * i]) * m[2 * i],
+                                                                (inv * dyv[2 * i + 1] - kk * y[2 * i + 1]) * m[2 * i + 1]);
+                gq[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            {   // the bias sees what the conv kernels see (bf16), where the ReLU was alive (mask byte != 4)
+                const uint32_t z0 = cur.mk.x << 5, z1 = cur.mk.y << 5;      // bit 2 -> sign bit of each byte
+                const uint32_t a0 = gq[0] & ~sign_mask16_lo(z0), a1 = gq[1] & ~sign_mask16_hi(z0);
+                const uint32_t a2 = gq[2] & ~sign_mask16_lo(z1), a3 = gq[3] & ~sign_mask16_hi(z1);
+                bsum[0] += __uint_as_float(a0 << 16); bsum[1] += __uint_as_float(a0 & 0xffff0000u);
+                bsum[2] += __uint_as_float(a1 << 16); bsum[3] += __uint_as_float(a1 & 0xffff0000u);
+                bsum[4] += __uint_as_float(a2 << 16); bsum[5] += __uint_as_float(a2 & 0xffff0000u);
+                bsum[6] += __uint_as_float(a3 << 16); bsum[7] += __uint_as_float(a3 & 0xffff0000u);
+            }
+            const int pw = (int)(r % PW);
+            const int64_t t2 = r / PW;
+            const int ph = (int)(t2 % PH);
+            const int64_t b = t2 / PH;
+            bf16* obase = dy + ((b * 2 * PH + 2 * ph) * (2 * PW) + 2 * pw) * C + lane * 8;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                // bytes equal to e -> 0x08 -> sign bit; prmt replicates the sign over each bf16
+                const uint32_t z0 = (0x08080808u - (cur.mk.x ^ (0x01010101u * e))) << 4;
+                const uint32_t z1 = (0x08080808u - (cur.mk.y ^ (0x01010101u * e))) << 4;
+                uint4 o;
+                o.x = gq[0] & sign_mask16_lo(z0); o.y = gq[1] & sign_mask16_hi(z0);
+                o.z = gq[2] & sign_mask16_lo(z1); o.w = gq[3] & sign_mask16_hi(z1);
+                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * PW) + (e & 1)) * C), o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = bsum[i];
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(db + threadIdx.x, t);
+    }
+}
+
+extern "C" int vqa_dropnorm_bwd_unpool(const void* dvn, const void* dvnd, const void* vn, const float* nrm, const uint8_t* mask,
+                                       void* dy, float* db, int B, int PH, int PW, int C, float p_img, float p_att,
+                                       uint64_t seed, void* stream) {
+    VQA_REQUIRE(B > 0 && PH > 0 && PW > 0 && vn && nrm && mask && dy && db && (dvn || dvnd), "dropnorm_bwd_unpool: bad arguments");
+    VQA_REQUIRE(C % 8 == 0 && C <= 256, "dropnorm_bwd_unpool: channel count %d must be a multiple of 8 and <= 256", C);
+    const int64_t R = (int64_t)B * PH * PW;
+    VQA_REQUIRE(R * (C / 8) < (1ll << 32), "dropnorm_bwd_unpool: tensor too large for the 32-bit dropout counter");
+    const Dropout di = make_dropout(seed, p_img), da = make_dropout(seed, p_att);
+    cudaStream_t st = (cudaStream_t)stream;
+    VQA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = ceil_div64(R, 8);
+    const unsigned grid = (unsigned)(want < (int64_t)sms * 3 ? want : (int64_t)sms * 3);     // one resident wave
+    dropnorm_bwd_unpool_kernel<<<grid, 256, 0, st>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, mask, (bf16*)dy, db,
+                                                     R, C, PH, PW, di, da);
+    VQA_CHECK_LAUNCH("dropnorm_bwd_unpool");
     return 0;
 }
 

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "vqa_conv_bwd_weight": [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vqa_dropnorm_fwd": [_vp, _vp, _vp, _vp, _i, _i64, _i, _f, _f, _u64, _vp],
     "vqa_dropnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _f, _u64, _vp],
+    "vqa_dropnorm_bwd_unpool": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u64, _vp],
     "vqa_embed_tanh_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_embed_tanh_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_lstm_step_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -9,6 +9,7 @@ PROTOTYPES = {
     "vqa_transpose_bf16": [_vp, _i, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_relu_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vqa_tc_conv3x3_bwd_data_unpool": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv_set_cta_group": [_i],
     "vqa_pack_conv3x3_weight": [_vp, _vp, _vp, _i, _i, _vp],
     "vqa_unpool_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -649,24 +649,47 @@ class VqaNet(nn.Module):
         fire(names)
 
         # ---- image encoder
-        da = empty(B * P, Cimg)
-        call("vqa_dropnorm_bwd", ptr(dvn_pool), ptr(dvnd), ptr(vn), ptr(ctx["nrm"]), ptr(da), dt, B * P, Cimg,
-             p_img, p_att, seed, st)
         nl = len(self.channels) - 1
+
+        def tc_path(i):
+            """layer i runs the tcgen05 un-pool + wgrad (+ dgrad) kernels with the bias gradient fused into the un-pool"""
+            _, _, nchw_i, _, _, _, Cin_i, Cout_i = ctx["conv_saved"][i]
+            return (self._tc_conv_ok(i) and nchw_i == 0 and Cin_i in (64, 128) and Cout_i % 128 == 0 and Cout_i <= 256)
+
+        dy_ready = None          # (un-pooled gradient, bias gradient) of the layer about to be processed, when a producer fused it
+        if tc and tc_path(nl - 1) and Cimg % 8 == 0 and Cimg <= 256:
+            # L2-norm / dropout backward fused with the last layer's max-pool backward and bias gradient
+            _, _, _, mask_l, IH_l, IW_l, _, _ = ctx["conv_saved"][nl - 1]
+            PH_l, PW_l = ((IH_l - self.KS) // self.stride + 1) // 2, ((IW_l - self.KS) // self.stride + 1) // 2
+            dy_l = empty(B, 2 * PH_l, 2 * PW_l, Cimg)
+            db_l = galloc(f"image.conv{nl - 1}.bias", Cimg)
+            call("vqa_dropnorm_bwd_unpool", ptr(dvn_pool), ptr(dvnd), ptr(vn), ptr(ctx["nrm"]), ptr(mask_l), ptr(dy_l), ptr(db_l),
+                 B, PH_l, PW_l, Cimg, p_img, p_att, seed, st, tag="unpool")
+            dy_ready = (dy_l, db_l)
+            da = None
+        else:
+            da = empty(B * P, Cimg)
+            call("vqa_dropnorm_bwd", ptr(dvn_pool), ptr(dvnd), ptr(vn), ptr(ctx["nrm"]), ptr(da), dt, B * P, Cimg,
+                 p_img, p_att, seed, st)
         names = []
         for i in range(nl - 1, -1, -1):
             conv = getattr(self.image, f"conv{i}")
             x, x_dt, nchw, mask, IH, IW, Cin, Cout = ctx["conv_saved"][i]
             PH, PW = ((IH - self.KS) // self.stride + 1) // 2, ((IW - self.KS) // self.stride + 1) // 2
             dW = galloc(f"image.conv{i}.weight", *conv.weight.shape)
-            db = galloc(f"image.conv{i}.bias", Cout)
             use_tc = self._tc_conv_ok(i) and nchw == 0
             dy = None
+            fused_db = False
+            if dy_ready is not None:         # the producer of this layer's gradient already un-pooled it and summed the bias gradient
+                dy, db = dy_ready
+                dy_ready, fused_db = None, True
+            else:
+                db = galloc(f"image.conv{i}.bias", Cout)
             tc0 = tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1
             if tc0:     # fused un-pool + weight gradient + bias gradient straight from (dpool, mask): no dY tensor
                 call("vqa_tc_conv0_bwd_weight_bias", ptr(x), ptr(da), ptr(mask), ptr(dW), ptr(db), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
-            elif use_tc:   # un-pooled gradient, shared by the weight and the data gradient
+            elif use_tc and dy is None:   # un-pooled gradient, shared by the weight and the data gradient
                 dy = empty(B, 2 * PH, 2 * PW, Cout)
                 fused_db = use_tc and Cin in (64, 128) and Cout % 128 == 0 and Cout <= 256
                 call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), ptr(db) if fused_db else None, B, PH, PW, Cout, st,
@@ -686,14 +709,25 @@ class VqaNet(nn.Module):
             grads[f"image.conv{i}.bias"] = db
             names += [f"image.conv{i}.weight", f"image.conv{i}.bias"]
             if i > 0:
-                dx = empty(B, IH, IW, Cin)
+                dx = None
                 if use_tc:
                     wd = empty(Cin, 9 * Cout)
                     call("vqa_pack_conv3x3_weight", ptr(conv.weight), None, ptr(wd), Cout, Cin, st, tag="w_cast")
-                    call("vqa_tc_conv3x3_bwd_data", ptr(dy), ptr(wd), ptr(dx), B, IH, IW, Cin, Cout, st,
-                         tag=f"conv{i}_dgrad")
+                    if tc_path(i - 1):
+                        # the data gradient lands directly in the layer below's UN-POOLED gradient (its max-pool backward
+                        # and bias gradient run in the dgrad epilogue): no dx tensor, no un-pool kernel
+                        dy_b = empty(B, 2 * IH, 2 * IW, Cin)
+                        db_b = galloc(f"image.conv{i - 1}.bias", Cin)
+                        call("vqa_tc_conv3x3_bwd_data_unpool", ptr(dy), ptr(wd), ptr(ctx["conv_saved"][i - 1][3]), ptr(dy_b),
+                             ptr(db_b), B, IH, IW, Cin, Cout, st, tag=f"conv{i}_dgrad")
+                        dy_ready = (dy_b, db_b)
+                    else:
+                        dx = empty(B, IH, IW, Cin)
+                        call("vqa_tc_conv3x3_bwd_data", ptr(dy), ptr(wd), ptr(dx), B, IH, IW, Cin, Cout, st,
+                             tag=f"conv{i}_dgrad")
                     del dy
                 else:
+                    dx = empty(B, IH, IW, Cin)
                     call("vqa_conv_bwd_data", ptr(da), ptr(mask), ptr(conv.weight), ptr(dx), dt,
                          B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_dgrad")
                 da = dx

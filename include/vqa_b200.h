@@ -74,6 +74,12 @@ int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, int act_dty
                      float p_img, float p_att, uint64_t seed, void* stream);
 int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* vn, const float* nrm, void* dx,
                      int act_dtype, int64_t R, int C, float p_img, float p_att, uint64_t seed, void* stream);
+/* bf16 arm: the same backward fused with the 2x2 max-pool backward of the last conv layer and its bias gradient:
+ * writes dy [B,2PH,2PW,C] (un-pooled gradient, zero where mask != window element) and db [C] (overwritten) instead of
+ * the compact gradient; mask [B,PH,PW,C] from the conv forward.  C % 8 == 0, C <= 256. */
+int vqa_dropnorm_bwd_unpool(const void* dvn, const void* dvnd, const void* vn, const float* nrm, const uint8_t* mask,
+                            void* dy, float* db, int B, int PH, int PW, int C, float p_img, float p_att,
+                            uint64_t seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Question encoder -- models/model.py:151-166
@@ -214,7 +220,13 @@ int vqa_tc_conv3x3_relu_pool_fwd(const void* x, const void* wp, const float* bia
  * dx [B,IH,IW,Cin] bf16 */
 int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
                             int B, int IH, int IW, int Cin, int Cout, void* stream);
-/* Tuning knob of the two entries above: 1 = single-CTA tcgen05.mma (cta_group::1), 2 = CTA pairs (cluster of 2,
+/* the same data gradient fused with the 2x2 max-pool backward and the bias gradient of the layer BELOW (whose pooled
+ * output [B,IH,IW,Cin] is this layer's input): mask_below [B,IH,IW,Cin] uint8 from that layer's forward; writes its
+ * un-pooled gradient dy_below [B,2IH,2IW,Cin] bf16 and bias gradient db_below [Cin] fp32 (both overwritten).
+ * Replaces vqa_tc_conv3x3_bwd_data followed by vqa_unpool_bf16. */
+int vqa_tc_conv3x3_bwd_data_unpool(const void* dy, const void* wd, const uint8_t* mask_below, void* dy_below,
+                                   float* db_below, int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* Tuning knob of the entries above: 1 = single-CTA tcgen05.mma (cta_group::1), 2 = CTA pairs (cluster of 2,
  * cta_group::2: each CTA stages half of the weight rows).  Process-wide; results are identical either way. */
 int vqa_tc_conv_set_cta_group(int cta_group);
 /* w fp32 OIHW [Cout,Cin,3,3] -> wp[co][tap][ci] and/or wd[ci][tap][co] (bf16; either may be NULL) */

@@ -150,6 +150,69 @@ def test_tc_conv_dgrad_matches_torch(B, IH, IW, Cin, Cout, conv_cta_group):
     assert err < 1e-2, err
 
 
+@pytest.mark.parametrize("conv_cta_group", [1, 2], indirect=True)
+@pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 54, 54, 128, 256), (3, 20, 36, 64, 128), (1, 13, 10, 256, 64),
+                                              (2, 17, 40, 128, 192)])
+def test_tc_conv_dgrad_fused_unpool_equals_dgrad_then_unpool(B, IH, IW, Cin, Cout, conv_cta_group):
+    """vqa_tc_conv3x3_bwd_data_unpool == vqa_tc_conv3x3_bwd_data followed by vqa_unpool_bf16 of the layer below
+    (bit-identical un-pooled gradient; bias gradient up to fp32 summation order)."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(IH * 7 + Cin)
+    OH, OW = ((IH - 2) // 2) * 2, ((IW - 2) // 2) * 2
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cout ** 0.5))
+    dy = torch.randn(B, OH, OW, Cout, device="cuda").bfloat16()
+    mask_below = torch.randint(0, 5, (B, IH, IW, Cin), device="cuda", dtype=torch.uint8)
+    wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_pack_conv3x3_weight", lib.ptr(w), None, lib.ptr(wd), Cout, Cin, lib.stream())
+    dx = torch.empty(B, IH, IW, Cin, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_tc_conv3x3_bwd_data", lib.ptr(dy), lib.ptr(wd), lib.ptr(dx), B, IH, IW, Cin, Cout, lib.stream())
+    want = torch.zeros(B, 2 * IH, 2 * IW, Cin, device="cuda")
+    for e in range(4):
+        want[:, e // 2::2, e % 2::2, :] = torch.where(mask_below == e, dx.float(), torch.zeros_like(dx.float()))
+    got = torch.full((B, 2 * IH, 2 * IW, Cin), 3.0, dtype=torch.bfloat16, device="cuda")
+    db = torch.full((Cin,), 5.0, device="cuda")
+    lib.call("vqa_tc_conv3x3_bwd_data_unpool", lib.ptr(dy), lib.ptr(wd), lib.ptr(mask_below), lib.ptr(got), lib.ptr(db),
+             B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(got.float(), want)
+    want_db = want.double().sum(dim=(0, 1, 2))
+    assert float((db.double() - want_db).abs().max()) < 1e-4 * float(want_db.abs().max() + 1)
+
+
+@pytest.mark.parametrize("B,PH,PW,C", [(3, 26, 26, 256), (2, 5, 9, 128), (1, 3, 3, 64)])
+@pytest.mark.parametrize("p_img,p_att", [(0.0, 0.0), (0.3, 0.2)])
+def test_dropnorm_bwd_fused_unpool_equals_the_two_kernels(B, PH, PW, C, p_img, p_att):
+    """vqa_dropnorm_bwd_unpool == vqa_dropnorm_bwd followed by vqa_unpool_bf16 (+ fused bias gradient)."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(PH + C)
+    R = B * PH * PW
+    v = torch.randn(R, C, device="cuda").bfloat16()
+    vn = torch.empty_like(v)
+    vnd = torch.empty_like(v)
+    nrm = torch.empty(R, device="cuda")
+    seed = 1234
+    lib.call("vqa_dropnorm_fwd", lib.ptr(v), lib.ptr(vn), lib.ptr(vnd), lib.ptr(nrm), lib.BF16, R, C, p_img, p_att, seed,
+             lib.stream())
+    dvn = torch.randn(R, C, device="cuda").bfloat16()
+    dvnd = torch.randn(R, C, device="cuda").bfloat16()
+    mask = torch.randint(0, 5, (B, PH, PW, C), device="cuda", dtype=torch.uint8)
+    da = torch.empty(R, C, dtype=torch.bfloat16, device="cuda")
+    lib.call("vqa_dropnorm_bwd", lib.ptr(dvn), lib.ptr(dvnd), lib.ptr(vn), lib.ptr(nrm), lib.ptr(da), lib.BF16, R, C,
+             p_img, p_att, seed, lib.stream())
+    want = torch.zeros(B, 2 * PH, 2 * PW, C, device="cuda")
+    daf = da.float().view(B, PH, PW, C)
+    for e in range(4):
+        want[:, e // 2::2, e % 2::2, :] = torch.where(mask == e, daf, torch.zeros_like(daf))
+    got = torch.full((B, 2 * PH, 2 * PW, C), 3.0, dtype=torch.bfloat16, device="cuda")
+    db = torch.full((C,), 5.0, device="cuda")
+    lib.call("vqa_dropnorm_bwd_unpool", lib.ptr(dvn), lib.ptr(dvnd), lib.ptr(vn), lib.ptr(nrm), lib.ptr(mask), lib.ptr(got),
+             lib.ptr(db), B, PH, PW, C, p_img, p_att, seed, lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(got.float(), want)
+    want_db = want.double().sum(dim=(0, 1, 2))
+    assert float((db.double() - want_db).abs().max()) < 1e-4 * float(want_db.abs().max() + 1)
+
+
 @pytest.mark.parametrize("B,IH,IW,Cin,Cout", [(2, 20, 36, 64, 128), (3, 111, 111, 64, 128), (2, 54, 54, 128, 256),
                                               (1, 13, 10, 64, 128)])
 def test_tc_conv_wgrad_matches_torch(B, IH, IW, Cin, Cout):
