@@ -1,4 +1,5 @@
 // ABI bookkeeping: version and per-thread error string.
+#include <stdlib.h>
 #include "common.cuh"
 #include <stdarg.h>
 
@@ -12,6 +13,11 @@ void vqa_set_error(const char* fmt, ...) {
 }
 
 static unsigned long long g_launches = 0;
+int vqa_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("VQA_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on;
+}
 void vqa_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 extern "C" uint64_t vqa_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 

@@ -33,6 +33,27 @@ void vqa_count_launch();
         }                                                                             \
     } while (0)
 
+// ---- programmatic dependent launch (PDL).  A kernel launched through vqa_launch_pdl may become resident while its
+// predecessor in the stream is still running: it runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch), then pdl_wait() blocks until the predecessor has completed and its writes are visible.  Rules for a
+// kernel launched this way: pdl_trigger() first (lets ITS successor do the same), and NO global-memory access of any
+// kind before pdl_wait().  Hides the ~2.5 us dependent-launch gap between the ~110 kernels of a step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int vqa_pdl_enabled();          // env VQA_PDL=0 turns the attribute off (kernels then serialise as usual)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vqa_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = vqa_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 #define VQA_CUDA(call)                                                                \
     do {                                                                              \
         cudaError_t e__ = (call);                                                     \

@@ -415,6 +415,8 @@ __global__ void __launch_bounds__(128)
 lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __restrict__ cs, float* __restrict__ dh,
                                float* __restrict__ dc, const bf16* __restrict__ dc_init, bf16* __restrict__ dg,
                                const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+    pdl_trigger();
+    pdl_wait();
     const int h8 = H >> 3;
     const int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over dirs*B*H/8
     if (i8 >= (int64_t)dirs * B * h8) return;
@@ -472,7 +474,8 @@ extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, f
     if (act_dtype == VQA_F32)
         lstm_bwd_pointwise_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)gates, cs, dh, dc, (const float*)dc_init, (float*)dg, q_len, s, T, B, H, dirs);
     else if (act_dtype == VQA_BF16 && H % 8 == 0)
-        lstm_bwd_pointwise_vec8_kernel<<<(unsigned)ceil_div64(n / 8, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
+        VQA_CUDA(vqa_launch_pdl(lstm_bwd_pointwise_vec8_kernel, dim3((unsigned)ceil_div64(n / 8, 128)), dim3(128), 0, (cudaStream_t)stream,
+                                (const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs));
     else if (act_dtype == VQA_BF16)
         lstm_bwd_pointwise_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
     else VQA_REQUIRE(false, "lstm bwd pointwise: bad dtype");

@@ -85,9 +85,25 @@ struct GemmSmem {
 
 // Epilogue of one accumulator row chunk: v[0..31] = columns nb..nb+31 of output row m (batch `batch`): bias / ReLU /
 // dropout / conversion / store (or fp32 atomics for split-K).
+// Called by all 32 lanes of the warp (lane = TMEM lane = output row); `row_ok` masks the stores of rows beyond M.
+// `bias_lane` = bias[nb + lane] + bias2[nb + lane] (0 beyond N): one coalesced load per chunk, fetched by the caller
+// before it waits for the accumulator, and broadcast here with shuffles -- 32 (x2) same-address loads per lane after
+// the TMEM wait doubled the time of the LSTM input projection.
+__device__ __forceinline__ float gemm_bias_lane(const float* bias, const float* bias2, int n, int N) {
+    float b = 0.f;
+    if (n < N) {
+        if (bias) b += __ldg(bias + n);
+        if (bias2) b += __ldg(bias2 + n);
+    }
+    return b;
+}
+
 __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (&v)[32], int batch, int m, int nb, int N,
-                                                 const float* bias, const float* bias2, uint32_t dkey) {
+                                                 bool has_bias, float bias_lane, uint32_t dkey, int M) {
+    const bool row_ok = m < M;
+    const int lane = threadIdx.x & 31;
     if (ep.atomic) {
+        if (!row_ok) return;
         float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
         if (nb + 32 <= N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {       // 8 vector reductions instead of 32 scalar ones
 #pragma unroll
@@ -98,16 +114,13 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
         }
         return;
     }
+    if (has_bias) {                                          // warp-uniform
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int n = nb + j;
-        float x = v[j];
-        if (n < N) {
-            if (bias) x += bias[n];
-            if (bias2) x += bias2[n];
-        }
-        if (ep.relu) x = fmaxf(x, 0.f);
-        v[j] = x;
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+    }
+    if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (ep.use_dropout) {
 #pragma unroll
@@ -123,21 +136,44 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
     }
     const bool full_chunk = nb + 32 <= N;
     if (ep.out_bf16) {
-        bf16* o = (bf16*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
-        if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        bf16* ob = (bf16*)ep.out + (int64_t)batch * ep.c_sb + nb;
+        // warp-uniform: every row's 64-byte chunk is 16-byte aligned
+        if (full_chunk && (ep.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
+            // A lane holds one row's 64 bytes as four 16-byte pieces.  4 x 4 transpose inside each lane quad: lane q ends
+            // with piece q of the quad's four rows, so one store instruction writes 64 contiguous bytes per row
+            // (8 lines per instruction instead of 32 -- the epilogue of the store-heavy GEMMs is LSU-wavefront bound).
+            uint32_t G[4][4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                *reinterpret_cast<uint4*>(o + j) = u;
+            for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
             }
-        } else {
+            const int q = lane & 3;
+#pragma unroll
+            for (int step = 0; step < 2; ++step) {
+                const int off = 1 << step;
+                const bool up = (q & off) != 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int lo = step == 0 ? 2 * i : i, hi = lo + off;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t r = __shfl_xor_sync(0xffffffffu, up ? G[lo][t] : G[hi][t], off);
+                        if (up) G[lo][t] = r; else G[hi][t] = r;
+                    }
+                }
+            }
+            const int mq = m - q;                            // first row of the quad
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (mq + j < M)
+                    *reinterpret_cast<uint4*>(ob + (int64_t)(mq + j) * ep.ldc + 8 * q) = make_uint4(G[j][0], G[j][1], G[j][2], G[j][3]);
+        } else if (row_ok) {
+            bf16* o = ob + (int64_t)m * ep.ldc;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = __float2bfloat16_rn(v[j]);
         }
-    } else {
+    } else if (row_ok) {
         float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
         if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -169,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* tmem_full = empty + S::STAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int batch = blockIdx.z / nsplit, split = blockIdx.z - batch * nsplit;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -188,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();                                         // operands / output of the previous kernel in the stream
 
     if (warp == 0) {
         if (lane == 0) {
@@ -239,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const float* bias = ep.bias ? ep.bias + (int64_t)batch * ep.bias_sb : nullptr;
         const float* bias2 = ep.bias2 ? ep.bias2 + (int64_t)batch * ep.bias_sb : nullptr;
         const uint32_t dkey = ep.use_dropout ? dropout_key(ep.drop, ep.site) : 0;
+        const bool has_bias = !ep.atomic && (bias || bias2);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= N) break;                     // warp-uniform
@@ -248,8 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            if (m >= M) continue;
-            gemm_store_chunk(ep, v, batch, m, n0 + c0, N, bias, bias2, dkey);
+            gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, has_bias ? gemm_bias_lane(bias, bias2, n0 + c0 + lane, N) : 0.f,
+                             dkey, M);
         }
     }
 
@@ -286,6 +325,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
     const int ntiles = mt * nt * nbatch;
@@ -302,6 +342,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -357,14 +398,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
             const int m = m0 + quarter * 32 + lane;
             const float* bias = ep.bias ? ep.bias + (int64_t)batch * ep.bias_sb : nullptr;
             const float* bias2 = ep.bias2 ? ep.bias2 + (int64_t)batch * ep.bias_sb : nullptr;
+            const bool has_bias = bias || bias2;
+            float bl[BN / 64];                               // this lane's column bias of each of the warp's chunks
+#pragma unroll
+            for (int k = 0; k < BN / 64; ++k) bl[k] = has_bias ? gemm_bias_lane(bias, bias2, n0 + half * 32 + 64 * k + lane, N) : 0.f;
             mbar_wait(&tmem_full[acc], use & 1);
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                if (n0 + c0 >= N) break;                     // warp-uniform
-                float v[32];
-                tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-                if (m < M) gemm_store_chunk(ep, v, batch, m, n0 + c0, N, bias, bias2, dkey);
+#pragma unroll
+            for (int k = 0; k < BN / 64; ++k) {
+                const int c0 = half * 32 + 64 * k;
+                if (n0 + c0 < N) {                           // warp-uniform
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                    gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, bl[k], dkey, M);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -385,7 +432,7 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PGemmSmem<BN>::BYTES));
         attr_set = true;
     }
-    kern<<<sms, PGEMM_THREADS, PGemmSmem<BN>::BYTES, st>>>(ta, tb, ep, M, N, K, nbatch);
+    VQA_CUDA(vqa_launch_pdl(kern, dim3(sms), dim3(PGEMM_THREADS), PGemmSmem<BN>::BYTES, st, ta, tb, ep, M, N, K, nbatch));
     VQA_CHECK_LAUNCH("gemm_tc_persistent");
     return 0;
 }
@@ -399,7 +446,7 @@ static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, ST>::BYTES));
         attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, GemmSmem<BN, ST>::BYTES, st>>>(ta, tb, ep, M, N, K, nsplit, kbps);
+    VQA_CUDA(vqa_launch_pdl(kern, grid, dim3(GEMM_THREADS), GemmSmem<BN, ST>::BYTES, st, ta, tb, ep, M, N, K, nsplit, kbps));
     VQA_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
