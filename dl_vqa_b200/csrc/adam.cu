@@ -10,6 +10,8 @@ adam_multi_kernel(float* const* __restrict__ params, const float* const* __restr
                   float* const* __restrict__ exp_avg, float* const* __restrict__ exp_avg_sq,
                   void* const* __restrict__ bf16_copy, const int64_t* __restrict__ sizes,
                   float lr_over_bc1, float beta1, float beta2, float eps, float inv_sqrt_bc2, float grad_scale) {
+    pdl_trigger();
+    pdl_wait();
     const int t = blockIdx.y;
     const int64_t n = sizes[t];
     float* p = params[t];
@@ -59,9 +61,9 @@ extern "C" int vqa_adam_multi(float* const* params, const float* const* grads, f
     int64_t gx = ceil_div64(max_size, 256 * 4);
     if (gx > 148 * 8) gx = 148 * 8;
     dim3 grid((unsigned)gx, (unsigned)n);
-    adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, bf16_copy, sizes,
+    VQA_CUDA(vqa_launch_pdl(adam_multi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, bf16_copy, sizes,
                                                              (float)(lr / bc1), beta1, beta2, eps,
-                                                             (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                             (float)(1.0 / sqrt(bc2)), grad_scale));
     VQA_CHECK_LAUNCH("adam_multi");
     return 0;
 }

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(NTHREADS)
 attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, const T* __restrict__ vn,
                      const float* __restrict__ wx, const float* __restrict__ bx, float* __restrict__ prob,
                      T* __restrict__ out, int64_t ldo, int P, int A, int C, Dropout drop) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     float* logit = sm;                 // [G][P]
     float* red = sm + G * P;           // [NW][G*256]
@@ -187,6 +189,8 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
                      const T* __restrict__ vn, const float* __restrict__ wx, const float* __restrict__ prob,
                      T* __restrict__ dvp, T* __restrict__ dvn, float* __restrict__ dqp, float* __restrict__ dwx_part,
                      float* __restrict__ dbx_part, int P, int A, int C, Dropout drop) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     float* pr = sm;                       // [G][P] softmax
     float* dl = pr + G * P;               // [G][P] dp, then dlogit
@@ -384,6 +388,8 @@ __global__ void __launch_bounds__(NTHR, 1)
 attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict__ qp, const bf16* __restrict__ vn,
                             const float* __restrict__ wx, const float* __restrict__ bx, float* __restrict__ prob,
                             bf16* __restrict__ out, int64_t ldo, int B, int P, Dropout drop) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int GP = G <= 2 ? G : 4;                 // glimpses padded to a power of two for the butterfly
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -584,11 +590,11 @@ int launch_fwd_stream(const void* vp, const float* qp, const void* vn, const flo
     if (d.threshold != 0) {
         auto kern = attention_fwd_stream_kernel<G, OP, true>;
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHR, smem, st>>>((const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d);
+        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d));
     } else {
         auto kern = attention_fwd_stream_kernel<G, OP, false>;
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHR, smem, st>>>((const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d);
+        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d));
     }
     VQA_CHECK_LAUNCH("attention_fwd_stream");
     return 0;
@@ -620,6 +626,8 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                             const bf16* __restrict__ vn, const float* __restrict__ wx, const float* __restrict__ prob,
                             bf16* __restrict__ dvp, bf16* __restrict__ dvn, float* __restrict__ dqp, float* __restrict__ dwx_part,
                             float* __restrict__ dbx_part, int B, int P, Dropout drop) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int GP = G <= 2 ? G : 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -854,13 +862,13 @@ int launch_bwd_stream(const void* dout, int64_t ldd, const void* vp, const float
     if (d.threshold != 0) {
         auto kern = attention_bwd_stream_kernel<G, OP, true>;
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHR, smem, st>>>((const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
-                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d);
+        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
+                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d));
     } else {
         auto kern = attention_bwd_stream_kernel<G, OP, false>;
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHR, smem, st>>>((const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
-                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d);
+        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
+                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d));
     }
     VQA_CHECK_LAUNCH("attention_bwd_stream");
     return 0;
@@ -874,7 +882,7 @@ int launch_fwd(const void* vp, const float* qp, const void* vn, const float* wx,
     const size_t smem = sizeof(float) * ((size_t)G * P + (size_t)NW * G * 256);
     auto kern = attention_fwd_kernel<T, G, OP>;
     if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, NTHREADS, smem, st>>>((const T*)vp, qp, (const T*)vn, wx, bx, prob, (T*)out, ldo, P, A, C, d);
+    VQA_CUDA(vqa_launch_pdl(kern, dim3(B), dim3(NTHREADS), smem, st, (const T*)vp, qp, (const T*)vn, wx, bx, prob, (T*)out, ldo, P, A, C, d));
     VQA_CHECK_LAUNCH("attention_fwd");
     return 0;
 }
@@ -886,8 +894,8 @@ int launch_bwd(const void* dout, int64_t ldd, const void* vp, const float* qp, c
     const size_t smem = sizeof(float) * ((size_t)2 * G * P + (size_t)G * C + (size_t)NW * (1 + G) * 256);
     auto kern = attention_bwd_kernel<T, G, OP>;
     if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, NTHREADS, smem, st>>>((const T*)dout, ldd, (const T*)vp, qp, (const T*)vn, wx, prob, (T*)dvp, (T*)dvn,
-                                    dqp, dwx_part, dbx_part, P, A, C, d);
+    VQA_CUDA(vqa_launch_pdl(kern, dim3(B), dim3(NTHREADS), smem, st, (const T*)dout, ldd, (const T*)vp, qp, (const T*)vn, wx, prob, (T*)dvp, (T*)dvn,
+                                    dqp, dwx_part, dbx_part, P, A, C, d));
     VQA_CHECK_LAUNCH("attention_bwd");
     return 0;
 }

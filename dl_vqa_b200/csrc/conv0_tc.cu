@@ -128,6 +128,7 @@ constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 
 template <bool STAGED>
 __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
@@ -152,6 +153,8 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
         if (STAGED) tma_prefetch_desc(&tma_x);
         fence_barrier_init();
     }
+    if (warp == 16) tmem_alloc(tmem_base_smem, 512);
+    pdl_wait();                                                // the weights below were written by the previous kernel (Adam)
     if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
         const int co = threadIdx.x;
         float v[32];
@@ -166,7 +169,6 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
         }
         fence_proxy_async();
     }
-    if (warp == 16) tmem_alloc(tmem_base_smem, 512);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -299,6 +301,7 @@ constexpr int C0B_XSTAGES = 3;
 
 template <bool STAGED>
 __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* xs = smem + 2 * C0B_STAGE_BYTES;                  // C0B_XSTAGES x 8 KB staged input regions
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();
 
     if (warp == 13) {
         if (STAGED && lane == 0) {
@@ -477,11 +481,11 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const 
         if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
         static bool attr_set = false;
         if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        conv0_fwd_tc_kernel<true><<<grid, C0F_THREADS, smem, (cudaStream_t)stream>>>(tx, p);
+        VQA_CUDA(vqa_launch_pdl(conv0_fwd_tc_kernel<true>, dim3(grid), dim3(C0F_THREADS), smem, (cudaStream_t)stream, tx, p));
     } else {
         static bool attr_set = false;
         if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        conv0_fwd_tc_kernel<false><<<grid, C0F_THREADS, smem, (cudaStream_t)stream>>>(tx, p);
+        VQA_CUDA(vqa_launch_pdl(conv0_fwd_tc_kernel<false>, dim3(grid), dim3(C0F_THREADS), smem, (cudaStream_t)stream, tx, p));
     }
     VQA_CHECK_LAUNCH("conv0_fwd_tc");
     return 0;
@@ -516,11 +520,11 @@ extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, c
         if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
         static bool attr_set = false;
         if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        conv0_bwd_tc_kernel<true><<<ctas, C0B_THREADS, smem, st>>>(tx, p);
+        VQA_CUDA(vqa_launch_pdl(conv0_bwd_tc_kernel<true>, dim3(ctas), dim3(C0B_THREADS), smem, st, tx, p));
     } else {
         static bool attr_set = false;
         if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        conv0_bwd_tc_kernel<false><<<ctas, C0B_THREADS, smem, st>>>(tx, p);
+        VQA_CUDA(vqa_launch_pdl(conv0_bwd_tc_kernel<false>, dim3(ctas), dim3(C0B_THREADS), smem, st, tx, p));
     }
     VQA_CHECK_LAUNCH("conv0_bwd_tc");
     return 0;

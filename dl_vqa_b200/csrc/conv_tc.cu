@@ -60,6 +60,7 @@ struct ConvParams {
 template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, ConvParams p) {
+    pdl_trigger();
     constexpr int BN_CTA = BN / NCTA;                 // weight rows held by this CTA
     constexpr int B_SLAB = BN_CTA * 128;              // one 64-wide k-slab of them
     extern __shared__ uint8_t smem_raw[];
@@ -99,6 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();                                       // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===== TMA producer (one per CTA; byte counts go to the leader's barriers) =====
@@ -443,10 +445,19 @@ static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvPar
     int grid = (nrounds < sms / NCTA ? nrounds : sms / NCTA) * NCTA;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = NCTA == 2 ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (NCTA == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = NCTA; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (vqa_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     VQA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     VQA_CHECK_LAUNCH("conv_tc");
     return 0;
@@ -581,6 +592,8 @@ extern "C" int vqa_tc_conv3x3_bwd_data_unpool(const void* dy, const void* wd, co
 // ------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ wp, bf16* __restrict__ wd,
                                         int Cout, int Cin) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over Cout*Cin*9 in OIHW order
     if (i >= (int64_t)Cout * Cin * 9) return;
     const int tap = (int)(i % 9);
@@ -594,7 +607,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __res
 extern "C" int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream) {
     VQA_REQUIRE(w && (wp || wd) && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
     const int64_t n = (int64_t)Cout * Cin * 9;
-    pack_conv_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, (bf16*)wd, Cout, Cin);
+    VQA_CUDA(vqa_launch_pdl(pack_conv_weight_kernel, dim3((unsigned)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, w, (bf16*)wp, (bf16*)wd, Cout, Cin));
     VQA_CHECK_LAUNCH("pack_conv_weight");
     return 0;
 }
@@ -605,6 +618,8 @@ extern "C" int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int C
 __global__ void __launch_bounds__(256)
 unpool_bf16_kernel(const bf16* __restrict__ dpool, const uint8_t* __restrict__ mask, bf16* __restrict__ dy,
                    float* __restrict__ db, int64_t npos, int PH, int PW, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[256][9];
     const int c8 = C >> 3;
     const int64_t total = npos * c8;
@@ -661,7 +676,7 @@ extern "C" int vqa_unpool_bf16(const void* dpool, const uint8_t* mask, void* dy,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = ceil_div64(npos * (C / 8), 256);
     const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-    unpool_bf16_kernel<<<grid, 256, 0, st>>>((const bf16*)dpool, mask, (bf16*)dy, db, npos, PH, PW, C);
+    VQA_CUDA(vqa_launch_pdl(unpool_bf16_kernel, dim3(grid), dim3(256), 0, st, (const bf16*)dpool, mask, (bf16*)dy, db, npos, PH, PW, C));
     VQA_CHECK_LAUNCH("unpool_bf16");
     return 0;
 }

@@ -41,6 +41,8 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 template <typename T, int NK>
 __global__ void dropnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ vn, T* __restrict__ vnd,
                                     float* __restrict__ nrm, int64_t R, int C, Dropout d_img, Dropout d_att) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
@@ -85,6 +87,8 @@ template <typename T, int NK>
 __global__ void dropnorm_bwd_kernel(const T* __restrict__ dvn, const T* __restrict__ dvnd, const T* __restrict__ vn,
                                     const float* __restrict__ nrm, T* __restrict__ dx, int64_t R, int C,
                                     Dropout d_img, Dropout d_att) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
@@ -141,11 +145,11 @@ extern "C" int vqa_dropnorm_fwd(const void* x, void* vn, void* vnd, float* nrm, 
     const unsigned grid = (unsigned)ceil_div64(R, wpb);
     // NK = groups of 8 channels per lane: 1 covers C <= 256 (the config.yaml shape) with a third of the registers
     if (act_dtype == VQA_F32) {
-        if (C <= 256) dropnorm_fwd_kernel<float, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
-        else dropnorm_fwd_kernel<float, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da);
+        if (C <= 256) VQA_CUDA(vqa_launch_pdl(dropnorm_fwd_kernel<float, 1>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da));
+        else VQA_CUDA(vqa_launch_pdl(dropnorm_fwd_kernel<float, DN_MAXK>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const float*)x, (float*)vn, (float*)vnd, nrm, R, C, di, da));
     } else if (act_dtype == VQA_BF16) {
-        if (C <= 256) dropnorm_fwd_kernel<bf16, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
-        else dropnorm_fwd_kernel<bf16, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da);
+        if (C <= 256) VQA_CUDA(vqa_launch_pdl(dropnorm_fwd_kernel<bf16, 1>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da));
+        else VQA_CUDA(vqa_launch_pdl(dropnorm_fwd_kernel<bf16, DN_MAXK>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)vn, (bf16*)vnd, nrm, R, C, di, da));
     } else VQA_REQUIRE(false, "dropnorm_fwd: bad dtype");
     VQA_CHECK_LAUNCH("dropnorm_fwd");
     return 0;
@@ -159,11 +163,11 @@ extern "C" int vqa_dropnorm_bwd(const void* dvn, const void* dvnd, const void* v
     const int wpb = 8;
     const unsigned grid = (unsigned)ceil_div64(R, wpb);
     if (act_dtype == VQA_F32) {
-        if (C <= 256) dropnorm_bwd_kernel<float, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
-        else dropnorm_bwd_kernel<float, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da);
+        if (C <= 256) VQA_CUDA(vqa_launch_pdl(dropnorm_bwd_kernel<float, 1>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da));
+        else VQA_CUDA(vqa_launch_pdl(dropnorm_bwd_kernel<float, DN_MAXK>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const float*)dvn, (const float*)dvnd, (const float*)vn, nrm, (float*)dx, R, C, di, da));
     } else if (act_dtype == VQA_BF16) {
-        if (C <= 256) dropnorm_bwd_kernel<bf16, 1><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
-        else dropnorm_bwd_kernel<bf16, DN_MAXK><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da);
+        if (C <= 256) VQA_CUDA(vqa_launch_pdl(dropnorm_bwd_kernel<bf16, 1>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da));
+        else VQA_CUDA(vqa_launch_pdl(dropnorm_bwd_kernel<bf16, DN_MAXK>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, (const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, (bf16*)dx, R, C, di, da));
     } else VQA_REQUIRE(false, "dropnorm_bwd: bad dtype");
     VQA_CHECK_LAUNCH("dropnorm_bwd");
     return 0;
@@ -178,6 +182,8 @@ __global__ void __launch_bounds__(256, 3)
 dropnorm_bwd_unpool_kernel(const bf16* __restrict__ dvn, const bf16* __restrict__ dvnd, const bf16* __restrict__ vn,
                            const float* __restrict__ nrm, const uint8_t* __restrict__ mask, bf16* __restrict__ dy,
                            float* __restrict__ db, int64_t R, int C, int PH, int PW, Dropout d_img, Dropout d_att) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Dropout8 di = make_dropout8(d_img, SITE_IMAGE), da = make_dropout8(d_att, SITE_ATT_V);
@@ -286,8 +292,8 @@ extern "C" int vqa_dropnorm_bwd_unpool(const void* dvn, const void* dvnd, const 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = ceil_div64(R, 8);
     const unsigned grid = (unsigned)(want < (int64_t)sms * 3 ? want : (int64_t)sms * 3);     // one resident wave
-    dropnorm_bwd_unpool_kernel<<<grid, 256, 0, st>>>((const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, mask, (bf16*)dy, db,
-                                                     R, C, PH, PW, di, da);
+    VQA_CUDA(vqa_launch_pdl(dropnorm_bwd_unpool_kernel, dim3(grid), dim3(256), 0, st, (const bf16*)dvn, (const bf16*)dvnd, (const bf16*)vn, nrm, mask, (bf16*)dy, db,
+                                                     R, C, PH, PW, di, da));
     VQA_CHECK_LAUNCH("dropnorm_bwd_unpool");
     return 0;
 }
@@ -301,6 +307,8 @@ template <typename T>
 __global__ void embed_tanh_fwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
                                       const float* __restrict__ emb, T* __restrict__ xs,
                                       int B, int T_, int E, int ldx, int dirs, Dropout d) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = blockIdx.x;                 // (dir, s, b)
     const int b = (int)(row % B);
     const int s = (int)((row / B) % T_);
@@ -324,6 +332,8 @@ template <typename T>
 __global__ void embed_tanh_bwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
                                       const T* __restrict__ xs, const T* __restrict__ dxs, float* __restrict__ demb,
                                       int B, int T_, int E, int ldx, int dirs, Dropout d) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = blockIdx.x;
     const int b = (int)(row % B);
     const int s = (int)((row / B) % T_);
@@ -347,9 +357,9 @@ extern "C" int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const 
     const Dropout d = make_dropout(seed, p);
     const unsigned grid = (unsigned)((int64_t)dirs * T * B);
     if (act_dtype == VQA_F32)
-        embed_tanh_fwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, emb, (float*)xs, B, T, E, ldx, dirs, d);
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, emb, (float*)xs, B, T, E, ldx, dirs, d));
     else if (act_dtype == VQA_BF16)
-        embed_tanh_fwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, emb, (bf16*)xs, B, T, E, ldx, dirs, d);
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, emb, (bf16*)xs, B, T, E, ldx, dirs, d));
     else VQA_REQUIRE(false, "embed_fwd: bad dtype");
     VQA_CHECK_LAUNCH("embed_tanh_fwd");
     return 0;
@@ -362,9 +372,9 @@ extern "C" int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const 
     const Dropout d = make_dropout(seed, p);
     const unsigned grid = (unsigned)((int64_t)dirs * T * B);
     if (act_dtype == VQA_F32)
-        embed_tanh_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, (const float*)xs, (const float*)dxs, demb, B, T, E, ldx, dirs, d);
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, (const float*)xs, (const float*)dxs, demb, B, T, E, ldx, dirs, d));
     else if (act_dtype == VQA_BF16)
-        embed_tanh_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_len, (const bf16*)xs, (const bf16*)dxs, demb, B, T, E, ldx, dirs, d);
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, (const bf16*)xs, (const bf16*)dxs, demb, B, T, E, ldx, dirs, d));
     else VQA_REQUIRE(false, "embed_bwd: bad dtype");
     VQA_CHECK_LAUNCH("embed_tanh_bwd");
     return 0;
@@ -378,6 +388,8 @@ __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const flo
                                           float* __restrict__ dh, float* __restrict__ dc,
                                           const T* __restrict__ dc_init, T* __restrict__ dg,
                                           const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over dirs*B*H
     if (i >= (int64_t)dirs * B * H) return;
     const int j = (int)(i % H);
@@ -472,12 +484,12 @@ extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, f
     const int64_t n = (int64_t)dirs * B * H;
     const unsigned grid = (unsigned)ceil_div64(n, 256);
     if (act_dtype == VQA_F32)
-        lstm_bwd_pointwise_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)gates, cs, dh, dc, (const float*)dc_init, (float*)dg, q_len, s, T, B, H, dirs);
+        VQA_CUDA(vqa_launch_pdl(lstm_bwd_pointwise_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)gates, cs, dh, dc, (const float*)dc_init, (float*)dg, q_len, s, T, B, H, dirs));
     else if (act_dtype == VQA_BF16 && H % 8 == 0)
         VQA_CUDA(vqa_launch_pdl(lstm_bwd_pointwise_vec8_kernel, dim3((unsigned)ceil_div64(n / 8, 128)), dim3(128), 0, (cudaStream_t)stream,
                                 (const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs));
     else if (act_dtype == VQA_BF16)
-        lstm_bwd_pointwise_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs);
+        VQA_CUDA(vqa_launch_pdl(lstm_bwd_pointwise_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)gates, cs, dh, dc, (const bf16*)dc_init, (bf16*)dg, q_len, s, T, B, H, dirs));
     else VQA_REQUIRE(false, "lstm bwd pointwise: bad dtype");
     VQA_CHECK_LAUNCH("lstm_step_bwd_pointwise");
     return 0;
@@ -489,6 +501,8 @@ extern "C" int vqa_lstm_step_bwd_pointwise(const void* gates, const float* cs, f
 template <typename T>
 __global__ void dropout_apply_kernel(const T* __restrict__ in, int64_t ld_in, T* __restrict__ out, int64_t ld_out,
                                      int64_t rows, int cols, Dropout d, uint32_t site) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int64_t r = i / cols; const int c = (int)(i - r * cols);
@@ -502,9 +516,9 @@ extern "C" int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64
     const Dropout d = make_dropout(seed, p);
     const unsigned grid = (unsigned)ceil_div64(rows * cols, 256);
     if (dtype == VQA_F32)
-        dropout_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, (float*)out, ld_out, rows, cols, d, site);
+        VQA_CUDA(vqa_launch_pdl(dropout_apply_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)in, ld_in, (float*)out, ld_out, rows, cols, d, site));
     else if (dtype == VQA_BF16)
-        dropout_apply_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols, d, site);
+        VQA_CUDA(vqa_launch_pdl(dropout_apply_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols, d, site));
     else VQA_REQUIRE(false, "dropout_apply: bad dtype");
     VQA_CHECK_LAUNCH("dropout_apply");
     return 0;
@@ -513,6 +527,8 @@ extern "C" int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64
 template <typename T>
 __global__ void add_dropped_kernel(const T* __restrict__ a, int64_t lda, const T* __restrict__ b, int64_t ldb,
                                    T* __restrict__ dst, int64_t ldd, int64_t rows, int cols, Dropout d, uint32_t site) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int64_t r = i / cols; const int c = (int)(i - r * cols);
@@ -528,9 +544,9 @@ extern "C" int vqa_add_dropped(const void* a, int64_t lda, const void* b, int64_
     const Dropout d = make_dropout(seed, p);
     const unsigned grid = (unsigned)ceil_div64(rows * cols, 256);
     if (dtype == VQA_F32)
-        add_dropped_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, (float*)dst, ldd, rows, cols, d, site);
+        VQA_CUDA(vqa_launch_pdl(add_dropped_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)a, lda, (const float*)b, ldb, (float*)dst, ldd, rows, cols, d, site));
     else if (dtype == VQA_BF16)
-        add_dropped_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)dst, ldd, rows, cols, d, site);
+        VQA_CUDA(vqa_launch_pdl(add_dropped_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)dst, ldd, rows, cols, d, site));
     else VQA_REQUIRE(false, "add_dropped: bad dtype");
     VQA_CHECK_LAUNCH("add_dropped");
     return 0;
@@ -539,6 +555,8 @@ extern "C" int vqa_add_dropped(const void* a, int64_t lda, const void* b, int64_
 template <typename T>
 __global__ void relu_drop_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz, int64_t n,
                                      float scale) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     dz[i] = from_f32<T>(to_f32(y[i]) > 0.f ? to_f32(dy[i]) * scale : 0.f);
@@ -550,9 +568,9 @@ extern "C" int vqa_relu_drop_bwd(const void* dy, const void* y, void* dz, int dt
     const float scale = 1.f / (1.f - p);
     const unsigned grid = (unsigned)ceil_div64(n, 256);
     if (dtype == VQA_F32)
-        relu_drop_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (float*)dz, n, scale);
+        VQA_CUDA(vqa_launch_pdl(relu_drop_bwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)dy, (const float*)y, (float*)dz, n, scale));
     else if (dtype == VQA_BF16)
-        relu_drop_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)y, (bf16*)dz, n, scale);
+        VQA_CUDA(vqa_launch_pdl(relu_drop_bwd_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dy, (const bf16*)y, (bf16*)dz, n, scale));
     else VQA_REQUIRE(false, "relu_drop_bwd: bad dtype");
     VQA_CHECK_LAUNCH("relu_drop_bwd");
     return 0;
@@ -560,6 +578,8 @@ extern "C" int vqa_relu_drop_bwd(const void* dy, const void* y, void* dz, int dt
 
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = from_f32<TD>(to_f32(s[i]));
 }
@@ -569,10 +589,10 @@ extern "C" int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype
     if (n == 0) return 0;
     const unsigned grid = (unsigned)ceil_div64(n, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
-    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
-    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
-    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(cast_kernel<float, bf16>, dim3(grid), dim3(256), 0, st, (const float*)src, (bf16*)dst, n));
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(cast_kernel<bf16, float>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (float*)dst, n));
+    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(cast_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, n));
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(cast_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, n));
     else VQA_REQUIRE(false, "cast: bad dtypes");
     VQA_CHECK_LAUNCH("cast");
     return 0;
@@ -582,6 +602,8 @@ extern "C" int vqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype
 template <typename TS, typename TD>
 __global__ void cast2d_kernel(const TS* __restrict__ s, int64_t lds, TD* __restrict__ d, int64_t ldd, int64_t rows,
                               int cols, int dst_cols) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * dst_cols) return;
     const int64_t r = i / dst_cols; const int c = (int)(i - r * dst_cols);
@@ -594,10 +616,10 @@ extern "C" int vqa_cast_2d(const void* src, int src_dtype, int64_t lds, void* ds
     if (rows == 0) return 0;
     const unsigned grid = (unsigned)ceil_div64(rows * dst_cols, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols);
-    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, dst_cols);
-    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, dst_cols);
-    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols);
+    if (src_dtype == VQA_F32 && dst_dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(cast2d_kernel<float, bf16>, dim3(grid), dim3(256), 0, st, (const float*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols));
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(cast2d_kernel<bf16, float>, dim3(grid), dim3(256), 0, st, (const bf16*)src, lds, (float*)dst, ldd, rows, cols, dst_cols));
+    else if (src_dtype == VQA_F32 && dst_dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(cast2d_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)src, lds, (float*)dst, ldd, rows, cols, dst_cols));
+    else if (src_dtype == VQA_BF16 && dst_dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(cast2d_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, dst_cols));
     else VQA_REQUIRE(false, "cast_2d: bad dtypes");
     VQA_CHECK_LAUNCH("cast_2d");
     return 0;
@@ -607,6 +629,8 @@ extern "C" int vqa_cast_2d(const void* src, int src_dtype, int64_t lds, void* ds
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ in, int64_t ld, const uint8_t* __restrict__ mask,
                               float* __restrict__ out, int64_t rows, int cols, int64_t rows_per_block) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -638,8 +662,8 @@ int vqa_colsum_impl(const void* in, int dtype, int64_t ld, const uint8_t* mask, 
     if (gy < 1) gy = 1;
     const int64_t rpb = ceil_div64(rows, gy);
     dim3 grid(gx, (unsigned)ceil_div64(rows, rpb)), block(32, 8);
-    if (dtype == VQA_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)in, ld, mask, out, rows, cols, rpb);
-    else if (dtype == VQA_BF16) colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, ld, mask, out, rows, cols, rpb);
+    if (dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(colsum_kernel<float>, dim3(grid), dim3(block), 0, st, (const float*)in, ld, mask, out, rows, cols, rpb));
+    else if (dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(block), 0, st, (const bf16*)in, ld, mask, out, rows, cols, rpb));
     else VQA_REQUIRE(false, "colsum: bad dtype");
     VQA_CHECK_LAUNCH("colsum");
     return 0;

@@ -570,6 +570,8 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
 template <typename TS>
 __global__ void transpose_bf16_kernel(const TS* __restrict__ src, int64_t lds, int64_t s_sb, bf16* __restrict__ dst,
                                       int64_t ldd, int64_t d_sb, int rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     src += (int64_t)blockIdx.z * s_sb; dst += (int64_t)blockIdx.z * d_sb;
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -590,8 +592,8 @@ extern "C" int vqa_transpose_bf16(const void* src, int src_dtype, int64_t lds, i
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, nbatch), block(32, 8);
     VQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: too many rows/batches for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == VQA_F32) transpose_bf16_kernel<float><<<grid, block, 0, st>>>((const float*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols);
-    else if (src_dtype == VQA_BF16) transpose_bf16_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols);
+    if (src_dtype == VQA_F32) VQA_CUDA(vqa_launch_pdl(transpose_bf16_kernel<float>, grid, block, 0, st, (const float*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols));
+    else if (src_dtype == VQA_BF16) VQA_CUDA(vqa_launch_pdl(transpose_bf16_kernel<bf16>, grid, block, 0, st, (const bf16*)src, lds, s_sb, (bf16*)dst, ldd, d_sb, rows, cols));
     else VQA_REQUIRE(false, "transpose: bad dtype");
     VQA_CHECK_LAUNCH("transpose_bf16");
     return 0;

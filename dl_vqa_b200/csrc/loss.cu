@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(LT)
 softloss_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ a_idx,
                      const int64_t* __restrict__ a_val, float* __restrict__ dlogits, float* __restrict__ loss_rows,
                      float* __restrict__ score_rows, int B, int N, int A) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     __shared__ int redi[32];
     __shared__ float s_bcast[2];
@@ -83,6 +85,8 @@ softloss_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict
 __global__ void __launch_bounds__(LT)
 softloss_reduce_kernel(const float* __restrict__ loss_rows, const float* __restrict__ score_rows,
                        float* __restrict__ loss_out, float* __restrict__ score_out, int B) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     float l = 0.f, s = 0.f;
     for (int i = threadIdx.x; i < B; i += LT) { l += loss_rows[i]; s += score_rows[i]; }
@@ -99,9 +103,9 @@ extern "C" int vqa_softloss_fwd_bwd(const float* logits, const int64_t* a_idx, c
     VQA_REQUIRE(B > 0 && N > 0 && A >= 0, "softloss: bad dims B=%d N=%d A=%d", B, N, A);
     VQA_REQUIRE(logits && a_idx && a_val && loss_rows && score_rows && loss_out && score_out, "softloss: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    softloss_rows_kernel<<<B, LT, 0, st>>>(logits, a_idx, a_val, dlogits, loss_rows, score_rows, B, N, A);
+    VQA_CUDA(vqa_launch_pdl(softloss_rows_kernel, dim3(B), dim3(LT), 0, st, logits, a_idx, a_val, dlogits, loss_rows, score_rows, B, N, A));
     VQA_CHECK_LAUNCH("softloss_rows");
-    softloss_reduce_kernel<<<1, LT, 0, st>>>(loss_rows, score_rows, loss_out, score_out, B);
+    VQA_CUDA(vqa_launch_pdl(softloss_reduce_kernel, dim3(1), dim3(LT), 0, st, loss_rows, score_rows, loss_out, score_out, B));
     VQA_CHECK_LAUNCH("softloss_reduce");
     return 0;
 }

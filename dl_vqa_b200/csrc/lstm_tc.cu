@@ -225,6 +225,8 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 
 // w_hh fp32 [4H][H] (gate-stacked i,f,g,o) -> bf16 [H/16][64][H], row u*4+gate of block j = source row gate*H + 16j + u
 __global__ void pack_lstm_whh_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int H) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)4 * H * H) return;
     const int k = (int)(i % H);
@@ -244,7 +246,7 @@ extern "C" int vqa_tc_lstm_cluster_size(void) { return g_lstm_cluster_ok < 0 ? 0
 extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream) {
     VQA_REQUIRE(w_hh && wp && H > 0 && H % 16 == 0, "pack_lstm_whh: bad arguments");
     const int64_t n = (int64_t)4 * H * H;
-    pack_lstm_whh_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh, (bf16*)wp, H);
+    VQA_CUDA(vqa_launch_pdl(pack_lstm_whh_kernel, dim3((unsigned)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, w_hh, (bf16*)wp, H));
     VQA_CHECK_LAUNCH("pack_lstm_whh");
     return 0;
 }

@@ -39,6 +39,7 @@ struct WgParams {
 template <int CIN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constant__ CUtensorMap tma_x, WgParams p) {
+    pdl_trigger();
     using S = WgSmem<CIN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -67,6 +68,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -163,7 +165,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams 
     p.chunks_per_split = (total + nsplit - 1) / nsplit;
     nsplit = (total + p.chunks_per_split - 1) / p.chunks_per_split;
     dim3 grid(units, nsplit);
-    kern<<<grid, WG_THREADS, WgSmem<CIN>::BYTES, st>>>(tdy, tx, p);
+    VQA_CUDA(vqa_launch_pdl(kern, grid, dim3(WG_THREADS), WgSmem<CIN>::BYTES, st, tdy, tx, p));
     VQA_CHECK_LAUNCH("wgrad_tc");
     return 0;
 }
@@ -197,6 +199,8 @@ extern "C" int vqa_tc_conv3x3_bwd_weight(const void* x, const void* dy, float* d
 // ------------------------------------------------------------------------------------------
 // x [B,H,W,C] bf16 NHWC -> xT [B,C,H,Wp] (zero padded columns W..Wp-1)
 __global__ void nhwc_to_nchw_pad_kernel(const bf16* __restrict__ x, bf16* __restrict__ xT, int H, int W, int C, int Wp) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ bf16 tile[32][34];
     const int bh = blockIdx.z;                       // b*H + h
     const int b = bh / H, h = bh - b * H;
@@ -217,7 +221,7 @@ extern "C" int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, 
     VQA_REQUIRE((int64_t)B * H <= 65535 * 32ll, "nhwc_to_nchw: too many rows");
     dim3 grid((Wp + 31) / 32, (C + 31) / 32, B * H), block(32, 8);
     VQA_REQUIRE(grid.z <= 65535u * 1024u, "nhwc_to_nchw: grid too large");
-    nhwc_to_nchw_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)xT, H, W, C, Wp);
+    VQA_CUDA(vqa_launch_pdl(nhwc_to_nchw_pad_kernel, grid, block, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)xT, H, W, C, Wp));
     VQA_CHECK_LAUNCH("nhwc_to_nchw_pad");
     return 0;
 }
@@ -225,6 +229,8 @@ extern "C" int vqa_nhwc_to_nchw_pad_bf16(const void* x, void* xT, int B, int H, 
 // (dpool, mask) [B,PH,PW,C] -> dyT [B,C,2PH,OWpp]: un-pooled gradient, channel-major, zero padded
 __global__ void unpool_nchw_kernel(const bf16* __restrict__ dpool, const uint8_t* __restrict__ mask, bf16* __restrict__ dyT,
                                    int PH, int PW, int C, int OWpp) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ bf16 g[32][34];
     __shared__ uint8_t m[32][36];
     const int bp = blockIdx.z;                       // b*PH + ph
@@ -260,7 +266,7 @@ extern "C" int vqa_unpool_nchw_bf16(const void* dpool, const uint8_t* mask, void
     VQA_REQUIRE(B > 0 && PH > 0 && PW > 0 && C > 0 && OWpp >= 2 * PW, "unpool_nchw: bad dims");
     // columns [2PW, OWpp) are covered because the pw range is rounded up to OWpp/2
     dim3 grid(((OWpp + 1) / 2 + 31) / 32, (C + 31) / 32, B * PH), block(32, 8);
-    unpool_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)dpool, mask, (bf16*)dyT, PH, PW, C, OWpp);
+    VQA_CUDA(vqa_launch_pdl(unpool_nchw_kernel, grid, block, 0, (cudaStream_t)stream, (const bf16*)dpool, mask, (bf16*)dyT, PH, PW, C, OWpp));
     VQA_CHECK_LAUNCH("unpool_nchw");
     return 0;
 }
