@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
     uint64_t* x_full = tmem_empty + 2;                         // [C0F_XSTAGES]
     uint64_t* x_empty = x_full + C0F_XSTAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + C0F_XSTAGES);
+    float* bias_s = reinterpret_cast<float*>(tmem_base_smem + 4);          // [64], read as broadcast LDS.128 by the epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
     pdl_wait();                                                // the weights below were written by the previous kernel (Adam)
     if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
         const int co = threadIdx.x;
+        bias_s[co] = p.bias[co];
         float v[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = k < C0_K ? p.w[co * C0_K + k] : 0.f;
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
             mbar_wait(&tmem_full[acc], use & 1);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16) + half * 32;
-#pragma unroll 1
+            uint32_t ob[4][4], mb[2][4];                       // this window's 32 channels: 64 B pooled (4 pieces), 32 B mask (2 pieces)
+#pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 16) {
                 float v0[16], v1[16], v2[16], v3[16];
                 tmem_ld_32x16(taddr + c0, v0);
@@ -255,31 +258,71 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
                 tmem_ld_32x16(taddr + 128 + c0, v2);
                 tmem_ld_32x16(taddr + 192 + c0, v3);
                 tmem_ld_wait();
-                if (ok) {
-                    const int nb = half * 32 + c0;
-                    uint32_t ob[8], mb[4];
+                const int nb = half * 32 + c0;
+                float bb[16];                                  // (same-address global loads here cost more than the pooling)
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float x[2]; uint32_t id[2];
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(bias_s + nb + j);
+                    bb[j] = q4.x; bb[j + 1] = q4.y; bb[j + 2] = q4.z; bb[j + 3] = q4.w;
+                }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const float a0 = v0[j + u], a1 = v1[j + u], a2 = v2[j + u], a3 = v3[j + u];
-                            // first maximum in element order (ties go to the lower id, as torch max_pool2d)
-                            const float m01 = fmaxf(a0, a1), m23 = fmaxf(a2, a3);
-                            const uint32_t i01 = a1 > a0 ? 1u : 0u, i23 = a3 > a2 ? 3u : 2u;
-                            float mx = fmaxf(m01, m23);
-                            uint32_t ix = m23 > m01 ? i23 : i01;
-                            mx += __ldg(p.bias + nb + j + u);
-                            if (!(mx > 0.f)) { mx = 0.f; ix = 4u; }
-                            x[u] = mx; id[u] = ix;
-                        }
-                        ob[j >> 1] = pack2(x[0], x[1]);
-                        const uint32_t pair = id[0] | (id[1] << 8);
-                        if ((j & 2) == 0) mb[j >> 2] = pair; else mb[j >> 2] |= pair << 16;
+                for (int j = 0; j < 16; j += 2) {
+                    float x[2]; uint32_t id[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float a0 = v0[j + u], a1 = v1[j + u], a2 = v2[j + u], a3 = v3[j + u];
+                        // first maximum in element order (ties go to the lower id, as torch max_pool2d)
+                        const float m01 = fmaxf(a0, a1), m23 = fmaxf(a2, a3);
+                        const uint32_t i01 = a1 > a0 ? 1u : 0u, i23 = a3 > a2 ? 3u : 2u;
+                        float mx = fmaxf(m01, m23);
+                        uint32_t ix = m23 > m01 ? i23 : i01;
+                        mx += bb[j + u];
+                        if (!(mx > 0.f)) { mx = 0.f; ix = 4u; }
+                        x[u] = mx; id[u] = ix;
                     }
-                    *reinterpret_cast<uint4*>(p.pooled + obase + nb) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-                    *reinterpret_cast<uint4*>(p.pooled + obase + nb + 8) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
-                    *reinterpret_cast<uint4*>(p.mask + obase + nb) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+                    ob[(c0 >> 3) + (j >> 3)][(j >> 1) & 3] = pack2(x[0], x[1]);
+                    const uint32_t pair = id[0] | (id[1] << 8);
+                    if ((j & 2) == 0) mb[c0 >> 4][j >> 2] = pair; else mb[c0 >> 4][j >> 2] |= pair << 16;
+                }
+            }
+            // Coalescing transposes: inside a lane quad (4 consecutive windows of one row) lane q ends with pooled piece
+            // q of the four windows; inside a lane pair lane s ends with mask piece s of both windows.  One store
+            // instruction then writes 64 (32) contiguous bytes per window instead of 16 bytes to 32 different lines.
+            {
+                const int q = lane & 3;
+#pragma unroll
+                for (int step = 0; step < 2; ++step) {
+                    const int off = 1 << step;
+                    const bool up = (q & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int lo = step == 0 ? 2 * i : i, hi = lo + off;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up ? ob[lo][w] : ob[hi][w], off);
+                            if (up) ob[lo][w] = rcv; else ob[hi][w] = rcv;
+                        }
+                    }
+                }
+                const bool up = (lane & 1) != 0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up ? mb[0][w] : mb[1][w], 1);
+                    if (up) mb[0][w] = rcv; else mb[1][w] = rcv;
+                }
+                // quad / pair base windows share this lane's row ph; window columns pw - q + j and pw - (lane & 1) + j
+                if (ph < p.PH) {
+                    const int64_t qbase = obase - (int64_t)q * 64 + half * 32 + 8 * q;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (pw - q + j < p.PW)
+                            *reinterpret_cast<uint4*>(p.pooled + qbase + j * 64) = make_uint4(ob[j][0], ob[j][1], ob[j][2], ob[j][3]);
+                    const int s1 = lane & 1;
+                    const int64_t pbase = obase - (int64_t)s1 * 64 + half * 32 + 16 * s1;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (pw - s1 + j < p.PW)
+                            *reinterpret_cast<uint4*>(p.mask + pbase + j * 64) = make_uint4(mb[j][0], mb[j][1], mb[j][2], mb[j][3]);
                 }
             }
             tcgen05_fence_before();
@@ -350,49 +393,47 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
         const int wr = t >> 4, wc = t & 15, sw = t & 7;
         uint8_t* stage = smem + g * C0B_STAGE_BYTES;
         uint32_t use = 0;
+        // Pooled gradient (64 channels bf16 = 128 B per window) and arg-max mask (64 B per window), loaded COALESCED: a
+        // warp covers two window rows of the tile; in load k lane l takes 16-byte chunk c = (k & 3) * 32 + l of row
+        // 2*warp + (k >> 2), i.e. window (c >> 3), channels 8*(c & 7)..+7 -- consecutive lanes read consecutive addresses
+        // (one window per lane would touch 32 lines per instruction).  Any thread may write any (window, chunk) of the
+        // swizzled A tiles.  Branch-free: out-of-image chunks read offset 0 and are replaced at use (with if/else
+        // diamonds ptxas recycled the address registers of one load for the next and the loads ran one after the other).
+        // (A register prefetch one iteration ahead was slower: 128-register cap, and the proxy fence drains the loads.)
+        const int wg = t >> 5, jc = lane & 7;
+        uint4 d[8]; uint2 mk[8];
         for (int i = g; i < nt; i += 2, ++use) {
             const int tile = t_begin + i;
             const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
             const int ph = (r / p.tiles_w) * C0_WH + wr, pw = (r % p.tiles_w) * C0_WW + wc;
-            const bool ok = ph < p.PH && pw < p.PW;
-            // the window's pooled gradient (64 channels bf16) and arg-max mask (64 bytes); loaded before the wait
-            uint4 d[8], mk[4];
-            if (ok) {
-                const int64_t off = (((int64_t)b * p.PH + ph) * p.PW + pw) * 64;
-                const uint4* dp = reinterpret_cast<const uint4*>(p.dpool + off);
-                const uint4* mp = reinterpret_cast<const uint4*>(p.bmask + off);
+            const int ph0 = ph - wr + 2 * wg, pw0 = pw - wc + (lane >> 3);       // first of the warp's two rows / lane's first window
+            const int64_t off0 = (((int64_t)b * p.PH + ph0) * p.PW + pw0) * 64 + 8 * jc;
+            bool valid[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) d[j] = __ldcs(dp + j);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) mk[j] = __ldcs(mp + j);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) d[j] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) mk[j] = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u);
+            for (int k = 0; k < 8; ++k) {
+                valid[k] = ph0 + (k >> 2) < p.PH && pw0 + (k & 3) * 4 < p.PW;
+                const int64_t off = valid[k] ? off0 + ((int64_t)(k >> 2) * p.PW + (k & 3) * 4) * 64 : (int64_t)(8 * jc);
+                d[k] = __ldcs(reinterpret_cast<const uint4*>(p.dpool + off));
+                mk[k] = __ldcs(reinterpret_cast<const uint2*>(p.bmask + off));
             }
             mbar_wait(&empty[g], (use & 1) ^ 1);
-            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows, 128B-swizzled)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                uint8_t* rowp = stage + e * C0_TILE_BYTES + t * 128;
+            for (int k = 0; k < 8; ++k)
+                if (!valid[k]) { d[k] = make_uint4(0, 0, 0, 0); mk[k] = make_uint2(0x04040404u, 0x04040404u); }
+            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows per window, 128B-swizzled)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                  // 8 channels per 16-byte chunk; their mask bytes: 2 words
-                    const uint32_t* mw = reinterpret_cast<const uint32_t*>(&mk[j >> 1]) + 2 * (j & 1);
+            for (int k = 0; k < 8; ++k) {
+                const int w = (2 * wg + (k >> 2)) * 16 + (k & 3) * 4 + (lane >> 3);      // window = row of the A tiles
+                uint8_t* chunkp = stage + w * 128 + ((jc ^ (w & 7)) << 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // bytes are 0..4: (8 - (byte ^ e)) has bit 3 set iff byte == e; move it to the byte's sign bit
+                    const uint32_t f0 = (0x08080808u - (mk[k].x ^ (0x01010101u * e))) << 4;
+                    const uint32_t f1 = (0x08080808u - (mk[k].y ^ (0x01010101u * e))) << 4;
                     uint4 o;
-                    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-                    const uint32_t* dw_ = reinterpret_cast<const uint32_t*>(&d[j]);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        // bytes are 0..4: (8 - (byte ^ e)) has bit 3 set iff byte == e; move it to the byte's sign bit
-                        const uint32_t f = (0x08080808u - (mw[h] ^ (0x01010101u * e))) << 4;
-                        uint32_t lo, hi;
-                        asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(lo) : "r"(f));      // bytes 0,1 -> two 16-bit masks
-                        asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(hi) : "r"(f));      // bytes 2,3
-                        ow[2 * h] = dw_[2 * h] & lo;
-                        ow[2 * h + 1] = dw_[2 * h + 1] & hi;
-                    }
-                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o;
+                    o.x = d[k].x & sign_mask16_lo(f0); o.y = d[k].y & sign_mask16_hi(f0);      // bytes 0,1 / 2,3 -> 16-bit masks
+                    o.z = d[k].z & sign_mask16_lo(f1); o.w = d[k].w & sign_mask16_hi(f1);
+                    *reinterpret_cast<uint4*>(chunkp + e * C0_TILE_BYTES) = o;
                 }
             }
             // the patch rows last: (d, mk) are dead by now, so the 48 patch values do not add to the register peak
