@@ -234,23 +234,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t taddr = tmem_base + (acc * MT + ti) * BN + ((uint32_t)(quarter * 32) << 16);
             const int rr = 4 * quarter + (lane >> 3), cc = lane & 7;         // position inside the 16x8 tile
             if (EPI == EPI_STORE) {
-                const int h = h0 + rr, w = w0 + cc;
-                const bool ok = live && h < p.valid_h && w < p.valid_w;
-                bf16* o = p.dx + (((int64_t)b * p.valid_h + h) * p.valid_w + w) * p.N;
+                // 4 x 4 transpose of the 16-byte pieces inside each lane quad (positions w..w+3 of one row): lane q stores
+                // piece q of the four positions, 64 contiguous bytes per position (8 lines per instruction, not 32)
+                const int q = lane & 3;
+                const int h = h0 + rr, wq = w0 + (cc & 4);
+                const bool okh = live && h < p.valid_h;
+                bf16* obase = p.dx + (((int64_t)b * p.valid_h + h) * p.valid_w + wq) * p.N + 8 * q;
 #pragma unroll 1
                 for (int c0 = half * 32; c0 < BN; c0 += 64) {
                     float v[32];
                     tmem_ld_32x32(taddr + c0, v);
-                    if (ok) {
+                    uint32_t G[4][4];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 u;
-                            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                            *reinterpret_cast<uint4*>(o + c0 + j) = u;
+                    for (int step = 0; step < 2; ++step) {
+                        const int off = 1 << step;
+                        const bool up = (q & off) != 0;
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const int lo = step == 0 ? 2 * m : m, hi = lo + off;
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const uint32_t r = __shfl_xor_sync(0xffffffffu, up ? G[lo][t] : G[hi][t], off);
+                                if (up) G[lo][t] = r; else G[hi][t] = r;
+                            }
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (okh && wq + j < p.valid_w)
+                            *reinterpret_cast<uint4*>(obase + (int64_t)j * p.N + c0) = make_uint4(G[j][0], G[j][1], G[j][2], G[j][3]);
                 }
             } else if (EPI == EPI_UNPOOL) {
                 // A lane owns one position (TMEM lane) and 32 channels = four 16-byte pieces.  A 4 x 4 transpose inside each

@@ -185,12 +185,63 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
     }
 }
 
+// Split-K epilogue only (fp32 vector reductions into a zeroed output): the ATOMIC instantiation of gemm_tc_kernel
+// carries nothing else -- these kernels run ~10 us (one LSTM backward step), code size is start-up latency.
+__device__ __forceinline__ void gemm_red_chunk(const GemmEpilogue& ep, float (&v)[32], int batch, int m, int nb, int N, int M) {
+    if (m >= M) return;
+    float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
+    if (nb + 32 <= N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) red_add_f32x4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(o + j, v[j]);
+    }
+}
+
+// Lean epilogue of the persistent kernel's FAST instantiation: bf16 output, optional bias, whole 32-column chunks,
+// 16-byte aligned rows -- no ReLU / dropout / fp32 / ragged / atomic paths in the instruction stream (the generic
+// epilogue's run-time flag tests and dead branches cost the store-heavy GEMMs ~20% in instruction-fetch stalls).
+__device__ __forceinline__ void gemm_store_chunk_bf16(const GemmEpilogue& ep, float (&v)[32], int batch, int m, int nb,
+                                                      bool has_bias, float bias_lane, int M) {
+    const int lane = threadIdx.x & 31;
+    if (has_bias) {                                          // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+    }
+    uint32_t G[4][4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    const int q = lane & 3;
+#pragma unroll
+    for (int step = 0; step < 2; ++step) {                   // quad transpose, see gemm_store_chunk
+        const int off = 1 << step;
+        const bool up = (q & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int lo = step == 0 ? 2 * i : i, hi = lo + off;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t r = __shfl_xor_sync(0xffffffffu, up ? G[lo][t] : G[hi][t], off);
+                if (up) G[lo][t] = r; else G[hi][t] = r;
+            }
+        }
+    }
+    bf16* ob = (bf16*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)(m - q) * ep.ldc + nb + 8 * q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (m - q + j < M) *reinterpret_cast<uint4*>(ob + (int64_t)j * ep.ldc) = make_uint4(G[j][0], G[j][1], G[j][2], G[j][3]);
+}
+
 // MAJ = 0: A [M,K], B [N,K] with K contiguous (K-major operands, one TMA box per operand per stage).
 // MAJ = 1: A [K,M], B [K,N] with M / N contiguous (MN-major operands: the weight-gradient form dW = dY^T X
 //          consumed without transposes; one TMA box per 64-wide column block per stage).
 // MAJ = 2: A [M,K] K-major, B [K,N] MN-major: the data-gradient form dX = dY W with W [N_red, K_out] read as stored
 //          (no transposed weight copy).
-template <int BN, int MAJ, int ST>
+template <int BN, int MAJ, int ST, bool ATOMIC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
@@ -287,8 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, has_bias ? gemm_bias_lane(bias, bias2, n0 + c0 + lane, N) : 0.f,
-                             dkey, M);
+            if (ATOMIC) gemm_red_chunk(ep, v, batch, m, n0 + c0, N, M);
+            else gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, has_bias ? gemm_bias_lane(bias, bias2, n0 + c0 + lane, N) : 0.f,
+                                  dkey, M);
         }
     }
 
@@ -305,12 +357,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 constexpr int PGEMM_THREADS = 64 + 8 * 32;
 template <int BN>
 struct PGemmSmem {
-    static constexpr int STAGES = 6;
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
 };
 
-template <int BN, bool BMN>
+template <int BN, bool BMN, bool FAST>
 __global__ void __launch_bounds__(PGEMM_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           GemmEpilogue ep, int M, int N, int K, int nbatch) {
@@ -410,7 +462,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
                 if (n0 + c0 < N) {                           // warp-uniform
                     float v[32];
                     tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-                    gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, bl[k], dkey, M);
+                    if (FAST) gemm_store_chunk_bf16(ep, v, batch, m, n0 + c0, has_bias, bl[k], M);
+                    else gemm_store_chunk(ep, v, batch, m, n0 + c0, N, has_bias, bl[k], dkey, M);
                 }
             }
             tcgen05_fence_before();
@@ -423,10 +476,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
-template <int BN, bool BMN>
-static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                                  int nbatch, int sms, cudaStream_t st) {
-    auto kern = gemm_tc_persistent_kernel<BN, BMN>;
+template <int BN, bool BMN, bool FAST>
+static int launch_gemm_persistent_f(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                                    int nbatch, int sms, cudaStream_t st) {
+    auto kern = gemm_tc_persistent_kernel<BN, BMN, FAST>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PGemmSmem<BN>::BYTES));
@@ -437,10 +490,19 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
     return 0;
 }
 
-template <int BN, int MAJ, int ST>
-static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                          dim3 grid, int nsplit, int kbps, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, MAJ, ST>;
+template <int BN, bool BMN>
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                                  int nbatch, int sms, cudaStream_t st) {
+    const bool fast = ep.out_bf16 && !ep.relu && !ep.use_dropout && !ep.atomic && N % 32 == 0 && (ep.ldc & 7) == 0 &&
+                      (ep.c_sb & 7) == 0 && ((uintptr_t)ep.out & 15) == 0;
+    if (fast) return launch_gemm_persistent_f<BN, BMN, true>(ta, tb, ep, M, N, K, nbatch, sms, st);
+    return launch_gemm_persistent_f<BN, BMN, false>(ta, tb, ep, M, N, K, nbatch, sms, st);
+}
+
+template <int BN, int MAJ, int ST, bool ATOMIC>
+static int launch_gemm_sta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                           dim3 grid, int nsplit, int kbps, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, MAJ, ST, ATOMIC>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, ST>::BYTES));
@@ -449,6 +511,13 @@ static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     VQA_CUDA(vqa_launch_pdl(kern, grid, dim3(GEMM_THREADS), GemmSmem<BN, ST>::BYTES, st, ta, tb, ep, M, N, K, nsplit, kbps));
     VQA_CHECK_LAUNCH("gemm_tc");
     return 0;
+}
+
+template <int BN, int MAJ, int ST>
+static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                          dim3 grid, int nsplit, int kbps, cudaStream_t st) {
+    if (ep.atomic) return launch_gemm_sta<BN, MAJ, ST, true>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+    return launch_gemm_sta<BN, MAJ, ST, false>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
 }
 
 template <int BN, int MAJ>
@@ -507,6 +576,18 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         const int64_t tiles128 = (int64_t)((M + BM - 1) / BM) * ((N + 127) / 128) * nbatch;
         if (tiles128 * 2 <= sms) BN = 64;
     }
+    // 256-wide tiles for the big store-heavy GEMMs (attention.v_conv and its data gradient, the LSTM input projection):
+    // with N = 128 the MMA's operand reads alone saturate the 128 B/clk of shared memory; at N = 256 the A tile is read
+    // once per 256 output columns.  Persistent kernel only (2 x 256 TMEM columns, 4 stages of 48 KB).  (Keeping the
+    // [256 x K] weight slice resident in shared memory instead of re-streaming it from L2 per tile measured SLOWER:
+    // v_conv 0.140 vs 0.126 ms -- the L2 -> SM traffic of B is not what bounds these GEMMs.)
+    if (BN == 128 && !splitk && !mn && N % 256 == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t tiles256 = (int64_t)((M + BM - 1) / BM) * (N / 256) * nbatch;
+        if (tiles256 >= 4 * (int64_t)sms) BN = 256;
+    }
     CUtensorMap ta, tb;
     if (!mn) {
         const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)nbatch};
@@ -550,6 +631,13 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         if (tiles >= 148) nsplit = 1;                       // enough tiles to fill the GPU: no split, no atomics
         if (nsplit < 1) nsplit = 1;
         if (nsplit == 1) ep.atomic = 0;                     // the output is zeroed, a plain store is equivalent
+    }
+    if (BN == 256) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (bmn) return launch_gemm_persistent<256, true>(ta, tb, ep, M, N, K, nbatch, sms, st);
+        return launch_gemm_persistent<256, false>(ta, tb, ep, M, N, K, nbatch, sms, st);
     }
     if (mn) {
         if (BN == 64) return launch_gemm<64, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, st);

@@ -227,12 +227,21 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 __global__ void pack_lstm_whh_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int H) {
     pdl_trigger();
     pdl_wait();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)4 * H * H) return;
-    const int k = (int)(i % H);
-    const int r = (int)(i / H);                 // packed row
+    const int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // 8 consecutive k per thread (H % 16 == 0)
+    const int h8 = H >> 3;
+    if (i8 >= (int64_t)4 * H * h8) return;
+    const int k = (int)(i8 % h8) * 8;
+    const int r = (int)(i8 / h8);               // packed row
     const int jblk = r >> 6, loc = r & 63, u = loc >> 2, gate = loc & 3;
-    wp[i] = __float2bfloat16_rn(w[((int64_t)gate * H + jblk * 16 + u) * H + k]);
+    const float4* src = reinterpret_cast<const float4*>(w + ((int64_t)gate * H + jblk * 16 + u) * H + k);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(a.x, a.y); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(a.z, a.w); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(b.x, b.y); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(b.z, b.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(wp + (int64_t)r * H + k) = o;
 }
 
 }  // namespace tc
@@ -246,7 +255,8 @@ extern "C" int vqa_tc_lstm_cluster_size(void) { return g_lstm_cluster_ok < 0 ? 0
 extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream) {
     VQA_REQUIRE(w_hh && wp && H > 0 && H % 16 == 0, "pack_lstm_whh: bad arguments");
     const int64_t n = (int64_t)4 * H * H;
-    VQA_CUDA(vqa_launch_pdl(pack_lstm_whh_kernel, dim3((unsigned)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, w_hh, (bf16*)wp, H));
+    VQA_REQUIRE(((uintptr_t)w_hh & 15) == 0 && ((uintptr_t)wp & 15) == 0, "pack_lstm_whh: pointers must be 16-byte aligned");
+    VQA_CUDA(vqa_launch_pdl(pack_lstm_whh_kernel, dim3((unsigned)ceil_div64(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, w_hh, (bf16*)wp, H));
     VQA_CHECK_LAUNCH("pack_lstm_whh");
     return 0;
 }

@@ -22,7 +22,7 @@ def _tc_gemm(A, B, out_dtype=torch.float32, bias=None, relu=False, splitk=False,
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 200, 320), (77, 3000, 1024),
-                                   (1000, 64, 72), (4096, 1024, 304), (130, 40, 8)])
+                                   (1000, 64, 72), (4096, 1024, 304), (130, 40, 8), (20000, 1024, 256), (19050, 768, 136)])
 def test_tc_gemm_matches_torch(M, N, K):
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda").bfloat16()

@@ -29,6 +29,7 @@ def run(M, N, K, ld, bias, out_dtype=torch.bfloat16, iters=10):
     return round(a.elapsed_time(b) / iters, 4)
 
 
+only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None
 res = {}
 for name, args in {
     "inproj_K300_ld304_bias2": (5888, 4096, 300, 304, 2),
@@ -38,6 +39,9 @@ for name, args in {
     "inproj_K256_ld256_bias2": (5888, 4096, 256, 256, 2),
     "vconv_K256_bias0": (173056, 1024, 256, 256, 0),
     "sq_4096_K1024": (4096, 4096, 1024, 1024, 0),
+    "vconv_dgrad_like_K1024_N256": (173056, 256, 1024, 1024, 0),
 }.items():
+    if only and name not in only:
+        continue
     res[name] = run(*args)
 print(json.dumps(res))
