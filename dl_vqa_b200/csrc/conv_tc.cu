@@ -33,8 +33,10 @@ constexpr int TILE_H = 16, TILE_W = 8;
 constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
 constexpr int HALO_BYTES = HALO_H * HALO_W * 128;            // 23040: one 64-channel slice of tile + halo
 constexpr int A_STAGE_BYTES = 23552;                          // padded to a multiple of 1024
-constexpr int EPI_WARPS = 8;
-constexpr int CONV_THREADS = 64 + EPI_WARPS * 32;
+// Epilogue warps: 8 (two per TMEM lane quarter, alternating 32-column chunks).  (16 for the POOL epilogue measured no
+// faster once the arg-max rode in the value bits: conv1 forward is then bound by the MMAs' shared-memory reads.)
+__host__ __device__ constexpr int conv_epi_warps(int) { return 8; }
+__host__ __device__ constexpr int conv_threads(int epi) { return 64 + conv_epi_warps(epi) * 32; }
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448 - 1024;                     // 227 KB minus alignment slack
 enum { EPI_POOL = 0, EPI_STORE = 1, EPI_UNPOOL = 2 };
@@ -58,7 +60,7 @@ struct ConvParams {
 // MT = tiles per CTA and round.  MT = 2 (streamed weights, BN <= 128): both tiles' MMAs share every weight slab, which
 // halves the TMA traffic of the B operand into shared memory and the mbarrier waits per MMA.
 template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(conv_threads(EPI), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, ConvParams p) {
     pdl_trigger();
     constexpr int BN_CTA = BN / NCTA;                 // weight rows held by this CTA
@@ -76,6 +78,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* tmem_full = emptyB + MAX_B_STAGES;     // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(bars + 64);            // POOL: [BN] conv bias, read as broadcast LDS.128
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0;
@@ -92,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
         for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < MAX_B_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS * NCTA); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], conv_epi_warps(EPI) * NCTA); }
         fence_barrier_init();
     }
     if (warp == 1) { if (NCTA == 2) tmem_alloc_pair(tmem_base_smem, TMEM_COLS); else tmem_alloc(tmem_base_smem, TMEM_COLS); }
@@ -101,6 +104,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     pdl_wait();                                       // everything above overlapped the previous kernel's tail
+    if (EPI == EPI_POOL) {
+        for (int i = threadIdx.x; i < BN; i += conv_threads(EPI)) bias_s[i] = p.bias[i];
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ===== TMA producer (one per CTA; byte counts go to the leader's barriers) =====
@@ -365,57 +372,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const bool ok = live && ph_ < p.PH && pw_ < p.PW;
                 const int bit0 = lane & 1, bitY = (lane >> 3) & 1;
                 const int64_t obase = (((int64_t)b * p.PH + ph_) * p.PW + pw_) * p.N;
+                // Max-pool with the arg-max carried IN the value: after the bias add, the two low mantissa bits of every
+                // fp32 are replaced by 3 - e (e = this lane's element id inside its window), so a plain fmaxf picks the
+                // maximum, ties go to the lowest e for positive values (torch's max_pool2d order; non-positive maxima
+                // are ReLU-dead and need no index), and the winner's id rides along -- no index selects, no index
+                // shuffles.  Cost: values are truncated by < 2^-21 relative before the bf16 rounding.
+                const uint32_t ekey = 3u - (uint32_t)(2 * bitY + bit0);
 #pragma unroll 1
-                for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                for (int c0 = half * 32; c0 < BN; c0 += 32 * (conv_epi_warps(EPI_POOL) / 4)) {     // half = 0..3 here
                     float v[32];
                     tmem_ld_32x32(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        v[j] = __uint_as_float((__float_as_uint(v[j] + bq.x) & ~3u) | ekey);
+                        v[j + 1] = __uint_as_float((__float_as_uint(v[j + 1] + bq.y) & ~3u) | ekey);
+                        v[j + 2] = __uint_as_float((__float_as_uint(v[j + 2] + bq.z) & ~3u) | ekey);
+                        v[j + 3] = __uint_as_float((__float_as_uint(v[j + 3] + bq.w) & ~3u) | ekey);
+                    }
                     // step 1 (partner lane^1, dx): keep 16 channels: [0,16) if bit0==0 else [16,32)
-                    float k1[16]; int i1[16];
+                    float k1[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float mine = bit0 ? v[16 + j] : v[j];
                         const float send = bit0 ? v[j] : v[16 + j];
-                        const float other = __shfl_xor_sync(0xffffffffu, send, 1);
-                        // element ids: mine = bit0, other = bit0^1 (same dy); ties go to the lower id
-                        const bool take_other = bit0 ? (other >= mine) : (other > mine);
-                        k1[j] = take_other ? other : mine;
-                        i1[j] = take_other ? (bit0 ^ 1) : bit0;
+                        k1[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));
                     }
                     // step 2 (partner lane^8, dy): keep 8 channels: first 8 if bitY==0 else last 8
-                    float k2[8]; int i2[8];
-                    uint32_t pack_send = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pack_send |= (uint32_t)(bitY ? i1[j] : i1[8 + j]) << (2 * j);
-                    const uint32_t pack_other = __shfl_xor_sync(0xffffffffu, pack_send, 8);
+                    float k2[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float mine = bitY ? k1[8 + j] : k1[j];
-                        const int mine_i = (bitY ? i1[8 + j] : i1[j]) + 2 * bitY;
                         const float send = bitY ? k1[j] : k1[8 + j];
-                        const float other = __shfl_xor_sync(0xffffffffu, send, 8);
-                        const int other_i = (int)((pack_other >> (2 * j)) & 3u) + 2 * (bitY ^ 1);
-                        const bool take_other = bitY ? (other >= mine) : (other > mine);
-                        k2[j] = take_other ? other : mine;
-                        i2[j] = take_other ? other_i : mine_i;
+                        k2[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 8));
                     }
                     if (ok) {
                         const int nb = c0 + 16 * bit0 + 8 * bitY;
-                        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb);
-                        const float4 b1 = *reinterpret_cast<const float4*>(p.bias + nb + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         uint4 u; uint2 mk;
-                        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-                        uint8_t* mb = reinterpret_cast<uint8_t*>(&mk);
+                        uint32_t mw[2] = {0u, 0u};
                         float o[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float x = k2[j] + bb[j];
-                            int id = i2[j];
-                            if (!(x > 0.f)) { x = 0.f; id = 4; }
-                            o[j] = x; mb[j] = (uint8_t)id;
+                            const uint32_t kb_ = __float_as_uint(k2[j]);
+                            const float x = __uint_as_float(kb_ & ~3u);
+                            const bool alive = x > 0.f;
+                            o[j] = alive ? x : 0.f;
+                            mw[j >> 2] |= (alive ? 3u - (kb_ & 3u) : 4u) << (8 * (j & 3));
                         }
+                        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(o[2 * t], o[2 * t + 1]);
+                        mk.x = mw[0]; mk.y = mw[1];
                         *reinterpret_cast<uint4*>(p.pooled + obase + nb) = u;
                         *reinterpret_cast<uint2*>(p.mask + obase + nb) = mk;
                     }
@@ -461,7 +468,7 @@ static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvPar
     const int nrounds = (ntiles + NCTA * MT - 1) / (NCTA * MT);
     int grid = (nrounds < sms / NCTA ? nrounds : sms / NCTA) * NCTA;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(conv_threads(EPI)); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (NCTA == 2) {
@@ -486,7 +493,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
     const int ncta = g_conv_cta_group;
     const int nkb = 9 * p.chunks;
     const int slab = (BN / ncta) * 128;
-    const int bars = 512;
+    const int bars = 512 + 1024;                   // mbarriers + the staged bias
     const int resident_bytes = nkb * slab;
     const bool resident = resident_bytes + 2 * A_STAGE_BYTES + bars <= SMEM_LIMIT;
     int smem;

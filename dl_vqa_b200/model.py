@@ -358,6 +358,7 @@ class VqaNet(nn.Module):
         x, x_dt, nchw = v, lib.F32, 1
         IH, IW = int(v.shape[2]), int(v.shape[3])
         conv_saved = []
+        conv_wd = {}                 # layer -> weights packed for the data gradient (training forward only)
         nl = len(self.channels) - 1
         for i in range(nl):
             conv = getattr(self.image, f"conv{i}")
@@ -373,7 +374,10 @@ class VqaNet(nn.Module):
                      B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
             elif self._tc_conv_ok(i) and nchw == 0:
                 wp = empty(Cout, 9 * Cin)
-                call("vqa_pack_conv3x3_weight", ptr(conv.weight), ptr(wp), None, Cout, Cin, st, tag="w_cast")
+                wd = empty(Cin, 9 * Cout) if (save and i > 0) else None      # data-gradient packing in the same pass
+                call("vqa_pack_conv3x3_weight", ptr(conv.weight), ptr(wp), ptr(wd), Cout, Cin, st, tag="w_cast")
+                if wd is not None:
+                    conv_wd[i] = wd
                 call("vqa_tc_conv3x3_relu_pool_fwd", ptr(x), ptr(wp), ptr(conv.bias), ptr(out), ptr(mask),
                      B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
             else:
@@ -416,7 +420,8 @@ class VqaNet(nn.Module):
             wp = empty(dirs, 4 * H, H)
             for d in range(dirs):
                 call("vqa_pack_lstm_whh", ptr(w_hh[d]), ptr(wp[d]), H, st, tag="w_cast")
-            hs_ext = torch.zeros(dirs, T + 1, B, H, dtype=adt, device=dev)      # slot 0 = h_{-1} = 0
+            hs_ext = torch.empty(dirs, T + 1, B, H, dtype=adt, device=dev)      # the kernel writes slots 1..T of every row
+            hs_ext[:, 0].zero_()                                                # slot 0 = h_{-1} = 0
             sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
             call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
                  T, B, H, dirs, st, tag="lstm_recurrence_fwd")
@@ -466,7 +471,7 @@ class VqaNet(nn.Module):
                    B, self.max_answers, self.hidden, bias=cl.lin2.bias, tag="lin2")
 
         if save:
-            ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
+            ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, conv_wd=conv_wd, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
                        xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
                        q=q, q_len=q_len, ldx=ldx, whh_stride=whh_stride,
                        p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
@@ -711,8 +716,10 @@ class VqaNet(nn.Module):
             if i > 0:
                 dx = None
                 if use_tc:
-                    wd = empty(Cin, 9 * Cout)
-                    call("vqa_pack_conv3x3_weight", ptr(conv.weight), None, ptr(wd), Cout, Cin, st, tag="w_cast")
+                    wd = ctx.get("conv_wd", {}).get(i)
+                    if wd is None:
+                        wd = empty(Cin, 9 * Cout)
+                        call("vqa_pack_conv3x3_weight", ptr(conv.weight), None, ptr(wd), Cout, Cin, st, tag="w_cast")
                     if tc_path(i - 1):
                         # the data gradient lands directly in the layer below's UN-POOLED gradient (its max-pool backward
                         # and bias gradient run in the dgrad epilogue): no dx tensor, no un-pool kernel
