@@ -135,6 +135,9 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// hardware tanh (bf16 tensor-core arm only; the fp32 arm keeps the precise forms)
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // ------------------------------------------------------------------------------------------
 // counter-based dropout.  Element i of dropout site `site` is kept iff a 16-bit word derived from

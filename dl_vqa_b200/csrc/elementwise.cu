@@ -16,6 +16,11 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]);
+// 8 values from `a` (bf16) when it is non-null, else from `b` (fp32)
+__device__ __forceinline__ void ld8(const bf16* a, const float* b, float (&v)[8]) {
+    if (a) ld8(a, v); else ld8(b, v);
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {       // 8 packed bf16 -> fp32
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -438,26 +443,27 @@ lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __re
     const int64_t i = ((int64_t)dir * B + b) * H + j;
     const int64_t row = ((int64_t)dir * T_ + s) * B + b;
     bf16* o = dg + row * 4 * H + j;
-    float dc_in[8];
-    if (dc_init) ld8(dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j, dc_in);
-    else ld8(dc + i, dc_in);
-    if (s >= (int)q_len[b]) {                     // frozen step: zero gate gradients, dc passes through unchanged
+    // every load is issued before the first dependent branch (this kernel is one L2 round trip long: a load that waits
+    // for q_len, or sits in an if/else diamond, doubles it)
+    const int len = (int)q_len[b];
+    const bf16* g = gates + row * 4 * H + j;
+    float dc_in[8], gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
+    ld8(dc_init ? dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j : nullptr, dc + i, dc_in);
+    ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go);
+    ld8(cs + row * H + j, c);
+    ld8(cs + (s > 0 ? row - B : row) * H + j, cp);
+    ld8(dh + i, dhv);
+    if (s >= len) {                               // frozen step: zero gate gradients, dc passes through unchanged
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o + g * H) = z;
+        for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(o + gq * H) = z;
         st8(dc + i, dc_in);
         return;
     }
-    const bf16* g = gates + row * 4 * H + j;
-    float gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
-    ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go);
-    ld8(cs + row * H + j, c);
-    if (s > 0) ld8(cs + (row - B) * H + j, cp);
-    else {
+    if (s == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) cp[k] = 0.f;
     }
-    ld8(dh + i, dhv);
     {   // read-and-clear: the next step's data gradient ACCUMULATES into dh (split-K with vector reductions)
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         st8(dh + i, z);
@@ -465,7 +471,7 @@ lstm_bwd_pointwise_vec8_kernel(const bf16* __restrict__ gates, const float* __re
     float di[8], df[8], dgg[8], dox[8], dcn[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float tc = tanhf(c[k]);
+        const float tc = tanh_approx(c[k]);            // the same hardware tanh as the persistent forward kernel
         const float dcv = dc_in[k] + dhv[k] * go[k] * (1.f - tc * tc);
         dcn[k] = dcv * gf[k];
         di[k] = dcv * gg[k] * gi[k] * (1.f - gi[k]);

@@ -142,20 +142,21 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
         for (int u = 0; u < 16; ++u) h_state[u] = 0.f;
         for (int s = 0; s < T; ++s) {
             if (active_tile) {
-                mbar_wait(&tmem_full[mt], s & 1);
-                tcgen05_fence_after();
                 const int64_t row = ((int64_t)dir * T + s) * p.Bp + p.b0 + b;
                 const bool step_on = row_ok && s < len;
                 bf16* g = p.gx + row * 4 * H + u0;
-                // x-projection (+biases) of this thread's 16 units, 4 gates: 8 x 16 B
+                // x-projection (+biases) of this thread's 16 units, 4 gates: 8 x 16 B -- independent of the recurrent
+                // MMAs, so in flight while this warp waits for them
                 uint4 xq[4][2];
                 if (step_on) {
 #pragma unroll
                     for (int gate = 0; gate < 4; ++gate) {
-                        xq[gate][0] = *reinterpret_cast<const uint4*>(g + (int64_t)gate * H);
-                        xq[gate][1] = *reinterpret_cast<const uint4*>(g + (int64_t)gate * H + 8);
+                        xq[gate][0] = __ldcs(reinterpret_cast<const uint4*>(g + (int64_t)gate * H));
+                        xq[gate][1] = __ldcs(reinterpret_cast<const uint4*>(g + (int64_t)gate * H + 8));
                     }
                 }
+                mbar_wait(&tmem_full[mt], s & 1);
+                tcgen05_fence_after();
                 uint4 oq[4][2];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {          // units 8*half .. 8*half+7 <-> accumulator columns 32*half ..
@@ -169,12 +170,14 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 #pragma unroll
                             for (int gate = 0; gate < 4; ++gate)
                                 xg[gate] = __bfloat162float(reinterpret_cast<const bf16*>(&xq[gate][half])[uu]);
-                            const float gi = sigmoidf_(v[uu * 4 + 0] + xg[0]);
-                            const float gf = sigmoidf_(v[uu * 4 + 1] + xg[1]);
-                            const float gg = tanhf(v[uu * 4 + 2] + xg[2]);
-                            const float go = sigmoidf_(v[uu * 4 + 3] + xg[3]);
+                            // MUFU.TANH (2^-11 relative error, below the bf16 rounding of the stored gates): the precise
+                            // tanhf / expf forms were ~1000 instructions per thread and step on the serial critical path
+                            const float gi = sigmoid_approx(v[uu * 4 + 0] + xg[0]);
+                            const float gf = sigmoid_approx(v[uu * 4 + 1] + xg[1]);
+                            const float gg = tanh_approx(v[uu * 4 + 2] + xg[2]);
+                            const float go = sigmoid_approx(v[uu * 4 + 3] + xg[3]);
                             c_state[u] = gf * c_state[u] + gi * gg;
-                            h_state[u] = go * tanhf(c_state[u]);
+                            h_state[u] = go * tanh_approx(c_state[u]);
                             reinterpret_cast<bf16*>(&oq[0][half])[uu] = __float2bfloat16_rn(gi);
                             reinterpret_cast<bf16*>(&oq[1][half])[uu] = __float2bfloat16_rn(gf);
                             reinterpret_cast<bf16*>(&oq[2][half])[uu] = __float2bfloat16_rn(gg);
@@ -182,6 +185,21 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                         }
                     }
                 }
+                if (row_ok) {
+                    // h_s first: it is what every CTA of the direction waits for
+                    bf16* hdst = p.hs + (((int64_t)dir * (T + 1) + s + 1) * p.Bp + p.b0 + b) * H + u0;
+                    uint4 q[2];
+                    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(h_state[2 * t], h_state[2 * t + 1]);
+                    *reinterpret_cast<uint4*>(hdst) = q[0];
+                    *reinterpret_cast<uint4*>(hdst + 8) = q[1];
+                }
+                tcgen05_fence_before();
+                // release this warp's h_s stores to the other CTAs of the direction (warps of unused m-tiles stay out)
+                __syncwarp();
+                if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
+                // everything only the backward pass reads goes out after the signal, off the step-to-step critical path
                 if (step_on) {
 #pragma unroll
                     for (int gate = 0; gate < 4; ++gate) {
@@ -195,27 +213,18 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
                         *reinterpret_cast<float4*>(cdst + 4 * t) = make_float4(c_state[4 * t], c_state[4 * t + 1], c_state[4 * t + 2], c_state[4 * t + 3]);
-                    bf16* hdst = p.hs + (((int64_t)dir * (T + 1) + s + 1) * p.Bp + p.b0 + b) * H + u0;
-                    uint4 q[2];
-                    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(h_state[2 * t], h_state[2 * t + 1]);
-                    *reinterpret_cast<uint4*>(hdst) = q[0];
-                    *reinterpret_cast<uint4*>(hdst + 8) = q[1];
                     if (s == T - 1) {
                         bf16* qdst = p.qf + (int64_t)(p.b0 + b) * p.dirs * H + (int64_t)dir * H + u0;
+                        uint4 q[2];
+                        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
 #pragma unroll
                         for (int t = 0; t < 8; ++t) hh[t] = __floats2bfloat162_rn(c_state[2 * t], c_state[2 * t + 1]);
                         *reinterpret_cast<uint4*>(qdst) = q[0];
                         *reinterpret_cast<uint4*>(qdst + 8) = q[1];
                     }
                 }
-                tcgen05_fence_before();
             }
-            // release this warp's h_s stores to the other CTAs of the direction (warps of unused m-tiles stay out)
             if (!active_tile) break;
-            __syncwarp();
-            if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
         }
     }
     tcgen05_fence_before();
