@@ -147,6 +147,22 @@ def test_eval_mode_matches_train_mode_with_zero_dropout():
     assert torch.equal(a[0], b[0])
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_float16_images_give_the_same_step_as_their_float32_widening(dtype):
+    """The reference keeps pre-processed images as float16 on disk (preprocessing/preprocess_images.py:40) and widens them
+    to float32 on the host (preprocessing/data_preprocessing.py:174).  Handing the float16 tensor to the model (half the
+    host->device bytes) must give bit-identical logits and loss, and the same gradients."""
+    cfg, V, sd, batch = _full_case(2, 5)
+    v, q, q_len, a_idx, a_val, a_len = batch
+    v16 = v.to(torch.float16)
+    a = _cuda_step(cfg, V, sd, (v16.float(), q, q_len, a_idx, a_val, a_len), dtype, train=True)
+    b = _cuda_step(cfg, V, sd, (v16, q, q_len, a_idx, a_val, a_len), dtype, train=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    if dtype == "float32":       # atomics (embedding gradient, split-K) make gradients order-dependent in the last bits only
+        for k in a[3]:
+            assert _err(b[3][k], a[3][k]) < 1e-5, k
+
+
 def test_loss_and_score_kernel_edge_cases():
     import dl_vqa_b200 as D
     torch.manual_seed(0)
