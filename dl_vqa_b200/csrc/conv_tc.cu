@@ -451,7 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // cta_group selection: 1 = single-CTA MMAs, 2 = CTA pairs.  Changed only by vqa_tc_conv_set_cta_group (tests/bench).
-static int g_conv_cta_group = 1;
+static int g_conv_cta_group = 0;        // 0 = per-shape choice (launch_conv), 1 / 2 = forced
 
 template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
 static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvParams p, int smem_bytes, cudaStream_t st) {
@@ -490,7 +490,12 @@ static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvPar
 // Chooses resident vs streamed weights and the ring depths from the shared-memory budget, then launches.
 template <int BN, int EPI>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, ConvParams p, cudaStream_t st) {
-    const int ncta = g_conv_cta_group;
+    // CTA pairs halve the B-operand (weight) reads from shared memory.  Measured on B200 at the config.yaml shapes they win
+    // where the weights are streamed for a 256-wide tile (conv2 forward: 0.353 -> 0.333 ms) and for the 64-wide data
+    // gradient (conv1 dgrad: 0.418 -> 0.406 ms), and lose where one CTA already keeps the weights resident for a 128-wide
+    // tile (conv1 forward) or shares each streamed slab between two tiles (MT = 2: conv2 dgrad).
+    const int ncta = g_conv_cta_group != 0 ? g_conv_cta_group
+                   : ((EPI == EPI_POOL && BN == 256) || (EPI == EPI_STORE && BN == 64)) ? 2 : 1;
     const int nkb = 9 * p.chunks;
     const int slab = (BN / ncta) * 128;
     const int bars = 512 + 1024;                   // mbarriers + the staged bias
@@ -538,7 +543,7 @@ static int weight_tmap(CUtensorMap* m, const void* base, int N, int K, int rows)
 using namespace tc;
 
 extern "C" int vqa_tc_conv_set_cta_group(int cta_group) {
-    VQA_REQUIRE(cta_group == 1 || cta_group == 2, "conv cta_group must be 1 or 2");
+    VQA_REQUIRE(cta_group >= 0 && cta_group <= 2, "conv cta_group must be 0 (per-shape choice), 1 or 2");
     g_conv_cta_group = cta_group;
     return 0;
 }

@@ -20,7 +20,7 @@ ATT_ADD, ATT_MUL = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN, GEMM_B_MN = 1, 2, 4, 8, 16
 SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CLS_HID = range(7)
 
-DEFAULT_CONV_CTA_GROUP = 1      # tcgen05 cta_group used by the 3x3 conv kernels (vqa_tc_conv_set_cta_group)
+DEFAULT_CONV_CTA_GROUP = 0      # tcgen05 cta_group of the 3x3 conv kernels: 0 = per-shape choice, 1 / 2 forced (vqa_tc_conv_set_cta_group)
 
 _vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
 

@@ -227,7 +227,8 @@ int vqa_tc_conv3x3_bwd_data(const void* dy, const void* wd, void* dx,
 int vqa_tc_conv3x3_bwd_data_unpool(const void* dy, const void* wd, const uint8_t* mask_below, void* dy_below,
                                    float* db_below, int B, int IH, int IW, int Cin, int Cout, void* stream);
 /* Tuning knob of the entries above: 1 = single-CTA tcgen05.mma (cta_group::1), 2 = CTA pairs (cluster of 2,
- * cta_group::2: each CTA stages half of the weight rows).  Process-wide; results are identical either way. */
+ * cta_group::2: each CTA stages half of the weight rows), 0 (default) = chosen per layer shape from measurements.
+ * Process-wide; results are identical either way. */
 int vqa_tc_conv_set_cta_group(int cta_group);
 /* w fp32 OIHW [Cout,Cin,3,3] -> wp[co][tap][ci] and/or wd[ci][tap][co] (bf16; either may be NULL) */
 int vqa_pack_conv3x3_weight(const float* w, void* wp, void* wd, int Cout, int Cin, void* stream);
