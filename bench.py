@@ -247,7 +247,7 @@ def run_ours(args):
     # ---- (1) device-resident throughput (no per-kernel events inside this region)
     tags = [f"conv{i}_{k}" for i in range(3) for k in ("fwd", "dgrad", "wgrad")] + \
            ["v_conv", "v_conv_dgrad", "v_conv_wgrad", "vqa_attention_fwd", "vqa_attention_bwd", "lstm_step_fwd",
-            "lstm_step_bwd", "lstm_recurrence_fwd", "lstm_bwd_pointwise", "lstm_inproj", "lstm_whh_wgrad", "lstm_wih_wgrad", "lstm_inproj_dgrad", "lin1", "lin2", "q_lin", "lin1_dgrad", "lin2_dgrad", "lin1_wgrad", "lin2_wgrad", "q_lin_dgrad", "q_lin_wgrad", "act_cast", "vqa_adam_multi", "act_transpose", "unpool", "w_cast", "w_transpose"]
+            "lstm_step_bwd", "lstm_recurrence_fwd", "lstm_bwd_pointwise", "lstm_bwd_persistent", "lstm_inproj", "lstm_whh_wgrad", "lstm_wih_wgrad", "lstm_inproj_dgrad", "lin1", "lin2", "q_lin", "lin1_dgrad", "lin2_dgrad", "lin1_wgrad", "lin2_wgrad", "q_lin_dgrad", "q_lin_wgrad", "act_cast", "vqa_adam_multi", "act_transpose", "unpool", "w_cast", "w_transpose"]
     clocks = ClockSampler(local)
     clocks.start()
     n0 = lib.launch_count()

@@ -139,6 +139,101 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
+// ---- 8-wide bf16 / fp32 register <-> memory helpers (128-bit accesses)
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]);
+// 8 values from `a` (bf16) when it is non-null, else from `b` (fp32)
+__device__ __forceinline__ void ld8(const bf16* a, const float* b, float (&v)[8]) {
+    if (a) ld8(a, v); else ld8(b, v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {       // 8 packed bf16 -> fp32
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// One item of the LSTM backward pointwise step (bf16 arm): 8 hidden units of sample b, direction dir, step s.
+// Gate activations `gates` [dirs][T][B][4H] (i,f,g,o as stored by the forward), cell states `cs` [dirs][T][B][H];
+// reads and CLEARS dh (the data-gradient GEMM of the next step accumulates into it), updates dc in place, writes the
+// gate gradients dg [dirs][T][B][4H].  Shared by lstm_bwd_pointwise_vec8_kernel and the persistent backward kernel.
+// DH_L2: read dh with ld.global.cg (L2 only) -- needed when OTHER SMs accumulate into dh between two calls inside one kernel.
+template <bool DH_L2>
+__device__ __forceinline__ void lstm_bwd_pointwise_item8(int64_t i8, const bf16* __restrict__ gates, const float* __restrict__ cs,
+                                                         float* dh, float* __restrict__ dc,
+                                                         const bf16* __restrict__ dc_init, bf16* __restrict__ dg,
+                                                         const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+    const int h8 = H >> 3;
+    const int j = (int)(i8 % h8) * 8;
+    const int b = (int)((i8 / h8) % B);
+    const int dir = (int)(i8 / ((int64_t)B * h8));
+    const int64_t i = ((int64_t)dir * B + b) * H + j;
+    const int64_t row = ((int64_t)dir * T_ + s) * B + b;
+    bf16* o = dg + row * 4 * H + j;
+    // every load is issued before the first dependent branch (this kernel is one L2 round trip long: a load that waits
+    // for q_len, or sits in an if/else diamond, doubles it)
+    const int len = (int)q_len[b];
+    const bf16* g = gates + row * 4 * H + j;
+    float dc_in[8], gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
+    ld8(dc_init ? dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j : nullptr, dc + i, dc_in);
+    ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go);
+    ld8(cs + row * H + j, c);
+    ld8(cs + (s > 0 ? row - B : row) * H + j, cp);
+    if (DH_L2) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(dh + i)), b4 = __ldcg(reinterpret_cast<const float4*>(dh + i) + 1);
+        dhv[0] = a.x; dhv[1] = a.y; dhv[2] = a.z; dhv[3] = a.w; dhv[4] = b4.x; dhv[5] = b4.y; dhv[6] = b4.z; dhv[7] = b4.w;
+    } else {
+        ld8(dh + i, dhv);
+    }
+    if (s >= len) {                               // frozen step: zero gate gradients, dc passes through unchanged
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(o + gq * H) = z;
+        st8(dc + i, dc_in);
+        return;
+    }
+    if (s == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp[k] = 0.f;
+    }
+    {   // read-and-clear: the next step's data gradient ACCUMULATES into dh (split-K with vector reductions)
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        st8(dh + i, z);
+    }
+    float di[8], df[8], dgg[8], dox[8], dcn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float tc = tanh_approx(c[k]);            // the same hardware tanh as the persistent forward kernel
+        const float dcv = dc_in[k] + dhv[k] * go[k] * (1.f - tc * tc);
+        dcn[k] = dcv * gf[k];
+        di[k] = dcv * gg[k] * gi[k] * (1.f - gi[k]);
+        df[k] = dcv * cp[k] * gf[k] * (1.f - gf[k]);
+        dgg[k] = dcv * gi[k] * (1.f - gg[k] * gg[k]);
+        dox[k] = dhv[k] * tc * go[k] * (1.f - go[k]);
+    }
+    st8(dc + i, dcn);
+    st8(o, di); st8(o + H, df); st8(o + 2 * H, dgg); st8(o + 3 * H, dox);
+}
+
 // ------------------------------------------------------------------------------------------
 // counter-based dropout.  Element i of dropout site `site` is kept iff a 16-bit word derived from
 // hash32(key(seed, site) ^ (i >> 1)) is >= threshold (p quantised to 1/65536).  Stateless, so the

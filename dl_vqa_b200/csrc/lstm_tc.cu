@@ -232,6 +232,166 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent LSTM recurrence, BACKWARD: one cooperative launch for all T steps and both directions instead of a
+// pointwise kernel + split-K GEMM launch pair per step.  Per step s = T-1 .. 0 every CTA
+//   phase P  computes its share of the gate gradients dg_s from (dh, dc, saved gates, cell states)  [grid-stride, 8 units per item]
+//   barrier  (dg_s complete and visible to the async proxy)
+//   phase G  (s > 0) runs one split-K tile of  dh_{s-1}[b, :] += dg_s[b, k-range] W_hh[k-range, :]  on tcgen05:
+//            A = dg_s K-major by TMA, B = the bf16 W_hh as stored [4H, H] (MN-major), fp32 vector reductions into dh
+//   barrier  (all partial sums in dh)
+// The mbarrier ring, the TMEM accumulator and the tensor maps live across steps; the two grid barriers per step are
+// release (threadfence + atomicAdd) / acquire (ld.acquire.gpu) on one counter, as in the forward kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LB_THREADS = 512;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue; all sixteen run the pointwise phase
+                                         // (148 x 512 threads >= the 65536 items of a step at B = 256, H = 1024: one round)
+constexpr int LB_STAGES = 6;
+constexpr int LB_A_BYTES = 128 * 64 * 2, LB_B_BYTES = 128 * 64 * 2;
+
+struct LstmBwdParams {
+    const bf16* gates; const float* cs; float* dh; float* dc; const bf16* dc_init; bf16* dg; const int64_t* len;
+    unsigned int* sync;
+    int T, B, H, dirs;
+    int mt, nt, nsplit, kbps;            // GEMM tiling: tiles = mt * nt * dirs, each split into nsplit k-ranges of kbps k-blocks
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* cnt, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(cnt) < target) {
+            if (++spins > (1u << 26)) { printf("vqa_b200: lstm backward grid barrier timeout (cta %d)\n", blockIdx.x); __trap(); }
+        }
+    }
+    __syncthreads();
+}
+
+// (A variant that kept a [512 x 128] block of W_hh resident per CTA and streamed only dg measured slower, 0.41 vs 0.33 ms:
+// the ring that is left beside 128 KB of weights holds too few bytes in flight, and the partial sums double.)
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __grid_constant__ CUtensorMap tma_w, LstmBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + LB_STAGES * LB_A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + LB_STAGES * (LB_A_BYTES + LB_B_BYTES));
+    uint64_t* empty = full + LB_STAGES;
+    uint64_t* tmem_full = empty + LB_STAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, B = p.B, H = p.H;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_dg); tma_prefetch_desc(&tma_w);
+        for (int i = 0; i < LB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, 128);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // this CTA's GEMM tile (fixed for all steps)
+    const int ntile_ctas = p.mt * p.nt * p.dirs * p.nsplit;
+    const bool has_tile = (int)blockIdx.x < ntile_ctas;
+    int t_ = blockIdx.x;
+    const int split = t_ % p.nsplit; t_ /= p.nsplit;
+    const int nidx = t_ % p.nt; t_ /= p.nt;
+    const int midx = t_ % p.mt; t_ /= p.mt;
+    const int dir = has_tile ? t_ : 0;
+    const int total_kb = 4 * H / 64;
+    const int kb_begin = split * p.kbps;
+    const int nkb = has_tile ? max(0, min(total_kb, kb_begin + p.kbps) - kb_begin) : 0;
+    const int m0 = midx * 128, n0 = nidx * 128;
+
+    const int64_t items = (int64_t)p.dirs * B * (H >> 3);
+    const unsigned int nctas = gridDim.x;
+    unsigned int bar = 0;
+    uint32_t it = 0;                                        // ring position, continues across steps (producer and MMA warp)
+    const uint32_t elected = elect_one();
+    constexpr uint32_t idesc = idesc_bf16(128, 128, 0, 1);
+    const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa));
+    const uint64_t b_desc0 = smem_desc_mn_sw128(smem_u32(sb), 8192);
+
+    for (int s = T - 1; s >= 0; --s) {
+        // ---- phase P
+        for (int64_t i8 = (int64_t)blockIdx.x * LB_THREADS + threadIdx.x; i8 < items; i8 += (int64_t)nctas * LB_THREADS)
+            lstm_bwd_pointwise_item8<true>(i8, p.gates, p.cs, p.dh, p.dc, s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs);
+        if (s == 0) break;
+        // the weight halves of the first ring-full of k-blocks do not depend on this step's dg: in flight across the barrier
+        const int npre = min(nkb, LB_STAGES);
+        if (warp == 0 && lane == 0) {
+            for (int i = 0; i < npre; ++i) {
+                const uint32_t iti = it + i;
+                const int st = iti % LB_STAGES;
+                mbar_wait(&empty[st], ((iti / LB_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[st], LB_A_BYTES + LB_B_BYTES);
+                const int kc = (kb_begin + i) * 64;
+                tma_load_3d(sb + st * LB_B_BYTES, &tma_w, &full[st], n0, kc, dir);
+                tma_load_3d(sb + st * LB_B_BYTES + 8192, &tma_w, &full[st], n0 + 64, kc, dir);
+            }
+        }
+        grid_barrier(p.sync, ++bar * nctas);
+        // ---- phase G
+        if (nkb > 0) {
+            if (warp == 0) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");          // dg_s was written through the generic proxy
+                    const int row0 = (dir * T + s) * B + m0;
+                    for (int i = 0; i < nkb; ++i, ++it) {
+                        const int st = it % LB_STAGES;
+                        const int kc = (kb_begin + i) * 64;
+                        if (i >= npre) {
+                            mbar_wait(&empty[st], ((it / LB_STAGES) & 1) ^ 1);
+                            mbar_expect_tx(&full[st], LB_A_BYTES + LB_B_BYTES);
+                            tma_load_3d(sb + st * LB_B_BYTES, &tma_w, &full[st], n0, kc, dir);
+                            tma_load_3d(sb + st * LB_B_BYTES + 8192, &tma_w, &full[st], n0 + 64, kc, dir);
+                        }
+                        tma_load_2d(sa + st * LB_A_BYTES, &tma_dg, &full[st], kc, row0);
+                    }
+                }
+            } else if (warp == 1) {
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int st = it % LB_STAGES;
+                    mbar_wait(&full[st], (it / LB_STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint64_t ad = a_desc0 + (uint64_t)(st * (LB_A_BYTES >> 4)), bd = b_desc0 + (uint64_t)(st * (LB_B_BYTES >> 4));
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_issue<1>(tmem_base, ad + 2 * k, bd + k * (2048 >> 4), idesc, (i > 0 || k > 0) ? 1u : 0u, elected);
+                    umma_commit_issue<1>(&empty[st], elected);
+                }
+                umma_commit_issue<1>(tmem_full, elected);
+            } else if (warp < 6) {
+                const int quarter = warp & 3;
+                const int m = m0 + quarter * 32 + lane;
+                mbar_wait(tmem_full, (uint32_t)((T - 1 - s) & 1));
+                tcgen05_fence_after();
+                float* orow = p.dh + ((int64_t)dir * B + m) * H + n0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                    if (m < B) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) red_add_f32x4(orow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+                tcgen05_fence_before();
+            }
+        }
+        grid_barrier(p.sync, ++bar * nctas);
+        tcgen05_fence_after();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
 // w_hh fp32 [4H][H] (gate-stacked i,f,g,o) -> bf16 [H/16][64][H], row u*4+gate of block j = source row gate*H + 16j + u
 __global__ void pack_lstm_whh_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int H) {
     pdl_trigger();
@@ -348,5 +508,62 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
         cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persistent_fwd_kernel<1>, th, tw, p);
         if (e != cudaSuccess) { vqa_set_error("lstm_persistent_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
+    return 0;
+}
+
+// Backward recurrence in one cooperative launch (see lstm_persistent_bwd_kernel).  gates / dg [dirs][T][B][4H] bf16,
+// cs [dirs][T][B][H] fp32, dh [dirs][B][H] fp32 ZEROED by the caller (gradient w.r.t. the final hidden state would be
+// added here), dc [dirs][B][H] fp32 scratch, dc_init [B][dirs*H] bf16 = gradient w.r.t. the final cell state,
+// whh [dirs][4H][H] bf16 (the recurrent weights as stored), sync: one zeroed uint32.  Same results as T calls of
+// vqa_lstm_step_bwd_pointwise interleaved with T-1 split-K vqa_tc_gemm calls (up to fp32 summation order).
+extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, float* dc, const void* dc_init, void* dg,
+                               const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
+                               void* stream) {
+    VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm bwd: bad dims");
+    VQA_REQUIRE(H % 128 == 0, "tc lstm bwd: hidden size %d must be a multiple of 128", H);
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    VQA_REQUIRE(coop, "tc lstm bwd: device does not support cooperative launch");
+    LstmBwdParams p{};
+    p.gates = (const bf16*)gates; p.cs = cs_; p.dh = dh; p.dc = dc; p.dc_init = (const bf16*)dc_init; p.dg = (bf16*)dg;
+    p.len = q_len; p.sync = sync; p.T = T; p.B = B; p.H = H; p.dirs = dirs;
+    p.mt = (B + 127) / 128; p.nt = H / 128;
+    const int tiles = p.mt * p.nt * dirs, total_kb = 4 * H / 64;
+    VQA_REQUIRE(tiles <= sms, "tc lstm bwd: %d output tiles but only %d SMs (use the per-step path)", tiles, sms);
+    int nsplit = sms / tiles;
+    if (nsplit > total_kb / 4) nsplit = total_kb / 4;          // at least 4 k-blocks per split
+    if (nsplit < 1) nsplit = 1;
+    p.kbps = (total_kb + nsplit - 1) / nsplit;
+    p.nsplit = (total_kb + p.kbps - 1) / p.kbps;
+    CUtensorMap tdg, tw;
+    {
+        const uint64_t dims[2] = {(uint64_t)4 * H, (uint64_t)dirs * T * B};
+        const uint64_t str[1] = {(uint64_t)4 * H * 2};
+        const uint32_t box[2] = {64, 128};
+        if (int e = make_tmap_bf16(&tdg, dg, 2, dims, str, box)) return e;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)H, (uint64_t)4 * H, (uint64_t)dirs};
+        const uint64_t str[2] = {(uint64_t)H * 2, (uint64_t)4 * H * H * 2};
+        const uint32_t box[3] = {64, 64, 1};
+        if (int e = make_tmap_bf16(&tw, whh, 3, dims, str, box)) return e;
+    }
+    const int smem = LB_STAGES * (LB_A_BYTES + LB_B_BYTES) + 1024 + 256;
+    static int attr_bytes = 0;
+    if (attr_bytes < smem) {
+        VQA_CUDA(cudaFuncSetAttribute(lstm_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_bytes = smem;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int), st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sms); cfg.blockDim = dim3(LB_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VQA_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_bwd_kernel, tdg, tw, p));
+    VQA_CHECK_LAUNCH("lstm_persistent_bwd");
     return 0;
 }

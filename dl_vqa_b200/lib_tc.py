@@ -18,6 +18,7 @@ PROTOTYPES = {
     "vqa_tc_conv0_bwd_weight_bias": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_pack_lstm_whh": [_vp, _vp, _i, _vp],
+    "vqa_tc_lstm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_cluster_size": [],
     "vqa_nhwc_to_nchw_pad_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_unpool_nchw_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

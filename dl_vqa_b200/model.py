@@ -13,6 +13,8 @@ state_dict names to the reference); their forward() is never called.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import torch
@@ -610,7 +612,16 @@ class VqaNet(nn.Module):
                 whhb = empty(dirs, 4 * H, H)
                 for d in range(dirs):
                     whhb[d].copy_(shs[d])
-        for s in range(T - 1, -1, -1):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        persistent_bwd = (tc and T > 1 and H % 128 == 0 and ((B + 127) // 128) * (H // 128) * dirs <= sms
+                          and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
+        if persistent_bwd:
+            # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
+            # two grid barriers per step) instead of 2T - 1 dependent launches
+            sync_b = torch.zeros(1, dtype=torch.int32, device=dev)
+            call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
+                 T, B, H, dirs, st, tag="lstm_bwd_persistent")
+        for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):
             call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
                  ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
             if s > 0:   # dh_{s-1} = dgates_s W_hh

@@ -262,6 +262,15 @@ int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_
 int vqa_tc_lstm_fwd(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len,
                     unsigned int* sync, int T, int B, int H, int dirs, void* stream);
 int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);
+/* backward recurrence of the same LSTM in ONE cooperative launch (autograd of models/model.py:164; replaces T calls of
+ * vqa_lstm_step_bwd_pointwise interleaved with T-1 split-K vqa_tc_gemm calls): gates / dg [dirs][T][B][4H] bf16
+ * (activated gates saved by the forward -> gate gradients), cs [dirs][T][B][H] fp32, dh [dirs][B][H] fp32 ZEROED by
+ * the caller, dc [dirs][B][H] fp32 scratch, dc_init [B][dirs*H] bf16 (gradient w.r.t. the final cell state),
+ * whh [dirs][4H][H] bf16 (recurrent weights as stored), sync: one uint32 of scratch.  H % 128 == 0 and
+ * ceil(B/128) * (H/128) * dirs <= #SMs. */
+int vqa_tc_lstm_bwd(const void* gates, const float* cs, float* dh, float* dc, const void* dc_init, void* dg,
+                    const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
+                    void* stream);
 /* diagnostic: 4 = vqa_tc_lstm_fwd runs as clusters of four CTAs with TMA multicast of h (opt-in through the
  * environment variable VQA_LSTM_CLUSTER=4), 1 = single CTAs (default, or the driver rejected the cooperative cluster
  * launch), 0 = not launched yet */

@@ -394,3 +394,52 @@ def test_persistent_lstm_cluster_multicast_variant_in_fresh_process():
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (5, 4, 128, 1), (130, 7, 256, 2), (300, 6, 256, 2)])
+def test_persistent_lstm_backward_matches_the_per_step_kernels(B, T, H, dirs):
+    """vqa_tc_lstm_bwd (one cooperative launch) == T x vqa_lstm_step_bwd_pointwise + (T-1) x split-K vqa_tc_gemm."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(B + T)
+    dev = "cuda"
+    gates = torch.rand(dirs, T, B, 4 * H, device=dev).bfloat16()                 # activated gates in (0, 1)
+    gates[:, :, :, 2 * H:3 * H] = (torch.rand(dirs, T, B, H, device=dev) * 2 - 1).bfloat16()   # g gate in (-1, 1)
+    cs = torch.randn(dirs, T, B, H, device=dev) * 0.5
+    dqf = (torch.randn(B, dirs * H, device=dev) * 0.1).bfloat16()
+    whh = (torch.randn(dirs, 4 * H, H, device=dev) / H ** 0.5).bfloat16()
+    q_len = torch.randint(1, T + 1, (B,), device=dev, dtype=torch.int64)
+    q_len[0] = T
+    st = lib.stream()
+
+    def per_step():
+        dh = torch.zeros(dirs, B, H, device=dev)
+        dc = torch.empty(dirs, B, H, device=dev)
+        dg = torch.empty(dirs, T, B, 4 * H, dtype=torch.bfloat16, device=dev)
+        for s in range(T - 1, -1, -1):
+            lib.call("vqa_lstm_step_bwd_pointwise", lib.ptr(gates), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc),
+                     lib.ptr(dqf) if s == T - 1 else None, lib.ptr(dg), lib.ptr(q_len), lib.BF16, s, T, B, H, dirs, st)
+            if s > 0:
+                lib.call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * 2, 4 * H, T * B * 4 * H, lib.ptr(whh), H, 4 * H * H,
+                         lib.ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs,
+                         lib.GEMM_SPLITK | lib.GEMM_B_MN, 0.0, 0, 0, st)
+        torch.cuda.synchronize()
+        return dg, dh, dc
+
+    def persistent():
+        dh = torch.zeros(dirs, B, H, device=dev)
+        dc = torch.empty(dirs, B, H, device=dev)
+        dg = torch.empty(dirs, T, B, 4 * H, dtype=torch.bfloat16, device=dev)
+        sync = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib.call("vqa_tc_lstm_bwd", lib.ptr(gates), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc), lib.ptr(dqf), lib.ptr(dg),
+                 lib.ptr(whh), lib.ptr(q_len), lib.ptr(sync), T, B, H, dirs, st)
+        torch.cuda.synchronize()
+        return dg, dh, dc
+
+    dg_a, dh_a, dc_a = per_step()
+    dg_b, dh_b, dc_b = persistent()
+
+    def err(a, b):
+        return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-20))
+    assert err(dg_b, dg_a) < 1e-2          # bf16 gate gradients; fp32 partial sums arrive in a different order
+    assert err(dc_b, dc_a) < 1e-4
+    assert err(dh_b, dh_a) < 1e-4
