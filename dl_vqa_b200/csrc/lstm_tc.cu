@@ -236,12 +236,12 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
 // Persistent LSTM recurrence, BACKWARD: one cooperative launch for all T steps and both directions instead of a
 // pointwise kernel + split-K GEMM launch pair per step.  Per step s = T-1 .. 0 every CTA
 //   phase P  computes its share of the gate gradients dg_s from (dh, dc, saved gates, cell states)  [grid-stride, 8 units per item]
-//   barrier  (dg_s complete and visible to the async proxy)
+//   signal   row_cnt[dir, m]: dg_s rows of this row tile complete (waited on by the TMA producers of that row tile)
 //   phase G  (s > 0) runs one split-K tile of  dh_{s-1}[b, :] += dg_s[b, k-range] W_hh[k-range, :]  on tcgen05:
 //            A = dg_s K-major by TMA, B = the bf16 W_hh as stored [4H, H] (MN-major), fp32 vector reductions into dh
-//   barrier  (all partial sums in dh)
-// The mbarrier ring, the TMEM accumulator and the tensor maps live across steps; the two grid barriers per step are
-// release (threadfence + atomicAdd) / acquire (ld.acquire.gpu) on one counter, as in the forward kernel.
+//   signal   tile_cnt[tile]: all partial sums of this dh block are in (waited on by the tile's own nsplit CTAs)
+// The mbarrier ring, the TMEM accumulator and the tensor maps live across steps; the two synchronisations per step are
+// release (threadfence + atomicAdd) / acquire (ld.acquire.gpu) on per-tile / per-row-tile counters, never grid-wide.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int LB_THREADS = 512;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue; all sixteen run the pointwise phase
                                          // (148 x 512 threads >= the 65536 items of a step at B = 256, H = 1024: one round)
@@ -255,17 +255,16 @@ struct LstmBwdParams {
     int mt, nt, nsplit, kbps;            // GEMM tiling: tiles = mt * nt * dirs, each split into nsplit k-ranges of kbps k-blocks
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* cnt, unsigned int target) {
+// release / acquire on monotonically growing counters in global memory (all CTAs are co-resident: cooperative launch)
+__device__ __forceinline__ void cta_signal(unsigned int* cnt) {          // after the CTA's writes / reductions
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(cnt, 1u);
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(cnt) < target) {
-            if (++spins > (1u << 26)) { printf("vqa_b200: lstm backward grid barrier timeout (cta %d)\n", blockIdx.x); __trap(); }
-        }
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
+}
+__device__ __forceinline__ void spin_until(const unsigned int* cnt, unsigned int target) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(cnt) < target) {
+        if (++spins > (1u << 26)) { printf("vqa_b200: lstm backward wait timeout (cta %d)\n", blockIdx.x); __trap(); }
     }
-    __syncthreads();
 }
 
 // (A variant that kept a [512 x 128] block of W_hh resident per CTA and streamed only dg measured slower, 0.41 vs 0.33 ms:
@@ -308,9 +307,14 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
     const int nkb = has_tile ? max(0, min(total_kb, kb_begin + p.kbps) - kb_begin) : 0;
     const int m0 = midx * 128, n0 = nidx * 128;
 
-    const int64_t items = (int64_t)p.dirs * B * (H >> 3);
-    const unsigned int nctas = gridDim.x;
-    unsigned int bar = 0;
+    // Synchronisation is point to point, not grid-wide.  The nsplit CTAs of an output tile (dir, m, n) are also the ones
+    // that run the pointwise phase for that tile's 128 x 128 (sample, unit) block, so
+    //   tile_cnt[tile]  (+1 per CTA after its reductions)  gates the next pointwise phase of those same nsplit CTAs, and
+    //   row_cnt[dir, m] (+1 per CTA after its dg stores)   gates the A-operand loads of the nt * nsplit CTAs of that row tile.
+    const int tile_id = (dir * p.mt + midx) * p.nt + nidx;
+    unsigned int* tile_cnt = p.sync + tile_id;
+    unsigned int* row_cnt = p.sync + p.mt * p.nt * p.dirs + dir * p.mt + midx;
+    const int h8 = H >> 3;
     uint32_t it = 0;                                        // ring position, continues across steps (producer and MMA warp)
     const uint32_t elected = elect_one();
     constexpr uint32_t idesc = idesc_bf16(128, 128, 0, 1);
@@ -318,9 +322,19 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
     const uint64_t b_desc0 = smem_desc_mn_sw128(smem_u32(sb), 8192);
 
     for (int s = T - 1; s >= 0; --s) {
-        // ---- phase P
-        for (int64_t i8 = (int64_t)blockIdx.x * LB_THREADS + threadIdx.x; i8 < items; i8 += (int64_t)nctas * LB_THREADS)
-            lstm_bwd_pointwise_item8<true>(i8, p.gates, p.cs, p.dh, p.dc, s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs);
+        if (!has_tile) break;
+        const unsigned int done = (unsigned int)(T - 1 - s);         // steps completed so far
+        // ---- phase P: this CTA's share (1 / nsplit) of the tile's 128 rows x 16 groups of 8 units
+        if (done > 0) {
+            if (threadIdx.x == 0) spin_until(tile_cnt, (unsigned int)p.nsplit * done);   // dh of this block is complete
+            __syncthreads();
+        }
+        for (int li = split * LB_THREADS + threadIdx.x; li < 128 * 16; li += p.nsplit * LB_THREADS) {
+            const int b = m0 + (li >> 4);
+            if (b < B)
+                lstm_bwd_pointwise_item8<true>(((int64_t)dir * B + b) * h8 + (n0 >> 3) + (li & 15), p.gates, p.cs, p.dh, p.dc,
+                                               s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs);
+        }
         if (s == 0) break;
         // the weight halves of the first ring-full of k-blocks do not depend on this step's dg: in flight across the barrier
         const int npre = min(nkb, LB_STAGES);
@@ -335,12 +349,13 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
                 tma_load_3d(sb + st * LB_B_BYTES + 8192, &tma_w, &full[st], n0 + 64, kc, dir);
             }
         }
-        grid_barrier(p.sync, ++bar * nctas);
+        cta_signal(row_cnt);
         // ---- phase G
         if (nkb > 0) {
             if (warp == 0) {
                 if (lane == 0) {
-                    asm volatile("fence.proxy.async;" ::: "memory");          // dg_s was written through the generic proxy
+                    spin_until(row_cnt, (unsigned int)(p.nt * p.nsplit) * (done + 1));     // dg_s rows of this row tile are written
+                    asm volatile("fence.proxy.async;" ::: "memory");          // ... through the generic proxy
                     const int row0 = (dir * T + s) * B + m0;
                     for (int i = 0; i < nkb; ++i, ++it) {
                         const int st = it % LB_STAGES;
@@ -384,7 +399,7 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
                 tcgen05_fence_before();
             }
         }
-        grid_barrier(p.sync, ++bar * nctas);
+        cta_signal(tile_cnt);
         tcgen05_fence_after();
     }
     tcgen05_fence_before();
@@ -514,7 +529,7 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
 // Backward recurrence in one cooperative launch (see lstm_persistent_bwd_kernel).  gates / dg [dirs][T][B][4H] bf16,
 // cs [dirs][T][B][H] fp32, dh [dirs][B][H] fp32 ZEROED by the caller (gradient w.r.t. the final hidden state would be
 // added here), dc [dirs][B][H] fp32 scratch, dc_init [B][dirs*H] bf16 = gradient w.r.t. the final cell state,
-// whh [dirs][4H][H] bf16 (the recurrent weights as stored), sync: one zeroed uint32.  Same results as T calls of
+// whh [dirs][4H][H] bf16 (the recurrent weights as stored), sync: scratch of (tiles + dirs * ceil(B/128)) uint32 (<= 256).  Same results as T calls of
 // vqa_lstm_step_bwd_pointwise interleaved with T-1 split-K vqa_tc_gemm calls (up to fp32 summation order).
 extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, float* dc, const void* dc_init, void* dg,
                                const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
@@ -557,9 +572,9 @@ extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, f
         attr_bytes = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int), st));
+    VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * (size_t)(tiles + dirs * p.mt), st));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(sms); cfg.blockDim = dim3(LB_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cfg.gridDim = dim3(tiles * p.nsplit); cfg.blockDim = dim3(LB_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;

@@ -618,7 +618,7 @@ class VqaNet(nn.Module):
         if persistent_bwd:
             # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
             # two grid barriers per step) instead of 2T - 1 dependent launches
-            sync_b = torch.zeros(1, dtype=torch.int32, device=dev)
+            sync_b = torch.zeros(256, dtype=torch.int32, device=dev)
             call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
                  T, B, H, dirs, st, tag="lstm_bwd_persistent")
         for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):

@@ -266,7 +266,7 @@ int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);
  * vqa_lstm_step_bwd_pointwise interleaved with T-1 split-K vqa_tc_gemm calls): gates / dg [dirs][T][B][4H] bf16
  * (activated gates saved by the forward -> gate gradients), cs [dirs][T][B][H] fp32, dh [dirs][B][H] fp32 ZEROED by
  * the caller, dc [dirs][B][H] fp32 scratch, dc_init [B][dirs*H] bf16 (gradient w.r.t. the final cell state),
- * whh [dirs][4H][H] bf16 (recurrent weights as stored), sync: one uint32 of scratch.  H % 128 == 0 and
+ * whh [dirs][4H][H] bf16 (recurrent weights as stored), sync: 256 uint32 of scratch.  H % 128 == 0 and
  * ceil(B/128) * (H/128) * dirs <= #SMs. */
 int vqa_tc_lstm_bwd(const void* gates, const float* cs, float* dh, float* dc, const void* dc_init, void* dg,
                     const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,

@@ -429,7 +429,7 @@ def test_persistent_lstm_backward_matches_the_per_step_kernels(B, T, H, dirs):
         dh = torch.zeros(dirs, B, H, device=dev)
         dc = torch.empty(dirs, B, H, device=dev)
         dg = torch.empty(dirs, T, B, 4 * H, dtype=torch.bfloat16, device=dev)
-        sync = torch.zeros(1, dtype=torch.int32, device=dev)
+        sync = torch.zeros(256, dtype=torch.int32, device=dev)
         lib.call("vqa_tc_lstm_bwd", lib.ptr(gates), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc), lib.ptr(dqf), lib.ptr(dg),
                  lib.ptr(whh), lib.ptr(q_len), lib.ptr(sync), T, B, H, dirs, st)
         torch.cuda.synchronize()
