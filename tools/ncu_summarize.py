@@ -35,6 +35,7 @@ def tag_of(name, seen):
     if "attention_bwd_stream_kernel" in name: return "vqa_attention_bwd"
     if "adam_multi_kernel" in name: return "vqa_adam_multi"
     if "lstm_persistent_fwd_kernel" in name: return "lstm_recurrence_fwd"
+    if "lstm_persistent_bwd_kernel" in name: return "lstm_bwd_persistent"
     if "dropnorm_bwd_unpool_kernel" in name: return "dropnorm_bwd_unpool"
     if "dropnorm_fwd_kernel" in name: return "dropnorm_fwd"
     if "dropnorm_bwd_kernel" in name: return "dropnorm_bwd"
