@@ -504,9 +504,22 @@ class VqaNet(nn.Module):
         def zeros(*shape, dtype=f32):
             return torch.zeros(shape, dtype=dtype, device=dev)
 
-        def fire(names):
-            if self.grad_ready_hook is not None:
+        deferred = []
+
+        def fire(names, defer=False):
+            """Hand finished gradients to the data-parallel hook.  `defer`: hold them back until flush_deferred() -- the
+            cooperative LSTM kernels need (nearly) every SM to themselves, and an all-reduce that is already running on the
+            communication stream would make their launch wait for it."""
+            if self.grad_ready_hook is None:
+                return
+            if defer:
+                deferred.append(list(names))
+            else:
                 self.grad_ready_hook([(n, grads[n]) for n in names])
+
+        def flush_deferred():
+            while deferred:
+                fire(deferred.pop(0))
 
         arena = None
         if self._arena is not None:
@@ -553,7 +566,7 @@ class VqaNet(nn.Module):
         mm.lin_bwd_weight(ptr(dz1), dt, hid, ptr(combd), dt, KC, dW1, B, hid, KC, tag="lin1_wgrad")
         grads["classifier.lin1.weight"] = dW1
         grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid, "classifier.lin1.bias")
-        fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"])
+        fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"], defer=True)
         if p_cls > 0:   # through classifier.drop1 (in place)
             call("vqa_dropout_apply", ptr(dcomb), KC, ptr(dcomb), KC, dt, B, KC, p_cls, seed, lib.SITE_CLS_IN, st)
 
@@ -584,7 +597,7 @@ class VqaNet(nn.Module):
         grads["attention.q_lin.weight"] = dWq
         grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A, "attention.q_lin.bias")
         fire(["attention.v_conv.weight", "attention.q_lin.weight", "attention.q_lin.bias",
-              "attention.x_conv.weight", "attention.x_conv.bias"])
+              "attention.x_conv.weight", "attention.x_conv.bias"], defer=True)
         # gradient w.r.t. the question feature: concat branch + (dropped) q_lin branch
         dqf = empty(B, QF)
         esz = dcomb.element_size()
@@ -635,6 +648,7 @@ class VqaNet(nn.Module):
                     call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,
                          ptr(w_hh[0]), lib.F32, 1, H, ctx["whh_stride"], ptr(dh), lib.F32, H, B * H,
                          None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
+        flush_deferred()             # classifier + attention gradients: their all-reduce starts behind the recurrence
         for d in range(dirs):
             dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
             mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(ctx["h_prev"][d]), dt, H, dWhh,
