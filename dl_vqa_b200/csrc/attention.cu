@@ -69,11 +69,21 @@ attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, con
         const int ch = cg * 32 + lane;
         const bool act = ch < nchunk;
         const int a0 = ch * 8;
-        float qv[8], wv[G][8];
+        // CAT ('|', models/model.py:192-193): x = relu(cat[v', q']) has 2A channels, x_conv's weight is [G][2A]; the q' half
+        // of x is the same for every position except for its dropout mask (element index (b, s, A + a) of the 2A-wide row).
+        constexpr bool CAT = OP == VQA_ATT_CAT;
+        const int W = CAT ? 2 * A : A;                 // row length of wx and of the dropout index space
+        float qv[8], wv[G][8], wq[CAT ? G : 1][8];
         if (act) {
             load8f(qp + (int64_t)b * A + a0, qv);
 #pragma unroll
-            for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * A + a0, wv[g]);
+            for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * W + a0, wv[g]);
+            if (CAT) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * W + A + a0, wq[CAT ? g : 0]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qv[i] = fmaxf(qv[i], 0.f);
+            }
         }
         for (int s0 = warp; s0 < P; s0 += 2 * NW) {
             const int s1 = s0 + NW;
@@ -85,22 +95,36 @@ attention_fwd_kernel(const T* __restrict__ vp, const float* __restrict__ qp, con
                 load8(vpb + (int64_t)s0 * A + a0, x0);
                 if (has1) load8(vpb + (int64_t)s1 * A + a0, x1);
                 float m[8];
-                drop8(d8, ((uint64_t)b * P + s0) * A + a0, m);
+                drop8(d8, ((uint64_t)b * P + s0) * W + a0, m);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float pre = OP == VQA_ATT_ADD ? x0[i] + qv[i] : x0[i] * qv[i];
+                    const float pre = CAT ? x0[i] : (OP == VQA_ATT_ADD ? x0[i] + qv[i] : x0[i] * qv[i]);
                     const float r = fmaxf(pre, 0.f) * m[i];
 #pragma unroll
                     for (int g = 0; g < G; ++g) acc0[g] = fmaf(r, wv[g][i], acc0[g]);
                 }
+                if (CAT) {
+                    drop8(d8, ((uint64_t)b * P + s0) * W + A + a0, m);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int g = 0; g < G; ++g) acc0[g] = fmaf(qv[i] * m[i], wq[CAT ? g : 0][i], acc0[g]);
+                }
                 if (has1) {
-                    drop8(d8, ((uint64_t)b * P + s1) * A + a0, m);
+                    drop8(d8, ((uint64_t)b * P + s1) * W + a0, m);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float pre = OP == VQA_ATT_ADD ? x1[i] + qv[i] : x1[i] * qv[i];
+                        const float pre = CAT ? x1[i] : (OP == VQA_ATT_ADD ? x1[i] + qv[i] : x1[i] * qv[i]);
                         const float r = fmaxf(pre, 0.f) * m[i];
 #pragma unroll
                         for (int g = 0; g < G; ++g) acc1[g] = fmaf(r, wv[g][i], acc1[g]);
+                    }
+                    if (CAT) {
+                        drop8(d8, ((uint64_t)b * P + s1) * W + A + a0, m);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+#pragma unroll
+                            for (int g = 0; g < G; ++g) acc1[g] = fmaf(qv[i] * m[i], wq[CAT ? g : 0][i], acc1[g]);
                     }
                 }
             }
@@ -195,9 +219,12 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
     float* pr = sm;                       // [G][P] softmax
     float* dl = pr + G * P;               // [G][P] dp, then dlogit
     float* dsm = dl + G * P;              // [G][C] upstream gradient
-    float* red = dsm + G * C;             // [NW][(1+G)*256]
+    float* red = dsm + G * C;             // [NW][(1+G)*256]   (CAT: [NW][(1+2G)*256])
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
+    constexpr bool CAT = OP == VQA_ATT_CAT;
+    constexpr int NR = CAT ? 1 + 2 * G : 1 + G;       // reduced rows per chunk: dq, dwx (v' half) and for CAT dwx (q' half)
+    const int W = CAT ? 2 * A : A;
 
     for (int i = tid; i < G * P; i += NTHREADS) { pr[i] = prob[(int64_t)b * G * P + i]; dl[i] = 0.f; }
     for (int i = tid; i < G * C; i += NTHREADS) dsm[i] = to_f32(dout[(int64_t)b * ldd + i]);
@@ -265,53 +292,83 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
         const int ch = cg * 32 + lane;
         const bool act = ch < nchunk;
         const int a0 = ch * 8;
-        float qv[8], wv[G][8], dq[8], dw[G][8];
+        float qv[8], wv[G][8], dq[8], dw[G][8], wq[CAT ? G : 1][8], dwq[CAT ? G : 1][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { dq[i] = 0.f; qv[i] = 0.f; }
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int i = 0; i < 8; ++i) { dw[g][i] = 0.f; wv[g][i] = 0.f; }
+#pragma unroll
+        for (int g = 0; g < (CAT ? G : 1); ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dwq[g][i] = 0.f; wq[g][i] = 0.f; }
         if (act) {
             load8f(qp + (int64_t)b * A + a0, qv);
 #pragma unroll
-            for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * A + a0, wv[g]);
+            for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * W + a0, wv[g]);
+            if (CAT) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) load8f(wx + (int64_t)g * W + A + a0, wq[CAT ? g : 0]);
+            }
             for (int s = warp; s < P; s += NW) {
                 float x[8], m[8], o[8], dls[G];
                 load8(vpb + (int64_t)s * A + a0, x);
-                drop8(d8, ((uint64_t)b * P + s) * A + a0, m);
+                drop8(d8, ((uint64_t)b * P + s) * W + a0, m);
 #pragma unroll
                 for (int g = 0; g < G; ++g) dls[g] = dl[g * P + s];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float pre = OP == VQA_ATT_ADD ? x[i] + qv[i] : x[i] * qv[i];
+                    const float pre = CAT ? x[i] : (OP == VQA_ATT_ADD ? x[i] + qv[i] : x[i] * qv[i]);
                     const bool alive = pre > 0.f;
                     const float xr = alive ? pre * m[i] : 0.f;
                     float dxt = 0.f;
 #pragma unroll
                     for (int g = 0; g < G; ++g) { dxt = fmaf(dls[g], wv[g][i], dxt); dw[g][i] = fmaf(dls[g], xr, dw[g][i]); }
                     const float dpre = alive ? dxt * m[i] : 0.f;
-                    if (OP == VQA_ATT_ADD) { o[i] = dpre; dq[i] += dpre; }
+                    if (CAT || OP == VQA_ATT_ADD) { o[i] = dpre; if (!CAT) dq[i] += dpre; }
                     else { o[i] = dpre * qv[i]; dq[i] = fmaf(dpre, x[i], dq[i]); }
+                }
+                if (CAT) {                           // the q' half of x: relu(q') * dropout(b, s, A + a)
+                    drop8(d8, ((uint64_t)b * P + s) * W + A + a0, m);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool alive = qv[i] > 0.f;
+                        const float xr = alive ? qv[i] * m[i] : 0.f;
+                        float dxt = 0.f;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            dxt = fmaf(dls[g], wq[CAT ? g : 0][i], dxt);
+                            dwq[CAT ? g : 0][i] = fmaf(dls[g], xr, dwq[CAT ? g : 0][i]);
+                        }
+                        if (alive) dq[i] = fmaf(dxt, m[i], dq[i]);
+                    }
                 }
                 store8(dvpb + (int64_t)s * A + a0, o);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) red[(warp * (1 + G)) * 256 + lane * 8 + i] = dq[i];
+        for (int i = 0; i < 8; ++i) red[(warp * NR) * 256 + lane * 8 + i] = dq[i];
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) red[(warp * (1 + G) + 1 + g) * 256 + lane * 8 + i] = dw[g][i];
+            for (int i = 0; i < 8; ++i) red[(warp * NR + 1 + g) * 256 + lane * 8 + i] = dw[g][i];
+        if (CAT) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) red[(warp * NR + 1 + G + g) * 256 + lane * 8 + i] = dwq[CAT ? g : 0][i];
+        }
         __syncthreads();
-        for (int t = tid; t < (1 + G) * 256; t += NTHREADS) {
+        for (int t = tid; t < NR * 256; t += NTHREADS) {
             const int k = t >> 8, a = cg * 256 + (t & 255);
             if (a < A) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) s += red[(w * (1 + G) + k) * 256 + (t & 255)];
+                for (int w = 0; w < NW; ++w) s += red[(w * NR + k) * 256 + (t & 255)];
                 if (k == 0) dqp[(int64_t)b * A + a] = s;
-                else dwx_part[((int64_t)b * G + (k - 1)) * A + a] = s;
+                else if (k <= G) dwx_part[((int64_t)b * G + (k - 1)) * W + a] = s;
+                else dwx_part[((int64_t)b * G + (k - 1 - G)) * W + A + a] = s;
             }
         }
         __syncthreads();
@@ -891,7 +948,7 @@ template <typename T, int G, int OP>
 int launch_bwd(const void* dout, int64_t ldd, const void* vp, const float* qp, const void* vn, const float* wx,
                const float* prob, void* dvp, void* dvn, float* dqp, float* dwx_part, float* dbx_part,
                int B, int P, int A, int C, Dropout d, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)2 * G * P + (size_t)G * C + (size_t)NW * (1 + G) * 256);
+    const size_t smem = sizeof(float) * ((size_t)2 * G * P + (size_t)G * C + (size_t)NW * (OP == VQA_ATT_CAT ? 1 + 2 * G : 1 + G) * 256);
     auto kern = attention_bwd_kernel<T, G, OP>;
     if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQA_CUDA(vqa_launch_pdl(kern, dim3(B), dim3(NTHREADS), smem, st, (const T*)dout, ldd, (const T*)vp, qp, (const T*)vn, wx, prob, (T*)dvp, (T*)dvn,
@@ -908,31 +965,39 @@ int launch_bwd(const void* dout, int64_t ldd, const void* vp, const float* qp, c
         switch (key__) {                                                                             \
             case 10:  return FN<float, 1, VQA_ATT_ADD>(__VA_ARGS__);                                 \
             case 11:  return FN<float, 1, VQA_ATT_MUL>(__VA_ARGS__);                                 \
+            case 12:  return FN<float, 1, VQA_ATT_CAT>(__VA_ARGS__);                                 \
             case 20:  return FN<float, 2, VQA_ATT_ADD>(__VA_ARGS__);                                 \
             case 21:  return FN<float, 2, VQA_ATT_MUL>(__VA_ARGS__);                                 \
+            case 22:  return FN<float, 2, VQA_ATT_CAT>(__VA_ARGS__);                                 \
             case 30:  return FN<float, 3, VQA_ATT_ADD>(__VA_ARGS__);                                 \
             case 31:  return FN<float, 3, VQA_ATT_MUL>(__VA_ARGS__);                                 \
+            case 32:  return FN<float, 3, VQA_ATT_CAT>(__VA_ARGS__);                                 \
             case 40:  return FN<float, 4, VQA_ATT_ADD>(__VA_ARGS__);                                 \
             case 41:  return FN<float, 4, VQA_ATT_MUL>(__VA_ARGS__);                                 \
+            case 42:  return FN<float, 4, VQA_ATT_CAT>(__VA_ARGS__);                                 \
             case 110: return FN<bf16, 1, VQA_ATT_ADD>(__VA_ARGS__);                                  \
             case 111: return FN<bf16, 1, VQA_ATT_MUL>(__VA_ARGS__);                                  \
+            case 112: return FN<bf16, 1, VQA_ATT_CAT>(__VA_ARGS__);                                  \
             case 120: return FN<bf16, 2, VQA_ATT_ADD>(__VA_ARGS__);                                  \
             case 121: return FN<bf16, 2, VQA_ATT_MUL>(__VA_ARGS__);                                  \
+            case 122: return FN<bf16, 2, VQA_ATT_CAT>(__VA_ARGS__);                                  \
             case 130: return FN<bf16, 3, VQA_ATT_ADD>(__VA_ARGS__);                                  \
             case 131: return FN<bf16, 3, VQA_ATT_MUL>(__VA_ARGS__);                                  \
+            case 132: return FN<bf16, 3, VQA_ATT_CAT>(__VA_ARGS__);                                  \
             case 140: return FN<bf16, 4, VQA_ATT_ADD>(__VA_ARGS__);                                  \
             case 141: return FN<bf16, 4, VQA_ATT_MUL>(__VA_ARGS__);                                  \
+            case 142: return FN<bf16, 4, VQA_ATT_CAT>(__VA_ARGS__);                                  \
         }                                                                                            \
     } while (0)
 
 static int att_check(int act_dtype, int op, int B, int P, int A, int C, int G, int64_t ld) {
     VQA_REQUIRE(act_dtype == VQA_F32 || act_dtype == VQA_BF16, "attention: bad dtype %d", act_dtype);
-    VQA_REQUIRE(op == VQA_ATT_ADD || op == VQA_ATT_MUL, "attention: do_option code %d not supported", op);
+    VQA_REQUIRE(op == VQA_ATT_ADD || op == VQA_ATT_MUL || op == VQA_ATT_CAT, "attention: do_option code %d not supported", op);
     VQA_REQUIRE(B > 0 && P > 0 && A > 0 && C > 0, "attention: bad dims");
     VQA_REQUIRE(G >= 1 && G <= 4, "attention: glimpses=%d not supported (1..4)", G);
     VQA_REQUIRE(A % 8 == 0 && C % 8 == 0, "attention: hidden_dim (%d) and image features (%d) must be multiples of 8", A, C);
     VQA_REQUIRE(ld >= (int64_t)G * C, "attention: row pitch %lld < G*C", (long long)ld);
-    VQA_REQUIRE((size_t)(2 * G * P + G * C + NW * (1 + G) * 256) * 4 <= 200 * 1024, "attention: spatial grid too large for shared memory");
+    VQA_REQUIRE((size_t)(2 * G * P + G * C + NW * (op == VQA_ATT_CAT ? 1 + 2 * G : 1 + G) * 256) * 4 <= 200 * 1024, "attention: spatial grid too large for shared memory");
     return 0;
 }
 
@@ -942,7 +1007,7 @@ extern "C" int vqa_attention_fwd(const void* vp, const float* qp, const void* vn
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldo)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && stream::fwd_stream_smem(G, P) <= 232448 &&
+    if (act_dtype == VQA_BF16 && op != VQA_ATT_CAT && A == stream::A_ && C == stream::C_ && G <= 2 && stream::fwd_stream_smem(G, P) <= 232448 &&
         stream::bwd_stream_smem(G, P) <= 232448) {     // tensor-core arm at the config.yaml shape
         VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
         if (G == 1) return op == VQA_ATT_ADD ? stream::launch_fwd_stream<1, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
@@ -962,7 +1027,7 @@ extern "C" int vqa_attention_bwd(const void* dout, int64_t ldd, const void* vp, 
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldd)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_BF16 && A == stream::A_ && C == stream::C_ && G <= 2 && stream::bwd_stream_smem(G, P) <= 232448 &&
+    if (act_dtype == VQA_BF16 && op != VQA_ATT_CAT && A == stream::A_ && C == stream::C_ && G <= 2 && stream::bwd_stream_smem(G, P) <= 232448 &&
         stream::fwd_stream_smem(G, P) <= 232448) {     // same condition as the forward: both recompute the fusion in bf16
         VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
         if (G == 1) return op == VQA_ATT_ADD ? stream::launch_bwd_stream<1, VQA_ATT_ADD>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)

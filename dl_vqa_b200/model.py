@@ -310,8 +310,6 @@ class VqaNet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, v, q, q_len):
-        if self.do_option == "|":
-            raise NotImplementedError("attention.do_option '|' is not implemented in the CUDA path yet")
         if not v.is_cuda:
             raise lib.VqaLibraryError("VqaNet.forward: inputs must be CUDA tensors (no CPU fallback); call model.cuda()")
         if v.requires_grad:
@@ -452,7 +450,7 @@ class VqaNet(nn.Module):
         KC = G * Cimg + QF
         comb = empty(B, KC)
         prob = empty(B, G, P, dtype=f32)
-        op = lib.ATT_ADD if self.do_option == "+" else lib.ATT_MUL
+        op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
         call("vqa_attention_fwd", ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
              ptr(prob), ptr(comb), KC, dt, op, B, P, A, Cimg, G, p_att, seed, st)
         # combined = cat([pooled, q])  (models/model.py:64)
@@ -575,13 +573,14 @@ class VqaNet(nn.Module):
         dvp = empty(B * P, A)
         dvn_pool = empty(B * P, Cimg)
         dqp = empty(B, A, dtype=f32)
-        dwx_part = empty(B, G * A, dtype=f32)
+        AW = 2 * A if self.do_option == "|" else A            # x_conv input channels (models/model.py:175-178)
+        dwx_part = empty(B, G * AW, dtype=f32)
         dbx_part = empty(B, G, dtype=f32)
-        op = lib.ATT_ADD if self.do_option == "+" else lib.ATT_MUL
+        op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
         call("vqa_attention_bwd", ptr(dcomb), KC, ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(prob),
              ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op, B, P, A, Cimg, G,
              p_att, seed, st)
-        grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * A, B, G * A, "attention.x_conv.weight").view(G, A, 1, 1)
+        grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * AW, B, G * AW, "attention.x_conv.weight").view(G, AW, 1, 1)
         grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G, "attention.x_conv.bias")
         # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)
         dvnd = empty(B * P, Cimg)

@@ -37,6 +37,7 @@ extern "C" {
 /* attention fusion operator, config.yaml train.attention.do_option (models/model.py:188-193) */
 #define VQA_ATT_ADD 0
 #define VQA_ATT_MUL 1
+#define VQA_ATT_CAT 2   /* '|': x = relu(cat[v', q']), x_conv weight [G][2A], dwx_part [B][G][2A] (generic kernels only) */
 
 const char* vqa_last_error_string(void);
 int vqa_abi_version(void);

@@ -45,7 +45,7 @@ def _cuda_step(cfg, V, sd, batch, dtype, train=True):
     return logits, loss.detach(), score.detach(), grads
 
 
-def _compare(name, got, want, tol):
+def _compare(name, got, want, tol, zero_grads=()):
     logits, loss, score, grads = got
     wl, wloss, wscore, wgrads = want
     rep = {"logits": _err(logits, wl), "loss": abs(float(loss) - float(wloss)) / max(1e-6, abs(float(wloss))),
@@ -53,7 +53,7 @@ def _compare(name, got, want, tol):
            "top1": float((logits.argmax(1).cpu() == wl.argmax(1)).float().mean())}
     gmax = max(float(g.abs().max()) for g in wgrads.values())
     for k, g in wgrads.items():
-        if k == "attention.x_conv.bias":
+        if k == "attention.x_conv.bias" or k in zero_grads:
             # exactly zero in exact arithmetic (softmax is shift invariant): both sides are rounding
             # noise, so bound it absolutely, relative to the largest gradient of the step
             rep["grad/" + k] = float((grads[k].detach().cpu() - g).abs().max()) / gmax
@@ -67,20 +67,63 @@ def _compare(name, got, want, tol):
     return rep
 
 
-@pytest.mark.parametrize("name", ["plus", "mul", "stride2", "unidir", "g3"])
+@pytest.mark.parametrize("name", ["plus", "mul", "cat", "stride2", "unidir", "g3"])
 def test_small_configs_fp32_vs_reference_golden(golden_small, name):
     fx = golden_small[name]
     batch = (fx["batch"][0].float(),) + tuple(fx["batch"][1:])
     got = _cuda_step(fx["cfg"], fx["V"], fx["sd"], batch, "float32")
     score = O.vqa_score(fx["logits"], batch[3], batch[4])
-    _compare(f"small_{name}_fp32", got, (fx["logits"], fx["loss"], score, fx["grads"]), FP32_TOL)
+    # do_option '|' without dropout: the q' half of cat[v', q'] adds the same constant to every position's logit, so the
+    # spatial softmax -- and with it every gradient that reaches q_lin -- is exactly zero in exact arithmetic
+    zero = ("attention.q_lin.weight", "attention.q_lin.bias") if name == "cat" else ()
+    _compare(f"small_{name}_fp32", got, (fx["logits"], fx["loss"], score, fx["grads"]), FP32_TOL, zero_grads=zero)
 
 
-def test_cat_option_raises(golden_small):
+def test_cat_option_train_mode_dropout_is_consistent_between_forward_and_backward(golden_small, dtype="float32"):
+    """do_option '|' with dropout on: the q' half of cat[v', q'] gets a per-position mask; forward and backward must
+    regenerate the same one -- checked by a directional finite difference of the loss along the x_conv weight."""
+    import dl_vqa_b200 as D
     fx = golden_small["cat"]
-    batch = (fx["batch"][0].float(),) + tuple(fx["batch"][1:])
-    with pytest.raises(NotImplementedError):
-        _cuda_step(fx["cfg"], fx["V"], fx["sd"], batch, "float32")
+    cfg = {**fx["cfg"]}
+    cfg["attention"] = {**cfg["attention"], "dropout": 0.4}
+    v, q, q_len, a_idx, a_val, a_len = (fx["batch"][0].float(),) + tuple(fx["batch"][1:])
+    m = D.VqaNet(cfg, fx["V"], compute_dtype=dtype)
+    m.load_state_dict(fx["sd"])
+    m.cuda().train(True)
+    seed = 1234
+    m._next_seed = lambda: seed                                    # same dropout masks for every evaluation
+
+    def loss_of():
+        loss, _ = D.run_batch(m, None, (v, q, a_idx, a_val, a_len, None, q_len), cfg["max_answers"])
+        return loss
+    loss = loss_of()
+    loss.backward()
+    w = m.attention.x_conv.weight
+    g = w.grad.detach().clone()
+    d = torch.randn_like(w)
+    d /= d.norm()
+    eps = 1e-2
+    with torch.no_grad():
+        w.add_(eps * d); lp = float(loss_of()); w.add_(-2 * eps * d); lm = float(loss_of()); w.add_(eps * d)
+    fd, an = (lp - lm) / (2 * eps), float((g * d).sum())
+    assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd)) + 1e-5, (fd, an)
+
+
+def test_cat_option_bf16_arm_matches_fp32_arm_at_config_shapes():
+    """do_option '|' on the tensor-core arm (generic bf16 attention kernels, x_conv weight [G, 2A]) against the exact arm."""
+    import dl_vqa_b200 as D
+    cfg = O.cfg_with(O.zero_dropout(O.DEFAULT_CFG), **{"attention.do_option": "|"})
+    V = 15000
+    torch.manual_seed(1)
+    sd = {k: t.detach().clone() for k, t in D.VqaNet(cfg, V).state_dict().items()}
+    assert tuple(sd["attention.x_conv.weight"].shape) == (2, 2048, 1, 1)
+    batch = O.synthetic_batch(2, cfg, V, seed=3)
+    a = _cuda_step(cfg, V, sd, batch, "float32")
+    b = _cuda_step(cfg, V, sd, batch, "bfloat16")
+    assert _err(b[0], a[0]) < 2e-2 and abs(float(b[1]) - float(a[1])) < 2e-2 * abs(float(a[1]))
+    for k in ("attention.x_conv.weight", "attention.v_conv.weight", "classifier.lin1.weight"):
+        ga, gb = a[3][k].double().reshape(-1), b[3][k].double().reshape(-1)
+        assert float((ga @ gb) / (ga.norm() * gb.norm() + 1e-30)) > 0.98, k
 
 
 def _full_case(B, seed):
