@@ -134,10 +134,11 @@ int vqa_gemm(const void* A, int a_dtype, int64_t a_sr, int64_t a_sk, int64_t a_s
              float p_drop, uint64_t seed, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Fused attention -- models/model.py:187-195 (tile, +/*, ReLU, dropout, x_conv 1x1) and
+ * Fused attention -- models/model.py:187-195 (tile, + / * / | fusion, ReLU, dropout, x_conv 1x1) and
  * models/model.py:208-221 (spatial softmax per glimpse, weighted pooling).  One memory-bound kernel.
  *   vp [B,P,A] act_dtype = v_conv output; qp [B,A] fp32 = q_lin output; vn [B,P,C] act_dtype (normalised,
- *   un-dropped features); wx [G,A], bx [G] fp32 = x_conv; prob [B,G,P] fp32 (softmax, saved);
+ *   un-dropped features); wx [G,A] (op VQA_ATT_CAT: [G,2A], v' half first), bx [G] fp32 = x_conv;
+ *   the backward's dwx_part is [B,G,A] ([B,G,2A] for CAT); prob [B,G,P] fp32 (softmax, saved);
  *   out: row b at out + b*ldo, [G*C] act_dtype, glimpse-major (the first G*C columns of `combined`)
  * --------------------------------------------------------------------------------------------- */
 int vqa_attention_fwd(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx,
