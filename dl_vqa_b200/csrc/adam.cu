@@ -9,9 +9,11 @@ __global__ void __launch_bounds__(256)
 adam_multi_kernel(float* const* __restrict__ params, const float* const* __restrict__ grads,
                   float* const* __restrict__ exp_avg, float* const* __restrict__ exp_avg_sq,
                   void* const* __restrict__ bf16_copy, const int64_t* __restrict__ sizes,
-                  float lr_over_bc1, float beta1, float beta2, float eps, float inv_sqrt_bc2, float grad_scale) {
+                  float lr_over_bc1, float beta1, float beta2, float eps, float inv_sqrt_bc2, float grad_scale,
+                  const VqaStepState* __restrict__ state) {
     pdl_trigger();
     pdl_wait();
+    if (state) { lr_over_bc1 = state->lr_over_bc1; inv_sqrt_bc2 = state->inv_sqrt_bc2; }     // published by vqa_step_tick
     const int t = blockIdx.y;
     const int64_t n = sizes[t];
     float* p = params[t];
@@ -63,7 +65,89 @@ extern "C" int vqa_adam_multi(float* const* params, const float* const* grads, f
     dim3 grid((unsigned)gx, (unsigned)n);
     VQA_CUDA(vqa_launch_pdl(adam_multi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, bf16_copy, sizes,
                                                              (float)(lr / bc1), beta1, beta2, eps,
-                                                             (float)(1.0 / sqrt(bc2)), grad_scale));
+                                                             (float)(1.0 / sqrt(bc2)), grad_scale, (const VqaStepState*)nullptr));
     VQA_CHECK_LAUNCH("adam_multi");
+    return 0;
+}
+
+extern "C" int vqa_adam_multi_dev(float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, void* const* bf16_copy, const int64_t* sizes, int n,
+                                  int64_t max_size, const VqaStepState* state, float beta1, float beta2, float eps,
+                                  float grad_scale, void* stream) {
+    VQA_REQUIRE(n > 0 && max_size > 0 && state, "adam_dev: bad arguments n=%d", n);
+    int64_t gx = ceil_div64(max_size, 256 * 4);
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid((unsigned)gx, (unsigned)n);
+    VQA_CUDA(vqa_launch_pdl(adam_multi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, bf16_copy, sizes,
+                            0.f, beta1, beta2, eps, 0.f, grad_scale, state));
+    VQA_CHECK_LAUNCH("adam_multi_dev");
+    return 0;
+}
+
+// ---- device-resident step state (include/vqa_b200.h: VqaStepState) ------------------------------------------------
+namespace {
+__global__ void step_tick_kernel(VqaStepState* st, double lr0, double half_life, double beta1, double beta2) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int64_t it = st->iteration;
+    const int64_t step = st->adam_step + 1;
+    const double lr = lr0 * exp2(-(double)it / half_life);                    // train.py:31-35
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    st->lr = (float)lr;
+    st->lr_over_bc1 = (float)(lr / bc1);
+    st->inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    st->adam_step = step;
+    st->iteration = it + 1;
+    uint64_t z = st->seed + 0x9E3779B97F4A7C15ull;                            // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    st->seed = (z ^ (z >> 31)) & ~VQA_SEED_ON_DEVICE;
+}
+
+__global__ void scale_by_scalar_kernel(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ scalar, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
+    const float k = __ldg(scalar);
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 ? n >> 2 : 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n4; i += nthr) {
+        float4 v = reinterpret_cast<const float4*>(src)[i];
+        v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+    for (int64_t i = 4 * n4 + tid; i < n; i += nthr) dst[i] = src[i] * k;
+}
+}  // namespace
+
+extern "C" int vqa_step_tick(VqaStepState* state, double lr0, double half_life, double beta1, double beta2, void* stream) {
+    VQA_REQUIRE(state && half_life > 0.0, "step_tick: bad arguments");
+    VQA_CUDA(vqa_launch_pdl(step_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, state, lr0, half_life, beta1, beta2));
+    VQA_CHECK_LAUNCH("step_tick");
+    return 0;
+}
+
+extern "C" int vqa_scale_by_device_scalar(const float* src, float* dst, const float* scalar, int64_t n, void* stream) {
+    VQA_REQUIRE(src && dst && scalar && n >= 0, "scale_by_device_scalar: bad arguments");
+    if (n == 0) return 0;
+    int64_t grid = ceil_div64(n, 256 * 4);
+    if (grid > 148 * 8) grid = 148 * 8;
+    VQA_CUDA(vqa_launch_pdl(scale_by_scalar_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, src, dst, scalar, n));
+    VQA_CHECK_LAUNCH("scale_by_device_scalar");
+    return 0;
+}
+
+extern "C" int vqa_zero(void* ptr, int64_t bytes, void* stream) {
+    VQA_REQUIRE(bytes >= 0 && (ptr || bytes == 0), "zero: bad arguments");
+    if (bytes == 0) return 0;
+    VQA_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+    return 0;
+}
+
+
+extern "C" int vqa_copy(void* dst, const void* src, int64_t bytes, void* stream) {
+    VQA_REQUIRE(bytes >= 0 && ((dst && src) || bytes == 0), "copy: bad arguments");
+    if (bytes == 0) return 0;
+    VQA_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }

@@ -147,6 +147,10 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]);
+// question length as the kernels use it: the reference's pack_padded_sequence raises for lengths outside 1..T; a device
+// kernel cannot, so the value is clamped to [0, T] (0 = no active step) and can never index outside the padded question
+__device__ __forceinline__ int clamp_len(int64_t len, int T_) { return len < 0 ? 0 : (len > T_ ? T_ : (int)len); }
+
 // 8 values from `a` (bf16) when it is non-null, else from `b` (fp32)
 __device__ __forceinline__ void ld8(const bf16* a, const float* b, float (&v)[8]) {
     if (a) ld8(a, v); else ld8(b, v);
@@ -191,7 +195,7 @@ __device__ __forceinline__ void lstm_bwd_pointwise_item8(int64_t i8, const bf16*
     bf16* o = dg + row * 4 * H + j;
     // every load is issued before the first dependent branch (this kernel is one L2 round trip long: a load that waits
     // for q_len, or sits in an if/else diamond, doubles it)
-    const int len = (int)q_len[b];
+    const int len = clamp_len(q_len[b], T_);
     const bf16* g = gates + row * 4 * H + j;
     float dc_in[8], gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
     ld8(dc_init ? dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j : nullptr, dc + i, dc_in);
@@ -244,6 +248,7 @@ __device__ __forceinline__ void lstm_bwd_pointwise_item8(int64_t i8, const bf16*
 // ------------------------------------------------------------------------------------------
 struct Dropout {
     uint64_t seed;
+    const uint64_t* seed_ptr;   // non-null: the seed is read from device memory when the kernel RUNS (VQA_SEED_ON_DEVICE)
     uint32_t threshold;   // 16-bit threshold: keep iff word >= threshold; 0 disables dropout
     float scale;          // 1/(1-p)
 };
@@ -251,6 +256,7 @@ struct Dropout {
 static inline Dropout make_dropout(uint64_t seed, float p) {
     Dropout d;
     d.seed = seed;
+    d.seed_ptr = (seed & VQA_SEED_ON_DEVICE) ? reinterpret_cast<const uint64_t*>(seed & ~VQA_SEED_ON_DEVICE) : nullptr;
     if (p <= 0.f) { d.threshold = 0; d.scale = 1.f; }
     else {
         double t = (double)p * 65536.0 + 0.5;
@@ -265,7 +271,8 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     return x;
 }
 __device__ __forceinline__ uint32_t dropout_key(const Dropout& d, uint32_t site) {
-    return hash32((uint32_t)d.seed ^ hash32((uint32_t)(d.seed >> 32) + site * 0x9E3779B9u + 0x85ebca6bu));
+    const uint64_t seed = d.seed_ptr ? __ldg(d.seed_ptr) : d.seed;      // after pdl_wait(): every caller is past it
+    return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + site * 0x9E3779B9u + 0x85ebca6bu));
 }
 // 32 random bits covering elements 2*pair and 2*pair+1
 __device__ __forceinline__ uint32_t dropout_word(uint32_t key, uint64_t pair) {

@@ -287,7 +287,7 @@ __global__ void embed_tanh_fwd_kernel(const int64_t* __restrict__ q, const int64
     const int b = (int)(row % B);
     const int s = (int)((row / B) % T_);
     const int dir = (int)(row / ((int64_t)B * T_));
-    const int len = (int)q_len[b];
+    const int len = clamp_len(q_len[b], T_);
     T* o = xs + row * ldx;
     const bool active = s < len;
     int t = 0; int64_t tok = 0;
@@ -312,7 +312,7 @@ __global__ void embed_tanh_bwd_kernel(const int64_t* __restrict__ q, const int64
     const int b = (int)(row % B);
     const int s = (int)((row / B) % T_);
     const int dir = (int)(row / ((int64_t)B * T_));
-    const int len = (int)q_len[b];
+    const int len = clamp_len(q_len[b], T_);
     if (s >= len) return;
     const int t = step_token_pos(dir, s, len);
     const int64_t tok = q[(int64_t)b * T_ + t];
@@ -373,7 +373,7 @@ __global__ void lstm_bwd_pointwise_kernel(const T* __restrict__ gates, const flo
     T* o = dg + row * 4 * H;
     // gradient w.r.t. the final cell state enters at the first processed step (s == T-1)
     const float dc_in = dc_init ? to_f32(dc_init[(int64_t)b * dirs * H + (int64_t)dir * H + j]) : dc[i];
-    if (s >= (int)q_len[b]) {
+    if (s >= clamp_len(q_len[b], T_)) {
         o[j] = o[H + j] = o[2 * H + j] = o[3 * H + j] = from_f32<T>(0.f);
         dc[i] = dc_in;                              // frozen step: dc passes through unchanged
         return;

@@ -57,7 +57,7 @@ softloss_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict
     float wsum = 0.f, lrow = 0.f, cnt = 0.f;
     for (int j = 0; j < A; ++j) {
         const int64_t id = a_idx[(int64_t)b * A + j];
-        if (id != 0) {
+        if (id >= 1 && id <= N) {                    // 0 = padding; ids outside 1..N (the reference would raise) are ignored
             const float w = (float)a_val[(int64_t)b * A + j] / 10.0f;
             wsum += w;
             lrow += w * (lse - y[id - 1]);
@@ -77,7 +77,7 @@ softloss_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict
         if (tid == 0)
             for (int j = 0; j < A; ++j) {
                 const int64_t id = a_idx[(int64_t)b * A + j];
-                if (id != 0) d[id - 1] -= ((float)a_val[(int64_t)b * A + j] / 10.0f) * invB;
+                if (id >= 1 && id <= N) d[id - 1] -= ((float)a_val[(int64_t)b * A + j] / 10.0f) * invB;
             }
     }
 }

@@ -22,7 +22,7 @@ SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CL
 
 DEFAULT_CONV_CTA_GROUP = 0      # tcgen05 cta_group of the 3x3 conv kernels: 0 = per-shape choice, 1 / 2 forced (vqa_tc_conv_set_cta_group)
 
-_vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
+_vp, _i, _i64, _u64, _u32, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float, C.c_double
 
 # name -> argtypes, mirrors include/vqa_b200.h one to one
 PROTOTYPES = {
@@ -49,7 +49,13 @@ PROTOTYPES = {
     "vqa_relu_drop_bwd": [_vp, _vp, _vp, _i, _i64, _f, _vp],
     "vqa_add_dropped": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i64, _i, _f, _u64, _u32, _vp],
     "vqa_adam_multi": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _i, _f, _vp],
+    "vqa_adam_multi_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _f, _f, _f, _f, _vp],
+    "vqa_step_tick": [_vp, _d, _d, _d, _d, _vp],
+    "vqa_scale_by_device_scalar": [_vp, _vp, _vp, _i64, _vp],
+    "vqa_zero": [_vp, _i64, _vp],
+    "vqa_copy": [_vp, _vp, _i64, _vp],
 }
+SEED_ON_DEVICE = 1 << 63
 
 _lib = None
 

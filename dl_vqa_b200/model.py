@@ -166,22 +166,27 @@ class _Math:
                  None, None, 0, M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
 
     # ---- dW[N,K] (fp32) = dy[M,N]^T x[M,K]      (reduction over the M rows)
-    def lin_bwd_weight(self, dy_ptr, dy_dt, ldy, x_ptr, x_dt, ldx, dW, M, N, K, tag=None):
+    def lin_bwd_weight(self, dy_ptr, dy_dt, ldy, x_ptr, x_dt, ldx, dW, M, N, K, tag=None, zeroed=False):
+        """`zeroed`: dW already holds zeros (the gradient arena is cleared once per backward pass)."""
         big = M >= 4096
+
+        def clear():
+            if not zeroed:
+                call("vqa_zero", ptr(dW), dW.numel() * dW.element_size(), self.st)
         if self.tc:
             if M == 0:
-                dW.zero_()
+                clear()
                 return
             # reduction index = row of both operands: MN-major tcgen05 operands, no transposes
             yp, ldy2, keep1 = self._as_bf16(dy_ptr, dy_dt, ldy, M, N)
             xp, ldx2, keep2 = self._as_bf16(x_ptr, x_dt, ldx, M, K)
             if big:
-                dW.zero_()
+                clear()
             call("vqa_tc_gemm", yp, ldy2, 0, xp, ldx2, 0, ptr(dW), lib.F32, K, 0, None, None, 0,
                  N, K, M, 1, lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if big else 0), 0.0, 0, 0, self.st, tag=tag)
         else:
             if big:
-                dW.zero_()
+                clear()
             call("vqa_gemm", dy_ptr, dy_dt, 1, ldy, 0, x_ptr, x_dt, 1, ldx, 0, ptr(dW), lib.F32, K, 0,
                  None, None, 0, N, K, M, 1, lib.GEMM_SPLITK if big else 0, 0.0, 0, 0, self.st, tag=tag)
 
@@ -227,8 +232,18 @@ class VqaNet(nn.Module):
         self._arena = None               # see use_gradient_arena()
         self._shadows = None             # see use_weight_shadows()
         self._whh_shadow = None
+        self._step_state = None          # see use_device_step_state()
 
     # ------------------------------------------------------------------ configuration
+    def use_device_step_state(self, state: Optional[torch.Tensor]) -> "VqaNet":
+        """Take the dropout seed of every training forward from a device-resident `VqaStepState` (include/vqa_b200.h;
+        a 64-byte CUDA tensor whose first 8 bytes are the seed) instead of drawing it on the host: the step can then be
+        captured in a CUDA graph and still draw a fresh mask on every replay (dl_vqa_b200/graph.py).  None switches back."""
+        if state is not None and (not state.is_cuda or state.numel() * state.element_size() < 64):
+            raise ValueError("step state must be a CUDA tensor of at least 64 bytes")
+        self._step_state = state
+        return self
+
     def set_compute_dtype(self, dt) -> "VqaNet":
         """'float32' (exact arm, SIMT fp32) or 'bfloat16' (tensor-core arm, fp32 accumulate)."""
         if isinstance(dt, str):
@@ -262,16 +277,21 @@ class VqaNet(nn.Module):
         if a and a.get("dev") == dev:
             return a
         named = list(self.named_parameters())
-        buckets, views = {}, {}
+        per_stage = {st: [(n, p) for n, p in named if n.startswith(st + ".")] for st in self.STAGES}
+        sizes = {st: _rup(sum(_rup(p.numel(), 4) for _, p in mine), 64) for st, mine in per_stage.items()}
+        # ONE allocation (a single memset clears it at the start of every backward pass); each stage's bucket is a
+        # 256-byte aligned slice of it, all-reduced on its own as soon as the stage is finished
+        whole = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+        buckets, views, base = {}, {}, 0
         for stage in self.STAGES:
-            mine = [(n, p) for n, p in named if n.startswith(stage + ".")]
-            flat = torch.zeros(sum(_rup(p.numel(), 4) for _, p in mine), dtype=torch.float32, device=dev)
+            flat = whole[base:base + sizes[stage]]
+            base += sizes[stage]
             off = 0
-            for n, p in mine:
+            for n, p in per_stage[stage]:
                 views[n] = flat[off:off + p.numel()].view(p.shape)
                 off += _rup(p.numel(), 4)                      # keep every view 16-byte aligned
             buckets[stage] = flat
-        self._arena = {"dev": dev, "views": views, "buckets": buckets}
+        self._arena = {"dev": dev, "views": views, "buckets": buckets, "whole": whole}
         return self._arena
 
     # ------------------------------------------------------------------ persistent bf16 weight shadows
@@ -322,7 +342,12 @@ class VqaNet(nn.Module):
         v = v.to(torch.float32).contiguous()
         params = self._params()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        seed = self._next_seed() if self.training else 0
+        if not self.training:
+            seed = 0
+        elif self._step_state is not None:       # seed lives in device memory, advanced by vqa_step_tick (graph replay)
+            seed = lib.SEED_ON_DEVICE | self._step_state.data_ptr()
+        else:
+            seed = self._next_seed()
         if need_grad:
             return _VqaFunction.apply(self, seed, v, q, q_len, *params)
         logits, _ = self._run_forward(v, q, q_len, seed, save=False)
@@ -421,8 +446,10 @@ class VqaNet(nn.Module):
             for d in range(dirs):
                 call("vqa_pack_lstm_whh", ptr(w_hh[d]), ptr(wp[d]), H, st, tag="w_cast")
             hs_ext = torch.empty(dirs, T + 1, B, H, dtype=adt, device=dev)      # the kernel writes slots 1..T of every row
-            hs_ext[:, 0].zero_()                                                # slot 0 = h_{-1} = 0
-            sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
+            for d in range(dirs):                                               # slot 0 = h_{-1} = 0
+                call("vqa_zero", ptr(hs_ext[d, 0]), B * H * hs_ext.element_size(), st)
+            sync = torch.empty(dirs, dtype=torch.int32, device=dev)
+            call("vqa_zero", ptr(sync), dirs * 4, st)
             call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
                  T, B, H, dirs, st, tag="lstm_recurrence_fwd")
             h_prev = [hs_ext[d, 1] for d in range(dirs)]     # h_0 .. h_{T-1} of direction d start here
@@ -500,7 +527,9 @@ class VqaNet(nn.Module):
             return torch.empty(shape, dtype=dtype, device=dev)
 
         def zeros(*shape, dtype=f32):
-            return torch.zeros(shape, dtype=dtype, device=dev)
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            call("vqa_zero", ptr(t), t.numel() * t.element_size(), st)
+            return t
 
         deferred = []
 
@@ -527,16 +556,17 @@ class VqaNet(nn.Module):
                 if p_.grad is not None and p_.grad.untyped_storage().data_ptr() in owned:
                     arena = None
                     break
+            if arena is not None:        # every accumulate-into gradient (split-K sums, column sums, embedding scatter) starts at 0
+                whole = self._arena["whole"]
+                call("vqa_zero", ptr(whole), whole.numel() * 4, st)
+        zeroed = arena is not None
 
         def galloc(name, *shape, zero=False):
             """fp32 gradient tensor of parameter `name`: a view of the stage arena, or a fresh tensor"""
             if arena is not None:
                 t = arena[name]
                 assert tuple(t.shape) == tuple(shape) or t.numel() == int(torch.Size(shape).numel()), name
-                t = t.view(*shape)
-                if zero:
-                    t.zero_()
-                return t
+                return t.view(*shape)                       # cleared above, together with the whole arena
             return zeros(*shape) if zero else empty(*shape, dtype=f32)
 
         def colsum(src, src_dt, ld, rows, cols, name):
@@ -552,7 +582,7 @@ class VqaNet(nn.Module):
         dh1d = empty(B, hid)
         mm.lin_bwd_data(ptr(dlogits), lib.F32, N, cl.lin2.weight, ptr(dh1d), dt, hid, B, N, hid, tag="lin2_dgrad")
         dW2 = galloc("classifier.lin2.weight", N, hid)
-        mm.lin_bwd_weight(ptr(dlogits), lib.F32, N, ptr(h1d), dt, hid, dW2, B, N, hid, tag="lin2_wgrad")
+        mm.lin_bwd_weight(ptr(dlogits), lib.F32, N, ptr(h1d), dt, hid, dW2, B, N, hid, tag="lin2_wgrad", zeroed=zeroed)
         grads["classifier.lin2.weight"] = dW2
         grads["classifier.lin2.bias"] = colsum(dlogits, lib.F32, N, B, N, "classifier.lin2.bias")
         # ---- classifier.lin1 (ReLU + drop2 folded: h1d > 0 <=> unit alive and kept)
@@ -561,7 +591,7 @@ class VqaNet(nn.Module):
         dcomb = empty(B, KC)
         mm.lin_bwd_data(ptr(dz1), dt, hid, cl.lin1.weight, ptr(dcomb), dt, KC, B, hid, KC, tag="lin1_dgrad")
         dW1 = galloc("classifier.lin1.weight", hid, KC)
-        mm.lin_bwd_weight(ptr(dz1), dt, hid, ptr(combd), dt, KC, dW1, B, hid, KC, tag="lin1_wgrad")
+        mm.lin_bwd_weight(ptr(dz1), dt, hid, ptr(combd), dt, KC, dW1, B, hid, KC, tag="lin1_wgrad", zeroed=zeroed)
         grads["classifier.lin1.weight"] = dW1
         grads["classifier.lin1.bias"] = colsum(dz1, dt, hid, B, hid, "classifier.lin1.bias")
         fire(["classifier.lin2.weight", "classifier.lin2.bias", "classifier.lin1.weight", "classifier.lin1.bias"], defer=True)
@@ -586,13 +616,13 @@ class VqaNet(nn.Module):
         dvnd = empty(B * P, Cimg)
         mm.lin_bwd_data(ptr(dvp), dt, A, att.v_conv.weight, ptr(dvnd), dt, Cimg, B * P, A, Cimg, tag="v_conv_dgrad")
         dWv = galloc("attention.v_conv.weight", A, Cimg)
-        mm.lin_bwd_weight(ptr(dvp), dt, A, ptr(v_in), dt, Cimg, dWv, B * P, A, Cimg, tag="v_conv_wgrad")
+        mm.lin_bwd_weight(ptr(dvp), dt, A, ptr(v_in), dt, Cimg, dWv, B * P, A, Cimg, tag="v_conv_wgrad", zeroed=zeroed)
         grads["attention.v_conv.weight"] = dWv.view(A, Cimg, 1, 1)
         # ---- attention.q_lin
         dqd = empty(B, QF)
         mm.lin_bwd_data(ptr(dqp), lib.F32, A, att.q_lin.weight, ptr(dqd), dt, QF, B, A, QF, tag="q_lin_dgrad")
         dWq = galloc("attention.q_lin.weight", A, QF)
-        mm.lin_bwd_weight(ptr(dqp), lib.F32, A, ptr(qd), dt, QF, dWq, B, A, QF, tag="q_lin_wgrad")
+        mm.lin_bwd_weight(ptr(dqp), lib.F32, A, ptr(qd), dt, QF, dWq, B, A, QF, tag="q_lin_wgrad", zeroed=zeroed)
         grads["attention.q_lin.weight"] = dWq
         grads["attention.q_lin.bias"] = colsum(dqp, lib.F32, A, B, A, "attention.q_lin.bias")
         fire(["attention.v_conv.weight", "attention.q_lin.weight", "attention.q_lin.bias",
@@ -623,14 +653,14 @@ class VqaNet(nn.Module):
             else:
                 whhb = empty(dirs, 4 * H, H)
                 for d in range(dirs):
-                    whhb[d].copy_(shs[d])
+                    call("vqa_copy", ptr(whhb[d]), ptr(shs[d]), 4 * H * H * 2, st)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         persistent_bwd = (tc and T > 1 and H % 128 == 0 and ((B + 127) // 128) * (H // 128) * dirs <= sms
                           and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
         if persistent_bwd:
             # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
             # two grid barriers per step) instead of 2T - 1 dependent launches
-            sync_b = torch.zeros(256, dtype=torch.int32, device=dev)
+            sync_b = zeros(256, dtype=torch.int32)
             call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
                  T, B, H, dirs, st, tag="lstm_bwd_persistent")
         for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):
@@ -651,16 +681,16 @@ class VqaNet(nn.Module):
         for d in range(dirs):
             dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
             mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(ctx["h_prev"][d]), dt, H, dWhh,
-                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad")
+                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad", zeroed=zeroed)
             dWih = galloc(f"text.lstm.weight_ih_l0{sfx[d]}", 4 * H, E)
-            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad")
+            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad", zeroed=zeroed)
             db = colsum(dg[d], dt, 4 * H, T * B, 4 * H, f"text.lstm.bias_ih_l0{sfx[d]}")
             grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
             grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
             grads[f"text.lstm.bias_ih_l0{sfx[d]}"] = db
             if arena is not None:        # b_ih and b_hh always enter as a sum: identical gradients, separate storage
                 db2 = galloc(f"text.lstm.bias_hh_l0{sfx[d]}", 4 * H)
-                db2.copy_(db)
+                call("vqa_copy", ptr(db2), ptr(db), 4 * H * 4, st)
             else:
                 db2 = db.clone() if self.grad_ready_hook is not None else db
             grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db2
@@ -729,7 +759,7 @@ class VqaNet(nn.Module):
                 call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
                 if not fused_db:
-                    db.zero_()
+                    call("vqa_zero", ptr(db), db.numel() * 4, st)
                     call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
             else:
                 call("vqa_conv_bwd_weight", ptr(x), x_dt, nchw, ptr(da), ptr(mask), ptr(dW), ptr(db), dt,
@@ -775,14 +805,24 @@ class _VqaFunction(torch.autograd.Function):
         ctx.model = model
         ctx.saved = saved
         ctx.names = [n for n, _ in model.named_parameters()]
+        ctx.params = params
         ctx.param_versions = [p._version for p in params]
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         model = ctx.model
+        if ctx.saved is None:
+            raise RuntimeError("VqaNet: backward through the same forward a second time (saved activations were freed)")
+        # backward re-reads the live fp32 weights and their optimizer-maintained bf16 shadows: an update between forward and
+        # backward would silently mix two parameter versions (torch raises for its own ops; so must this node)
+        for n, p, ver in zip(ctx.names, ctx.params, ctx.param_versions):
+            if p._version != ver:
+                raise RuntimeError(f"VqaNet: parameter {n} was modified in place between forward and backward "
+                                   f"(version {ver} -> {p._version}); run backward before optimizer.step() / load_state_dict()")
         grads = model._run_backward(ctx.saved, dlogits)
         ctx.saved = None
+        ctx.params = None
         out = []
         for n, need in zip(ctx.names, ctx.needs_input_grad[5:]):
             out.append(grads[n] if need else None)

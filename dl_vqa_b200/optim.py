@@ -17,6 +17,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}
         self._shadow = {}          # id(param) -> (bf16 tensor, validity entry [tensor, param, version]) : VqaNet.use_weight_shadows
+        self._dev_state = None     # device-resident VqaStepState (lr / bias corrections read on the GPU): use_device_step_state()
 
     _RING = 4
 
@@ -26,6 +27,27 @@ class FusedAdam(torch.optim.Optimizer):
         if shadow.numel() != param.numel() or shadow.dtype != torch.bfloat16 or not shadow.is_contiguous():
             raise ValueError("bf16 shadow must be a contiguous bf16 tensor with the parameter's element count")
         self._shadow[id(param)] = (shadow, entry)
+
+    def use_device_step_state(self, state):
+        """Read lr and the Adam step count from a device-resident `VqaStepState` (include/vqa_b200.h) that `vqa_step_tick`
+        advances, instead of from `param_groups[..]['lr']` and the host-side step counter: the optimizer step can then be
+        part of a captured CUDA graph (dl_vqa_b200/graph.py).  The host counters keep being advanced as well, so
+        `state_dict()` stays meaningful.  None switches back."""
+        self._dev_state = state
+        return self
+
+    def after_replay(self):
+        """Host bookkeeping for one optimizer step that ran inside a replayed CUDA graph (no kernel is launched): advance the
+        per-parameter step counters, bump the parameters' autograd versions and re-validate the bf16 shadows."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] += 1
+                    torch.autograd.graph.increment_version(p)
+                    sh = self._shadow.get(id(p))
+                    if sh is not None:
+                        sh[1][2] = p._version
 
     def _table(self, gi, tensors_key, lists):
         """Device-resident pointer tables, rebuilt only when a pointer changes (gradient tensors usually do change
@@ -86,10 +108,18 @@ class FusedAdam(torch.optim.Optimizer):
             table = self._table(gi, key, lists)
             n = len(ps)
             b1, b2 = group["betas"]
-            call("vqa_adam_multi", ptr(table[0]), ptr(table[1]), ptr(table[2]), ptr(table[3]),
-                 ptr(table[5]) if shadowed else None, ptr(table[4]),
-                 n, max(t.numel() for t in lists["p"]), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                 int(step), float(grad_scale), lib.stream())
+            if self._dev_state is not None:
+                call("vqa_adam_multi_dev", ptr(table[0]), ptr(table[1]), ptr(table[2]), ptr(table[3]),
+                     ptr(table[5]) if shadowed else None, ptr(table[4]),
+                     n, max(t.numel() for t in lists["p"]), ptr(self._dev_state), float(b1), float(b2), float(group["eps"]),
+                     float(grad_scale), lib.stream())
+            else:
+                call("vqa_adam_multi", ptr(table[0]), ptr(table[1]), ptr(table[2]), ptr(table[3]),
+                     ptr(table[5]) if shadowed else None, ptr(table[4]),
+                     n, max(t.numel() for t in lists["p"]), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                     int(step), float(grad_scale), lib.stream())
+            for p in ps:                       # the kernel wrote through p.data: tell autograd (VqaNet's backward checks it)
+                torch.autograd.graph.increment_version(p)
             for p, entry in shadowed:          # the kernel has just rewritten these shadows from the updated masters
                 entry[2] = p._version
         return loss

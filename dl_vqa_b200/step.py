@@ -26,13 +26,19 @@ class _SoftTargetLoss(torch.autograd.Function):
         call("vqa_softloss_fwd_bwd", ptr(logits), ptr(a_indices), ptr(a_values), ptr(dlogits), ptr(rows[0]),
              ptr(rows[1]), ptr(out[0:1]), ptr(out[1:2]), B, N, A, lib.stream())
         ctx.save_for_backward(dlogits)
-        ctx.mark_non_differentiable(out[1])
-        return out[0], out[1]
+        loss, score = out[0], out[1]                  # bind the views ONCE: the object marked is the object returned
+        ctx.mark_non_differentiable(score)
+        return loss, score
 
     @staticmethod
     def backward(ctx, g_loss, g_score):
         (dlogits,) = ctx.saved_tensors
-        return dlogits * g_loss, None, None
+        # d loss / d logits was produced by the forward kernel for g_loss = 1; scale by the incoming gradient, which is a
+        # device scalar (no host read, no ATen kernel)
+        g = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_contiguous()) else g_loss.to(torch.float32).contiguous()
+        out = torch.empty_like(dlogits)
+        call("vqa_scale_by_device_scalar", ptr(dlogits), ptr(out), ptr(g), dlogits.numel(), lib.stream())
+        return out, None, None
 
 
 def soft_target_loss_and_score(logits: torch.Tensor, a_indices: torch.Tensor, a_values: torch.Tensor):
@@ -56,7 +62,14 @@ def run_batch(model, log_softmax, batch_data, max_answers):
     y_hat = model(v, q, q_len)
     if y_hat.shape[1] != max_answers:
         raise ValueError(f"model produces {y_hat.shape[1]} answers, max_answers={max_answers}")
-    return soft_target_loss_and_score(y_hat, a_indices, a_values)
+    loss, score = soft_target_loss_and_score(y_hat, a_indices, a_values)
+    if not torch.is_grad_enabled():
+        # evaluation (train.py:144-169 runs under @torch.no_grad()): the reference's batch_accuracy returns a CPU tensor
+        # and evaluate() accumulates it into `score = torch.tensor(0.0)` (a CPU tensor, train.py:155,165) -- hand the
+        # score over on the host there.  In training the loop adds it to a Python number (train.py:87), so the device
+        # tensor is kept and the step stays free of host synchronisation.
+        score = score.cpu()
+    return loss, score
 
 
 def update_learning_rate(optimizer, iteration, initial_lr):

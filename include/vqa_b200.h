@@ -17,7 +17,10 @@
  *   - image activations are NHWC ([B, H, W, C], channel contiguous); the network input is the
  *     reference's NCHW fp32 tensor;
  *   - dropout is a stateless counter-based mask keyed by (seed, site, element index): forward and
- *     backward entries take the same (p, seed) and regenerate the same mask.
+ *     backward entries take the same (p, seed) and regenerate the same mask.  A `seed` argument with
+ *     VQA_SEED_ON_DEVICE set carries, in its low 63 bits, the DEVICE ADDRESS of a uint64 seed that is
+ *     read when the kernel runs: a captured CUDA graph of the step then draws a fresh mask on every
+ *     replay (vqa_step_tick advances the seed; the reference draws a new mask per call, models/model.py:84,156,185,194).
  */
 #ifndef VQA_B200_H
 #define VQA_B200_H
@@ -33,6 +36,7 @@ extern "C" {
 #define VQA_BF16 1
 #define VQA_ERR_INVALID_ARGUMENT (-1)
 #define VQA_ERR_UNSUPPORTED (-2)
+#define VQA_SEED_ON_DEVICE (1ull << 63)
 
 /* attention fusion operator, config.yaml train.attention.do_option (models/model.py:188-193) */
 #define VQA_ATT_ADD 0
@@ -191,6 +195,40 @@ int vqa_adam_multi(float* const* params, const float* const* grads, float* const
                    float* const* exp_avg_sq, void* const* bf16_copy, const int64_t* sizes, int n,
                    int64_t max_size, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident step state -- the per-iteration host work of the training loop (train.py:69-81) moved onto the
+ * GPU so that the whole step (forward, loss, backward, all-reduce, Adam) can be ONE captured CUDA graph that is
+ * replayed with no per-step host arithmetic:
+ *   seed        dropout seed of the step (read by every kernel whose seed argument is VQA_SEED_ON_DEVICE | &state->seed)
+ *   iteration   train.py:50,81 total_iterations
+ *   adam_step   torch.optim.Adam's per-parameter `step`
+ *   lr          train.py:31-35 update_learning_rate: lr0 * 0.5 ** (iteration / half_life)
+ *   lr_over_bc1, inv_sqrt_bc2   Adam's bias corrections folded as the update kernel consumes them
+ * vqa_step_tick (one thread) runs FIRST in the step: it publishes lr / bias corrections for the CURRENT
+ * iteration, then advances iteration, adam_step and the seed (splitmix64) -- the order of train.py:76-81.
+ * vqa_adam_multi_dev is vqa_adam_multi with lr and step taken from the state instead of from the host.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct VqaStepState {
+    uint64_t seed;
+    int64_t iteration;
+    int64_t adam_step;
+    float lr;
+    float lr_over_bc1;
+    float inv_sqrt_bc2;
+    float reserved[7];
+} VqaStepState;                                   /* 64 bytes */
+int vqa_step_tick(VqaStepState* state, double lr0, double half_life, double beta1, double beta2, void* stream);
+int vqa_adam_multi_dev(float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, void* const* bf16_copy, const int64_t* sizes, int n,
+                       int64_t max_size, const VqaStepState* state, float beta1, float beta2, float eps,
+                       float grad_scale, void* stream);
+/* dst[i] = src[i] * *scalar (fp32; dst may alias src): the incoming d(loss) of the loss node, without a host read */
+int vqa_scale_by_device_scalar(const float* src, float* dst, const float* scalar, int64_t n, void* stream);
+/* bytes of device memory set to zero on `stream` (a memset node under graph capture, not a kernel) */
+int vqa_zero(void* ptr, int64_t bytes, void* stream);
+/* device-to-device copy of `bytes` bytes on `stream` (a memcpy node under graph capture) */
+int vqa_copy(void* dst, const void* src, int64_t bytes, void* stream);
 
 /* =============================================================================================
  * Tensor-core arm (bf16 operands, fp32 accumulation): tcgen05.mma with TMEM accumulators, operands
