@@ -456,6 +456,33 @@ extern "C" int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64
     return 0;
 }
 
+// keep[i] = 1 when element i of dropout site `site` is kept.  vector8 = 0: the per-element scheme (dropout_mult: embedding,
+// classifier, q' sites); 1: the 8-element vector scheme (dropout_mult8: image, v and attention x sites).
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, int64_t n, Dropout d, uint32_t site, int vector8) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m;
+    if (vector8) {
+        float m8[8];
+        dropout_mult8(make_dropout8(d, site), (uint32_t)(i >> 3), m8);
+        m = m8[i & 7];
+    } else {
+        m = dropout_mult(d, site, (uint64_t)i);
+    }
+    keep[i] = m != 0.f;
+}
+
+extern "C" int vqa_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, int vector8, void* stream) {
+    VQA_REQUIRE(keep && n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+    if (n == 0) return 0;
+    const Dropout d = make_dropout(seed, p);
+    VQA_CUDA(vqa_launch_pdl(dropout_mask_kernel, dim3((unsigned)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, keep, n, d, site, vector8));
+    VQA_CHECK_LAUNCH("dropout_mask");
+    return 0;
+}
+
 template <typename T>
 __global__ void add_dropped_kernel(const T* __restrict__ a, int64_t lda, const T* __restrict__ b, int64_t ldb,
                                    T* __restrict__ dst, int64_t ldd, int64_t rows, int cols, Dropout d, uint32_t site) {

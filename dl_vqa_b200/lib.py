@@ -54,6 +54,7 @@ PROTOTYPES = {
     "vqa_scale_by_device_scalar": [_vp, _vp, _vp, _i64, _vp],
     "vqa_zero": [_vp, _i64, _vp],
     "vqa_copy": [_vp, _vp, _i64, _vp],
+    "vqa_dropout_mask": [_vp, _i64, _f, _u64, _u32, _i, _vp],
 }
 SEED_ON_DEVICE = 1 << 63
 

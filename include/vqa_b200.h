@@ -172,6 +172,18 @@ int vqa_softloss_fwd_bwd(const float* logits, const int64_t* a_idx, const int64_
 /* out[r, c] = in[r, c] * dropout(site, r*cols + c); in/out row pitches ld_in/ld_out (elements) */
 int vqa_dropout_apply(const void* in, int64_t ld_in, void* out, int64_t ld_out, int dtype, int64_t rows,
                       int cols, float p, uint64_t seed, uint32_t site, void* stream);
+/* keep[i] = 1 iff element i of dropout site `site` (the VQA_SITE_* stream of one nn.Dropout call site) survives under
+ * (p, seed).  vector8 = 0: the per-element scheme used by the embedding / classifier / q' sites; 1: the 8-element vector
+ * scheme used by the image, v and attention-x sites.  Exposes the stateless mask so that a caller (the parity tests) can
+ * restate a train-mode forward/backward exactly; the step itself never materialises a mask. */
+#define VQA_SITE_IMAGE 0    /* models/model.py:84   image.drop,        element = NHWC index of the last conv output   */
+#define VQA_SITE_ATT_V 1    /* models/model.py:185  attention.drop(v), element = index into vn [B*P, C]               */
+#define VQA_SITE_EMBED 2    /* models/model.py:156  text.drop,         element = (b*T + t)*E + e                      */
+#define VQA_SITE_ATT_Q 3    /* models/model.py:186  attention.drop(q), element = index into q [B, dirs*H]             */
+#define VQA_SITE_ATT_X 4    /* models/model.py:194  attention.drop(x), element = (b*P + s)*A + a                      */
+#define VQA_SITE_CLS_IN 5   /* models/model.py:201  classifier.drop1,  element = index into combined [B, G*C + QF]    */
+#define VQA_SITE_CLS_HID 6  /* models/model.py:204  classifier.drop2,  element = index into hidden [B, hidden]        */
+int vqa_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, int vector8, void* stream);
 /* out[c] += sum_r in[r*ld + c]   (fp32 out, caller zeroes); mask != NULL: only rows where mask[r*ld+c] < 4 */
 int vqa_colsum(const void* in, int dtype, int64_t ld, const uint8_t* mask, float* out, int64_t rows, int cols,
                void* stream);

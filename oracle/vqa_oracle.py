@@ -83,25 +83,33 @@ def l2_normalise(v: torch.Tensor) -> torch.Tensor:
 
 
 def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
-                    bidirectional: bool, rnd=_ident) -> torch.Tensor:
+                    bidirectional: bool, rnd=_ident, pre=None) -> torch.Tensor:
     """models/model.py:159-166: pack_padded_sequence + nn.LSTM, keep the final CELL state of every
     direction, laid out [B, dirs*H] as (c_fwd | c_bwd).  Explicit loop; gate order i,f,g,o
-    (torch.nn.LSTM); forward direction consumes t=0..len-1, reverse consumes t=len-1..0."""
-    B, T, _ = x.shape
+    (torch.nn.LSTM); forward direction consumes t=0..len-1, reverse consumes t=len-1..0.
+    `pre` (test aid): per direction a [B, T, 4H] tensor of input projections W_ih x_t + b_ih + b_hh indexed by TOKEN
+    position t, used instead of computing them from x -- lets a test hand the recurrence the very numbers a kernel saw
+    and take gradients with respect to them."""
+    B, T = x.shape[:2]
     outs = []
-    for suffix, reverse in (("", False), ("_reverse", True)):
+    for d, (suffix, reverse) in enumerate((("", False), ("_reverse", True))):
         if reverse and not bidirectional:
             break
-        w_ih = sd[f"text.lstm.weight_ih_l0{suffix}"]
         w_hh = sd[f"text.lstm.weight_hh_l0{suffix}"]
-        bias = sd[f"text.lstm.bias_ih_l0{suffix}"] + sd[f"text.lstm.bias_hh_l0{suffix}"]
+        if pre is None:
+            w_ih = sd[f"text.lstm.weight_ih_l0{suffix}"]
+            bias = sd[f"text.lstm.bias_ih_l0{suffix}"] + sd[f"text.lstm.bias_hh_l0{suffix}"]
         h = x.new_zeros(B, hidden)
         c = x.new_zeros(B, hidden)
         for s in range(T):
             active = (s < lengths)                                   # [B]
             t_idx = (lengths - 1 - s).clamp_min(0) if reverse else torch.full_like(lengths, s)
-            xt = x[torch.arange(B), t_idx]                           # [B, E]
-            gates = rnd(xt @ w_ih.t() + bias) + h @ w_hh.t()
+            if pre is None:
+                xt = x[torch.arange(B), t_idx]                       # [B, E]
+                proj = xt @ w_ih.t() + bias
+            else:
+                proj = pre[d][torch.arange(B), t_idx]                # [B, 4H]
+            gates = rnd(proj) + h @ w_hh.t()
             gi, gf, gg, go = gates.chunk(4, dim=1)
             c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
             h_new = rnd(torch.sigmoid(go) * torch.tanh(c_new))
@@ -167,6 +175,84 @@ def forward(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor, q: torch.Te
     if intermediates is not None:
         intermediates.update(img=img, vn=vn, qf=qf, att=att, pooled=pooled, comb=comb)
     return logits
+
+
+def forward_gated(sd: Dict[str, torch.Tensor], cfg: dict, v: torch.Tensor, q: torch.Tensor, q_len: torch.Tensor,
+                  gates: dict) -> torch.Tensor:
+    """models/model.py:53-67 with every piecewise-constant GATING decision taken from `gates` instead of from the
+    activations (test aid for reduced-precision implementations).  A ReLU / max-pool network is piecewise smooth: inside
+    one gating pattern the reference's gradient is a smooth function of weights and inputs, but a bf16 forward flips a
+    fraction of a percent of the decisions against fp32 and every flip moves gradient entries by 100 %.  Freezing the
+    pattern to the one the implementation under test took, and running the reference arithmetic in fp32 under it, gives
+    the gradient that implementation must reproduce to rounding accuracy.
+        gates["pool"][i]   int64 [B, C_i, PH_i, PW_i]  0..3 = (dy*2+dx) of the window element that was the maximum, 4 = ReLU-dead
+        gates["att"]       bool  [B, A, S1, S2]        attention ReLU alive   (models/model.py:188-193)
+        gates["cls"]       bool  [B, hidden]           classifier ReLU alive  (models/model.py:202)
+    Smooth stages (L2 norm, tanh, LSTM, softmax pooling, the linear maps, the loss) are exactly forward()'s."""
+    n_layers = len(cfg["image"]["num_channels"]) - 1
+    x = v
+    for i in range(n_layers):
+        y = F.conv2d(x, sd[f"image.conv{i}.weight"], sd[f"image.conv{i}.bias"], stride=cfg["image"]["stride"])
+        m = gates["pool"][i]
+        B, C, PH, PW = m.shape
+        win = y[:, :, :2 * PH, :2 * PW].reshape(B, C, PH, 2, PW, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, PH, PW, 4)
+        x = win.gather(4, m.clamp(max=3).unsqueeze(-1)).squeeze(-1) * (m < 4).to(y.dtype)
+    vn = l2_normalise(x)
+    qf = question_encoder(sd, cfg, q, q_len)
+    vp = F.conv2d(vn, sd["attention.v_conv.weight"])
+    qp = qf @ sd["attention.q_lin.weight"].t() + sd["attention.q_lin.bias"]
+    qt = qp[:, :, None, None].expand_as(vp)
+    opt = cfg["attention"]["do_option"]
+    if opt == "+":
+        xa = (vp + qt) * gates["att"].to(vp.dtype)
+    elif opt == "*":
+        xa = (vp * qt) * gates["att"].to(vp.dtype)
+    else:
+        xa = torch.cat([vp, qt], dim=1) * gates["att"].to(vp.dtype)
+    att = F.conv2d(xa, sd["attention.x_conv.weight"], sd["attention.x_conv.bias"])
+    pooled = glimpse_pool(vn, att)
+    comb = torch.cat([pooled, qf], dim=1)
+    h = (comb @ sd["classifier.lin1.weight"].t() + sd["classifier.lin1.bias"]) * gates["cls"].to(comb.dtype)
+    return h @ sd["classifier.lin2.weight"].t() + sd["classifier.lin2.bias"]
+
+
+def gates_of_forward(sd, cfg, v, q, q_len) -> dict:
+    """The gating pattern forward() itself takes (fp32): forward_gated(.., gates_of_forward(..)) == forward(..)."""
+    n_layers = len(cfg["image"]["num_channels"]) - 1
+    gates = {"pool": []}
+    x = v
+    for i in range(n_layers):
+        y = F.conv2d(x, sd[f"image.conv{i}.weight"], sd[f"image.conv{i}.bias"], stride=cfg["image"]["stride"])
+        pooled, idx = F.max_pool2d(y, 2, 2, return_indices=True)
+        OW = y.shape[3]
+        r, c = idx // OW, idx % OW
+        e = (r % 2) * 2 + (c % 2)
+        gates["pool"].append(torch.where(pooled > 0, e, torch.full_like(e, 4)))
+        x = torch.clamp_min(pooled, 0.0)
+    vn = l2_normalise(x)
+    qf = question_encoder(sd, cfg, q, q_len)
+    vp = F.conv2d(vn, sd["attention.v_conv.weight"])
+    qp = qf @ sd["attention.q_lin.weight"].t() + sd["attention.q_lin.bias"]
+    qt = qp[:, :, None, None].expand_as(vp)
+    opt = cfg["attention"]["do_option"]
+    pre = vp + qt if opt == "+" else (vp * qt if opt == "*" else torch.cat([vp, qt], dim=1))
+    gates["att"] = pre > 0
+    att = F.conv2d(torch.clamp_min(pre, 0.0), sd["attention.x_conv.weight"], sd["attention.x_conv.bias"])
+    comb = torch.cat([glimpse_pool(vn, att), qf], dim=1)
+    gates["cls"] = (comb @ sd["classifier.lin1.weight"].t() + sd["classifier.lin1.bias"]) > 0
+    return gates
+
+
+def step_with_grads_gated(sd, cfg, batch, gates):
+    """forward_gated + loss + autograd backward.  Returns (logits, loss, grads)."""
+    v, q, q_len, a_idx, a_val, _ = batch
+    leaves = {k: t.detach().clone().requires_grad_(True) for k, t in sd.items()}
+    logits = forward_gated(leaves, cfg, v, q, q_len, gates)
+    loss = soft_target_loss_dense(logits, a_idx, a_val)
+    loss.backward()
+    grads = {k: (t.grad if t.grad is not None else torch.zeros_like(t)) for k, t in leaves.items()}
+    grads["text.embedding.weight"][0].zero_()
+    return logits.detach(), loss.detach(), grads
 
 
 # ----------------------------------------------------------------------------------------------

@@ -113,3 +113,65 @@ def test_streaming_bf16_backward_matches_generic(B, P, G, p_drop, op):
         assert err < 2e-2, (n, err)
     # the gate must be identical: dvp is exactly zero in the same places (ReLU-dead or dropped)
     assert bool(((got[0].float() == 0) == (want[0] == 0)).float().mean() > 0.999)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# train mode (dropout on) against a torch restatement that consumes the SAME mask, read back through vqa_dropout_mask
+# ------------------------------------------------------------------------------------------------------------------
+def _keep_mask(B, P, A, p_drop, seed):
+    from dl_vqa_b200 import lib
+    keep = torch.empty(B * P * A, dtype=torch.uint8, device="cuda")
+    SITE_ATT_X = 4
+    lib.call("vqa_dropout_mask", lib.ptr(keep), keep.numel(), p_drop, seed, SITE_ATT_X, 1, lib.stream())
+    return keep.view(B, P, A).bool()
+
+
+def _ste_bf16(t):
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def _ref_forward_train(vp, qp, vn, wx, bx, op, keep, p_drop, bf16_fusion):
+    """models/model.py:187-195 + 208-221 with the dropout of :194 given as an explicit keep mask.  bf16_fusion restates the
+    streaming kernel's arithmetic: q' rounded to bf16, fusion result rounded to bf16 (straight-through gradients)."""
+    q = _ste_bf16(qp) if bf16_fusion else qp
+    x = vp + q[:, None, :] if op == "+" else vp * q[:, None, :]
+    if bf16_fusion:
+        x = _ste_bf16(x)
+    x = torch.relu(x) * keep.float() / (1.0 - p_drop)
+    logit = torch.einsum("bpa,ga->bgp", x, wx) + bx[None, :, None]
+    prob = torch.softmax(logit, dim=2)
+    out = torch.einsum("bgp,bpc->bgc", prob, vn).flatten(1)
+    return prob, out
+
+
+@pytest.mark.parametrize("op", ["+", "*"])
+@pytest.mark.parametrize("dtype,B,P,A,C,G,p_drop", [
+    (torch.bfloat16, 300, 676, 1024, 256, 2, 0.3),      # streaming kernels, more samples than CTAs
+    (torch.bfloat16, 3, 41, 1024, 256, 1, 0.4),
+    (torch.bfloat16, 7, 676, 1024, 256, 2, 0.0),
+    (torch.float32, 3, 676, 1024, 256, 2, 0.3),         # generic kernels (exact arm)
+    (torch.float32, 2, 37, 64, 32, 3, 0.5),
+])
+def test_train_mode_forward_and_backward_match_torch_with_the_same_mask(dtype, B, P, A, C, G, p_drop, op):
+    vp, qp, vn, wx, bx = _inputs(B, P, A, C, G, 31 + B + P, dtype)
+    seed = 0xD0D0 + B
+    streaming = dtype == torch.bfloat16
+    keep = _keep_mask(B, P, A, p_drop, seed) if p_drop > 0 else torch.ones(B, P, A, dtype=torch.bool, device="cuda")
+    if p_drop > 0 and keep.numel() > 1000000:
+        assert abs(float(keep.float().mean()) - (1 - p_drop)) < 5e-3
+    prob, out = _call_fwd(vp, qp, vn, wx, bx, op, p_drop, seed)
+    leaves = [t.detach().float().clone().requires_grad_(True) for t in (vp, qp, vn, wx, bx)]
+    rprob, rout = _ref_forward_train(*leaves, op, keep, p_drop, bf16_fusion=streaming)
+    tol = 2e-2 if streaming else 1e-4
+    assert float((prob - rprob).abs().max()) < tol * float(rprob.max())
+    assert _rel(out, rout) < tol, _rel(out, rout)
+    dout = torch.randn(B, G * C, device="cuda").to(dtype)
+    rout.backward(dout.float())
+    dvp, dvn, dqp, dwx, dbx = _call_bwd(dout, vp, qp, vn, wx, prob, op, p_drop, seed)
+    for name, got, want in (("dvp", dvp, leaves[0].grad), ("dvn", dvn, leaves[2].grad), ("dqp", dqp, leaves[1].grad),
+                            ("dwx", dwx, leaves[3].grad)):
+        assert _rel(got, want) < (2e-2 if streaming else 2e-4), (name, _rel(got, want))
+    assert float((dbx - leaves[4].grad).abs().max()) < (1e-2 if streaming else 1e-4) * max(1.0, float(dwx.abs().max()))
+    # the kernels gate exactly the elements the restatement gates: dropped or ReLU-dead <=> zero gradient
+    dead = leaves[0].grad == 0
+    assert float(((dvp.float() == 0) == dead).float().mean()) > 0.9995

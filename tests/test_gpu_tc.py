@@ -443,3 +443,86 @@ def test_persistent_lstm_backward_matches_the_per_step_kernels(B, T, H, dirs):
     assert err(dg_b, dg_a) < 1e-2          # bf16 gate gradients; fp32 partial sums arrive in a different order
     assert err(dc_b, dc_a) < 1e-4
     assert err(dh_b, dh_a) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# persistent LSTM kernels against the ORACLE (not against another kernel of this library)
+# ------------------------------------------------------------------------------------------------------------------
+def _step_index(pre_tok, q_len, reverse):
+    """token-indexed [B,T,X] -> step-indexed [T,B,X]: step s of the reverse direction holds token len-1-s"""
+    B, T, _ = pre_tok.shape
+    s = torch.arange(T, device=pre_tok.device)[None, :]
+    t = (q_len[:, None] - 1 - s).clamp_min(0) if reverse else s.expand(B, T)
+    out = pre_tok.gather(1, t[:, :, None].expand_as(pre_tok))
+    out = out * (s < q_len[:, None])[:, :, None]
+    return out.transpose(0, 1).contiguous()
+
+
+def _token_index(step_major, q_len, reverse):
+    """inverse of _step_index for gradients: [T,B,X] step-indexed -> [B,T,X] token-indexed (zero where t >= len)"""
+    x = step_major.transpose(0, 1)
+    B, T, _ = x.shape
+    t = torch.arange(T, device=x.device)[None, :]
+    s = (q_len[:, None] - 1 - t).clamp_min(0) if reverse else t.expand(B, T)
+    out = x.gather(1, s[:, :, None].expand_as(x))
+    return out * (t < q_len[:, None])[:, :, None]
+
+
+@pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (1024, 12, 1024, 2), (130, 7, 256, 2), (5, 4, 128, 1), (600, 9, 256, 2)])
+def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs):
+    """vqa_tc_lstm_fwd / vqa_tc_lstm_bwd (cooperative tcgen05 kernels) against oracle.lstm_final_cell + autograd
+    (reference models/model.py:159-166) on the same bf16-rounded input projections and recurrent weights; the oracle
+    rounds what the kernel stores in bf16 (input projection, h) with a straight-through gradient."""
+    from dl_vqa_b200 import lib
+    from oracle import vqa_oracle as O
+    torch.manual_seed(B + T + H)
+    dev = "cuda"
+    pre_tok = [(torch.randn(B, T, 4 * H) * 0.8).bfloat16().float() for _ in range(dirs)]
+    w_hh = [(torch.randn(4 * H, H) / H ** 0.5).bfloat16().float() for _ in range(dirs)]
+    q_len = torch.randint(1, T + 1, (B,))
+    q_len[0] = T
+    q_len[-1] = 1
+    dqf = (torch.randn(B, dirs * H) * 0.1).bfloat16().float()
+
+    # ---- oracle
+    sd = {"text.lstm.weight_hh_l0": w_hh[0]}
+    if dirs == 2:
+        sd["text.lstm.weight_hh_l0_reverse"] = w_hh[1]
+    leaves = [p.clone().requires_grad_(True) for p in pre_tok]
+    c_n = O.lstm_final_cell(sd, torch.zeros(B, T, 1), q_len, H, dirs == 2, rnd=O.bf16_round_ste, pre=leaves)
+    (c_n * dqf).sum().backward()
+
+    # ---- kernels
+    st = lib.stream()
+    ql = q_len.to(dev)
+    gx = torch.stack([_step_index(pre_tok[d].to(dev), ql, d == 1) for d in range(dirs)]).bfloat16().contiguous()
+    cs = torch.empty(dirs, T, B, H, device=dev)
+    hs = torch.zeros(dirs, T + 1, B, H, device=dev, dtype=torch.bfloat16)
+    qf = torch.empty(B, dirs * H, device=dev, dtype=torch.bfloat16)
+    wp = torch.empty(dirs, 4 * H, H, device=dev, dtype=torch.bfloat16)
+    whh = torch.stack(w_hh).to(dev)
+    for d in range(dirs):
+        lib.call("vqa_pack_lstm_whh", lib.ptr(whh[d]), lib.ptr(wp[d]), H, st)
+    sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
+    lib.call("vqa_tc_lstm_fwd", lib.ptr(gx), lib.ptr(cs), lib.ptr(hs), lib.ptr(qf), lib.ptr(wp), lib.ptr(ql),
+             lib.ptr(sync), T, B, H, dirs, st)
+    dh = torch.zeros(dirs, B, H, device=dev)
+    dc = torch.empty(dirs, B, H, device=dev)
+    dg = torch.empty(dirs, T, B, 4 * H, dtype=torch.bfloat16, device=dev)
+    sync_b = torch.zeros(256, dtype=torch.int32, device=dev)
+    whh_b = whh.bfloat16().contiguous()
+    lib.call("vqa_tc_lstm_bwd", lib.ptr(gx), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc), lib.ptr(dqf.to(dev).bfloat16()), lib.ptr(dg),
+             lib.ptr(whh_b), lib.ptr(ql), lib.ptr(sync_b), T, B, H, dirs, st)
+    torch.cuda.synchronize()
+
+    def err(a, b):
+        a, b = a.float().cpu(), b.float().cpu()
+        return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+    assert err(qf, c_n.detach()) < 2e-2, err(qf, c_n.detach())
+    for d in range(dirs):
+        got = _token_index(dg[d].float(), ql, d == 1)
+        e = err(got, leaves[d].grad)
+        assert e < 2e-2, (d, e)
+        # inactive steps: exactly zero on both sides
+        inactive = (torch.arange(T)[None, :] >= q_len[:, None])
+        assert float(leaves[d].grad[inactive].abs().max() if inactive.any() else 0.0) == 0.0
