@@ -88,16 +88,53 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference step, timed on the host cores
 # --------------------------------------------------------------------------------------------------
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use the host's cores."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_steps(steps, warmup, batch=32):
+    """The reference's CPU path of the step on the host cores: the UNMODIFIED reference from oracle/_ref (models/model.py
+    VqaNet, train.py run_batch / update_learning_rate, torch.optim.Adam as train.py:55) when that copy is present
+    (kind "reference"), else the oracle port of the same arithmetic (kind "port").  fp32, train() mode with the
+    config.yaml dropouts, config.yaml shapes (BASELINE.json configs[0])."""
+    import warnings
     import torch
     from oracle import vqa_oracle as O
+    from oracle import ref_loader
+    threads = _use_all_host_threads()
     cfg = O.DEFAULT_CFG
     V = 15000
+    v, q, q_len, a_idx, a_val, a_len = O.synthetic_batch(batch, cfg, V, seed=1)
+    times = []
+    if ref_loader.available():
+        ref = ref_loader.load()
+        torch.manual_seed(1)
+        model = ref.VqaNet(cfg, V).train(True)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)            # reference train.py:55
+        log_softmax = torch.nn.LogSoftmax(dim=1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                loss, _ = ref.train.run_batch(model, log_softmax, (v, q, a_idx, a_val, a_len, None, q_len), cfg["max_answers"])
+                opt.zero_grad()
+                ref.train.update_learning_rate(opt, it, 5e-4)
+                loss.backward()
+                opt.step()
+                dt = time.perf_counter() - t0
+                if it >= warmup:
+                    times.append(dt)
+        return times, batch, threads, "reference"
     sd = O.random_params(cfg, V, seed=1)
     leaves = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
-    opt = torch.optim.Adam(list(leaves.values()), lr=5e-4)          # reference train.py:55
-    v, q, q_len, a_idx, a_val, _ = O.synthetic_batch(batch, cfg, V, seed=1)
-    times = []
+    opt = torch.optim.Adam(list(leaves.values()), lr=5e-4)
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         logits = O.forward(leaves, cfg, v, q, q_len)
@@ -110,7 +147,7 @@ def cpu_reference_steps(steps, warmup, batch=32):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times, batch, torch.get_num_threads()
+    return times, batch, threads, "port"
 
 
 def run_reference(args):
@@ -121,17 +158,19 @@ def run_reference(args):
     # bounded sample: B=32 per step (about 3 s of CPU work each); cap the total at a few minutes
     steps_eff = min(steps, 40)
     warm = min(args.warmup, 3)
-    times, batch, threads = cpu_reference_steps(steps_eff, warm, batch=32)
+    times, batch, threads, kind = cpu_reference_steps(steps_eff, warm, batch=32)
     ms = 1000.0 * sum(times) / len(times)
     val = batch / (ms / 1000.0)
-    sample = (f"oracle port of models/model.py fwd + train.py loss + bwd + torch Adam, fp32, batch {batch} per step "
-              f"(bounded sample of the 256-sample step), {steps_eff} timed steps, {threads} torch threads")
+    what = ("unmodified reference (oracle/_ref: models/model.py VqaNet + train.py run_batch) + torch Adam" if kind == "reference"
+            else "oracle port of models/model.py fwd + train.py loss + bwd + torch Adam")
+    sample = (f"{what}, fp32, dropout 0.3, batch {batch} per step (bounded sample of the 256-sample step), "
+              f"{steps_eff} timed steps, {threads} torch threads, os.cpu_count()={os.cpu_count()}")
     line = {"impl": "reference", "metric": "train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": steps_eff, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "single-B200 training step of BASELINE.json configs[1]: full VqaNet fwd+loss+bwd+Adam "
                                    "at config.yaml shapes, timed here on the host CPU", "batch_per_step": batch},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
@@ -188,39 +227,31 @@ def run_ours(args):
     torch.manual_seed(1)
     model = D.VqaNet(cfg, synth.DEFAULT_TOKENS, compute_dtype=args.dtype).to(dev).train(True)
     opt = D.FusedAdam(model.parameters(), lr=5e-4)
-    model.use_gradient_arena(True)        # gradients live in persistent per-stage buckets (all-reduced in place for N > 1)
+    model.use_gradient_arena(True)        # gradients live in one persistent arena (all-reduced in place, bucket by bucket, for N > 1)
     if args.dtype == "bfloat16":
         model.use_weight_shadows(opt)     # FusedAdam keeps the bf16 GEMM weight shadows current (no per-step re-casts)
     ddp = GradientAllReduce(model)
     ddp.broadcast_parameters()
+    # the loop body of train.py:69-81 as one CUDA graph per input buffer set (--no-graph: enqueue kernel by kernel)
+    gstep = D.GraphedTrainStep(model, opt, cfg["max_answers"], ddp=ddp if world > 1 else None, lr=5e-4,
+                               enabled=not args.no_graph)
 
     host = synth.make_batch(B, cfg, seed=1 + rank, pin=True)
     hv, hq, hai, hav, hal, _, hql = host
-    h2d_bytes = sum(t.numel() * t.element_size() for t in (hv, hq, hai, hav, hql))
+    hv16 = hv.to(torch.float16).pin_memory()          # the reference's on-disk image dtype (preprocessing/preprocess_images.py:40)
+    assert torch.equal(hv16.float(), hv)
+    small_bytes = sum(t.numel() * t.element_size() for t in (hq, hai, hav, hql))
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
-    def to_dev():
-        return tuple(t.to(dev, non_blocking=True) for t in (hv, hq, hai, hav, hal, hql))
-
-    state = {"it": 0}
-
     def step(dbatch):
-        dv, dq, dai, dav, dal, dql = dbatch
-        loss, score = D.run_batch(model, None, (dv, dq, dai, dav, dal, None, dql), cfg["max_answers"])
-        opt.zero_grad(set_to_none=True)
-        D.update_learning_rate(opt, state["it"], 5e-4)
-        loss.backward()
-        ddp.finish()
-        opt.step(grad_scale=ddp.grad_scale)
-        state["it"] += 1
-        return loss, score
+        return gstep(dbatch)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    host = {"enqueue_ms": 0.0}
+    hostt = {"enqueue_ms": 0.0}
 
     def timed(fn, n):
         barrier()
@@ -230,7 +261,7 @@ def run_ours(args):
         for _ in range(n):
             fn()
         b.record()
-        host["enqueue_ms"] = 1000.0 * (time.perf_counter() - t0)      # host time to enqueue the region (no sync inside)
+        hostt["enqueue_ms"] = 1000.0 * (time.perf_counter() - t0)      # host time to enqueue the region (no sync inside)
         barrier()
         ms = a.elapsed_time(b)
         if world > 1:
@@ -239,73 +270,110 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    dbatch = to_dev()
-    for _ in range(max(3, args.warmup)):
+    dbatch = tuple(t.to(dev, non_blocking=True) for t in (hv, hq, hai, hav, hal)) + (None, hql.to(dev, non_blocking=True))
+    for _ in range(max(3, args.warmup)):      # call 1 runs eagerly, call 2 captures + replays, the rest replay
         step(dbatch)
     torch.cuda.synchronize()
 
     # ---- (1) device-resident throughput (no per-kernel events inside this region)
     tags = [f"conv{i}_{k}" for i in range(3) for k in ("fwd", "dgrad", "wgrad")] + \
            ["v_conv", "v_conv_dgrad", "v_conv_wgrad", "vqa_attention_fwd", "vqa_attention_bwd", "lstm_step_fwd",
-            "lstm_step_bwd", "lstm_recurrence_fwd", "lstm_bwd_pointwise", "lstm_bwd_persistent", "lstm_inproj", "lstm_whh_wgrad", "lstm_wih_wgrad", "lstm_inproj_dgrad", "lin1", "lin2", "q_lin", "lin1_dgrad", "lin2_dgrad", "lin1_wgrad", "lin2_wgrad", "q_lin_dgrad", "q_lin_wgrad", "act_cast", "vqa_adam_multi", "act_transpose", "unpool", "w_cast", "w_transpose"]
+            "lstm_step_bwd", "lstm_recurrence_fwd", "lstm_bwd_pointwise", "lstm_bwd_persistent", "lstm_inproj", "lstm_whh_wgrad",
+            "lstm_wih_wgrad", "lstm_inproj_dgrad", "lin1", "lin2", "q_lin", "lin1_dgrad", "lin2_dgrad", "lin1_wgrad", "lin2_wgrad",
+            "q_lin_dgrad", "q_lin_wgrad", "act_cast", "vqa_adam_multi", "vqa_adam_multi_dev", "act_transpose", "unpool", "w_cast",
+            "w_transpose", "embed_fwd", "embed_bwd", "vqa_dropnorm_fwd", "vqa_softloss_fwd_bwd", "vqa_colsum", "vqa_zero"]
     clocks = ClockSampler(local)
     clocks.start()
-    n0 = lib.launch_count()
+    n0, r0 = lib.launch_count(), gstep.replays
     ms_dev = timed(lambda: step(dbatch), args.steps)
-    host_ms_dev = host["enqueue_ms"] / args.steps
-    launches = lib.launch_count() - n0
+    host_ms_dev = hostt["enqueue_ms"] / args.steps
+    # kernels of this library inside the timed region: counted at enqueue time, plus (replayed graphs) x (kernels captured per graph)
+    launches = (lib.launch_count() - n0) + (gstep.replays - r0) * gstep.launches_per_replay
 
     if args.profile_mode:            # under ncu: no second timed region, no breakdown pass, no CPU leg
         clocks.stop()
         if rank == 0:
-            _emit({"profile_mode": True, "ms_per_step": ms_dev / args.steps})
+            _emit({"profile_mode": True, "ms_per_step": ms_dev / args.steps, "graph": not args.no_graph})
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- (2) end to end through the public API: every step's inputs come from pinned host memory through
-    # DevicePrefetcher (copy of batch i+1 on a side stream while batch i computes) and the loss / score of every
-    # step are read back to the host.  One H2D copy of the full batch per step happens inside the timed region.
-    himg = {"v": hv}
+    # DevicePrefetcher (copy of batch i+1 on a side stream while batch i computes, two fixed device buffer sets ->
+    # two captured graphs) and the loss / score of every step are read back to the host.  One H2D copy of the full
+    # batch per step happens inside the timed region.  Images are handed over as float16, the dtype the reference's
+    # preprocessing writes (preprocessing/preprocess_images.py:40; its Dataset widens on the host at
+    # data_preprocessing.py:174); the first-layer kernels read float16 directly.  `e2e_fp32_input` is the same loop fed
+    # with the widened float32 images (twice the host->device bytes).
+    class HostBatches:
+        def __init__(self, v):
+            self.v, self.n = v, 0
 
-    def host_batches(n):
-        for _ in range(n):
-            yield (himg["v"], hq, hai, hav, hal, None, hql)
+        def __iter__(self):
+            for _ in range(self.n):
+                yield (self.v, hq, hai, hav, hal, None, hql)
 
-    def e2e_run(n):
-        for dv, dq, dai, dav, dal, _, dql in D.DevicePrefetcher(host_batches(n), dev):
-            loss, score = step((dv, dq, dai, dav, dal, dql))
-            loss_host[0].copy_(loss.detach(), non_blocking=True)
-            loss_host[1].copy_(score.detach(), non_blocking=True)
+    def make_e2e(v):
+        src = HostBatches(v)
+        pf = D.DevicePrefetcher(src, dev)
 
-    e2e_run(2)
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
-    host_ms_e2e = host["enqueue_ms"] / args.steps
+        def run(n):
+            src.n = n
+            for dbt in pf:
+                loss, score = step(dbt)
+                loss_host[0].copy_(loss, non_blocking=True)
+                loss_host[1].copy_(score, non_blocking=True)
+        return run
+
+    e2e16, e2e32 = make_e2e(hv16), make_e2e(hv)
+    e2e16(4)                                              # both buffer sets: first sighting (eager) + capture
+    ms_e2e = timed(lambda: e2e16(args.steps), 1)
+    host_ms_e2e = hostt["enqueue_ms"] / args.steps
     clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
+    h2d_bytes = small_bytes + hv16.numel() * 2
+    e2e32(4)
+    ms_e2e32 = timed(lambda: e2e32(args.steps), 1)
+    h2d32_bytes = small_bytes + hv.numel() * 4
 
-    # ---- (2b) the same end-to-end loop fed with float16 images: the dtype the reference's preprocessing writes to disk
-    # (preprocessing/preprocess_images.py:40) before its Dataset widens every sample to float32 on the host
-    # (preprocessing/data_preprocessing.py:174).  Halves the host->device bytes; reported beside `e2e`, never instead of it.
-    himg["v"] = hv.to(torch.float16).pin_memory()
-    e2e_run(2)
-    ms_e2e16 = timed(lambda: e2e_run(args.steps), 1)
-    h2d16_bytes = h2d_bytes - hv.numel() * 2
-    himg["v"] = hv
-
-    # ---- (3) per-kernel breakdown: a separate pass with CUDA events around every tagged C-ABI call (the events add
-    # launch gaps, so this pass is not part of `value` / `e2e`)
-    # Per-step collection and the MEDIAN over steps per kernel: the events bracket host enqueue too, so one host hiccup
-    # (GC, the clock sampler) while the queue is empty would otherwise be booked on whatever kernel came next.
+    # ---- (3) per-kernel breakdown: a separate pass, kernel by kernel (no graph), with CUDA events around every tagged
+    # C-ABI call (the events add launch gaps, so this pass is not part of `value` / `e2e`).  Per-step collection and the
+    # MEDIAN over steps per kernel: the events bracket host enqueue too, so one host hiccup (GC, the clock sampler) while
+    # the queue is empty would otherwise be booked on whatever kernel came next.
     nb = min(args.steps, 7)
     per_step_times = []
+    wait_ms = []
+    if world > 1:
+        ddp.wait_events = []
     for _ in range(nb):
         lib.enable_kernel_timing(tags)
-        step(dbatch)
+        gstep.eager_step(dbatch)
         per_step_times.append(lib.collect_kernel_timing())
+    if world > 1:
+        torch.cuda.synchronize()
+        wait_ms = sorted(a.elapsed_time(b) for a, b in ddp.wait_events)
+        ddp.wait_events = None
     ktimes = {}
     for k in per_step_times[0]:
         ms = sorted(t[k][1] for t in per_step_times if k in t)
         ktimes[k] = (per_step_times[0][k][0] * nb, ms[len(ms) // 2] * nb)
+
+    # ---- (4) exposed communication (N > 1): (a) time the compute stream spends waiting in GradientAllReduce.finish()
+    # for the bucket all-reduces (CUDA events, kernel-by-kernel pass above); (b) the same graph-replayed step with the
+    # all-reduces removed -- the difference to `ms_per_step` is everything communication costs: exposed waits plus the
+    # slow-down of the kernels it overlaps.  Run last: without the exchange the replicas drift apart.
+    comm = None
+    if world > 1:
+        model.grad_ready_hook = None
+        g2 = D.GraphedTrainStep(model, opt, cfg["max_answers"], ddp=None, lr=5e-4, enabled=not args.no_graph)
+        for _ in range(3):
+            g2(dbatch)
+        ms_nocomm = timed(lambda: g2(dbatch), args.steps)
+        comm = {"finish_wait_ms_median": wait_ms[len(wait_ms) // 2] if wait_ms else None,
+                "finish_wait_ms_max": wait_ms[-1] if wait_ms else None,
+                "ms_per_step_without_allreduce": ms_nocomm / args.steps,
+                "ms_per_step_delta": (ms_dev - ms_nocomm) / args.steps,
+                "note": "finish_wait = compute-stream wait for the bucket all-reduces after backward (rank 0, CUDA events, "
+                        "kernel-by-kernel pass); delta = graph step with minus without all-reduce (max over ranks)"}
 
     if rank != 0:
         if world > 1:
@@ -317,8 +385,9 @@ def run_ours(args):
     value = world * B / (per_step / 1000.0)
     e2e_val = world * B / (ms_e2e / args.steps / 1000.0)
 
-    # dominant kernel: the tag with the largest device time inside the timed region
     breakdown = {k: {"calls_per_step": n / nb, "ms_per_step": ms / nb} for k, (n, ms) in ktimes.items()}
+    if "vqa_adam_multi_dev" in breakdown:
+        breakdown["vqa_adam_multi"] = breakdown.pop("vqa_adam_multi_dev")
     # roofline of the dominant kernel: the tagged kernel with the largest device time whose algorithmic work is known
     esz = 2 if args.dtype in ("bf16", "bfloat16") else 4
     work = {}
@@ -327,16 +396,20 @@ def run_ours(args):
             work[f"conv{i}_{k}"] = ("tensor", CONV_FLOP[i] * B)
     for k in ("v_conv", "v_conv_dgrad", "v_conv_wgrad"):
         work[k] = ("tensor", 2.0 * B * 676 * 256 * 1024)
-    # conv0 (K = 27): HBM-bound.  fwd reads the fp32 NCHW image and writes pooled bf16 + uint8 mask [B,111,111,64]; the
-    # fused backward reads the image, the pooled gradient and the mask (the un-pooled gradient never exists)
+    # conv0 (K = 27): HBM-bound.  fwd reads the NCHW image (fp32 in the device-resident loop) and writes pooled bf16 +
+    # uint8 mask [B,111,111,64]; the fused backward reads the image, the pooled gradient and the mask
     work["conv0_fwd"] = ("hbm", B * (3 * 224 * 224 * 4 + 111 * 111 * 64 * (esz + 1)))
     work["conv0_wgrad"] = ("hbm", B * (3 * 224 * 224 * 4 + 111 * 111 * 64 * (esz + 1)))
     work["vqa_attention_fwd"] = ("hbm", B * ((676 * 1024 + 676 * 256 + 512) * esz + 1024 * 4 + 2 * 676 * 4))
     work["vqa_attention_bwd"] = ("hbm", B * ((2 * 676 * 1024 + 2 * 676 * 256 + 512) * esz + 2 * 1024 * 4 + 2 * 676 * 4 + 2 * 1024 * 4))
+    work["vqa_adam_multi"] = ("hbm", 23793242 * (4 * 7 + 2 * 0.98))       # p, g, m, v read; p, m, v written; bf16 shadows of the GEMM weights
+    # LSTM recurrences: dense T = 23 FLOP of the recurrent GEMMs (what the kernels execute; mean length is 12)
+    work["lstm_recurrence_fwd"] = ("tensor", 2.0 * 2 * B * 23 * 1024 * 4096)
+    work["lstm_bwd_persistent"] = ("tensor", 2.0 * 2 * B * 22 * 1024 * 4096)
     roofline = None
     known = {k: v for k, v in breakdown.items() if k in work and v["calls_per_step"] > 0}
     if known:
-        top = max(known, key=lambda k: known[k]["ms_per_step"])
+        top = max((k for k in known if not k.startswith("lstm_")), key=lambda k: known[k]["ms_per_step"])
         bound, amount = work[top]
         dur_ms = known[top]["ms_per_step"] / known[top]["calls_per_step"]
         traffic, traffic_src = _ncu_traffic(top)
@@ -360,14 +433,29 @@ def run_ours(args):
         att_roof = {"kernel": "vqa_attention_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": byt,
                     "traffic": _ncu_traffic("vqa_attention_fwd")[0]}
+    lstm = {}
+    for k, steps_ in (("lstm_recurrence_fwd", 23), ("lstm_bwd_persistent", 23)):
+        if k in breakdown and breakdown[k]["calls_per_step"] > 0:
+            ms = breakdown[k]["ms_per_step"]
+            lstm[k] = {"ms": ms, "us_per_time_step": 1000.0 * ms / steps_, "TFLOPs_dense": work[k][1] / ms / 1e9,
+                       "frac_of_tensor_peak": work[k][1] / ms / 1e9 / peaks["tflops"]}
+
+    micro_att = micro_lstm = None
+    if world == 1 and not args.no_micro:
+        del dbatch
+        torch.cuda.empty_cache()
+        from tools import microbench
+        micro_att = microbench.attention_microbench(hbm_peak_gbs=peaks["hbm_gbs"])
+        micro_lstm = microbench.lstm_microbench(tflops_peak=peaks["tflops"])
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        times, cb, threads = cpu_reference_steps(3, 1, batch=32)
+        times, cb, threads, kind = cpu_reference_steps(4, 1, batch=32)
         cms = sum(times) / len(times)
-        cpu = {"value": cb / cms, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"oracle port, fp32, batch {cb}, 1 warm-up + 3 timed steps of fwd+loss+bwd+Adam "
-                         f"({cms:.2f} s/step), os.cpu_count()={os.cpu_count()}"}
+        cpu = {"value": cb / cms, "unit": "samples/s", "cores": threads, "kind": kind,
+               "sample": f"{'unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port'}, fp32, dropout 0.3, "
+                         f"batch {cb}, 1 warm-up + 4 timed steps of fwd+loss+bwd+Adam ({cms:.2f} s/step), "
+                         f"os.cpu_count()={os.cpu_count()}"}
 
     line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
@@ -375,18 +463,22 @@ def run_ours(args):
             "config": {"workload": "single-B200 training step (BASELINE.json configs[1]): full VqaNet fwd + soft-target loss "
                                    "+ bwd + Adam, config.yaml shapes, dropout 0.3, random init, V=15000, T=23",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "step_launch": "one CUDA graph replay per step (GraphedTrainStep)" if not args.no_graph else "kernel by kernel",
                        "l2_policy": "inputs + activations per step (>2 GB) far exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
-                    "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / args.steps},
-            "e2e_fp16_input": {"value": world * B / (ms_e2e16 / args.steps / 1000.0), "unit": "samples/s",
-                               "h2d_bytes_per_step": h2d16_bytes * world, "ms_per_step": ms_e2e16 / args.steps,
-                               "note": "images handed over as float16 (the reference's on-disk dtype), widened on the GPU"},
+                    "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / args.steps,
+                    "input": "float16 images (the reference's stored dtype), int64 questions / answers, pinned host memory, "
+                             "DevicePrefetcher double buffering, loss + score read back every step"},
+            "e2e_fp32_input": {"value": world * B / (ms_e2e32 / args.steps / 1000.0), "unit": "samples/s",
+                               "h2d_bytes_per_step": h2d32_bytes * world, "ms_per_step": ms_e2e32 / args.steps,
+                               "note": "same loop, images widened to float32 on the host as the reference's Dataset does"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "host_enqueue_ms_per_step": {"device_resident": host_ms_dev, "e2e": host_ms_e2e},
             "host_cpu_binding": numa,
-            "clocks": clk, "roofline": roofline, "attention_roofline": att_roof,
+            "clocks": clk, "roofline": roofline, "attention_roofline": att_roof, "lstm_recurrence": lstm,
             "step_tensor_frac": (STEP_FLOP_PER_SAMPLE * B / (per_step / 1000.0) / 1e12) / peaks["tflops"],
-            "roofline_frac_by_kernel": per_kernel_frac, "kernels": breakdown, "cpu_baseline": cpu}
+            "roofline_frac_by_kernel": per_kernel_frac, "kernels": breakdown,
+            "exposed_comm": comm, "attention_microbench": micro_att, "lstm_microbench": micro_lstm, "cpu_baseline": cpu}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -414,6 +506,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bfloat16", "float32"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--no-micro", action="store_true", help="skip the configs[2] / configs[3] micro-benchmarks")
     ap.add_argument("--conv-cta-group", type=int, default=0, help="override the conv kernels' tcgen05 cta_group (1 or 2)")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + timed steps only (for ncu)")
     args = ap.parse_args()

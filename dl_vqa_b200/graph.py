@@ -125,6 +125,13 @@ class GraphedTrainStep:
         self.iteration += 1
         return out
 
+    def eager_step(self, batch):
+        """One training step enqueued kernel by kernel (never captured): profiling passes, debugging."""
+        self._host_lr()
+        out = self._eager(batch)
+        self.iteration += 1
+        return out
+
     def read_state(self) -> dict:
         """Device state copied to the host (synchronises): for tests and checkpoints."""
         h = self.state.cpu()

@@ -40,8 +40,13 @@ class _QuestionParams(nn.Module):
             self.lstm = nn.LSTM(input_size=embedding_features, hidden_size=lstm_features, num_layers=num_lstm_layers,
                                 dropout=drop, bidirectional=bidirectional)
 
-    def forward(self, *a, **k):
-        raise RuntimeError("parameter container only; the fused step in VqaNet.forward computes this stage")
+    def forward(self, q, q_len):
+        """reference questionNet.forward (models/model.py:151-166) on the CUDA kernels of the owning VqaNet"""
+        owner = self.__dict__.get("_owner")
+        net = owner() if owner is not None else None
+        if net is None:
+            raise RuntimeError("question encoder parameters without an owning VqaNet")
+        return net.encode_question(q, q_len)
 
 
 class _ImageParams(nn.Module):
@@ -224,6 +229,8 @@ class VqaNet(nn.Module):
         self.attention = _AttentionParams(self.channels[-1], lstm_out, self.A, self.G, self.do_option, self.p_att)
         self.classifier = _ClassifierParams(self.G * self.channels[-1] + lstm_out, self.hidden, self.max_answers,
                                             self.p_cls)
+        import weakref
+        self.text.__dict__["_owner"] = weakref.ref(self)       # not a sub-module registration: no cycle in the module tree
         self.compute_dtype = torch.float32
         if compute_dtype is not None:
             self.set_compute_dtype(compute_dtype)
@@ -420,46 +427,8 @@ class VqaNet(nn.Module):
         v_in = vnd if vnd is not None else vn
 
         # ---------------- question encoder (models/model.py:151-166)
-        T, E, H, dirs = int(q.shape[1]), self.E, self.H, self.dirs
-        lstm = self.text.lstm
-        sfx = ["", "_reverse"][:dirs]
-        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
-        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
-        b_ih = [getattr(lstm, f"bias_ih_l0{s}") for s in sfx]
-        b_hh = [getattr(lstm, f"bias_hh_l0{s}") for s in sfx]
-        ldx = _rup(E, 8) if tc else E
-        xs = empty(dirs, T, B, ldx)
-        call("vqa_embed_tanh_fwd", ptr(q), ptr(q_len), ptr(self.text.embedding.weight), ptr(xs), dt,
-             B, T, E, ldx, dirs, p_text, seed, st)
-        gx = empty(dirs, T, B, 4 * H)
-        for d in range(dirs):   # hoisted input projection: x W_ih^T + b_ih + b_hh for all steps at once
-            mm.lin_fwd(ptr(xs[d]), dt, ldx, w_ih[d], ptr(gx[d]), dt, 4 * H, T * B, 4 * H, E,
-                       bias=b_ih[d], bias2=b_hh[d], tag="lstm_inproj")
-        cs = empty(dirs, T, B, H, dtype=f32)
-        qf = empty(B, dirs * H)
-        whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        persistent = tc and H % 64 == 0 and H <= 1024 and dirs * (H // 16) <= sms
-        if persistent:
-            # one cooperative launch for all steps and directions; W_hh resident in shared memory
-            wp = empty(dirs, 4 * H, H)
-            for d in range(dirs):
-                call("vqa_pack_lstm_whh", ptr(w_hh[d]), ptr(wp[d]), H, st, tag="w_cast")
-            hs_ext = torch.empty(dirs, T + 1, B, H, dtype=adt, device=dev)      # the kernel writes slots 1..T of every row
-            for d in range(dirs):                                               # slot 0 = h_{-1} = 0
-                call("vqa_zero", ptr(hs_ext[d, 0]), B * H * hs_ext.element_size(), st)
-            sync = torch.empty(dirs, dtype=torch.int32, device=dev)
-            call("vqa_zero", ptr(sync), dirs * 4, st)
-            call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
-                 T, B, H, dirs, st, tag="lstm_recurrence_fwd")
-            h_prev = [hs_ext[d, 1] for d in range(dirs)]     # h_0 .. h_{T-1} of direction d start here
-            hs = hs_ext
-        else:
-            hs = empty(dirs, T, B, H)
-            for s in range(T):
-                call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
-                     dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
-            h_prev = [hs[d, 0] for d in range(dirs)]
+        tx = self._text_forward(q, q_len, seed, mm, st, p_text)
+        T, H, dirs, qf = tx["T"], self.H, self.dirs, tx["qf"]
 
         # ---------------- attention (models/model.py:183-195, :208-221)
         att = self.attention
@@ -499,10 +468,182 @@ class VqaNet(nn.Module):
 
         if save:
             ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, conv_wd=conv_wd, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
-                       xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
-                       q=q, q_len=q_len, ldx=ldx, whh_stride=whh_stride,
+                       text=tx, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
+                       q=q, q_len=q_len,
                        p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
         return logits, ctx
+
+    # ------------------------------------------------------------------ question encoder (reference questionNet)
+    def _text_forward(self, q, q_len, seed: int, mm: "_Math", st, p_text: float) -> dict:
+        """models/model.py:151-166: embedding -> dropout -> tanh -> (bi)LSTM, final CELL state [B, dirs*H].
+        Returns the output `qf` and everything the backward needs."""
+        adt = self.compute_dtype
+        dt = lib.dtype_code(adt)
+        tc = adt == torch.bfloat16
+        dev = q.device
+        f32 = torch.float32
+        B = int(q.shape[0])
+
+        def empty(*shape, dtype=adt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        T, E, H, dirs = int(q.shape[1]), self.E, self.H, self.dirs
+        lstm = self.text.lstm
+        sfx = ["", "_reverse"][:dirs]
+        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
+        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
+        b_ih = [getattr(lstm, f"bias_ih_l0{s}") for s in sfx]
+        b_hh = [getattr(lstm, f"bias_hh_l0{s}") for s in sfx]
+        ldx = _rup(E, 8) if tc else E
+        xs = empty(dirs, T, B, ldx)
+        call("vqa_embed_tanh_fwd", ptr(q), ptr(q_len), ptr(self.text.embedding.weight), ptr(xs), dt,
+             B, T, E, ldx, dirs, p_text, seed, st, tag="embed_fwd")
+        gx = empty(dirs, T, B, 4 * H)
+        for d in range(dirs):   # hoisted input projection: x W_ih^T + b_ih + b_hh for all steps at once
+            mm.lin_fwd(ptr(xs[d]), dt, ldx, w_ih[d], ptr(gx[d]), dt, 4 * H, T * B, 4 * H, E,
+                       bias=b_ih[d], bias2=b_hh[d], tag="lstm_inproj")
+        cs = empty(dirs, T, B, H, dtype=f32)
+        qf = empty(B, dirs * H)
+        whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        persistent = tc and H % 64 == 0 and H <= 1024 and dirs * (H // 16) <= sms
+        if persistent:
+            # one cooperative launch for all steps and directions; W_hh resident in shared memory
+            wp = empty(dirs, 4 * H, H)
+            for d in range(dirs):
+                call("vqa_pack_lstm_whh", ptr(w_hh[d]), ptr(wp[d]), H, st, tag="w_cast")
+            hs_ext = torch.empty(dirs, T + 1, B, H, dtype=adt, device=dev)      # the kernel writes slots 1..T of every row
+            for d in range(dirs):                                               # slot 0 = h_{-1} = 0
+                call("vqa_zero", ptr(hs_ext[d, 0]), B * H * hs_ext.element_size(), st)
+            sync = torch.empty(dirs, dtype=torch.int32, device=dev)            # cleared by the entry itself
+            call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
+                 T, B, H, dirs, st, tag="lstm_recurrence_fwd")
+            h_prev = [hs_ext[d, 1] for d in range(dirs)]     # h_0 .. h_{T-1} of direction d start here
+            hs = hs_ext
+        else:
+            hs = empty(dirs, T, B, H)
+            for s in range(T):
+                call("vqa_lstm_step_fwd", ptr(gx), ptr(cs), ptr(hs), ptr(qf), ptr(w_hh[0]), whh_stride, ptr(q_len),
+                     dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
+            h_prev = [hs[d, 0] for d in range(dirs)]
+        return dict(T=T, B=B, xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qf=qf, ldx=ldx, whh_stride=whh_stride,
+                    q=q, q_len=q_len, seed=seed, p_text=p_text)
+
+    def _text_backward(self, tx: dict, dqf, mm: "_Math", st, galloc, colsum, zeroed: bool, after_recurrence=None,
+                       duplicate_bias: bool = True) -> dict:
+        """BPTT through _text_forward (only c_n feeds the model, models/model.py:164-166).  `dqf` [B, dirs*H] is the gradient
+        w.r.t. the final cell states.  `after_recurrence()` is called once the serial part is enqueued (the data-parallel
+        wrapper starts its first all-reduces there).  Returns {state_dict key: gradient} of the text parameters."""
+        adt = self.compute_dtype
+        dt = lib.dtype_code(adt)
+        tc = adt == torch.bfloat16
+        dev = dqf.device
+        f32 = torch.float32
+        H, E, dirs = self.H, self.E, self.dirs
+        T, B, seed, p_text = tx["T"], tx["B"], tx["seed"], tx["p_text"]
+        grads = {}
+
+        def empty(*shape, dtype=adt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        def zeros(*shape, dtype=f32):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            call("vqa_zero", ptr(t), t.numel() * t.element_size(), st)
+            return t
+
+        lstm = self.text.lstm
+        sfx = ["", "_reverse"][:dirs]
+        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
+        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
+        gx, cs, hs, xs, ldx = tx["gx"], tx["cs"], tx["hs"], tx["xs"], tx["ldx"]
+        q, q_len = tx["q"], tx["q_len"]
+        dh = zeros(dirs, B, H)
+        dc = empty(dirs, B, H, dtype=f32)
+        dg = empty(dirs, T, B, 4 * H)
+        gsz = dg.element_size()
+        if tc and T > 1:
+            # bf16 shadow of W_hh as stored [dirs, 4H, H]: MN-major B operand of dh = dg W_hh
+            shs = [mm.wbf(w_hh[d])[0] for d in range(dirs)]          # Adam-maintained shadows when valid, else one cast each
+            base = getattr(self, "_whh_shadow", None)
+            if base is not None and all(shs[d].data_ptr() == base[d].data_ptr() for d in range(dirs)):
+                whhb = base
+            else:
+                whhb = empty(dirs, 4 * H, H)
+                for d in range(dirs):
+                    call("vqa_copy", ptr(whhb[d]), ptr(shs[d]), 4 * H * H * 2, st)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        persistent_bwd = (tc and T > 1 and H % 128 == 0 and ((B + 127) // 128) * (H // 128) * dirs <= sms
+                          and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
+        if persistent_bwd:
+            # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
+            # two point-to-point synchronisations per step) instead of 2T - 1 dependent launches
+            sync_b = torch.empty(256, dtype=torch.int32, device=dev)           # cleared by the entry itself
+            call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
+                 T, B, H, dirs, st, tag="lstm_bwd_persistent")
+        for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):
+            call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
+                 ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
+            if s > 0:   # dh_{s-1} = dgates_s W_hh
+                if tc:
+                    # split-K with vector reductions into dh, which the pointwise kernel above has just cleared:
+                    # M = B is small, so an unsplit GEMM leaves most SMs idle and each CTA ingests all of K
+                    call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhb), H,
+                         4 * H * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs,
+                         lib.GEMM_SPLITK | lib.GEMM_B_MN, 0.0, 0, 0, st, tag="lstm_step_bwd")
+                else:
+                    call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,
+                         ptr(w_hh[0]), lib.F32, 1, H, tx["whh_stride"], ptr(dh), lib.F32, H, B * H,
+                         None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
+        if after_recurrence is not None:
+            after_recurrence()
+        for d in range(dirs):
+            dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
+            mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(tx["h_prev"][d]), dt, H, dWhh,
+                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad", zeroed=zeroed)
+            dWih = galloc(f"text.lstm.weight_ih_l0{sfx[d]}", 4 * H, E)
+            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad", zeroed=zeroed)
+            db = colsum(dg[d], dt, 4 * H, T * B, 4 * H, f"text.lstm.bias_ih_l0{sfx[d]}")
+            grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
+            grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
+            grads[f"text.lstm.bias_ih_l0{sfx[d]}"] = db
+            if duplicate_bias:           # b_ih and b_hh always enter as a sum: identical gradients, separate storage
+                db2 = galloc(f"text.lstm.bias_hh_l0{sfx[d]}", 4 * H)
+                call("vqa_copy", ptr(db2), ptr(db), 4 * H * 4, st)
+            else:
+                db2 = db
+            grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db2
+        dxs = empty(dirs, T, B, ldx)
+        for d in range(dirs):
+            mm.lin_bwd_data(ptr(dg[d]), dt, 4 * H, w_ih[d], ptr(dxs[d]), dt, ldx, T * B, 4 * H, E, tag="lstm_inproj_dgrad")
+        demb = galloc("text.embedding.weight", *self.text.embedding.weight.shape, zero=True)
+        call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
+             p_text, seed, st, tag="embed_bwd")
+        grads["text.embedding.weight"] = demb
+        return grads
+
+    def encode_question(self, q, q_len):
+        """The question encoder alone -- reference `questionNet.forward(q, q_len)` (models/model.py:151-166), which is also
+        what `model.text(q, q_len)` computes: q int64 [B,T] zero padded, q_len [B] (tensor or list) -> [B, dirs*H] in the
+        compute dtype, differentiable w.r.t. the text parameters.  BASELINE.json configs[3] measures this stage."""
+        if not q.is_cuda:
+            raise lib.VqaLibraryError("encode_question: inputs must be CUDA tensors (no CPU fallback)")
+        dev = q.device
+        if isinstance(q_len, (list, tuple)):
+            q_len = torch.as_tensor([int(x) for x in q_len], dtype=torch.int64)
+        q_len = q_len.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        q = q.to(dtype=torch.int64).contiguous()
+        params = list(self.text.parameters())
+        if not self.training:
+            seed = 0
+        elif self._step_state is not None:
+            seed = lib.SEED_ON_DEVICE | self._step_state.data_ptr()
+        else:
+            seed = self._next_seed()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _TextFunction.apply(self, seed, q, q_len, *params)
+        st = lib.stream()
+        mm = _Math(self.compute_dtype == torch.bfloat16, dev, st, shadows=self._shadows if self.compute_dtype == torch.bfloat16 else None)
+        return self._text_forward(q, q_len, seed, mm, st, self._p(self.p_text))["qf"]
 
     # ------------------------------------------------------------------ backward
     def _run_backward(self, ctx, dlogits: torch.Tensor):
@@ -634,73 +775,10 @@ class VqaNet(nn.Module):
              p_att, seed, lib.SITE_ATT_Q, st)
 
         # ---- question encoder: BPTT (only c_n feeds the model, models/model.py:164-166)
-        lstm = self.text.lstm
+        tgrads = self._text_backward(ctx["text"], dqf, mm, st, galloc, colsum, zeroed, after_recurrence=flush_deferred,
+                                     duplicate_bias=(arena is not None or self.grad_ready_hook is not None))
+        grads.update(tgrads)
         sfx = ["", "_reverse"][:dirs]
-        w_ih = [getattr(lstm, f"weight_ih_l0{s}") for s in sfx]
-        w_hh = [getattr(lstm, f"weight_hh_l0{s}") for s in sfx]
-        gx, cs, hs, xs, ldx = ctx["gx"], ctx["cs"], ctx["hs"], ctx["xs"], ctx["ldx"]
-        q, q_len = ctx["q"], ctx["q_len"]
-        dh = zeros(dirs, B, H)
-        dc = empty(dirs, B, H, dtype=f32)
-        dg = empty(dirs, T, B, 4 * H)
-        gsz = dg.element_size()
-        if tc and T > 1:
-            # bf16 shadow of W_hh as stored [dirs, 4H, H]: MN-major B operand of dh = dg W_hh
-            shs = [mm.wbf(w_hh[d])[0] for d in range(dirs)]          # Adam-maintained shadows when valid, else one cast each
-            base = getattr(self, "_whh_shadow", None)
-            if base is not None and all(shs[d].data_ptr() == base[d].data_ptr() for d in range(dirs)):
-                whhb = base
-            else:
-                whhb = empty(dirs, 4 * H, H)
-                for d in range(dirs):
-                    call("vqa_copy", ptr(whhb[d]), ptr(shs[d]), 4 * H * H * 2, st)
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        persistent_bwd = (tc and T > 1 and H % 128 == 0 and ((B + 127) // 128) * (H // 128) * dirs <= sms
-                          and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
-        if persistent_bwd:
-            # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
-            # two grid barriers per step) instead of 2T - 1 dependent launches
-            sync_b = zeros(256, dtype=torch.int32)
-            call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
-                 T, B, H, dirs, st, tag="lstm_bwd_persistent")
-        for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):
-            call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
-                 ptr(dqf) if s == T - 1 else None, ptr(dg), ptr(q_len), dt, s, T, B, H, dirs, st, tag="lstm_bwd_pointwise")
-            if s > 0:   # dh_{s-1} = dgates_s W_hh
-                if tc:
-                    # split-K with vector reductions into dh, which the pointwise kernel above has just cleared:
-                    # M = B is small, so an unsplit GEMM leaves most SMs idle and each CTA ingests all of K
-                    call("vqa_tc_gemm", dg.data_ptr() + s * B * 4 * H * gsz, 4 * H, T * B * 4 * H, ptr(whhb), H,
-                         4 * H * H, ptr(dh), lib.F32, H, B * H, None, None, 0, B, H, 4 * H, dirs,
-                         lib.GEMM_SPLITK | lib.GEMM_B_MN, 0.0, 0, 0, st, tag="lstm_step_bwd")
-                else:
-                    call("vqa_gemm", dg.data_ptr() + s * B * 4 * H * gsz, dt, 4 * H, 1, T * B * 4 * H,
-                         ptr(w_hh[0]), lib.F32, 1, H, ctx["whh_stride"], ptr(dh), lib.F32, H, B * H,
-                         None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
-        flush_deferred()             # classifier + attention gradients: their all-reduce starts behind the recurrence
-        for d in range(dirs):
-            dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
-            mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(ctx["h_prev"][d]), dt, H, dWhh,
-                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad", zeroed=zeroed)
-            dWih = galloc(f"text.lstm.weight_ih_l0{sfx[d]}", 4 * H, E)
-            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad", zeroed=zeroed)
-            db = colsum(dg[d], dt, 4 * H, T * B, 4 * H, f"text.lstm.bias_ih_l0{sfx[d]}")
-            grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
-            grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih
-            grads[f"text.lstm.bias_ih_l0{sfx[d]}"] = db
-            if arena is not None:        # b_ih and b_hh always enter as a sum: identical gradients, separate storage
-                db2 = galloc(f"text.lstm.bias_hh_l0{sfx[d]}", 4 * H)
-                call("vqa_copy", ptr(db2), ptr(db), 4 * H * 4, st)
-            else:
-                db2 = db.clone() if self.grad_ready_hook is not None else db
-            grads[f"text.lstm.bias_hh_l0{sfx[d]}"] = db2
-        dxs = empty(dirs, T, B, ldx)
-        for d in range(dirs):
-            mm.lin_bwd_data(ptr(dg[d]), dt, 4 * H, w_ih[d], ptr(dxs[d]), dt, ldx, T * B, 4 * H, E, tag="lstm_inproj_dgrad")
-        demb = galloc("text.embedding.weight", *self.text.embedding.weight.shape, zero=True)
-        call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
-             p_text, seed, st)
-        grads["text.embedding.weight"] = demb
         names = ["text.embedding.weight"]
         for s_ in sfx:
             names += [f"text.lstm.weight_ih_l0{s_}", f"text.lstm.weight_hh_l0{s_}", f"text.lstm.bias_ih_l0{s_}",
@@ -827,3 +905,48 @@ class _VqaFunction(torch.autograd.Function):
         for n, need in zip(ctx.names, ctx.needs_input_grad[5:]):
             out.append(grads[n] if need else None)
         return (None, None, None, None, None, *out)
+
+
+class _TextFunction(torch.autograd.Function):
+    """Autograd node of VqaNet.encode_question (the question encoder alone)."""
+
+    @staticmethod
+    def forward(ctx, model: VqaNet, seed: int, q, q_len, *params):
+        st = lib.stream()
+        tc = model.compute_dtype == torch.bfloat16
+        mm = _Math(tc, q.device, st, shadows=model._shadows if tc else None)
+        tx = model._text_forward(q, q_len, seed, mm, st, model._p(model.p_text))
+        ctx.model, ctx.tx, ctx.wcache = model, tx, mm._w
+        ctx.names = ["text." + n for n, _ in model.text.named_parameters()]
+        ctx.params, ctx.param_versions = params, [p._version for p in params]
+        return tx["qf"]
+
+    @staticmethod
+    def backward(ctx, dqf):
+        model = ctx.model
+        if ctx.tx is None:
+            raise RuntimeError("encode_question: backward through the same forward a second time")
+        for n, p, ver in zip(ctx.names, ctx.params, ctx.param_versions):
+            if p._version != ver:
+                raise RuntimeError(f"VqaNet: parameter {n} was modified in place between forward and backward")
+        st = lib.stream()
+        dev = dqf.device
+        tc = model.compute_dtype == torch.bfloat16
+        mm = _Math(tc, dev, st, ctx.wcache, shadows=model._shadows if tc else None)
+
+        def galloc(name, *shape, zero=False):
+            t = torch.empty(shape, dtype=torch.float32, device=dev)
+            if zero:
+                call("vqa_zero", ptr(t), t.numel() * 4, st)
+            return t
+
+        def colsum(src, src_dt, ld, rows, cols, name):
+            out = galloc(name, cols, zero=True)
+            call("vqa_colsum", ptr(src), src_dt, ld, None, ptr(out), rows, cols, st)
+            return out
+
+        dqf = dqf.to(model.compute_dtype).contiguous()
+        grads = model._text_backward(ctx.tx, dqf, mm, st, galloc, colsum, False, duplicate_bias=False)
+        ctx.tx = None
+        ctx.params = None
+        return (None, None, None, None, *[grads[n] if need else None for n, need in zip(ctx.names, ctx.needs_input_grad[4:])])
