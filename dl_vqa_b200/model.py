@@ -346,7 +346,7 @@ class VqaNet(nn.Module):
             q_len = torch.as_tensor([int(x) for x in q_len], dtype=torch.int64)
         q_len = q_len.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         q = q.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-        v = v.to(torch.float32).contiguous()
+        v = self._image_input(v)
         params = self._params()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if not self.training:
@@ -359,6 +359,17 @@ class VqaNet(nn.Module):
             return _VqaFunction.apply(self, seed, v, q, q_len, *params)
         logits, _ = self._run_forward(v, q, q_len, seed, save=False)
         return logits
+
+    def _image_input(self, v: torch.Tensor) -> torch.Tensor:
+        """The network input as the first-layer kernels take it: contiguous NCHW, float32 (the reference's dtype) or -- where
+        the tcgen05 first-layer kernels run -- float16 read natively (the dtype the reference stores its pre-processed
+        images in, preprocessing/preprocess_images.py:40; widening fp16 -> fp32 is exact, so results are bit-identical)."""
+        if v.dtype == torch.float16 and self._conv0_reads_fp16():
+            return v.contiguous()
+        return v.to(torch.float32).contiguous()
+
+    def _conv0_reads_fp16(self) -> bool:
+        return False
 
     # dropout probabilities in effect
     def _p(self, p: float) -> float:
@@ -646,8 +657,10 @@ class VqaNet(nn.Module):
         return self._text_forward(q, q_len, seed, mm, st, self._p(self.p_text))["qf"]
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, ctx, dlogits: torch.Tensor):
-        """Returns {state_dict key: gradient}.  Order: classifier, attention, text, image."""
+    def _run_backward(self, ctx, dlogits: torch.Tensor, before_image=None):
+        """Returns {state_dict key: gradient}.  Order: classifier, attention, text, image.  `before_image()` is called when
+        the classifier / attention / text gradients (98 % of the bytes) are complete and only the convolution backward
+        remains (GraphedTrainStep splits its CUDA graph there and starts the all-reduce of those buckets)."""
         B, P, T, seed = ctx["B"], ctx["P"], ctx["T"], ctx["seed"]
         p_text, p_img, p_att, p_cls = ctx["p"]
         dt, adt = ctx["dt"], ctx["adt"]
@@ -784,6 +797,8 @@ class VqaNet(nn.Module):
             names += [f"text.lstm.weight_ih_l0{s_}", f"text.lstm.weight_hh_l0{s_}", f"text.lstm.bias_ih_l0{s_}",
                       f"text.lstm.bias_hh_l0{s_}"]
         fire(names)
+        if before_image is not None:
+            before_image()
 
         # ---- image encoder
         nl = len(self.channels) - 1
