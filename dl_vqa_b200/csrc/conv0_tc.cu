@@ -28,7 +28,7 @@ constexpr int C0_TILE_BYTES = 128 * 128;           // 128 windows x 128 B
 constexpr int C0_WH = 8, C0_WW = 16;               // windows per tile
 
 struct Conv0Params {
-    const float* x;                    // [B,3,IH,IW] NCHW fp32
+    const void* x;                     // [B,3,IH,IW] NCHW, fp32 or fp16 (template parameter XHALF)
     int B, IH, IW, PH, PW, tiles_h, tiles_w;
     // forward
     const float* w; const float* bias; bf16* pooled; uint8_t* mask;
@@ -57,9 +57,29 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 // The 4x4x3 input patch of window (ph,pw) of image b, straight from global memory (coordinates clamped so that
 // out-of-range tile windows read valid memory; their results are discarded / multiplied by zero).
+template <bool XHALF>
 __device__ __forceinline__ void load_patch_global(const Conv0Params& p, int b, int ph, int pw, float (&v)[3][4][4]) {
     const int phc = min(ph, p.PH - 1), pwc = min(pw, p.PW - 1);
-    const float* src = p.x + ((int64_t)b * 3 * p.IH + 2 * phc) * p.IW + 2 * pwc;
+    if (XHALF) {                                      // float16 images (the reference's stored dtype), widened exactly
+        const __half* src = reinterpret_cast<const __half*>(p.x) + ((int64_t)b * 3 * p.IH + 2 * phc) * p.IW + 2 * pwc;
+        const bool al4 = (p.IW & 1) == 0;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const __half* q = src + ((int64_t)ci * p.IH + r) * p.IW;
+                if (al4) {
+                    const float2 a = __half22float2(__ldg(reinterpret_cast<const __half2*>(q)));
+                    const float2 c = __half22float2(__ldg(reinterpret_cast<const __half2*>(q) + 1));
+                    v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[ci][r][c] = __half2float(__ldg(q + c));
+                }
+            }
+        return;
+    }
+    const float* src = reinterpret_cast<const float*>(p.x) + ((int64_t)b * 3 * p.IH + 2 * phc) * p.IW + 2 * pwc;
     const bool al8 = (p.IW & 1) == 0;                 // even row pitch: every (row, 2*pw) address is 8-byte aligned
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
@@ -79,7 +99,22 @@ __device__ __forceinline__ void load_patch_global(const Conv0Params& p, int b, i
 constexpr int C0_XROWS = 2 * C0_WH + 2, C0_XCOLS = 2 * C0_WW + 4;      // 18 x 36 (34 used; 36 keeps rows 16-byte multiples)
 constexpr int C0_XBYTES = 3 * C0_XROWS * C0_XCOLS * 4;                 // 7776
 constexpr int C0_XSTAGE = 8192;
+constexpr int C0_XCOLS_H = 40;                                          // fp16 regions: 40 columns = 80-byte rows (TMA boxes need 16-byte multiples)
+constexpr int C0_XBYTES_H = 3 * C0_XROWS * C0_XCOLS_H * 2;              // 4320
+template <bool XHALF>
 __device__ __forceinline__ void load_patch_staged(const uint8_t* xs, int wr, int wc, float (&v)[3][4][4]) {
+    if (XHALF) {
+        const __half* base = reinterpret_cast<const __half*>(xs) + (2 * wr) * C0_XCOLS_H + 2 * wc;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const __half2* q = reinterpret_cast<const __half2*>(base + (ci * C0_XROWS + r) * C0_XCOLS_H);
+                const float2 a = __half22float2(q[0]), c = __half22float2(q[1]);
+                v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+            }
+        return;
+    }
     const float* base = reinterpret_cast<const float*>(xs) + (2 * wr) * C0_XCOLS + 2 * wc;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
@@ -126,7 +161,7 @@ constexpr int C0F_XSTAGES = 6;
 constexpr int C0F_STAGES = 4;                      // two per builder group
 constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 
-template <bool STAGED>
+template <bool STAGED, bool XHALF>
 __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -185,7 +220,7 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
                 const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
                 const int q = it % C0F_XSTAGES;
                 mbar_wait(&x_empty[q], ((it / C0F_XSTAGES) & 1) ^ 1);
-                mbar_expect_tx(&x_full[q], C0_XBYTES);
+                mbar_expect_tx(&x_full[q], XHALF ? C0_XBYTES_H : C0_XBYTES);
                 tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * pw0, 2 * ph0, 0, b);
             }
         }
@@ -202,10 +237,10 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
             if (STAGED) {
                 const int q = it % C0F_XSTAGES;
                 mbar_wait(&x_full[q], (it / C0F_XSTAGES) & 1);
-                load_patch_staged(xs + q * C0_XSTAGE, wr, wc, v);
+                load_patch_staged<XHALF>(xs + q * C0_XSTAGE, wr, wc, v);
                 mbar_arrive(&x_empty[q]);                      // the values are in registers: the region can be refilled
             } else {
-                load_patch_global(p, b, ph0 + wr, pw0 + wc, v);
+                load_patch_global<XHALF>(p, b, ph0 + wr, pw0 + wc, v);
             }
             mbar_wait(&a_empty[s], ((it / C0F_STAGES) & 1) ^ 1);
             store_patch_rows(sa + s * C0F_STAGE_BYTES, t, v);
@@ -342,7 +377,7 @@ constexpr int C0B_THREADS = 14 * 32;
 constexpr int C0B_STAGE_BYTES = 6 * C0_TILE_BYTES;            // 4 masked-gradient tiles (A) + 2 patch tiles (B)
 constexpr int C0B_XSTAGES = 3;
 
-template <bool STAGED>
+template <bool STAGED, bool XHALF>
 __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -384,7 +419,7 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
                 const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
                 const int q = i % C0B_XSTAGES;
                 mbar_wait(&x_empty[q], ((i / C0B_XSTAGES) & 1) ^ 1);
-                mbar_expect_tx(&x_full[q], C0_XBYTES);
+                mbar_expect_tx(&x_full[q], XHALF ? C0_XBYTES_H : C0_XBYTES);
                 tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * (r % p.tiles_w) * C0_WW, 2 * (r / p.tiles_w) * C0_WH, 0, b);
             }
         }
@@ -441,10 +476,10 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
             if (STAGED) {
                 const int q = i % C0B_XSTAGES;
                 mbar_wait(&x_full[q], (i / C0B_XSTAGES) & 1);
-                load_patch_staged(xs + q * C0_XSTAGE, wr, wc, v);
+                load_patch_staged<XHALF>(xs + q * C0_XSTAGE, wr, wc, v);
                 mbar_arrive(&x_empty[q]);
             } else {
-                load_patch_global(p, b, ph, pw, v);
+                load_patch_global<XHALF>(p, b, ph, pw, v);
             }
             store_patch_rows(stage + 4 * C0_TILE_BYTES, t, v);
             fence_proxy_async();
@@ -499,11 +534,34 @@ static int sm_count() {
     return sms;
 }
 
-// x [B,3,IH,IW] fp32 NCHW; w [64,3,3,3] fp32; out/mask [B,PH,PW,64] (bf16 / uint8)
-extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias, void* out, uint8_t* mask,
-                                          int B, int IH, int IW, int Cin, int Cout, void* stream) {
+// Tensor map of the NCHW network input for the staged (TMA) path; false when the layout does not allow it
+static bool conv0_input_map(CUtensorMap* tx, const void* x, bool half, int B, int IH, int IW, int* err) {
+    const int esz = half ? 2 : 4;
+    *err = 0;
+    if ((IW * esz) % 16 != 0 || ((uintptr_t)x & 15) != 0) return false;      // TMA needs 16-byte aligned rows
+    const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)IW * esz, (uint64_t)IH * IW * esz, (uint64_t)3 * IH * IW * esz};
+    const uint32_t box[4] = {(uint32_t)(half ? C0_XCOLS_H : C0_XCOLS), C0_XROWS, 3, 1};
+    *err = make_tmap(tx, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     x, 4, dims, str, box);
+    return *err == 0;
+}
+
+template <void (*Kern)(const CUtensorMap, Conv0Params)>
+static int conv0_launch(int grid, int threads, int smem, cudaStream_t st, const CUtensorMap& tx, const Conv0Params& p) {
+    static bool attr_set = false;               // one flag per kernel instantiation
+    if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    VQA_CUDA(vqa_launch_pdl(Kern, dim3(grid), dim3(threads), smem, st, tx, p));
+    return 0;
+}
+
+// x [B,3,IH,IW] NCHW, x_dtype VQA_F32 or VQA_F16; w [64,3,3,3] fp32; out/mask [B,PH,PW,64] (bf16 / uint8)
+extern "C" int vqa_tc_conv0_relu_pool_fwd_x(const void* x, int x_dtype, const float* w, const float* bias, void* out, uint8_t* mask,
+                                            int B, int IH, int IW, int Cin, int Cout, void* stream) {
     VQA_REQUIRE(Cin == 3 && Cout == 64, "tc conv0 fwd: only Cin=3, Cout=64 (got %d, %d); use vqa_conv_relu_pool_fwd", Cin, Cout);
     VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4, "tc conv0 fwd: bad dims");
+    VQA_REQUIRE(x_dtype == VQA_F32 || x_dtype == VQA_F16, "tc conv0 fwd: input dtype %d (fp32 or fp16)", x_dtype);
+    const bool half = x_dtype == VQA_F16;
     Conv0Params p{};
     p.x = x; p.B = B; p.IH = IH; p.IW = IW;
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
@@ -513,31 +571,34 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const 
     const int ntiles = B * p.tiles_h * p.tiles_w;
     const int sms = sm_count();
     const int grid = ntiles < sms ? ntiles : sms;
-    const bool staged = (IW % 4) == 0 && ((uintptr_t)x & 15) == 0;     // TMA needs 16-byte aligned rows
     CUtensorMap tx{};
-    if (staged) {
-        const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
-        const uint64_t str[3] = {(uint64_t)IW * 4, (uint64_t)IH * IW * 4, (uint64_t)3 * IH * IW * 4};
-        const uint32_t box[4] = {C0_XCOLS, C0_XROWS, 3, 1};
-        if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
-        static bool attr_set = false;
-        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        VQA_CUDA(vqa_launch_pdl(conv0_fwd_tc_kernel<true>, dim3(grid), dim3(C0F_THREADS), smem, (cudaStream_t)stream, tx, p));
-    } else {
-        static bool attr_set = false;
-        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        VQA_CUDA(vqa_launch_pdl(conv0_fwd_tc_kernel<false>, dim3(grid), dim3(C0F_THREADS), smem, (cudaStream_t)stream, tx, p));
-    }
+    int err = 0;
+    const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err);
+    if (err) return err;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (staged) rc = half ? conv0_launch<conv0_fwd_tc_kernel<true, true>>(grid, C0F_THREADS, smem, st, tx, p)
+                          : conv0_launch<conv0_fwd_tc_kernel<true, false>>(grid, C0F_THREADS, smem, st, tx, p);
+    else rc = half ? conv0_launch<conv0_fwd_tc_kernel<false, true>>(grid, C0F_THREADS, smem, st, tx, p)
+                   : conv0_launch<conv0_fwd_tc_kernel<false, false>>(grid, C0F_THREADS, smem, st, tx, p);
+    if (rc) return rc;
     VQA_CHECK_LAUNCH("conv0_fwd_tc");
     return 0;
 }
 
-// x [B,3,IH,IW] fp32 NCHW; dpool [B,PH,PW,64] bf16 = gradient w.r.t. the pooled output; mask [B,PH,PW,64] from the
+extern "C" int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias, void* out, uint8_t* mask,
+                                          int B, int IH, int IW, int Cin, int Cout, void* stream) {
+    return vqa_tc_conv0_relu_pool_fwd_x(x, VQA_F32, w, bias, out, mask, B, IH, IW, Cin, Cout, stream);
+}
+
+// x [B,3,IH,IW] NCHW (fp32 / fp16); dpool [B,PH,PW,64] bf16 = gradient w.r.t. the pooled output; mask [B,PH,PW,64] from the
 // forward; dw [64,3,3,3] and db [64] fp32 (both overwritten)
-extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_t* mask, float* dw, float* db,
-                                            int B, int IH, int IW, int Cin, int Cout, void* stream) {
+extern "C" int vqa_tc_conv0_bwd_weight_bias_x(const void* x, int x_dtype, const void* dpool, const uint8_t* mask, float* dw, float* db,
+                                              int B, int IH, int IW, int Cin, int Cout, void* stream) {
     VQA_REQUIRE(Cin == 3 && Cout == 64, "tc conv0 backward: only Cin=3, Cout=64 (got %d, %d)", Cin, Cout);
     VQA_REQUIRE(B > 0 && IH >= 4 && IW >= 4, "tc conv0 backward: bad dims");
+    VQA_REQUIRE(x_dtype == VQA_F32 || x_dtype == VQA_F16, "tc conv0 backward: input dtype %d (fp32 or fp16)", x_dtype);
+    const bool half = x_dtype == VQA_F16;
     cudaStream_t st = (cudaStream_t)stream;
     VQA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 64 * C0_K, st));
     VQA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 64, st));
@@ -552,21 +613,21 @@ extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, c
     p.tiles_per_cta = (total + ctas - 1) / ctas;
     ctas = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
     const int smem = 2 * C0B_STAGE_BYTES + C0B_XSTAGES * C0_XSTAGE + 1024 + 256;
-    const bool staged = (IW % 4) == 0 && ((uintptr_t)x & 15) == 0;     // TMA needs 16-byte aligned rows
     CUtensorMap tx{};
-    if (staged) {
-        const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
-        const uint64_t str[3] = {(uint64_t)IW * 4, (uint64_t)IH * IW * 4, (uint64_t)3 * IH * IW * 4};
-        const uint32_t box[4] = {C0_XCOLS, C0_XROWS, 3, 1};
-        if (int e = make_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, x, 4, dims, str, box)) return e;
-        static bool attr_set = false;
-        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        VQA_CUDA(vqa_launch_pdl(conv0_bwd_tc_kernel<true>, dim3(ctas), dim3(C0B_THREADS), smem, st, tx, p));
-    } else {
-        static bool attr_set = false;
-        if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(conv0_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-        VQA_CUDA(vqa_launch_pdl(conv0_bwd_tc_kernel<false>, dim3(ctas), dim3(C0B_THREADS), smem, st, tx, p));
-    }
+    int err = 0;
+    const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err);
+    if (err) return err;
+    int rc;
+    if (staged) rc = half ? conv0_launch<conv0_bwd_tc_kernel<true, true>>(ctas, C0B_THREADS, smem, st, tx, p)
+                          : conv0_launch<conv0_bwd_tc_kernel<true, false>>(ctas, C0B_THREADS, smem, st, tx, p);
+    else rc = half ? conv0_launch<conv0_bwd_tc_kernel<false, true>>(ctas, C0B_THREADS, smem, st, tx, p)
+                   : conv0_launch<conv0_bwd_tc_kernel<false, false>>(ctas, C0B_THREADS, smem, st, tx, p);
+    if (rc) return rc;
     VQA_CHECK_LAUNCH("conv0_bwd_tc");
     return 0;
+}
+
+extern "C" int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_t* mask, float* dw, float* db,
+                                            int B, int IH, int IW, int Cin, int Cout, void* stream) {
+    return vqa_tc_conv0_bwd_weight_bias_x(x, VQA_F32, dpool, mask, dw, db, B, IH, IW, Cin, Cout, stream);
 }

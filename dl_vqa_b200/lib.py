@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2          # F16: network input only
 ATT_ADD, ATT_MUL, ATT_CAT = 0, 1, 2
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN, GEMM_B_MN = 1, 2, 4, 8, 16
 SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CLS_HID = range(7)

@@ -369,7 +369,8 @@ class VqaNet(nn.Module):
         return v.to(torch.float32).contiguous()
 
     def _conv0_reads_fp16(self) -> bool:
-        return False
+        ch = self.channels
+        return (self.compute_dtype == torch.bfloat16 and ch[0] == 3 and ch[1] == 64 and self.KS == 3 and self.stride == 1)
 
     # dropout probabilities in effect
     def _p(self, p: float) -> float:
@@ -398,7 +399,7 @@ class VqaNet(nn.Module):
 
         # ---------------- image encoder: fused conv+ReLU+pool per layer (models/model.py:72-84)
         assert v.shape[1] == self.channels[0], "image channel count"
-        x, x_dt, nchw = v, lib.F32, 1
+        x, x_dt, nchw = v, (lib.F16 if v.dtype == torch.float16 else lib.F32), 1
         IH, IW = int(v.shape[2]), int(v.shape[3])
         conv_saved = []
         conv_wd = {}                 # layer -> weights packed for the data gradient (training forward only)
@@ -413,7 +414,7 @@ class VqaNet(nn.Module):
             out = empty(B, PH, PW, Cout)
             mask = empty(B, PH, PW, Cout, dtype=torch.uint8)
             if tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1:
-                call("vqa_tc_conv0_relu_pool_fwd", ptr(x), ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
+                call("vqa_tc_conv0_relu_pool_fwd_x", ptr(x), x_dt, ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
                      B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
             elif self._tc_conv_ok(i) and nchw == 0:
                 wp = empty(Cout, 9 * Cin)
@@ -839,7 +840,7 @@ class VqaNet(nn.Module):
                 db = galloc(f"image.conv{i}.bias", Cout)
             tc0 = tc and nchw == 1 and Cin == 3 and Cout == 64 and self.KS == 3 and self.stride == 1
             if tc0:     # fused un-pool + weight gradient + bias gradient straight from (dpool, mask): no dY tensor
-                call("vqa_tc_conv0_bwd_weight_bias", ptr(x), ptr(da), ptr(mask), ptr(dW), ptr(db), B, IH, IW, Cin, Cout, st,
+                call("vqa_tc_conv0_bwd_weight_bias_x", ptr(x), x_dt, ptr(da), ptr(mask), ptr(dW), ptr(db), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
             elif use_tc and dy is None:   # un-pooled gradient, shared by the weight and the data gradient
                 dy = empty(B, 2 * PH, 2 * PW, Cout)

@@ -34,6 +34,7 @@ extern "C" {
 #define VQA_ABI_VERSION 1
 #define VQA_F32 0
 #define VQA_BF16 1
+#define VQA_F16 2    /* network INPUT only: the reference stores its pre-processed images as float16 (preprocessing/preprocess_images.py:40) */
 #define VQA_ERR_INVALID_ARGUMENT (-1)
 #define VQA_ERR_UNSUPPORTED (-2)
 #define VQA_SEED_ON_DEVICE (1ull << 63)
@@ -304,6 +305,14 @@ int vqa_tc_conv0_relu_pool_fwd(const float* x, const float* w, const float* bias
                                int B, int IH, int IW, int Cin, int Cout, void* stream);
 int vqa_tc_conv0_bwd_weight_bias(const float* x, const void* dpool, const uint8_t* mask, float* dw, float* db,
                                  int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* the same two entries with the input dtype explicit: x_dtype VQA_F32 or VQA_F16.  Float16 is what the reference's
+ * preprocessing stores (preprocessing/preprocess_images.py:40) and its Dataset widens on the host
+ * (preprocessing/data_preprocessing.py:174); reading it here directly halves the host->device copy and the input reads
+ * of both kernels and needs no cast kernel.  Widening fp16 -> fp32 is exact, so results are bit-identical. */
+int vqa_tc_conv0_relu_pool_fwd_x(const void* x, int x_dtype, const float* w, const float* bias, void* out, uint8_t* mask,
+                                 int B, int IH, int IW, int Cin, int Cout, void* stream);
+int vqa_tc_conv0_bwd_weight_bias_x(const void* x, int x_dtype, const void* dpool, const uint8_t* mask, float* dw, float* db,
+                                   int B, int IH, int IW, int Cin, int Cout, void* stream);
 /* Persistent LSTM recurrence, all steps and directions in one cooperative launch (replaces the cuDNN RNN of
  * models/model.py:164).  W_hh stays resident in shared memory (64 gate rows per CTA), h is exchanged through L2.
  *   gx [dirs][T][B][4H] bf16 (in: x W_ih^T + b_ih + b_hh, out: activated gates), cs [dirs][T][B][H] fp32,

@@ -526,3 +526,36 @@ def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs):
         # inactive steps: exactly zero on both sides
         inactive = (torch.arange(T)[None, :] >= q_len[:, None])
         assert float(leaves[d].grad[inactive].abs().max() if inactive.any() else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("B,IH,IW", [(3, 224, 224), (2, 64, 64), (2, 39, 45), (1, 20, 36), (2, 38, 38)])
+def test_tc_conv0_reads_float16_images_bit_identically(B, IH, IW):
+    """vqa_tc_conv0_*_x with x_dtype = VQA_F16 (the dtype the reference stores its images in) against the same entries fed
+    with the exact float32 widening: forward outputs, masks and the weight / bias gradients must be IDENTICAL bit for
+    bit -- staged (TMA, row pitch a multiple of 16 bytes) and direct-load paths, odd widths included."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(IH + IW)
+    Cin, Cout = 3, 64
+    x16 = torch.randn(B, Cin, IH, IW, device="cuda").half()
+    x32 = x16.float()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / 5
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    dpool = torch.randn(B, PH, PW, Cout, device="cuda").bfloat16()
+    res = []
+    for x, code in ((x32, lib.F32), (x16, lib.F16)):
+        out = torch.empty(B, PH, PW, Cout, dtype=torch.bfloat16, device="cuda")
+        mask = torch.empty(B, PH, PW, Cout, dtype=torch.uint8, device="cuda")
+        lib.call("vqa_tc_conv0_relu_pool_fwd_x", lib.ptr(x), code, lib.ptr(w), lib.ptr(bias), lib.ptr(out), lib.ptr(mask),
+                 B, IH, IW, Cin, Cout, lib.stream())
+        dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+        db = torch.empty(Cout, device="cuda")
+        lib.call("vqa_tc_conv0_bwd_weight_bias_x", lib.ptr(x), code, lib.ptr(dpool), lib.ptr(mask), lib.ptr(dw), lib.ptr(db),
+                 B, IH, IW, Cin, Cout, lib.stream())
+        torch.cuda.synchronize()
+        res.append((out, mask, dw, db))
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # fp32 atomics across CTAs: the order of the partial sums is not fixed, so compare to rounding of the sum
+    assert float((a[2] - b[2]).abs().max()) <= 1e-5 * float(a[2].abs().max())
+    assert float((a[3] - b[3]).abs().max()) <= 1e-5 * float(a[3].abs().max())
