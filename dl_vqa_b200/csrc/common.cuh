@@ -185,7 +185,10 @@ template <bool DH_L2>
 __device__ __forceinline__ void lstm_bwd_pointwise_item8(int64_t i8, const bf16* __restrict__ gates, const float* __restrict__ cs,
                                                          float* dh, float* __restrict__ dc,
                                                          const bf16* __restrict__ dc_init, bf16* __restrict__ dg,
-                                                         const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs) {
+                                                         const int64_t* __restrict__ q_len, int s, int T_, int B, int H, int dirs,
+                                                         const int* __restrict__ order = nullptr) {
+    // `order` (length-sorted batches, vqa_length_order): row b of every LSTM tensor is sample order[b]; only dc_init
+    // [B][dirs*H] is in the caller's sample order
     const int h8 = H >> 3;
     const int j = (int)(i8 % h8) * 8;
     const int b = (int)((i8 / h8) % B);
@@ -198,7 +201,7 @@ __device__ __forceinline__ void lstm_bwd_pointwise_item8(int64_t i8, const bf16*
     const int len = clamp_len(q_len[b], T_);
     const bf16* g = gates + row * 4 * H + j;
     float dc_in[8], gi[8], gf[8], gg[8], go[8], c[8], cp[8], dhv[8];
-    ld8(dc_init ? dc_init + (int64_t)b * dirs * H + (int64_t)dir * H + j : nullptr, dc + i, dc_in);
+    ld8(dc_init ? dc_init + (int64_t)(order ? order[b] : b) * dirs * H + (int64_t)dir * H + j : nullptr, dc + i, dc_in);
     ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go);
     ld8(cs + row * H + j, c);
     ld8(cs + (s > 0 ? row - B : row) * H + j, cp);

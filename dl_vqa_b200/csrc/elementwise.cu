@@ -277,14 +277,17 @@ extern "C" int vqa_dropnorm_bwd_unpool(const void* dvn, const void* dvnd, const 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int step_token_pos(int dir, int s, int len) { return dir == 0 ? s : len - 1 - s; }
 
+// `order` (optional, vqa_length_order): row b of the step-indexed output holds sample order[b]; the dropout mask stays a
+// function of the SAMPLE index, so ordering the batch does not change which elements are dropped
 template <typename T>
 __global__ void embed_tanh_fwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
+                                      const int* __restrict__ order,
                                       const float* __restrict__ emb, T* __restrict__ xs,
                                       int B, int T_, int E, int ldx, int dirs, Dropout d) {
     pdl_trigger();
     pdl_wait();
     const int64_t row = blockIdx.x;                 // (dir, s, b)
-    const int b = (int)(row % B);
+    const int b = order ? order[(int)(row % B)] : (int)(row % B);
     const int s = (int)((row / B) % T_);
     const int dir = (int)(row / ((int64_t)B * T_));
     const int len = clamp_len(q_len[b], T_);
@@ -304,12 +307,13 @@ __global__ void embed_tanh_fwd_kernel(const int64_t* __restrict__ q, const int64
 
 template <typename T>
 __global__ void embed_tanh_bwd_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ q_len,
+                                      const int* __restrict__ order,
                                       const T* __restrict__ xs, const T* __restrict__ dxs, float* __restrict__ demb,
                                       int B, int T_, int E, int ldx, int dirs, Dropout d) {
     pdl_trigger();
     pdl_wait();
     const int64_t row = blockIdx.x;
-    const int b = (int)(row % B);
+    const int b = order ? order[(int)(row % B)] : (int)(row % B);
     const int s = (int)((row / B) % T_);
     const int dir = (int)(row / ((int64_t)B * T_));
     const int len = clamp_len(q_len[b], T_);
@@ -325,32 +329,78 @@ __global__ void embed_tanh_bwd_kernel(const int64_t* __restrict__ q, const int64
     }
 }
 
-extern "C" int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb, void* xs, int act_dtype,
-                                  int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream) {
+extern "C" int vqa_embed_tanh_fwd_ordered(const int64_t* q, const int64_t* q_len, const int* order, const float* emb, void* xs,
+                                          int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream) {
     VQA_REQUIRE(B > 0 && T > 0 && E > 0 && ldx >= E && (dirs == 1 || dirs == 2), "embed_fwd: bad dims");
     const Dropout d = make_dropout(seed, p);
     const unsigned grid = (unsigned)((int64_t)dirs * T * B);
     if (act_dtype == VQA_F32)
-        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, emb, (float*)xs, B, T, E, ldx, dirs, d));
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, order, emb, (float*)xs, B, T, E, ldx, dirs, d));
     else if (act_dtype == VQA_BF16)
-        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, emb, (bf16*)xs, B, T, E, ldx, dirs, d));
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_fwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, order, emb, (bf16*)xs, B, T, E, ldx, dirs, d));
     else VQA_REQUIRE(false, "embed_fwd: bad dtype");
     VQA_CHECK_LAUNCH("embed_tanh_fwd");
+    return 0;
+}
+
+extern "C" int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb, void* xs, int act_dtype,
+                                  int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream) {
+    return vqa_embed_tanh_fwd_ordered(q, q_len, nullptr, emb, xs, act_dtype, B, T, E, ldx, dirs, p, seed, stream);
+}
+
+extern "C" int vqa_embed_tanh_bwd_ordered(const int64_t* q, const int64_t* q_len, const int* order, const void* xs, const void* dxs,
+                                          float* demb, int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed,
+                                          void* stream) {
+    VQA_REQUIRE(B > 0 && T > 0 && E > 0 && ldx >= E && (dirs == 1 || dirs == 2), "embed_bwd: bad dims");
+    const Dropout d = make_dropout(seed, p);
+    const unsigned grid = (unsigned)((int64_t)dirs * T * B);
+    if (act_dtype == VQA_F32)
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, order, (const float*)xs, (const float*)dxs, demb, B, T, E, ldx, dirs, d));
+    else if (act_dtype == VQA_BF16)
+        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, order, (const bf16*)xs, (const bf16*)dxs, demb, B, T, E, ldx, dirs, d));
+    else VQA_REQUIRE(false, "embed_bwd: bad dtype");
+    VQA_CHECK_LAUNCH("embed_tanh_bwd");
     return 0;
 }
 
 extern "C" int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, const void* dxs, float* demb,
                                   int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed,
                                   void* stream) {
-    VQA_REQUIRE(B > 0 && T > 0 && E > 0 && ldx >= E && (dirs == 1 || dirs == 2), "embed_bwd: bad dims");
-    const Dropout d = make_dropout(seed, p);
-    const unsigned grid = (unsigned)((int64_t)dirs * T * B);
-    if (act_dtype == VQA_F32)
-        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<float>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, (const float*)xs, (const float*)dxs, demb, B, T, E, ldx, dirs, d));
-    else if (act_dtype == VQA_BF16)
-        VQA_CUDA(vqa_launch_pdl(embed_tanh_bwd_kernel<bf16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, q, q_len, (const bf16*)xs, (const bf16*)dxs, demb, B, T, E, ldx, dirs, d));
-    else VQA_REQUIRE(false, "embed_bwd: bad dtype");
-    VQA_CHECK_LAUNCH("embed_tanh_bwd");
+    return vqa_embed_tanh_bwd_ordered(q, q_len, nullptr, xs, dxs, demb, act_dtype, B, T, E, ldx, dirs, p, seed, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Length order of a batch of questions (what pack_padded_sequence(enforce_sorted=False) computes on the host in the
+// reference, models/model.py:160): order[j] = sample at position j when the batch is sorted by DESCENDING length, ties
+// in sample order (stable, deterministic); len_sorted[j] = clamp(q_len[order[j]], 0, T).  With the batch in this order
+// the rows that are still active at step s are a prefix, so the persistent LSTM kernels drop whole 128-row tiles from
+// the late steps (mean question length is about half of T).  One CTA; rank by counting (B <= 8192).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) length_order_kernel(const int64_t* __restrict__ q_len, int* __restrict__ order,
+                                                            int64_t* __restrict__ len_sorted, int B, int T_) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ int lens[];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) lens[b] = clamp_len(q_len[b], T_);
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int mine = lens[b];
+        int rank = 0;
+        for (int o = 0; o < B; ++o) {
+            const int l = lens[o];                 // broadcast read
+            rank += (l > mine) || (l == mine && o < b);
+        }
+        order[rank] = b;
+        len_sorted[rank] = mine;
+    }
+}
+
+extern "C" int vqa_length_order(const int64_t* q_len, int* order, int64_t* len_sorted, int B, int T, void* stream) {
+    VQA_REQUIRE(q_len && order && len_sorted && B > 0 && T > 0, "length_order: bad arguments");
+    VQA_REQUIRE(B <= 8192, "length_order: batch %d too large (<= 8192)", B);
+    const int threads = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
+    VQA_CUDA(vqa_launch_pdl(length_order_kernel, dim3(1), dim3(threads), (size_t)B * sizeof(int), (cudaStream_t)stream, q_len, order, len_sorted, B, T));
+    VQA_CHECK_LAUNCH("length_order");
     return 0;
 }
 

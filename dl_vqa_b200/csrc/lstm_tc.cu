@@ -28,7 +28,8 @@ struct LstmParams {
     float* cs;           // [dirs][T][B][H]
     bf16* hs;            // [dirs][T+1][B][H]  slot 0 = zeros, slot s+1 = h after step s
     bf16* qf;            // [B][dirs*H]
-    const int64_t* len;  // [B]
+    const int64_t* len;  // [B]  (row order of the tensors: the length-sorted lengths when `order` is given)
+    const int* order;    // optional [B]: row b of gx/cs/hs is sample order[b] (vqa_length_order); qf is written in sample order
     unsigned int* sync;  // [dirs] zero-initialised counters
     int T, B, H, dirs, ctas_per_dir, mtiles;
     int Bp, b0;          // batch pitch of the tensors and first sequence of this launch (B = sequences in this launch, <= 256)
@@ -53,10 +54,21 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
     uint64_t* w_full = empty + LSTM_STAGES;
     uint64_t* tmem_full = w_full + 1;                          // [2] one per m-tile
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 2);
+    int* tile_len = reinterpret_cast<int*>(tmem_base_smem + 2);    // [2] longest sequence of each 128-row tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.x / p.ctas_per_dir, j = blockIdx.x - dir * p.ctas_per_dir;
     const int T = p.T, B = p.B, H = p.H;
+
+    // A 128-row tile takes part in step s only while one of its sequences is still running (s < its longest length):
+    // with the batch in descending length order (vqa_length_order) the short half of the batch leaves the recurrent
+    // GEMM, the h ingest and the step barrier early.  Correct for any row order (unsorted: every tile runs to ~T).
+    if (threadIdx.x < 2) tile_len[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 256 && (int)threadIdx.x < B) {
+        const int64_t l = p.len[p.b0 + threadIdx.x];
+        atomicMax(&tile_len[threadIdx.x >> 7], l < 0 ? 0 : (l > T ? T : (int)l));
+    }
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_h); tma_prefetch_desc(&tma_w);
@@ -73,6 +85,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
     constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
     constexpr int SLICE_ROWS = 128 / CS;
     const uint32_t tmem_base = *tmem_base_smem;
+    const int tlen0 = tile_len[0], tlen1 = p.mtiles > 1 ? tile_len[1] : 0;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -81,17 +94,21 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
             for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(sw + kb * 8192, &tma_w, w_full, kb * 64, j * 64, dir);
             uint32_t it = 0;
             const unsigned int* cnt = p.sync + dir;
-            const unsigned int per_step = (unsigned int)p.ctas_per_dir * 4u * (unsigned int)p.mtiles;   // arriving warps
+            const unsigned int per_tile = (unsigned int)p.ctas_per_dir * 4u;       // arriving warps per active tile and step
+            unsigned int target = 0;                                               // arrivals of all previous steps
             for (int s = 0; s < T; ++s) {
+                const int nact = (s < tlen0) + (s < tlen1);
+                if (nact == 0) break;                          // lengths only shrink the active set: nothing left
                 if (s > 0) {                                   // h_{s-1} of every CTA of this direction is in L2
-                    const unsigned int target = per_step * (unsigned int)s;
                     uint32_t spins = 0;
                     while (ld_acquire_gpu(cnt) < target) {
                         if (++spins > (1u << 24)) { printf("vqa_b200: lstm step barrier timeout (cta %d step %d)\n", blockIdx.x, s); __trap(); }
                     }
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
-                for (int mt = 0; mt < p.mtiles; ++mt)
+                target += per_tile * (unsigned int)nact;
+                for (int mt = 0; mt < p.mtiles; ++mt) {
+                    if (s >= (mt == 0 ? tlen0 : tlen1)) continue;
                     for (int kb = 0; kb < kblocks; ++kb, ++it) {
                         const int st = it % LSTM_STAGES;
                         const uint32_t ph = (it / LSTM_STAGES) & 1;
@@ -103,6 +120,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                         else
                             tma_load_3d(sa + st * LSTM_A_BYTES, &tma_h, &full[st], kb * 64, s * p.Bp + p.b0 + mt * 128, dir);
                     }
+                }
             }
         }
     } else if (warp == 1) {
@@ -114,6 +132,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
         uint32_t it = 0;
         for (int s = 0; s < T; ++s)
             for (int mt = 0; mt < p.mtiles; ++mt) {
+                if (s >= (mt == 0 ? tlen0 : tlen1)) continue;  // same skips as the producer: the ring positions stay in step
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int st = it % LSTM_STAGES;
                     mbar_wait(&full[st], (it / LSTM_STAGES) & 1);
@@ -131,6 +150,7 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
         const int mt = ew >> 2, quarter = warp & 3;
         const int b = mt * 128 + quarter * 32 + lane;
         const bool active_tile = mt < p.mtiles;
+        const int tlen = mt == 0 ? tlen0 : tlen1;
         const bool row_ok = active_tile && b < B;
         const int len = row_ok ? (int)p.len[p.b0 + b] : 0;
         const int u0 = j * 16;
@@ -144,6 +164,9 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
             if (active_tile) {
                 const int64_t row = ((int64_t)dir * T + s) * p.Bp + p.b0 + b;
                 const bool step_on = row_ok && s < len;
+                // a tile past its longest sequence has no MMAs to wait for and nobody waits for it: its warps only copy the
+                // frozen state forward (h for the weight gradient's operand, c, the final cell) and never signal
+                const bool tile_on = s < tlen;
                 bf16* g = p.gx + row * 4 * H + u0;
                 // x-projection (+biases) of this thread's 16 units, 4 gates: 8 x 16 B -- independent of the recurrent
                 // MMAs, so in flight while this warp waits for them
@@ -155,11 +178,14 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                         xq[gate][1] = __ldcs(reinterpret_cast<const uint4*>(g + (int64_t)gate * H + 8));
                     }
                 }
-                mbar_wait(&tmem_full[mt], s & 1);
-                tcgen05_fence_after();
+                if (tile_on) {
+                    mbar_wait(&tmem_full[mt], s & 1);          // one commit per active step; active steps are 0 .. tlen-1
+                    tcgen05_fence_after();
+                }
                 uint4 oq[4][2];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {          // units 8*half .. 8*half+7 <-> accumulator columns 32*half ..
+                    if (!tile_on) break;
                     float v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + mt * 64 + half * 32, v);
                     if (step_on) {
@@ -195,10 +221,12 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                     *reinterpret_cast<uint4*>(hdst) = q[0];
                     *reinterpret_cast<uint4*>(hdst + 8) = q[1];
                 }
-                tcgen05_fence_before();
-                // release this warp's h_s stores to the other CTAs of the direction (warps of unused m-tiles stay out)
-                __syncwarp();
-                if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
+                if (tile_on) {
+                    tcgen05_fence_before();
+                    // release this warp's h_s stores to the other CTAs of the direction (warps of unused m-tiles stay out)
+                    __syncwarp();
+                    if (lane == 0) { asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); atomicAdd(p.sync + dir, 1u); }
+                }
                 // everything only the backward pass reads goes out after the signal, off the step-to-step critical path
                 if (step_on) {
 #pragma unroll
@@ -214,7 +242,8 @@ lstm_persistent_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __gr
                     for (int t = 0; t < 4; ++t)
                         *reinterpret_cast<float4*>(cdst + 4 * t) = make_float4(c_state[4 * t], c_state[4 * t + 1], c_state[4 * t + 2], c_state[4 * t + 3]);
                     if (s == T - 1) {
-                        bf16* qdst = p.qf + (int64_t)(p.b0 + b) * p.dirs * H + (int64_t)dir * H + u0;
+                        const int sample = p.order ? p.order[p.b0 + b] : p.b0 + b;
+                        bf16* qdst = p.qf + (int64_t)sample * p.dirs * H + (int64_t)dir * H + u0;
                         uint4 q[2];
                         __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(q);
 #pragma unroll
@@ -250,6 +279,7 @@ constexpr int LB_A_BYTES = 128 * 64 * 2, LB_B_BYTES = 128 * 64 * 2;
 
 struct LstmBwdParams {
     const bf16* gates; const float* cs; float* dh; float* dc; const bf16* dc_init; bf16* dg; const int64_t* len;
+    const int* order;                    // optional: row b of the LSTM tensors is sample order[b] (dc_init is in sample order)
     unsigned int* sync;
     int T, B, H, dirs;
     int mt, nt, nsplit, kbps;            // GEMM tiling: tiles = mt * nt * dirs, each split into nsplit k-ranges of kbps k-blocks
@@ -279,9 +309,20 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
     uint64_t* empty = full + LB_STAGES;
     uint64_t* tmem_full = empty + LB_STAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    int* tile_len_s = reinterpret_cast<int*>(tmem_base_smem + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, B = p.B, H = p.H;
+    if (threadIdx.x == 0) *tile_len_s = 0;
+    __syncthreads();
+    {   // longest sequence of this CTA's 128-row tile: steps s >= tile_len have no gate gradient in the tile (see below)
+        const int midx_ = ((int)blockIdx.x / p.nsplit / p.nt) % p.mt;
+        const int b = midx_ * 128 + (int)threadIdx.x;
+        if (threadIdx.x < 128 && b < B) {
+            const int64_t l = p.len[b];
+            atomicMax(tile_len_s, l < 0 ? 0 : (l > T ? T : (int)l));
+        }
+    }
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_dg); tma_prefetch_desc(&tma_w);
         for (int i = 0; i < LB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -320,10 +361,25 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
     constexpr uint32_t idesc = idesc_bf16(128, 128, 0, 1);
     const uint64_t a_desc0 = smem_desc_k_sw128(smem_u32(sa));
     const uint64_t b_desc0 = smem_desc_mn_sw128(smem_u32(sb), 8192);
+    // Steps s >= tile_len: every row of this CTA's tile is frozen, so dg_s is zero there and dh_{s-1} gets no
+    // contribution: only the pointwise phase runs (zero gate gradients, dc passes through, dc_init enters at s = T-1);
+    // it touches this thread's own items only, so those steps need neither of the two synchronisations.  The counters
+    // therefore count ACTIVE steps.  All CTAs that share a counter share the row tile and skip the same steps.  With the
+    // batch in descending length order (vqa_length_order) the short half of the batch skips about half of its steps.
+    const int tile_len = *tile_len_s;
 
     for (int s = T - 1; s >= 0; --s) {
         if (!has_tile) break;
-        const unsigned int done = (unsigned int)(T - 1 - s);         // steps completed so far
+        if (s >= tile_len) {
+            for (int li = split * LB_THREADS + threadIdx.x; li < 128 * 16; li += p.nsplit * LB_THREADS) {
+                const int b = m0 + (li >> 4);
+                if (b < B)
+                    lstm_bwd_pointwise_item8<true>(((int64_t)dir * B + b) * h8 + (n0 >> 3) + (li & 15), p.gates, p.cs, p.dh, p.dc,
+                                                   s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs, p.order);
+            }
+            continue;
+        }
+        const unsigned int done = (unsigned int)(tile_len - 1 - s);  // active steps completed so far
         // ---- phase P: this CTA's share (1 / nsplit) of the tile's 128 rows x 16 groups of 8 units
         if (done > 0) {
             if (threadIdx.x == 0) spin_until(tile_cnt, (unsigned int)p.nsplit * done);   // dh of this block is complete
@@ -333,7 +389,7 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
             const int b = m0 + (li >> 4);
             if (b < B)
                 lstm_bwd_pointwise_item8<true>(((int64_t)dir * B + b) * h8 + (n0 >> 3) + (li & 15), p.gates, p.cs, p.dh, p.dc,
-                                               s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs);
+                                               s == T - 1 ? p.dc_init : nullptr, p.dg, p.len, s, T, B, H, p.dirs, p.order);
         }
         if (s == 0) break;
         // the weight halves of the first ring-full of k-blocks do not depend on this step's dg: in flight across the barrier
@@ -384,7 +440,7 @@ lstm_persistent_bwd_kernel(const __grid_constant__ CUtensorMap tma_dg, const __g
             } else if (warp < 6) {
                 const int quarter = warp & 3;
                 const int m = m0 + quarter * 32 + lane;
-                mbar_wait(tmem_full, (uint32_t)((T - 1 - s) & 1));
+                mbar_wait(tmem_full, (uint32_t)(done & 1u));
                 tcgen05_fence_after();
                 float* orow = p.dh + ((int64_t)dir * B + m) * H + n0;
 #pragma unroll 1
@@ -447,8 +503,11 @@ extern "C" int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* strea
 
 // gx [dirs][T][B][4H] bf16, cs [dirs][T][B][H] fp32, hs [dirs][T+1][B][H] bf16 (slot 0 must be zero),
 // qf [B][dirs*H] bf16, wp [dirs][4H][H] bf16 from vqa_pack_lstm_whh, sync: dirs zeroed uint32 counters.
-extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const void* wp, const int64_t* q_len,
-                               unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
+// `order` (optional, from vqa_length_order): the rows of gx / cs / hs are the samples in descending length order
+// (row j = sample order[j]) and q_len is the matching len_sorted; qf is still written in SAMPLE order.  The kernels are
+// correct for any row order -- the order only decides how early whole 128-row tiles drop out of the recurrence.
+extern "C" int vqa_tc_lstm_fwd_ordered(void* gx, float* cs_, void* hs, void* qf, const void* wp, const int64_t* q_len, const int* order,
+                                       unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
     VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm: bad dims");
     VQA_REQUIRE(H % 64 == 0 && H >= 64 && H <= 1024, "tc lstm: hidden size %d must be a multiple of 64 and <= 1024 (weights resident in shared memory)", H);
     int dev = 0, sms = 148, coop = 0;
@@ -495,7 +554,7 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
     // at most 256 sequences (two 128-row accumulator tiles) per cooperative launch: larger batches run chunk by chunk
     for (int b0 = 0; b0 < B; b0 += 256) {
         LstmParams p{};
-        p.gx = (bf16*)gx; p.cs = cs_; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.sync = sync;
+        p.gx = (bf16*)gx; p.cs = cs_; p.hs = (bf16*)hs; p.qf = (bf16*)qf; p.len = q_len; p.order = order; p.sync = sync;
         p.T = T; p.B = B - b0 < 256 ? B - b0 : 256; p.Bp = B; p.b0 = b0;
         p.H = H; p.dirs = dirs; p.ctas_per_dir = ctas_per_dir; p.mtiles = (p.B + 127) / 128;
         VQA_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned int) * dirs, st));
@@ -526,14 +585,20 @@ extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const v
     return 0;
 }
 
+extern "C" int vqa_tc_lstm_fwd(void* gx, float* cs_, void* hs, void* qf, const void* wp, const int64_t* q_len,
+                               unsigned int* sync, int T, int B, int H, int dirs, void* stream) {
+    return vqa_tc_lstm_fwd_ordered(gx, cs_, hs, qf, wp, q_len, nullptr, sync, T, B, H, dirs, stream);
+}
+
 // Backward recurrence in one cooperative launch (see lstm_persistent_bwd_kernel).  gates / dg [dirs][T][B][4H] bf16,
 // cs [dirs][T][B][H] fp32, dh [dirs][B][H] fp32 ZEROED by the caller (gradient w.r.t. the final hidden state would be
 // added here), dc [dirs][B][H] fp32 scratch, dc_init [B][dirs*H] bf16 = gradient w.r.t. the final cell state,
 // whh [dirs][4H][H] bf16 (the recurrent weights as stored), sync: scratch of (tiles + dirs * ceil(B/128)) uint32 (<= 256).  Same results as T calls of
 // vqa_lstm_step_bwd_pointwise interleaved with T-1 split-K vqa_tc_gemm calls (up to fp32 summation order).
-extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, float* dc, const void* dc_init, void* dg,
-                               const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
-                               void* stream) {
+// `order` as for vqa_tc_lstm_fwd_ordered: rows in descending length order, q_len = len_sorted, dc_init in SAMPLE order.
+extern "C" int vqa_tc_lstm_bwd_ordered(const void* gates, const float* cs_, float* dh, float* dc, const void* dc_init, void* dg,
+                                       const void* whh, const int64_t* q_len, const int* order, unsigned int* sync, int T, int B, int H,
+                                       int dirs, void* stream) {
     VQA_REQUIRE(T > 0 && B > 0 && (dirs == 1 || dirs == 2), "tc lstm bwd: bad dims");
     VQA_REQUIRE(H % 128 == 0, "tc lstm bwd: hidden size %d must be a multiple of 128", H);
     int dev = 0, sms = 148, coop = 0;
@@ -543,7 +608,7 @@ extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, f
     VQA_REQUIRE(coop, "tc lstm bwd: device does not support cooperative launch");
     LstmBwdParams p{};
     p.gates = (const bf16*)gates; p.cs = cs_; p.dh = dh; p.dc = dc; p.dc_init = (const bf16*)dc_init; p.dg = (bf16*)dg;
-    p.len = q_len; p.sync = sync; p.T = T; p.B = B; p.H = H; p.dirs = dirs;
+    p.len = q_len; p.order = order; p.sync = sync; p.T = T; p.B = B; p.H = H; p.dirs = dirs;
     p.mt = (B + 127) / 128; p.nt = H / 128;
     const int tiles = p.mt * p.nt * dirs, total_kb = 4 * H / 64;
     VQA_REQUIRE(tiles <= sms, "tc lstm bwd: %d output tiles but only %d SMs (use the per-step path)", tiles, sms);
@@ -581,4 +646,10 @@ extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, f
     VQA_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_bwd_kernel, tdg, tw, p));
     VQA_CHECK_LAUNCH("lstm_persistent_bwd");
     return 0;
+}
+
+extern "C" int vqa_tc_lstm_bwd(const void* gates, const float* cs_, float* dh, float* dc, const void* dc_init, void* dg,
+                               const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
+                               void* stream) {
+    return vqa_tc_lstm_bwd_ordered(gates, cs_, dh, dc, dc_init, dg, whh, q_len, nullptr, sync, T, B, H, dirs, stream);
 }

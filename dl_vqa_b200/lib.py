@@ -34,6 +34,9 @@ PROTOTYPES = {
     "vqa_dropnorm_bwd_unpool": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u64, _vp],
     "vqa_embed_tanh_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_embed_tanh_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_length_order": [_vp, _vp, _vp, _i, _i, _vp],
+    "vqa_embed_tanh_fwd_ordered": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_embed_tanh_bwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_lstm_step_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "vqa_lstm_step_bwd_pointwise": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "vqa_gemm": [_vp, _i, _i64, _i64, _i64, _vp, _i, _i64, _i64, _i64, _vp, _i, _i64, _i64,

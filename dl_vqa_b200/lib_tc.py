@@ -19,6 +19,8 @@ PROTOTYPES = {
     "vqa_tc_conv0_relu_pool_fwd_x": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv0_bwd_weight_bias_x": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_tc_lstm_fwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_tc_lstm_bwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_pack_lstm_whh": [_vp, _vp, _i, _vp],
     "vqa_tc_lstm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_cluster_size": [],

@@ -507,8 +507,20 @@ class VqaNet(nn.Module):
         b_ih = [getattr(lstm, f"bias_ih_l0{s}") for s in sfx]
         b_hh = [getattr(lstm, f"bias_hh_l0{s}") for s in sfx]
         ldx = _rup(E, 8) if tc else E
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        persistent = tc and H % 64 == 0 and H <= 1024 and dirs * (H // 16) <= sms
+        # Length order (what pack_padded_sequence(enforce_sorted=False) computes on the host, models/model.py:160): on the
+        # persistent kernels the rows of every step-indexed buffer are the samples in descending length order, so whole
+        # 128-row tiles leave the recurrence once their longest question has ended.  qf comes back in sample order.
+        ordered = (persistent and T > 1 and B <= 8192 and self._persistent_lstm_bwd_ok(B, T, sms)
+                   and os.environ.get("VQA_LSTM_ORDER", "1") != "0")
+        order = len_rows = None
+        if ordered:
+            order = torch.empty(B, dtype=torch.int32, device=dev)
+            len_rows = torch.empty(B, dtype=torch.int64, device=dev)
+            call("vqa_length_order", ptr(q_len), ptr(order), ptr(len_rows), B, T, st, tag="embed_fwd")
         xs = empty(dirs, T, B, ldx)
-        call("vqa_embed_tanh_fwd", ptr(q), ptr(q_len), ptr(self.text.embedding.weight), ptr(xs), dt,
+        call("vqa_embed_tanh_fwd_ordered", ptr(q), ptr(q_len), ptr(order), ptr(self.text.embedding.weight), ptr(xs), dt,
              B, T, E, ldx, dirs, p_text, seed, st, tag="embed_fwd")
         gx = empty(dirs, T, B, 4 * H)
         for d in range(dirs):   # hoisted input projection: x W_ih^T + b_ih + b_hh for all steps at once
@@ -517,8 +529,6 @@ class VqaNet(nn.Module):
         cs = empty(dirs, T, B, H, dtype=f32)
         qf = empty(B, dirs * H)
         whh_stride = _elem_stride(w_hh[0], w_hh[1]) if dirs == 2 else 0
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        persistent = tc and H % 64 == 0 and H <= 1024 and dirs * (H // 16) <= sms
         if persistent:
             # one cooperative launch for all steps and directions; W_hh resident in shared memory
             wp = empty(dirs, 4 * H, H)
@@ -528,8 +538,8 @@ class VqaNet(nn.Module):
             for d in range(dirs):                                               # slot 0 = h_{-1} = 0
                 call("vqa_zero", ptr(hs_ext[d, 0]), B * H * hs_ext.element_size(), st)
             sync = torch.empty(dirs, dtype=torch.int32, device=dev)            # cleared by the entry itself
-            call("vqa_tc_lstm_fwd", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(q_len), ptr(sync),
-                 T, B, H, dirs, st, tag="lstm_recurrence_fwd")
+            call("vqa_tc_lstm_fwd_ordered", ptr(gx), ptr(cs), ptr(hs_ext), ptr(qf), ptr(wp), ptr(len_rows if ordered else q_len),
+                 ptr(order), ptr(sync), T, B, H, dirs, st, tag="lstm_recurrence_fwd")
             h_prev = [hs_ext[d, 1] for d in range(dirs)]     # h_0 .. h_{T-1} of direction d start here
             hs = hs_ext
         else:
@@ -539,7 +549,14 @@ class VqaNet(nn.Module):
                      dt, s, T, B, H, dirs, st, tag="lstm_step_fwd")
             h_prev = [hs[d, 0] for d in range(dirs)]
         return dict(T=T, B=B, xs=xs, gx=gx, cs=cs, hs=hs, h_prev=h_prev, qf=qf, ldx=ldx, whh_stride=whh_stride,
-                    q=q, q_len=q_len, seed=seed, p_text=p_text)
+                    q=q, q_len=q_len, seed=seed, p_text=p_text, order=order, len_rows=len_rows)
+
+    def _persistent_lstm_bwd_ok(self, B: int, T: int, sms: int) -> bool:
+        """Shapes the one-launch backward recurrence (vqa_tc_lstm_bwd) covers; decided in the forward as well, because the
+        length-ordered row layout is only understood by the two persistent kernels."""
+        H, dirs = self.H, self.dirs
+        return (self.compute_dtype == torch.bfloat16 and T > 1 and H % 128 == 0
+                and ((B + 127) // 128) * (H // 128) * dirs <= sms and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
 
     def _text_backward(self, tx: dict, dqf, mm: "_Math", st, galloc, colsum, zeroed: bool, after_recurrence=None,
                        duplicate_bias: bool = True) -> dict:
@@ -584,13 +601,15 @@ class VqaNet(nn.Module):
                 for d in range(dirs):
                     call("vqa_copy", ptr(whhb[d]), ptr(shs[d]), 4 * H * H * 2, st)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        persistent_bwd = (tc and T > 1 and H % 128 == 0 and ((B + 127) // 128) * (H // 128) * dirs <= sms
-                          and os.environ.get("VQA_LSTM_BWD_PERSISTENT", "1") != "0")
+        order, len_rows = tx.get("order"), tx.get("len_rows")
+        # rows in length order exist only where the forward saw that this backward would be the persistent one
+        persistent_bwd = order is not None or self._persistent_lstm_bwd_ok(B, T, sms)
         if persistent_bwd:
             # all T steps and both directions in one cooperative launch (pointwise + split-K tcgen05 GEMM per step,
             # two point-to-point synchronisations per step) instead of 2T - 1 dependent launches
             sync_b = torch.empty(256, dtype=torch.int32, device=dev)           # cleared by the entry itself
-            call("vqa_tc_lstm_bwd", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb), ptr(q_len), ptr(sync_b),
+            call("vqa_tc_lstm_bwd_ordered", ptr(gx), ptr(cs), ptr(dh), ptr(dc), ptr(dqf), ptr(dg), ptr(whhb),
+                 ptr(len_rows if order is not None else q_len), ptr(order), ptr(sync_b),
                  T, B, H, dirs, st, tag="lstm_bwd_persistent")
         for s in (range(T - 1, -1, -1) if not persistent_bwd else ()):
             call("vqa_lstm_step_bwd_pointwise", ptr(gx), ptr(cs), ptr(dh), ptr(dc),
@@ -628,7 +647,7 @@ class VqaNet(nn.Module):
         for d in range(dirs):
             mm.lin_bwd_data(ptr(dg[d]), dt, 4 * H, w_ih[d], ptr(dxs[d]), dt, ldx, T * B, 4 * H, E, tag="lstm_inproj_dgrad")
         demb = galloc("text.embedding.weight", *self.text.embedding.weight.shape, zero=True)
-        call("vqa_embed_tanh_bwd", ptr(q), ptr(q_len), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
+        call("vqa_embed_tanh_bwd_ordered", ptr(q), ptr(q_len), ptr(order), ptr(xs), ptr(dxs), ptr(demb), dt, B, T, E, ldx, dirs,
              p_text, seed, st, tag="embed_bwd")
         grads["text.embedding.weight"] = demb
         return grads

@@ -102,6 +102,18 @@ int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb,
  * (padding_idx, models/model.py:138-140) receives nothing */
 int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, const void* dxs, float* demb,
                        int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream);
+/* Length order of the batch -- the sort pack_padded_sequence(enforce_sorted=False) does on the host in the reference
+ * (models/model.py:160): order[j] (int32) = sample at position j of the batch sorted by DESCENDING length, ties in sample
+ * order; len_sorted[j] (int64) = q_len[order[j]] clamped to [0, T].  No host synchronisation.  B <= 8192. */
+int vqa_length_order(const int64_t* q_len, int* order, int64_t* len_sorted, int B, int T, void* stream);
+/* The same two kernels with the step-indexed rows in that order: row j of xs / dxs belongs to sample order[j]
+ * (order == NULL: identity).  q and q_len stay in sample order; the dropout mask is a function of the sample index, so
+ * ordering the batch does not change it. */
+int vqa_embed_tanh_fwd_ordered(const int64_t* q, const int64_t* q_len, const int* order, const float* emb, void* xs,
+                               int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream);
+int vqa_embed_tanh_bwd_ordered(const int64_t* q, const int64_t* q_len, const int* order, const void* xs, const void* dxs,
+                               float* demb, int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed,
+                               void* stream);
 
 /* one LSTM time step for all directions (nn.LSTM, models/model.py:164): gates = gx[:,s] + h_{s-1} W_hh^T,
  * i,f,g,o nonlinearities, c/h update fused in the GEMM epilogue.
@@ -332,6 +344,17 @@ int vqa_pack_lstm_whh(const float* w_hh, void* wp, int H, void* stream);
 int vqa_tc_lstm_bwd(const void* gates, const float* cs, float* dh, float* dc, const void* dc_init, void* dg,
                     const void* whh, const int64_t* q_len, unsigned int* sync, int T, int B, int H, int dirs,
                     void* stream);
+/* Length-ordered forms (what the packed sequence buys the reference's cuDNN RNN, models/model.py:160-164): the rows of
+ * gx / cs / hs / gates / dg are the samples in descending length order (row j = sample order[j], vqa_length_order),
+ * q_len is the matching len_sorted; qf is written and dc_init is read in SAMPLE order.  Both kernels drop a 128-row
+ * tile from every step at which none of its sequences is active, so with ordered rows the short half of the batch
+ * leaves the recurrent GEMMs, the operand ingest and the step synchronisation early.  They are correct for any row
+ * order (order == NULL: rows are samples, which is what the two entries above pass). */
+int vqa_tc_lstm_fwd_ordered(void* gx, float* cs, void* hs, void* qf, const void* wp, const int64_t* q_len, const int* order,
+                            unsigned int* sync, int T, int B, int H, int dirs, void* stream);
+int vqa_tc_lstm_bwd_ordered(const void* gates, const float* cs, float* dh, float* dc, const void* dc_init, void* dg,
+                            const void* whh, const int64_t* q_len, const int* order, unsigned int* sync, int T, int B, int H,
+                            int dirs, void* stream);
 /* diagnostic: 4 = vqa_tc_lstm_fwd runs as clusters of four CTAs with TMA multicast of h (opt-in through the
  * environment variable VQA_LSTM_CLUSTER=4), 1 = single CTAs (default, or the driver rejected the cooperative cluster
  * launch), 0 = not launched yet */

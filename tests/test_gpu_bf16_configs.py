@@ -1,0 +1,144 @@
+"""Config coverage of the tensor-core (bf16) arm beyond config.yaml's defaults: the values the
+reference's own sweep and config_eval.yaml use (config/config.yaml:116-124, config/config_eval.yaml:52-69) -- stride 2,
+do_option '*' and '|', unidirectional LSTM, 3 glimpses -- and a longer `num_channels` list, all at the config.yaml
+WIDTHS (1024 / 256 / 1024) so that the tcgen05 kernels (or, where a shape is outside their range, the generic bf16
+kernels of the same library) take part.
+
+Bar (BASELINE.json north_star): logits, loss and EVERY parameter gradient <= 2e-2 max-norm against the fp32 oracle run
+under the gating pattern the bf16 forward took (oracle.forward_gated; why the gates are frozen: tests/test_oracle.py).
+Reference path: models/model.py:53-67, :72-84 (stride), :151-166 (bidirectional), :183-195 (do_option), train.py:190-206."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+# name -> (config overrides, image size, batch)
+VARIANTS = {
+    "mul": ({"attention.do_option": "*"}, 96, 4),
+    "cat": ({"attention.do_option": "|"}, 96, 3),
+    # the reference's evaluated configuration: stride 2, '*' (config_eval.yaml:52-69; dropout is 0 here for the gradient check)
+    "eval_yaml_stride2_mul": ({"image.stride": 2, "attention.do_option": "*"}, 224, 4),
+    "stride2_plus": ({"image.stride": 2}, 160, 5),
+    "unidir": ({"text.bidirectional": False}, 96, 4),
+    "g3": ({"attention.glimpses": 3}, 96, 4),
+    "g1": ({"attention.glimpses": 1}, 64, 4),
+    "channels5": ({"image.num_channels": [3, 64, 128, 256, 512]}, 128, 3),
+    "channels_narrow": ({"image.num_channels": [3, 32, 64, 128, 256]}, 128, 3),
+}
+
+
+def _err(a, b):
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-7))
+
+
+def _export_gates(saved, model, B):
+    """The gating pattern of one bf16 forward, from what the step saved for its own backward.  The attention ReLU is
+    evaluated the way the kernel that ran evaluates it: the streaming kernels (A = 1024, C = 256, '+' / '*', G <= 2) add
+    in packed bf16, relu(bf16(v' (+|*) bf16(q'))); the generic kernels widen v' and use the fp32 q'."""
+    gates = {"pool": [cs[3].permute(0, 3, 1, 2).long().cpu() for cs in saved["conv_saved"]]}
+    P, A = saved["P"], model.A
+    vp = saved["vp"].view(B, P, A)
+    streaming = model.A == 1024 and model.channels[-1] == 256 and model.do_option in "+*" and model.G <= 2
+    if streaming:
+        qp = saved["qp"].to(vp.dtype)[:, None, :]
+    else:
+        vp, qp = vp.float(), saved["qp"].float()[:, None, :]
+    if model.do_option == "+":
+        pre = vp + qp
+    elif model.do_option == "*":
+        pre = vp * qp
+    else:
+        pre = torch.cat([vp, qp.expand_as(vp)], dim=2)
+    # the spatial grid need not be square in general; here it is (square synthetic images)
+    side = int(round(P ** 0.5))
+    assert side * side == P
+    gates["att"] = (pre > 0).permute(0, 2, 1).reshape(B, pre.shape[2], side, side).cpu()
+    gates["cls"] = (saved["h1d"] > 0).cpu()
+    return gates
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_bf16_arm_config_variants_under_the_same_gating(name):
+    import dl_vqa_b200 as D
+    over, size, B = VARIANTS[name]
+    cfg = O.cfg_with(O.zero_dropout(O.DEFAULT_CFG), image_size=size, **over)
+    V = 2000
+    torch.manual_seed(1)
+    m = D.VqaNet(cfg, V, compute_dtype="bfloat16")
+    sd = {k: t.detach().clone() for k, t in m.state_dict().items()}
+    batch = O.synthetic_batch(B, cfg, V, seed=31, T=11)
+    v, q, q_len, a_idx, a_val, a_len = batch
+    m.cuda().train(True)
+    logits = m(v.cuda(), q.cuda(), q_len.cuda())
+    gates = _export_gates(logits.grad_fn.saved, m, B)
+    loss, _ = D.soft_target_loss_and_score(logits, a_idx, a_val)
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().float().cpu() for k, p in m.named_parameters()}
+
+    wl, wloss, want = O.step_with_grads_gated(sd, cfg, batch, gates)
+    rep = {"logits": _err(logits, wl), "loss": abs(float(loss) - float(wloss)) / abs(float(wloss))}
+    gmax = max(float(g.abs().max()) for g in want.values())
+    # gradients that are exactly zero in exact arithmetic: the softmax is shift invariant (x_conv bias; for '|' also the
+    # position-independent q' half of cat[v', q'], hence everything behind q_lin) -- bounded absolutely
+    zero = {"attention.x_conv.bias"} | ({"attention.q_lin.weight", "attention.q_lin.bias"} if cfg["attention"]["do_option"] == "|" else set())
+    for k, g in want.items():
+        rep["grad/" + k] = float((got[k] - g).abs().max()) / gmax if k in zero else _err(got[k], g)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"parity_bf16_variant_{name}.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    bad = {k: e for k, e in rep.items() if e > BF16_TOL}
+    assert not bad, f"{name}: over {BF16_TOL}: {bad}"
+
+    # the exact arm on the same inputs: logits / loss / top-1 to the same bar (the exact arm is pinned to the reference at 1e-4)
+    mf = D.VqaNet(cfg, V, compute_dtype="float32")
+    mf.load_state_dict(sd)
+    mf.cuda().eval()
+    m.eval()
+    with torch.no_grad():
+        lf, lb = mf(v.cuda(), q.cuda(), q_len.cuda()), m(v.cuda(), q.cuda(), q_len.cuda())
+    assert _err(lb, lf) < BF16_TOL
+
+
+def test_length_ordered_question_encoder_equals_the_unordered_one(monkeypatch):
+    """The persistent LSTM kernels run the batch in descending length order (vqa_length_order; what the reference's
+    pack_padded_sequence(enforce_sorted=False) does on the host, models/model.py:160).  Rows are independent in the
+    recurrence, so the encoder output must be BIT-identical to the unordered run, the dropout mask must not move, and the
+    weight gradients may differ only by fp32 summation order."""
+    import dl_vqa_b200 as D
+    cfg = O.cfg_with(O.DEFAULT_CFG)                      # dropout 0.3 on the embedding: the mask must follow the sample
+    V, B, T = 3000, 256, 23
+    torch.manual_seed(1)
+    m = D.VqaNet(cfg, V, compute_dtype="bfloat16").cuda().train(True)
+    g = torch.Generator().manual_seed(7)
+    q_len = torch.randint(1, T + 1, (B,), generator=g)
+    q_len[3] = T
+    q = (torch.randint(1, V, (B, T), generator=g) * (torch.arange(T)[None, :] < q_len[:, None])).cuda()
+    q_len = q_len.cuda()
+    dqf = (torch.randn(B, 2048, generator=g) * 0.1).cuda().bfloat16()
+    m._next_seed = lambda: 4242                          # the same dropout masks in both runs
+
+    def run(flag):
+        monkeypatch.setenv("VQA_LSTM_ORDER", flag)
+        for p in m.text.parameters():
+            p.grad = None
+        out = m.text(q, q_len)
+        out.backward(dqf)
+        torch.cuda.synchronize()
+        return out.detach().clone(), {k: p.grad.detach().clone() for k, p in m.text.named_parameters()}
+
+    out0, g0 = run("0")
+    out1, g1 = run("1")
+    assert torch.equal(out0, out1)
+    for k in g0:
+        assert _err(g1[k], g0[k]) < 2e-3, (k, _err(g1[k], g0[k]))

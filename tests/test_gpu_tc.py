@@ -468,11 +468,14 @@ def _token_index(step_major, q_len, reverse):
     return out * (t < q_len[:, None])[:, :, None]
 
 
+@pytest.mark.parametrize("ordered", [False, True])
 @pytest.mark.parametrize("B,T,H,dirs", [(256, 23, 1024, 2), (1024, 12, 1024, 2), (130, 7, 256, 2), (5, 4, 128, 1), (600, 9, 256, 2)])
-def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs):
+def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs, ordered):
     """vqa_tc_lstm_fwd / vqa_tc_lstm_bwd (cooperative tcgen05 kernels) against oracle.lstm_final_cell + autograd
     (reference models/model.py:159-166) on the same bf16-rounded input projections and recurrent weights; the oracle
-    rounds what the kernel stores in bf16 (input projection, h) with a straight-through gradient."""
+    rounds what the kernel stores in bf16 (input projection, h) with a straight-through gradient.
+    ordered: rows handed over in descending length order (vqa_length_order) through the *_ordered entries, so that whole
+    128-row tiles drop out of the late steps; qf / dc_init stay in sample order."""
     from dl_vqa_b200 import lib
     from oracle import vqa_oracle as O
     torch.manual_seed(B + T + H)
@@ -496,6 +499,13 @@ def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs):
     st = lib.stream()
     ql = q_len.to(dev)
     gx = torch.stack([_step_index(pre_tok[d].to(dev), ql, d == 1) for d in range(dirs)]).bfloat16().contiguous()
+    order = len_rows = None
+    if ordered:
+        order = torch.empty(B, dtype=torch.int32, device=dev)
+        len_rows = torch.empty(B, dtype=torch.int64, device=dev)
+        lib.call("vqa_length_order", lib.ptr(ql), lib.ptr(order), lib.ptr(len_rows), B, T, st)
+        gx = gx[:, :, order.long()].contiguous()              # row j of the step-indexed buffers = sample order[j]
+    rows_len = len_rows if ordered else ql
     cs = torch.empty(dirs, T, B, H, device=dev)
     hs = torch.zeros(dirs, T + 1, B, H, device=dev, dtype=torch.bfloat16)
     qf = torch.empty(B, dirs * H, device=dev, dtype=torch.bfloat16)
@@ -504,16 +514,26 @@ def test_persistent_lstm_forward_and_backward_against_the_oracle(B, T, H, dirs):
     for d in range(dirs):
         lib.call("vqa_pack_lstm_whh", lib.ptr(whh[d]), lib.ptr(wp[d]), H, st)
     sync = torch.zeros(dirs, dtype=torch.int32, device=dev)
-    lib.call("vqa_tc_lstm_fwd", lib.ptr(gx), lib.ptr(cs), lib.ptr(hs), lib.ptr(qf), lib.ptr(wp), lib.ptr(ql),
-             lib.ptr(sync), T, B, H, dirs, st)
+    lib.call("vqa_tc_lstm_fwd_ordered", lib.ptr(gx), lib.ptr(cs), lib.ptr(hs), lib.ptr(qf), lib.ptr(wp), lib.ptr(rows_len),
+             lib.ptr(order), lib.ptr(sync), T, B, H, dirs, st)
     dh = torch.zeros(dirs, B, H, device=dev)
     dc = torch.empty(dirs, B, H, device=dev)
     dg = torch.empty(dirs, T, B, 4 * H, dtype=torch.bfloat16, device=dev)
     sync_b = torch.zeros(256, dtype=torch.int32, device=dev)
     whh_b = whh.bfloat16().contiguous()
-    lib.call("vqa_tc_lstm_bwd", lib.ptr(gx), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc), lib.ptr(dqf.to(dev).bfloat16()), lib.ptr(dg),
-             lib.ptr(whh_b), lib.ptr(ql), lib.ptr(sync_b), T, B, H, dirs, st)
+    lib.call("vqa_tc_lstm_bwd_ordered", lib.ptr(gx), lib.ptr(cs), lib.ptr(dh), lib.ptr(dc), lib.ptr(dqf.to(dev).bfloat16()), lib.ptr(dg),
+             lib.ptr(whh_b), lib.ptr(rows_len), lib.ptr(order), lib.ptr(sync_b), T, B, H, dirs, st)
     torch.cuda.synchronize()
+    if ordered:
+        o = order.long()
+        assert torch.equal(len_rows, ql[o]) and bool((len_rows[:-1] >= len_rows[1:]).all())
+        assert torch.equal(torch.sort(o).values, torch.arange(B, device=dev))
+        same = len_rows[:-1] == len_rows[1:]
+        assert bool((o[1:][same] > o[:-1][same]).all())            # ties keep sample order
+        inv = torch.empty_like(o)
+        inv[o] = torch.arange(B, device=dev)
+        dg = dg[:, :, inv].contiguous()                            # back to sample order for the comparison
+        assert bool(torch.isfinite(hs.float()).all())              # frozen rows are copied forward, never left unwritten
 
     def err(a, b):
         a, b = a.float().cpu(), b.float().cpu()

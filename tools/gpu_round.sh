@@ -7,6 +7,11 @@ what=" $* "
 mkdir -p gpurun_out
 has() { [[ "$what" == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+if has lstmtests; then
+  timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_bf16_configs.py -m gpu -q -k "lstm or variants or ordered" > gpurun_out/${tag}_pytest_lstm.log 2>&1
+  echo "pytest exit $?" >> gpurun_out/${tag}_pytest_lstm.log
+  tail -15 gpurun_out/${tag}_pytest_lstm.log
+fi
 if has tests; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1
   echo "pytest exit $?" >> gpurun_out/${tag}_pytest_gpu.log
@@ -15,6 +20,12 @@ fi
 if has bench; then
   timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
   echo "bench exit $?"; head -c 600 gpurun_out/${tag}_bench_n1.json; echo
+fi
+if has benchab; then          # A/B of the length-ordered LSTM on the device-resident step
+  for o in 0 1; do
+    VQA_LSTM_ORDER=$o timeout 300 python bench.py --steps 20 --warmup 5 --only-device > gpurun_out/${tag}_bench_order$o.json 2> gpurun_out/${tag}_bench_order$o.err
+    echo "order=$o exit $?"; cat gpurun_out/${tag}_bench_order$o.json
+  done
 fi
 if has ref; then
   timeout 400 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${tag}_bench_reference_arm.json 2> gpurun_out/${tag}_bench_ref.err
@@ -35,7 +46,15 @@ if has full; then
     --profile-from-start off python bench.py --steps 1 --warmup 3 --profile-mode --no-graph > gpurun_out/${tag}_ncu_full.log 2>&1
   echo "full exit $?"
   ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
-  ls -la gpurun_out/${tag}_full*
+  # per-instruction view of the kernels under work; the report itself (> 64 MiB) cannot travel back
+  for k in ${NCU_SRC_KERNELS:-attention_fwd_stream conv0_fwd_tc conv0_bwd_tc}; do
+    ncu -i gpurun_out/${tag}_full.ncu-rep --page source --csv --print-source cuda,sass --kernel-name regex:$k \
+      > gpurun_out/${tag}_src_$k.csv 2> gpurun_out/${tag}_src_$k.err || \
+    ncu -i gpurun_out/${tag}_full.ncu-rep --page source --csv --kernel-name regex:$k > gpurun_out/${tag}_src_$k.csv 2>> gpurun_out/${tag}_src_$k.err
+    gzip -f gpurun_out/${tag}_src_$k.csv
+  done
+  ls -la gpurun_out/${tag}_full* gpurun_out/${tag}_src_*
+  rm -f gpurun_out/${tag}_full.ncu-rep
 fi
 if has sanitize; then
   for tool in ${SAN_TOOLS:-racecheck synccheck}; do
