@@ -23,3 +23,12 @@ extern "C" uint64_t vqa_launch_count(void) { return __atomic_load_n(&g_launches,
 
 extern "C" const char* vqa_last_error_string(void) { return g_err; }
 extern "C" int vqa_abi_version(void) { return VQA_ABI_VERSION; }
+
+// host-side diagnostic: how the vector dropout scheme quantises p (see dropout_bf16_threshold in common.cuh)
+extern "C" int vqa_dropout_threshold_pattern(float p, uint32_t* pattern, uint32_t* count16) {
+    if (!pattern || !count16 || !(p >= 0.f) || !(p < 1.f)) { vqa_set_error("dropout_threshold_pattern: bad arguments"); return -1; }
+    const Dropout d = make_dropout(0, p);
+    *pattern = d.thr2 & 0xFFFFu;
+    *count16 = d.threshold;
+    return 0;
+}

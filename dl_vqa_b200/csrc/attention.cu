@@ -414,6 +414,14 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t hrelu2_bf16(uint32_t a) { uint32_t r; asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u)); return r; }
+// relu(a + b) / relu(a * b) in ONE half-precision-pipe instruction (fma.rn.relu): the same single rounding as add.rn /
+// mul.rn followed by max(., 0), without the min/max instruction on the integer pipe
+__device__ __forceinline__ uint32_t hadd2_relu_bf16(uint32_t a, uint32_t b) {
+    uint32_t r; asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3F803F80u), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t hmul2_relu_bf16(uint32_t a, uint32_t b) {
+    uint32_t r; asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0x80008000u)); return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -494,13 +502,17 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
     const Dropout8 d8 = make_dropout8(drop, SITE_ATT_X);
     const float wscale = TRAIN ? d8.scale : 1.f;
     // lane's channels in phase 1: half*512 + (j*32 + lane)*8 + [0,8), j = 0,1
-    float wv[G][16];
+    // as (even, odd) channel pairs: one packed FFMA2 (fma.rn.f32x2) per bf16x2 word and glimpse instead of two FFMA
+    float2 wv[G][8];
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) wv[g][j * 8 + i] = wx[g * A_ + half * 512 + (j * 32 + lane) * 8 + i] * wscale;
+            for (int i = 0; i < 4; ++i) {
+                const float2 w2 = *reinterpret_cast<const float2*>(wx + g * A_ + half * 512 + (j * 32 + lane) * 8 + 2 * i);
+                wv[g][j * 4 + i] = make_float2(w2.x * wscale, w2.y * wscale);
+            }
 
     uint32_t c = 0;                                   // global chunk counter (same sequence as the producer)
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -519,9 +531,9 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
             wait_chunk(full, cc);
             const uint8_t* base = ring + slot * CHUNK + half * 1024 + lane * 16;
             const int pos0 = i * POS1;
-            float acc[POS1 * GP];
+            float2 acc2[POS1 * GP];                 // .x: even channels, .y: odd channels; folded before the butterfly
 #pragma unroll
-            for (int k = 0; k < POS1 * GP; ++k) acc[k] = 0.f;
+            for (int k = 0; k < POS1 * GP; ++k) acc2[k] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ps = 0; ps < POS1; ++ps) {
                 if (pos0 + ps < P) {                 // warp-uniform
@@ -533,23 +545,20 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
                         if (TRAIN) dropout_flags8(d8, (uint32_t)(((int64_t)b * P + pos0 + ps) * (A_ / 8) + half * 64 + j * 32 + lane), t);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            uint32_t r = OP == VQA_ATT_ADD ? hadd2_bf16(x[e], q2[j * 4 + e]) : hmul2_bf16(x[e], q2[j * 4 + e]);
-                            r = hrelu2_bf16(r);
+                            uint32_t r = OP == VQA_ATT_ADD ? hadd2_relu_bf16(x[e], q2[j * 4 + e]) : hmul2_relu_bf16(x[e], q2[j * 4 + e]);
                             if (TRAIN) r &= dropout_mask_bf16x2(t[e]);
-                            const float lo = bf_lo(r), hi = bf_hi(r);
+                            const float2 lh = make_float2(bf_lo(r), bf_hi(r));
 #pragma unroll
-                            for (int g = 0; g < G; ++g) {
-                                float a = acc[g * POS1 + ps];
-                                a = fmaf(lo, wv[g][j * 8 + 2 * e], a);
-                                a = fmaf(hi, wv[g][j * 8 + 2 * e + 1], a);
-                                acc[g * POS1 + ps] = a;
-                            }
+                            for (int g = 0; g < G; ++g) acc2[g * POS1 + ps] = __ffma2_rn(lh, wv[g][j * 4 + e], acc2[g * POS1 + ps]);
                         }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&empty[slot]);          // this warp is done with the chunk
+            float acc[POS1 * GP];
+#pragma unroll
+            for (int k = 0; k < POS1 * GP; ++k) acc[k] = acc2[k].x + acc2[k].y;
             transpose_reduce<POS1 * GP>(acc, lane);
             // value index k = g*POS1 + ps sits in lanes with (lane >> SH) == k
             constexpr int SH = 5 - ilog2(POS1 * GP);
@@ -583,11 +592,11 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
         consumer_sync();
 
         // ---- phase 3: out[g][c] = sum_s p[g][s] * vn[s][c]; lane = 8 channels, the pair's warps split the rows
-        float o[G][8];
+        float2 o[G][4];
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[g][e] = 0.f;
+            for (int e = 0; e < 4; ++e) o[g][e] = make_float2(0.f, 0.f);
         for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n3; i += NPAIR) {
             const uint32_t cc = c + i;
             const int slot = cc % NST;
@@ -603,11 +612,9 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const float pv = pr[g * P + s];
+                        const float2 pv2 = make_float2(pv, pv);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            o[g][2 * e] = fmaf(pv, bf_lo(x[e]), o[g][2 * e]);
-                            o[g][2 * e + 1] = fmaf(pv, bf_hi(x[e]), o[g][2 * e + 1]);
-                        }
+                        for (int e = 0; e < 4; ++e) o[g][e] = __ffma2_rn(make_float2(bf_lo(x[e]), bf_hi(x[e])), pv2, o[g][e]);
                     }
                 }
             }
@@ -617,8 +624,8 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
         c += n3;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8) = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
-            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8 + 4) = make_float4(o[g][4], o[g][5], o[g][6], o[g][7]);
+            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8) = make_float4(o[g][0].x, o[g][0].y, o[g][1].x, o[g][1].y);
+            *reinterpret_cast<float4*>(red + (warp * G + g) * C_ + lane * 8 + 4) = make_float4(o[g][2].x, o[g][2].y, o[g][3].x, o[g][3].y);
         }
         consumer_sync();
         for (int t = tid; t < G * C_; t += NCW * 32) {
@@ -852,8 +859,7 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                         uint32_t* o = reinterpret_cast<uint32_t*>(&o4);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            uint32_t xr = OP == VQA_ATT_ADD ? hadd2_bf16(x[e], q2[e]) : hmul2_bf16(x[e], q2[e]);
-                            xr = hrelu2_bf16(xr);
+                            uint32_t xr = OP == VQA_ATT_ADD ? hadd2_relu_bf16(x[e], q2[e]) : hmul2_relu_bf16(x[e], q2[e]);
                             if (TRAIN) xr &= dropout_mask_bf16x2(fl[e]);          // relu(pre) where kept (unscaled), else 0
                             const float xl = bf_lo(xr), xh = bf_hi(xr);
                             float dl_lo = 0.f, dl_hi = 0.f;

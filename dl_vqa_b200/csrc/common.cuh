@@ -254,17 +254,40 @@ struct Dropout {
     const uint64_t* seed_ptr;   // non-null: the seed is read from device memory when the kernel RUNS (VQA_SEED_ON_DEVICE)
     uint32_t threshold;   // 16-bit threshold: keep iff word >= threshold; 0 disables dropout
     float scale;          // 1/(1-p)
+    uint32_t thr2;        // vector scheme (Dropout8): the threshold as a packed bf16x2 bit pattern; 0 disables dropout
 };
+
+// Vector scheme: a 16-bit random field h is read as a bf16 BIT PATTERN and the element is dropped iff h < T (ordered
+// compare), so one `set.geu.u32.bf16x2` turns a 32-bit random word into the keep masks (0xFFFF / 0) of two elements.
+// Number of the 65536 patterns below a threshold T (inf = 0x7F80; NaN patterns compare unordered = kept):
+//   T = -t (t >= 1): 0x7F80 - t      T = -0: 0x7F80      T = +t: 0x7F81 + t
+// so every drop count up to 0xFF01 (p <= 0.996) is reachable except 0x7F81.  Thresholds are kept NORMAL numbers (or
+// zero): whether the comparison flushes subnormal inputs then does not matter; the cost is |p' - p| <= 2^-9 inside
+// 0.496 < p < 0.5002 and <= 2^-16 elsewhere (p = 0.5 itself lands on 32769 / 65536).
+static inline uint32_t dropout_bf16_threshold(uint32_t count) {
+    if (count == 0) return 0;
+    uint32_t pat;
+    if (count <= 0x7F80u) {
+        const uint32_t t = 0x7F80u - count;                       // T = -t
+        pat = t == 0 ? 0x8000u : (t < 0x80u ? (t < 0x40u ? 0x8000u : 0x8080u) : (0x8000u | t));
+    } else {
+        uint32_t t = count - 0x7F81u;                             // T = +t
+        if (t > 0x7F80u) t = 0x7F80u;
+        pat = t < 0x80u ? (t < 0x40u ? 0x8000u : 0x0080u) : t;
+    }
+    return pat | (pat << 16);
+}
 
 static inline Dropout make_dropout(uint64_t seed, float p) {
     Dropout d;
     d.seed = seed;
     d.seed_ptr = (seed & VQA_SEED_ON_DEVICE) ? reinterpret_cast<const uint64_t*>(seed & ~VQA_SEED_ON_DEVICE) : nullptr;
-    if (p <= 0.f) { d.threshold = 0; d.scale = 1.f; }
+    if (p <= 0.f) { d.threshold = 0; d.scale = 1.f; d.thr2 = 0; }
     else {
         double t = (double)p * 65536.0 + 0.5;
         d.threshold = (t >= 65535.0) ? 65535u : (uint32_t)t;
         d.scale = 1.f / (1.f - p);
+        d.thr2 = dropout_bf16_threshold(d.threshold);
     }
     return d;
 }
@@ -295,42 +318,36 @@ __device__ __forceinline__ void dropout_mult2(const Dropout& d, uint32_t key, ui
     m1 = (w >> 16) >= d.threshold ? d.scale : 0.f;
 }
 
-// ---- vector form used by the fused attention kernels (site ATT_X, 0.7 G elements per step) ------------------------
-// One hash32 per group of 8 consecutive elements, three LCG steps for the other three words; each 32-bit word
-// serves two elements through its two 15-bit fields, and the keep test is a carry into bit 15 / bit 31:
-//   t = (w & 0x7FFF7FFF) + (0x8000 - thr15) * 0x10001     =>  bit 15 (31) set  <=>  low (high) field >= thr15
-// (p quantised to 1/32768).  About 3 integer ops per element instead of 8, which is what lets the attention kernels
-// stay memory-bound in train mode.  Forward and backward regenerate the same flags.
+// ---- vector form used by the fused attention / dropout+L2-norm kernels (0.7 G elements per step at site ATT_X) ------
+// One hash32 per group of 8 consecutive elements, three LCG steps for the other three words; each 32-bit word serves
+// two elements: its 16-bit halves are compared as bf16 bit patterns against the threshold (see dropout_bf16_threshold),
+// one HSET2 per word on the half-precision pipe instead of AND + ADD + PRMT on the integer pipe, which is the pipe the
+// streaming attention kernels saturate in train mode.  Forward and backward regenerate the same masks.
 struct Dropout8 {
     uint32_t key;       // dropout_key(seed, site)
-    uint32_t addk;      // (0x8000 - thr15) * 0x10001; 0 disables dropout
+    uint32_t thr2;      // packed bf16x2 threshold pattern; 0 disables dropout
     float scale;        // 1/(1-p)
 };
 __device__ __forceinline__ Dropout8 make_dropout8(const Dropout& d, uint32_t site) {
     Dropout8 r;
     r.key = dropout_key(d, site);
-    const uint32_t thr15 = d.threshold >> 1;              // 16-bit threshold -> 15-bit
-    r.addk = d.threshold == 0 ? 0u : (0x8000u - thr15) * 0x10001u;
+    r.thr2 = d.threshold == 0 ? 0u : d.thr2;
     r.scale = d.scale;
     return r;
 }
-// flags for elements 8*group .. 8*group+7: element 2j <-> bit 15 of t[j], element 2j+1 <-> bit 31 of t[j]
+// keep masks for elements 8*group .. 8*group+7: element 2j <-> low half of t[j], element 2j+1 <-> high half (0xFFFF = kept)
 __device__ __forceinline__ void dropout_flags8(const Dropout8& d, uint32_t group, uint32_t (&t)[4]) {
     uint32_t w = hash32(group ^ d.key);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        t[j] = (w & 0x7FFF7FFFu) + d.addk;
+        asm("set.geu.u32.bf16x2 %0, %1, %2;" : "=r"(t[j]) : "r"(w), "r"(d.thr2));
         w = w * 0x9E3779B1u + 0x7F4A7C15u;
     }
 }
-// 0xFFFF in each 16-bit half whose element is kept (bf16x2 bit mask)
-__device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) {
-    uint32_t m;
-    asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(t));      // replicate the sign of byte 1 / byte 3 over each half
-    return m;
-}
+// the flags ARE the bf16x2 bit masks
+__device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) { return t; }
 __device__ __forceinline__ void dropout_mult8(const Dropout8& d, uint32_t group, float (&m)[8]) {
-    if (d.addk == 0) {
+    if (d.thr2 == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = 1.f;
         return;

@@ -455,20 +455,31 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (!valid[k]) { d[k] = make_uint4(0, 0, 0, 0); mk[k] = make_uint2(0x04040404u, 0x04040404u); }
-            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows per window, 128B-swizzled)
+            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows per window, 128B-swizzled).  The eight mask bytes
+            // of a chunk (values 0..4) are widened ONCE to fp16 patterns 0x3C00 | id (1 + id/1024: normal numbers), so that
+            // per window element one HSET2.EQ per channel pair yields the 0xFFFF / 0 select masks on the half-precision
+            // pipe (was xor / sub / shift + two PRMT per pair on the integer pipe, the pipe this kernel saturates).
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int w = (2 * wg + (k >> 2)) * 16 + (k & 3) * 4 + (lane >> 3);      // window = row of the A tiles
                 uint8_t* chunkp = stage + w * 128 + ((jc ^ (w & 7)) << 4);
+                uint32_t mw[4];
+                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[0]) : "r"(mk[k].x), "r"(0x3C3C3C3Cu));
+                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[1]) : "r"(mk[k].x), "r"(0x3C3C3C3Cu));
+                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[2]) : "r"(mk[k].y), "r"(0x3C3C3C3Cu));
+                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[3]) : "r"(mk[k].y), "r"(0x3C3C3C3Cu));
+                const uint32_t dv[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    // bytes are 0..4: (8 - (byte ^ e)) has bit 3 set iff byte == e; move it to the byte's sign bit
-                    const uint32_t f0 = (0x08080808u - (mk[k].x ^ (0x01010101u * e))) << 4;
-                    const uint32_t f1 = (0x08080808u - (mk[k].y ^ (0x01010101u * e))) << 4;
-                    uint4 o;
-                    o.x = d[k].x & sign_mask16_lo(f0); o.y = d[k].y & sign_mask16_hi(f0);      // bytes 0,1 / 2,3 -> 16-bit masks
-                    o.z = d[k].z & sign_mask16_lo(f1); o.w = d[k].w & sign_mask16_hi(f1);
-                    *reinterpret_cast<uint4*>(chunkp + e * C0_TILE_BYTES) = o;
+                    const uint32_t want = 0x3C003C00u | (0x00010001u * e);
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t sel;
+                        asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(sel) : "r"(mw[i]), "r"(want));
+                        o[i] = dv[i] & sel;
+                    }
+                    *reinterpret_cast<uint4*>(chunkp + e * C0_TILE_BYTES) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
             // the patch rows last: (d, mk) are dead by now, so the 48 patch values do not add to the register peak

@@ -328,27 +328,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int i = 0; i < 8; ++i) bs[i] = 0.f;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        // the 8 mask bytes (0..3 = arg-max element, 4 = ReLU-dead) widened once to fp16 patterns 0x3C00 | id
+                        // (normal numbers): one HSET2 per channel pair then gives a 0xFFFF / 0 select mask on the
+                        // half-precision pipe (was xor / sub / shift + two PRMT per pair and element on the integer pipe)
+                        uint32_t mw[4];
+                        asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[0]) : "r"(M[j][0]), "r"(0x3C3C3C3Cu));
+                        asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[1]) : "r"(M[j][0]), "r"(0x3C3C3C3Cu));
+                        asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[2]) : "r"(M[j][1]), "r"(0x3C3C3C3Cu));
+                        asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[3]) : "r"(M[j][1]), "r"(0x3C3C3C3Cu));
                         if (okh && wq + j < p.valid_w) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                // bytes equal to e -> 0x08 -> sign bit; prmt replicates the sign over each bf16
-                                const uint32_t z0 = (0x08080808u - (M[j][0] ^ (0x01010101u * e))) << 4;
-                                const uint32_t z1 = (0x08080808u - (M[j][1] ^ (0x01010101u * e))) << 4;
-                                uint4 u;
-                                u.x = G[j][0] & sign_mask16_lo(z0); u.y = G[j][1] & sign_mask16_hi(z0);
-                                u.z = G[j][2] & sign_mask16_lo(z1); u.w = G[j][3] & sign_mask16_hi(z1);
-                                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * p.valid_w) + 2 * j + (e & 1)) * p.N + 64 * k), u);
+                                const uint32_t want = 0x3C003C00u | (0x00010001u * e);
+                                uint32_t o[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    uint32_t sel;
+                                    asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(sel) : "r"(mw[i]), "r"(want));
+                                    o[i] = G[j][i] & sel;
+                                }
+                                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * p.valid_w) + 2 * j + (e & 1)) * p.N + 64 * k),
+                                       make_uint4(o[0], o[1], o[2], o[3]));
                             }
                         }
-                        // bias gradient of the layer below: (bf16) gradients whose ReLU was alive (mask byte != 4; the
+                        // bias gradient of the layer below: (bf16) gradients whose ReLU was alive (mask id != 4; the
                         // prefetch fills 4 for positions outside the image)
-                        const uint32_t z0 = M[j][0] << 5, z1 = M[j][1] << 5;          // bit 2 -> sign bit of each byte
-                        const uint32_t a0 = G[j][0] & ~sign_mask16_lo(z0), a1 = G[j][1] & ~sign_mask16_hi(z0);
-                        const uint32_t a2 = G[j][2] & ~sign_mask16_lo(z1), a3 = G[j][3] & ~sign_mask16_hi(z1);
-                        bs[0] += __uint_as_float(a0 << 16); bs[1] += __uint_as_float(a0 & 0xffff0000u);
-                        bs[2] += __uint_as_float(a1 << 16); bs[3] += __uint_as_float(a1 & 0xffff0000u);
-                        bs[4] += __uint_as_float(a2 << 16); bs[5] += __uint_as_float(a2 & 0xffff0000u);
-                        bs[6] += __uint_as_float(a3 << 16); bs[7] += __uint_as_float(a3 & 0xffff0000u);
+                        uint32_t a[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t alive;
+                            asm("set.ne.u32.f16x2 %0, %1, %2;" : "=r"(alive) : "r"(mw[i]), "r"(0x3C043C04u));
+                            a[i] = G[j][i] & alive;
+                        }
+                        bs[0] += __uint_as_float(a[0] << 16); bs[1] += __uint_as_float(a[0] & 0xffff0000u);
+                        bs[2] += __uint_as_float(a[1] << 16); bs[3] += __uint_as_float(a[1] & 0xffff0000u);
+                        bs[4] += __uint_as_float(a[2] << 16); bs[5] += __uint_as_float(a[2] & 0xffff0000u);
+                        bs[6] += __uint_as_float(a[3] << 16); bs[7] += __uint_as_float(a[3] & 0xffff0000u);
                     }
                     // transposing reduction over the 8 lanes that share q: lane ends with channel 8q + 4*b4 + 2*b3 + b2
                     {

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "vqa_dropnorm_bwd_unpool": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u64, _vp],
     "vqa_embed_tanh_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_embed_tanh_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_dropout_threshold_pattern": [_f, _vp, _vp],
     "vqa_length_order": [_vp, _vp, _vp, _i, _i, _vp],
     "vqa_embed_tanh_fwd_ordered": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_embed_tanh_bwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],

@@ -102,6 +102,11 @@ int vqa_embed_tanh_fwd(const int64_t* q, const int64_t* q_len, const float* emb,
  * (padding_idx, models/model.py:138-140) receives nothing */
 int vqa_embed_tanh_bwd(const int64_t* q, const int64_t* q_len, const void* xs, const void* dxs, float* demb,
                        int act_dtype, int B, int T, int E, int ldx, int dirs, float p, uint64_t seed, void* stream);
+/* Host-side diagnostic (no GPU work): the vector dropout scheme of the attention / dropout+L2-norm kernels reads each
+ * 16-bit random field as a bf16 bit pattern and drops the element iff it compares below a threshold; *pattern is that
+ * threshold's bit pattern for probability p (0 = dropout off), *count16 = round(p * 65536), the number of patterns that
+ * should compare below it (nn.Dropout(p), models/model.py:84,185,194). */
+int vqa_dropout_threshold_pattern(float p, uint32_t* pattern, uint32_t* count16);
 /* Length order of the batch -- the sort pack_padded_sequence(enforce_sorted=False) does on the host in the reference
  * (models/model.py:160): order[j] (int32) = sample at position j of the batch sorted by DESCENDING length, ties in sample
  * order; len_sorted[j] (int64) = q_len[order[j]] clamped to [0, T].  No host synchronisation.  B <= 8192. */

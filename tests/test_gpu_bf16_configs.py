@@ -20,18 +20,21 @@ pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
-# name -> (config overrides, image size, batch)
+# name -> (config overrides, image size, batch).  Batches of 16: the x_conv weight gradient is sum_s dlogit[s] * x[s] with
+# sum_s dlogit[s] = 0, i.e. it only sees how x varies over the positions, while bf16 rounds x = relu(v' + q') relative to
+# |q'| -- with a handful of samples on a small grid that single tensor sits AT the 2e-2 bar (measured 1.0e-2 ... 3.4e-2
+# at B = 3 ... 5), with 16 it is inside it like every other gradient.
 VARIANTS = {
-    "mul": ({"attention.do_option": "*"}, 96, 4),
-    "cat": ({"attention.do_option": "|"}, 96, 3),
+    "mul": ({"attention.do_option": "*"}, 96, 16),
+    "cat": ({"attention.do_option": "|"}, 96, 16),
     # the reference's evaluated configuration: stride 2, '*' (config_eval.yaml:52-69; dropout is 0 here for the gradient check)
-    "eval_yaml_stride2_mul": ({"image.stride": 2, "attention.do_option": "*"}, 224, 4),
-    "stride2_plus": ({"image.stride": 2}, 160, 5),
-    "unidir": ({"text.bidirectional": False}, 96, 4),
-    "g3": ({"attention.glimpses": 3}, 96, 4),
-    "g1": ({"attention.glimpses": 1}, 64, 4),
-    "channels5": ({"image.num_channels": [3, 64, 128, 256, 512]}, 128, 3),
-    "channels_narrow": ({"image.num_channels": [3, 32, 64, 128, 256]}, 128, 3),
+    "eval_yaml_stride2_mul": ({"image.stride": 2, "attention.do_option": "*"}, 224, 16),
+    "stride2_plus": ({"image.stride": 2}, 320, 16),
+    "unidir": ({"text.bidirectional": False}, 96, 16),
+    "g3": ({"attention.glimpses": 3}, 96, 16),
+    "g1": ({"attention.glimpses": 1}, 96, 16),
+    "channels5": ({"image.num_channels": [3, 64, 128, 256, 512]}, 160, 16),
+    "channels_narrow": ({"image.num_channels": [3, 32, 64, 128, 256]}, 160, 16),
 }
 
 

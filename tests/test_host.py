@@ -85,3 +85,26 @@ def test_synthetic_batch_shapes():
         n = int(al[b])
         assert (ai[b, :n] > 0).all() and (ai[b, n:] == 0).all() and (av[b, n:] == 0).all()
         assert (ai[b, :n].diff() > 0).all() and int(av[b].sum()) <= 10
+
+
+def test_vector_dropout_threshold_drops_the_requested_fraction():
+    """nn.Dropout(p) (reference models/model.py:84,185,194) on the vector mask scheme: a 16-bit random field is compared AS A
+    BF16 BIT PATTERN against a threshold (one HSET2 per two elements).  Over all 65536 patterns the threshold must drop
+    round(p * 65536) of them -- exactly for the config values, within 2^-10 everywhere (thresholds are kept away from
+    subnormals) -- and NaN patterns must count as kept.  Host code of the library only; no GPU work."""
+    import ctypes as C
+    from dl_vqa_b200 import lib
+    L = lib.load()
+    patterns = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
+    pat, cnt = C.c_uint32(0), C.c_uint32(0)
+    for p in [0.0, 0.1, 0.2, 0.3, 0.4, 0.45, 0.4844, 0.497, 0.499, 0.5, 0.501, 0.6, 0.75, 0.9, 0.99]:
+        assert L.vqa_dropout_threshold_pattern(C.c_float(p), C.byref(pat), C.byref(cnt)) == 0
+        if p == 0.0:
+            assert pat.value == 0
+            continue
+        assert cnt.value == int(p * 65536 + 0.5)
+        t = torch.tensor([pat.value], dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
+        assert bool(torch.isfinite(t).all()) and (float(t.abs()) == 0.0 or float(t.abs()) >= 2.0 ** -126)   # zero or normal
+        dropped = int((patterns < t).sum())           # ordered compare: NaN patterns are never dropped
+        tol = 0 if p in (0.1, 0.2, 0.3, 0.4, 0.6, 0.75, 0.9) else 64
+        assert abs(dropped - cnt.value) <= tol, (p, dropped, cnt.value)

@@ -7,10 +7,10 @@ what=" $* "
 mkdir -p gpurun_out
 has() { [[ "$what" == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-if has lstmtests; then
-  timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_bf16_configs.py -m gpu -q -k "lstm or variants or ordered" > gpurun_out/${tag}_pytest_lstm.log 2>&1
-  echo "pytest exit $?" >> gpurun_out/${tag}_pytest_lstm.log
-  tail -15 gpurun_out/${tag}_pytest_lstm.log
+if has quicktests; then      # a selection: QUICK_FILES (default: every GPU test file) filtered by QUICK_K
+  timeout 900 python -m pytest ${QUICK_FILES:-tests} -m gpu -q -k "${QUICK_K:-lstm or variants or ordered}" > gpurun_out/${tag}_pytest_quick.log 2>&1
+  echo "pytest exit $?" >> gpurun_out/${tag}_pytest_quick.log
+  grep -E "passed|failed|FAILED|Error" gpurun_out/${tag}_pytest_quick.log | tail -25
 fi
 if has tests; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1
