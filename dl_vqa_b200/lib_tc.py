@@ -21,6 +21,12 @@ PROTOTYPES = {
     "vqa_tc_lstm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_fwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_bwd_ordered": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_im2col": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vqa_conv_weight_pack_im2col": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_conv_weight_grad_unpack_im2col": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_pool2x2_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_unpool2x2_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vqa_col2im": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vqa_pack_lstm_whh": [_vp, _vp, _i, _vp],
     "vqa_tc_lstm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vqa_tc_lstm_cluster_size": [],

@@ -382,6 +382,12 @@ class VqaNet(nn.Module):
         return (self.compute_dtype == torch.bfloat16 and self.KS == 3 and self.stride == 1 and Cin % 64 == 0
                 and Cout in (64, 128, 256))
 
+    def _im2col_conv_ok(self, i: int) -> bool:
+        """Layer i runs as im2col + tcgen05 GEMM + pool (bf16 arm, shapes the direct kernels do not cover)."""
+        Cin, Cout = self.channels[i], self.channels[i + 1]
+        return (self.compute_dtype == torch.bfloat16 and Cout % 8 == 0 and (i == 0 or Cin % 8 == 0)
+                and os.environ.get("VQA_CONV_IM2COL", "1") != "0")
+
     def _run_forward(self, v, q, q_len, seed: int, save: bool):
         adt = self.compute_dtype
         dt = lib.dtype_code(adt)
@@ -403,6 +409,7 @@ class VqaNet(nn.Module):
         IH, IW = int(v.shape[2]), int(v.shape[3])
         conv_saved = []
         conv_wd = {}                 # layer -> weights packed for the data gradient (training forward only)
+        conv_cols = {}               # layer -> (patch matrix, packed weights, Kp) of the im2col + GEMM layers
         nl = len(self.channels) - 1
         for i in range(nl):
             conv = getattr(self.image, f"conv{i}")
@@ -424,6 +431,22 @@ class VqaNet(nn.Module):
                     conv_wd[i] = wd
                 call("vqa_tc_conv3x3_relu_pool_fwd", ptr(x), ptr(wp), ptr(conv.bias), ptr(out), ptr(mask),
                      B, IH, IW, Cin, Cout, st, tag=f"conv{i}_fwd")
+            elif self._im2col_conv_ok(i):
+                # any stride / kernel size / channel list on the tensor cores: patch matrix -> tcgen05 GEMM with bias + ReLU
+                # in its epilogue -> 2x2 max-pool + arg-max mask (im2col.cu); e.g. the stride-2 encoder of config_eval.yaml
+                K = self.KS * self.KS * Cin
+                Kp = _rup(K, 8)
+                M = B * OH * OW
+                wp = empty(Cout, Kp)
+                call("vqa_conv_weight_pack_im2col", ptr(conv.weight), ptr(wp), Cout, Cin, self.KS, Kp, st, tag="w_cast")
+                col = empty(M, Kp)
+                call("vqa_im2col", ptr(x), x_dt, nchw, ptr(col), B, IH, IW, Cin, self.KS, self.stride, Kp, st, tag=f"conv{i}_fwd")
+                y = empty(M, Cout)
+                call("vqa_tc_gemm", ptr(col), Kp, 0, ptr(wp), Kp, 0, ptr(y), lib.BF16, Cout, 0, ptr(conv.bias), None, 0,
+                     M, Cout, Kp, 1, lib.GEMM_RELU, 0.0, 0, 0, st, tag=f"conv{i}_fwd")
+                call("vqa_pool2x2_fwd", ptr(y), ptr(out), ptr(mask), B, OH, OW, Cout, st, tag=f"conv{i}_fwd")
+                if save:
+                    conv_cols[i] = (col, wp, Kp)
             else:
                 call("vqa_conv_relu_pool_fwd", ptr(x), x_dt, nchw, ptr(conv.weight), ptr(conv.bias), ptr(out), ptr(mask),
                      dt, B, IH, IW, Cin, Cout, self.KS, self.stride, st, tag=f"conv{i}_fwd")
@@ -479,7 +502,7 @@ class VqaNet(nn.Module):
                    B, self.max_answers, self.hidden, bias=cl.lin2.bias, tag="lin2")
 
         if save:
-            ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, conv_wd=conv_wd, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
+            ctx.update(wcache=mm._w, B=B, P=P, T=T, seed=seed, conv_saved=conv_saved, conv_wd=conv_wd, conv_cols=conv_cols, vn=vn, v_in=v_in, nrm=nrm, a_last=x,
                        text=tx, qd=qd, qp=qp, vp=vp, prob=prob, combd=combd, h1d=h1d,
                        q=q, q_len=q_len,
                        p=(p_text, p_img, p_att, p_cls), dt=dt, adt=adt)
@@ -866,8 +889,23 @@ class VqaNet(nn.Module):
                 fused_db = use_tc and Cin in (64, 128) and Cout % 128 == 0 and Cout <= 256
                 call("vqa_unpool_bf16", ptr(da), ptr(mask), ptr(dy), ptr(db) if fused_db else None, B, PH, PW, Cout, st,
                      tag="unpool")
+            cols = ctx.get("conv_cols", {}).get(i)
             if tc0:
                 pass
+            elif cols is not None:
+                # im2col layer: un-pool -> weight gradient (reduction-major tcgen05 GEMM over the saved patch matrix) and data
+                # gradient (GEMM against the packed weights as stored, then col2im)
+                col, wp, Kp = cols
+                OH, OW = (IH - self.KS) // self.stride + 1, (IW - self.KS) // self.stride + 1
+                M = B * OH * OW
+                dy = empty(M, Cout)
+                call("vqa_unpool2x2_bwd", ptr(da), ptr(mask), ptr(dy), B, OH, OW, Cout, st, tag="unpool")
+                call("vqa_zero", ptr(db), db.numel() * 4, st)
+                call("vqa_colsum", ptr(da), dt, Cout, ptr(mask), ptr(db), B * PH * PW, Cout, st)
+                dwp = zeros(Cout, Kp)
+                call("vqa_tc_gemm", ptr(dy), Cout, 0, ptr(col), Kp, 0, ptr(dwp), lib.F32, Kp, 0, None, None, 0,
+                     Cout, Kp, M, 1, lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if M >= 4096 else 0), 0.0, 0, 0, st, tag=f"conv{i}_wgrad")
+                call("vqa_conv_weight_grad_unpack_im2col", ptr(dwp), ptr(dW), Cout, Cin, self.KS, Kp, st, tag=f"conv{i}_wgrad")
             elif use_tc and Cin in (64, 128) and Cout % 128 == 0:
                 call("vqa_tc_conv3x3_bwd_weight", ptr(x), ptr(dy), ptr(dW), B, IH, IW, Cin, Cout, st,
                      tag=f"conv{i}_wgrad")
@@ -882,7 +920,15 @@ class VqaNet(nn.Module):
             names += [f"image.conv{i}.weight", f"image.conv{i}.bias"]
             if i > 0:
                 dx = None
-                if use_tc:
+                if cols is not None:
+                    col, wp, Kp = cols
+                    dcol = empty(M, Kp)
+                    call("vqa_tc_gemm", ptr(dy), Cout, 0, ptr(wp), Kp, 0, ptr(dcol), lib.BF16, Kp, 0, None, None, 0,
+                         M, Kp, Cout, 1, lib.GEMM_B_MN, 0.0, 0, 0, st, tag=f"conv{i}_dgrad")
+                    dx = empty(B, IH, IW, Cin)
+                    call("vqa_col2im", ptr(dcol), ptr(dx), B, IH, IW, Cin, self.KS, self.stride, Kp, st, tag=f"conv{i}_dgrad")
+                    del dy, dcol
+                elif use_tc:
                     wd = ctx.get("conv_wd", {}).get(i)
                     if wd is None:
                         wd = empty(Cin, 9 * Cout)

@@ -330,6 +330,27 @@ int vqa_tc_conv0_relu_pool_fwd_x(const void* x, int x_dtype, const float* w, con
                                  int B, int IH, int IW, int Cin, int Cout, void* stream);
 int vqa_tc_conv0_bwd_weight_bias_x(const void* x, int x_dtype, const void* dpool, const uint8_t* mask, float* dw, float* db,
                                    int B, int IH, int IW, int Cin, int Cout, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * General convolution layers on the tensor-core arm (models/model.py:72-84 for ANY cfg image.stride /
+ * image.kernel_size / image.num_channels, e.g. config/config_eval.yaml:52-62: stride 2): the layers outside the range
+ * of the direct kernels above run as  vqa_im2col -> vqa_tc_gemm (bias + ReLU epilogue) -> vqa_pool2x2_fwd  and, backward,
+ * vqa_unpool2x2_bwd -> vqa_tc_gemm (VQA_GEMM_OPERANDS_MN: weight gradient) / vqa_tc_gemm (VQA_GEMM_B_MN) -> vqa_col2im.
+ * Patch-matrix column order: k = (kh*KS + kw)*Cin + ci, zero padded to Kp (multiple of 8).  OH = (IH-KS)/stride + 1.
+ * --------------------------------------------------------------------------------------------- */
+/* col [B*OH*OW][Kp] bf16 from x: NCHW (nchw = 1; fp32 / fp16 / bf16) or NHWC (nchw = 0) */
+int vqa_im2col(const void* x, int x_dtype, int nchw, void* col, int B, int IH, int IW, int Cin, int KS, int stride,
+               int Kp, void* stream);
+/* w [Cout][Cin][KS][KS] fp32 (nn.Conv2d layout) -> wp [Cout][Kp] bf16 in patch order; and the fp32 gradient back */
+int vqa_conv_weight_pack_im2col(const float* w, void* wp, int Cout, int Cin, int KS, int Kp, void* stream);
+int vqa_conv_weight_grad_unpack_im2col(const float* dwp, float* dw, int Cout, int Cin, int KS, int Kp, void* stream);
+/* nn.MaxPool2d(2, 2) (floor) of y = relu(conv + bias) [B][OH][OW][C] bf16 -> out [B][OH/2][OW/2][C] and the arg-max mask
+ * of the direct kernels (0..3 = dy*2+dx of the first maximum, 4 = ReLU-dead); C % 8 == 0 */
+int vqa_pool2x2_fwd(const void* y, void* out, uint8_t* mask, int B, int OH, int OW, int C, void* stream);
+/* its backward: da [B][OH/2][OW/2][C] -> dy [B][OH][OW][C] (rows / columns dropped by the floor get zeros) */
+int vqa_unpool2x2_bwd(const void* da, const uint8_t* mask, void* dy, int B, int OH, int OW, int C, void* stream);
+/* dx [B][IH][IW][Cin] bf16 = overlap-add of dcol [B*OH*OW][Kp]; Cin % 8 == 0 */
+int vqa_col2im(const void* dcol, void* dx, int B, int IH, int IW, int Cin, int KS, int stride, int Kp, void* stream);
+
 /* Persistent LSTM recurrence, all steps and directions in one cooperative launch (replaces the cuDNN RNN of
  * models/model.py:164).  W_hh stays resident in shared memory (64 gate rows per CTA), h is exchanged through L2.
  *   gx [dirs][T][B][4H] bf16 (in: x W_ih^T + b_ih + b_hh, out: activated gates), cs [dirs][T][B][H] fp32,
