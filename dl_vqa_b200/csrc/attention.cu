@@ -414,20 +414,53 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t hrelu2_bf16(uint32_t a) { uint32_t r; asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u)); return r; }
-// relu(a + b) / relu(a * b) in ONE half-precision-pipe instruction (fma.rn.relu): the same single rounding as add.rn /
-// mul.rn followed by max(., 0), without the min/max instruction on the integer pipe
-__device__ __forceinline__ uint32_t hadd2_relu_bf16(uint32_t a, uint32_t b) {
-    uint32_t r; asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3F803F80u), "r"(b)); return r;
-}
-__device__ __forceinline__ uint32_t hmul2_relu_bf16(uint32_t a, uint32_t b) {
-    uint32_t r; asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0x80008000u)); return r;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+// ---- v' (and the packed copy of q') as bf16x2 (H = false) or f16x2 (H = true).  The '+' fusion rounds v' + q' to the
+// 16-bit format; q' is an order of magnitude larger than the spatial variation of v' that the x_conv weight gradient
+// sees (sum_s dlogit[s] = 0 removes the constant part), so the 8-bit mantissa of bf16 puts 1-2 % of max-norm error on
+// that one gradient.  With v' written as fp16 by the v_conv GEMM (11-bit mantissa; |v'| <= ||W_row||, nowhere near the
+// fp16 range, and the GEMM saturates instead of producing infinities) the same instructions are 8 x more precise, and
+// the widening to fp32 moves from the integer pipe (shift / and) to the half-precision pipe.
+template <bool H> __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    if (H) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool H> __device__ __forceinline__ float2 widen_h2(uint32_t x) {
+    if (H) {
+        float2 f;
+        asm("{\n.reg .f16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(f.x), "=f"(f.y) : "r"(x));
+        return f;
+    }
+    return make_float2(bf_lo(x), bf_hi(x));
+}
+// relu(a + b) / relu(a * b) in ONE half-precision-pipe instruction (fma.rn.relu): the same single rounding as add.rn /
+// mul.rn followed by max(., 0), without the min/max instruction on the integer pipe
+template <bool H> __device__ __forceinline__ uint32_t add_relu_h2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if (H) asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3C003C00u), "r"(b));
+    else asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3F803F80u), "r"(b));
+    return r;
+}
+template <bool H> __device__ __forceinline__ uint32_t mul_relu_h2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if (H) asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0x80008000u));
+    else asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0x80008000u));
+    return r;
+}
+template <bool H> __device__ __forceinline__ uint32_t ne_mask_h2(uint32_t a) {      // 0xFFFF in each half that is non-zero
+    uint32_t r;
+    if (H) asm("set.ne.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+    else asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+    return r;
+}
 
 // fold n = 8*GP per-lane values over the 32 lanes; afterwards v[0] of lane l holds the total of value index
 // l >> (5 - log2 n) (the other lanes of that group hold the same total)
@@ -448,7 +481,7 @@ __device__ __forceinline__ void transpose_reduce(float (&v)[N], int lane) {
     for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
 }
 
-template <int G, int OP, bool TRAIN>
+template <int G, int OP, bool TRAIN, bool VPH>
 __global__ void __launch_bounds__(NTHR, 1)
 attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict__ qp, const bf16* __restrict__ vn,
                             const float* __restrict__ wx, const float* __restrict__ bx, float* __restrict__ prob,
@@ -516,13 +549,13 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
 
     uint32_t c = 0;                                   // global chunk counter (same sequence as the producer)
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        uint32_t q2[8];                               // q' of this sample, rounded to bf16 (packed pairs)
+        uint32_t q2[8];                               // q' of this sample, rounded to the format of v' (packed pairs)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 f = *reinterpret_cast<const float2*>(qp + (int64_t)b * A_ + half * 512 + (j * 32 + lane) * 8 + 2 * i);
-                q2[j * 4 + i] = pack_bf16x2(f.x, f.y);
+                q2[j * 4 + i] = pack_h2<VPH>(f.x, f.y);
             }
         // ---- phase 1: per-position glimpse logits
         for (int i = (int)((pair + NPAIR - (c % NPAIR)) % NPAIR); i < n1; i += NPAIR) {
@@ -545,9 +578,9 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
                         if (TRAIN) dropout_flags8(d8, (uint32_t)(((int64_t)b * P + pos0 + ps) * (A_ / 8) + half * 64 + j * 32 + lane), t);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            uint32_t r = OP == VQA_ATT_ADD ? hadd2_relu_bf16(x[e], q2[j * 4 + e]) : hmul2_relu_bf16(x[e], q2[j * 4 + e]);
+                            uint32_t r = OP == VQA_ATT_ADD ? add_relu_h2<VPH>(x[e], q2[j * 4 + e]) : mul_relu_h2<VPH>(x[e], q2[j * 4 + e]);
                             if (TRAIN) r &= dropout_mask_bf16x2(t[e]);
-                            const float2 lh = make_float2(bf_lo(r), bf_hi(r));
+                            const float2 lh = widen_h2<VPH>(r);
 #pragma unroll
                             for (int g = 0; g < G; ++g) acc2[g * POS1 + ps] = __ffma2_rn(lh, wv[g][j * 4 + e], acc2[g * POS1 + ps]);
                         }
@@ -643,25 +676,29 @@ static size_t fwd_stream_smem(int G, int P) {
     return (size_t)NST * CHUNK + sizeof(float) * ((size_t)NCW * G * C_ + 3 * (size_t)G * P + 2) + 2 * NST * 8 + 256;
 }
 
-template <int G, int OP>
-int launch_fwd_stream(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
-                      void* out, int64_t ldo, int B, int P, Dropout d, cudaStream_t st) {
+template <int G, int OP, bool TRAIN, bool VPH>
+int launch_fwd_stream_t(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
+                        void* out, int64_t ldo, int B, int P, Dropout d, cudaStream_t st) {
     const size_t smem = fwd_stream_smem(G, P);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = B < sms ? B : sms;
-    if (d.threshold != 0) {
-        auto kern = attention_fwd_stream_kernel<G, OP, true>;
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d));
-    } else {
-        auto kern = attention_fwd_stream_kernel<G, OP, false>;
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d));
-    }
+    auto kern = attention_fwd_stream_kernel<G, OP, TRAIN, VPH>;
+    VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)vp, qp, (const bf16*)vn, wx, bx, prob, (bf16*)out, ldo, B, P, d));
     VQA_CHECK_LAUNCH("attention_fwd_stream");
     return 0;
+}
+// vph: v' is fp16 (written so by the v_conv GEMM), else bf16
+template <int G, int OP>
+int launch_fwd_stream(const void* vp, bool vph, const float* qp, const void* vn, const float* wx, const float* bx, float* prob,
+                      void* out, int64_t ldo, int B, int P, Dropout d, cudaStream_t st) {
+    const bool train = d.threshold != 0;
+    if (vph) return train ? launch_fwd_stream_t<G, OP, true, true>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                          : launch_fwd_stream_t<G, OP, false, true>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
+    return train ? launch_fwd_stream_t<G, OP, true, false>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                 : launch_fwd_stream_t<G, OP, false, false>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -678,13 +715,7 @@ constexpr int BCHUNK = 32768, BNST = 5;
 constexpr int BPOSA = BCHUNK / (C_ * 2);          // 64 rows of v per chunk
 constexpr int BPOSC = BCHUNK / (A_ * 2);          // 16 rows of v' per chunk
 
-__device__ __forceinline__ uint32_t ne_mask_bf16x2(uint32_t a) {      // 0xFFFF in each half that is non-zero
-    uint32_t r;
-    asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
-    return r;
-}
-
-template <int G, int OP, bool TRAIN>
+template <int G, int OP, bool TRAIN, bool VPH>
 __global__ void __launch_bounds__(NTHR, 1)
 attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf16* __restrict__ vp, const float* __restrict__ qp,
                             const bf16* __restrict__ vn, const float* __restrict__ wx, const float* __restrict__ prob,
@@ -829,8 +860,9 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float2 f = *reinterpret_cast<const float2*>(qp + (int64_t)b * A_ + a0 + 2 * e);
-                q2[e] = pack_bf16x2(f.x, f.y);
-                qf[2 * e] = bf_lo(q2[e]); qf[2 * e + 1] = bf_hi(q2[e]);
+                q2[e] = pack_h2<VPH>(f.x, f.y);
+                const float2 qw = widen_h2<VPH>(q2[e]);
+                qf[2 * e] = qw.x; qf[2 * e + 1] = qw.y;
             }
             float dq[8], dw[G][8];
 #pragma unroll
@@ -859,9 +891,10 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                         uint32_t* o = reinterpret_cast<uint32_t*>(&o4);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            uint32_t xr = OP == VQA_ATT_ADD ? hadd2_relu_bf16(x[e], q2[e]) : hmul2_relu_bf16(x[e], q2[e]);
+                            uint32_t xr = OP == VQA_ATT_ADD ? add_relu_h2<VPH>(x[e], q2[e]) : mul_relu_h2<VPH>(x[e], q2[e]);
                             if (TRAIN) xr &= dropout_mask_bf16x2(fl[e]);          // relu(pre) where kept (unscaled), else 0
-                            const float xl = bf_lo(xr), xh = bf_hi(xr);
+                            const float2 xw = widen_h2<VPH>(xr);
+                            const float xl = xw.x, xh = xw.y;
                             float dl_lo = 0.f, dl_hi = 0.f;
 #pragma unroll
                             for (int g = 0; g < G; ++g) {
@@ -871,15 +904,16 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
                                 dw[g][2 * e + 1] = fmaf(dls[g], xh, dw[g][2 * e + 1]);
                             }
                             // gradient w.r.t. the pre-activation, gated by (alive and kept) <=> xr != 0
-                            const uint32_t dpre = pack_bf16x2(dl_lo, dl_hi) & ne_mask_bf16x2(xr);
+                            const uint32_t dpre = pack_bf16x2(dl_lo, dl_hi) & ne_mask_h2<VPH>(xr);
                             const float pl = bf_lo(dpre), phh = bf_hi(dpre);
                             if (OP == VQA_ATT_ADD) {
                                 o[e] = dpre;
                                 dq[2 * e] += pl; dq[2 * e + 1] += phh;
                             } else {
                                 o[e] = pack_bf16x2(pl * qf[2 * e], phh * qf[2 * e + 1]);
-                                dq[2 * e] = fmaf(pl, bf_lo(x[e]), dq[2 * e]);
-                                dq[2 * e + 1] = fmaf(phh, bf_hi(x[e]), dq[2 * e + 1]);
+                                const float2 vw = widen_h2<VPH>(x[e]);
+                                dq[2 * e] = fmaf(pl, vw.x, dq[2 * e]);
+                                dq[2 * e + 1] = fmaf(phh, vw.y, dq[2 * e + 1]);
                             }
                         }
                         __stcs(reinterpret_cast<uint4*>(dvpb + (int64_t)sidx * A_ + a0), o4);
@@ -913,28 +947,31 @@ static size_t bwd_stream_smem(int G, int P) {
     return (size_t)BNST * BCHUNK + sizeof(float) * ((size_t)4 * (1 + G) * A_ + 2 * (size_t)G * P + (size_t)G * C_) + 2 * BNST * 8 + 256;
 }
 
-template <int G, int OP>
-int launch_bwd_stream(const void* dout, int64_t ldd, const void* vp, const float* qp, const void* vn, const float* wx,
-                      const float* prob, void* dvp, void* dvn, float* dqp, float* dwx_part, float* dbx_part,
-                      int B, int P, Dropout d, cudaStream_t st) {
+template <int G, int OP, bool TRAIN, bool VPH>
+int launch_bwd_stream_t(const void* dout, int64_t ldd, const void* vp, const float* qp, const void* vn, const float* wx,
+                        const float* prob, void* dvp, void* dvn, float* dqp, float* dwx_part, float* dbx_part,
+                        int B, int P, Dropout d, cudaStream_t st) {
     const size_t smem = bwd_stream_smem(G, P);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = B < sms ? B : sms;
-    if (d.threshold != 0) {
-        auto kern = attention_bwd_stream_kernel<G, OP, true>;
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
-                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d));
-    } else {
-        auto kern = attention_bwd_stream_kernel<G, OP, false>;
-        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
-                                       (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d));
-    }
+    auto kern = attention_bwd_stream_kernel<G, OP, TRAIN, VPH>;
+    VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQA_CUDA(vqa_launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, (const bf16*)dout, ldd, (const bf16*)vp, qp, (const bf16*)vn, wx, prob, (bf16*)dvp,
+                            (bf16*)dvn, dqp, dwx_part, dbx_part, B, P, d));
     VQA_CHECK_LAUNCH("attention_bwd_stream");
     return 0;
+}
+template <int G, int OP>
+int launch_bwd_stream(const void* dout, int64_t ldd, const void* vp, bool vph, const float* qp, const void* vn, const float* wx,
+                      const float* prob, void* dvp, void* dvn, float* dqp, float* dwx_part, float* dbx_part,
+                      int B, int P, Dropout d, cudaStream_t st) {
+    const bool train = d.threshold != 0;
+    if (vph) return train ? launch_bwd_stream_t<G, OP, true, true>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                          : launch_bwd_stream_t<G, OP, false, true>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
+    return train ? launch_bwd_stream_t<G, OP, true, false>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                 : launch_bwd_stream_t<G, OP, false, false>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
 }
 
 }  // namespace stream
@@ -1007,22 +1044,58 @@ static int att_check(int act_dtype, int op, int B, int P, int A, int C, int G, i
     return 0;
 }
 
-extern "C" int vqa_attention_fwd(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx,
-                                 float* prob, void* out, int64_t ldo, int act_dtype, int op,
-                                 int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream) {
+// 1 when the streaming kernels take this configuration (the shapes v' may be handed over as fp16 for), else 0
+extern "C" int vqa_attention_streaming_ok(int act_dtype, int op, int P, int A, int C, int G) {
+    return act_dtype == VQA_BF16 && (op == VQA_ATT_ADD || op == VQA_ATT_MUL) && A == stream::A_ && C == stream::C_ && G >= 1 && G <= 2 &&
+           P > 0 && stream::fwd_stream_smem(G, P) <= 232448 && stream::bwd_stream_smem(G, P) <= 232448;
+}
+
+extern "C" int vqa_attention_fwd_x(const void* vp, int vp_dtype, const float* qp, const void* vn, const float* wx, const float* bx,
+                                   float* prob, void* out, int64_t ldo, int act_dtype, int op,
+                                   int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream) {
     if (int e = att_check(act_dtype, op, B, P, A, C, G, ldo)) return e;
     const Dropout d = make_dropout(seed, p_drop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_BF16 && op != VQA_ATT_CAT && A == stream::A_ && C == stream::C_ && G <= 2 && stream::fwd_stream_smem(G, P) <= 232448 &&
-        stream::bwd_stream_smem(G, P) <= 232448) {     // tensor-core arm at the config.yaml shape
+    const bool vph = vp_dtype == VQA_F16;
+    VQA_REQUIRE(vph || vp_dtype == act_dtype, "attention: v' dtype %d (the activation dtype, or fp16 on the streaming kernels)", vp_dtype);
+    if (vqa_attention_streaming_ok(act_dtype, op, P, A, C, G)) {     // tensor-core arm at the config.yaml shape
         VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
-        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_fwd_stream<1, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
-                                             : stream::launch_fwd_stream<1, VQA_ATT_MUL>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
-        return op == VQA_ATT_ADD ? stream::launch_fwd_stream<2, VQA_ATT_ADD>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
-                                 : stream::launch_fwd_stream<2, VQA_ATT_MUL>(vp, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
+        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_fwd_stream<1, VQA_ATT_ADD>(vp, vph, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                                             : stream::launch_fwd_stream<1, VQA_ATT_MUL>(vp, vph, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
+        return op == VQA_ATT_ADD ? stream::launch_fwd_stream<2, VQA_ATT_ADD>(vp, vph, qp, vn, wx, bx, prob, out, ldo, B, P, d, st)
+                                 : stream::launch_fwd_stream<2, VQA_ATT_MUL>(vp, vph, qp, vn, wx, bx, prob, out, ldo, B, P, d, st);
     }
+    VQA_REQUIRE(!vph, "attention: fp16 v' is only taken by the streaming kernels (see vqa_attention_streaming_ok)");
     ATT_DISPATCH(launch_fwd, vp, qp, vn, wx, bx, prob, out, ldo, B, P, A, C, d, st);
     VQA_REQUIRE(false, "attention_fwd: no kernel for this configuration");
+    return 0;
+}
+
+extern "C" int vqa_attention_fwd(const void* vp, const float* qp, const void* vn, const float* wx, const float* bx,
+                                 float* prob, void* out, int64_t ldo, int act_dtype, int op,
+                                 int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream) {
+    return vqa_attention_fwd_x(vp, act_dtype, qp, vn, wx, bx, prob, out, ldo, act_dtype, op, B, P, A, C, G, p_drop, seed, stream);
+}
+
+extern "C" int vqa_attention_bwd_x(const void* dout, int64_t ldd, const void* vp, int vp_dtype, const float* qp, const void* vn,
+                                   const float* wx, const float* prob, void* dvp, void* dvn, float* dqp,
+                                   float* dwx_part, float* dbx_part, int act_dtype, int op,
+                                   int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream) {
+    if (int e = att_check(act_dtype, op, B, P, A, C, G, ldd)) return e;
+    const Dropout d = make_dropout(seed, p_drop);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vph = vp_dtype == VQA_F16;
+    VQA_REQUIRE(vph || vp_dtype == act_dtype, "attention: v' dtype %d (the activation dtype, or fp16 on the streaming kernels)", vp_dtype);
+    if (vqa_attention_streaming_ok(act_dtype, op, P, A, C, G)) {     // same condition as the forward: both recompute the fusion in 16 bits
+        VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
+        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_bwd_stream<1, VQA_ATT_ADD>(dout, ldd, vp, vph, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                                             : stream::launch_bwd_stream<1, VQA_ATT_MUL>(dout, ldd, vp, vph, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
+        return op == VQA_ATT_ADD ? stream::launch_bwd_stream<2, VQA_ATT_ADD>(dout, ldd, vp, vph, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
+                                 : stream::launch_bwd_stream<2, VQA_ATT_MUL>(dout, ldd, vp, vph, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
+    }
+    VQA_REQUIRE(!vph, "attention: fp16 v' is only taken by the streaming kernels (see vqa_attention_streaming_ok)");
+    ATT_DISPATCH(launch_bwd, dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, A, C, d, st);
+    VQA_REQUIRE(false, "attention_bwd: no kernel for this configuration");
     return 0;
 }
 
@@ -1030,18 +1103,6 @@ extern "C" int vqa_attention_bwd(const void* dout, int64_t ldd, const void* vp, 
                                  const float* wx, const float* prob, void* dvp, void* dvn, float* dqp,
                                  float* dwx_part, float* dbx_part, int act_dtype, int op,
                                  int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream) {
-    if (int e = att_check(act_dtype, op, B, P, A, C, G, ldd)) return e;
-    const Dropout d = make_dropout(seed, p_drop);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (act_dtype == VQA_BF16 && op != VQA_ATT_CAT && A == stream::A_ && C == stream::C_ && G <= 2 && stream::bwd_stream_smem(G, P) <= 232448 &&
-        stream::fwd_stream_smem(G, P) <= 232448) {     // same condition as the forward: both recompute the fusion in bf16
-        VQA_REQUIRE((int64_t)B * P * (A / 8) < (1ll << 32), "attention: batch too large for the 32-bit dropout counter");
-        if (G == 1) return op == VQA_ATT_ADD ? stream::launch_bwd_stream<1, VQA_ATT_ADD>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
-                                             : stream::launch_bwd_stream<1, VQA_ATT_MUL>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
-        return op == VQA_ATT_ADD ? stream::launch_bwd_stream<2, VQA_ATT_ADD>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st)
-                                 : stream::launch_bwd_stream<2, VQA_ATT_MUL>(dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, d, st);
-    }
-    ATT_DISPATCH(launch_bwd, dout, ldd, vp, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, B, P, A, C, d, st);
-    VQA_REQUIRE(false, "attention_bwd: no kernel for this configuration");
-    return 0;
+    return vqa_attention_bwd_x(dout, ldd, vp, act_dtype, qp, vn, wx, prob, dvp, dvn, dqp, dwx_part, dbx_part, act_dtype, op,
+                               B, P, A, C, G, p_drop, seed, stream);
 }

@@ -67,7 +67,7 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, CUtensorMapSwizzle sw
 constexpr int BM = 128, BK = 64, GEMM_THREADS = 192;
 
 struct GemmEpilogue {
-    void* out; int out_bf16; int64_t ldc, c_sb;
+    void* out; int out_bf16; int64_t ldc, c_sb;       // out_bf16: 0 = fp32, 1 = bf16, 2 = fp16 (16-bit outputs share every store path)
     const float* bias; const float* bias2; int64_t bias_sb;
     int relu, atomic, use_dropout;
     uint32_t site; Dropout drop;
@@ -89,6 +89,15 @@ struct GemmSmem {
 // `bias_lane` = bias[nb + lane] + bias2[nb + lane] (0 beyond N): one coalesced load per chunk, fetched by the caller
 // before it waits for the accumulator, and broadcast here with shuffles -- 32 (x2) same-address loads per lane after
 // the TMEM wait doubled the time of the LSTM input projection.
+// two fp32 -> one packed 16-bit pair: bf16x2, or f16x2 (saturating to the largest finite value: a later consumer adds in
+// fp16 and must never see an infinity)
+__device__ __forceinline__ uint32_t gemm_pack16(float lo, float hi, bool f16) {
+    uint32_t r;
+    if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ float gemm_bias_lane(const float* bias, const float* bias2, int n, int N) {
     float b = 0.f;
     if (n < N) {
@@ -143,11 +152,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
             // with piece q of the quad's four rows, so one store instruction writes 64 contiguous bytes per row
             // (8 lines per instruction instead of 32 -- the epilogue of the store-heavy GEMMs is LSU-wavefront bound).
             uint32_t G[4][4];
+            const bool f16 = ep.out_bf16 == 2;               // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
-            }
+            for (int j = 0; j < 16; ++j) G[j >> 2][j & 3] = gemm_pack16(v[2 * j], v[2 * j + 1], f16);
             const int q = lane & 3;
 #pragma unroll
             for (int step = 0; step < 2; ++step) {
@@ -171,7 +178,11 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, float (
         } else if (row_ok) {
             bf16* o = ob + (int64_t)m * ep.ldc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < N) o[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j)
+                if (nb + j < N) {
+                    if (ep.out_bf16 == 2) reinterpret_cast<__half*>(o)[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+                    else o[j] = __float2bfloat16_rn(v[j]);
+                }
         }
     } else if (row_ok) {
         float* o = (float*)ep.out + (int64_t)batch * ep.c_sb + (int64_t)m * ep.ldc + nb;
@@ -210,10 +221,12 @@ __device__ __forceinline__ void gemm_store_chunk_bf16(const GemmEpilogue& ep, fl
         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
     }
     uint32_t G[4][4];
+    if (ep.out_bf16 == 2) {                                  // warp-uniform; two straight-line blocks, no per-element select
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        G[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&h2);
+        for (int j = 0; j < 16; ++j) G[j >> 2][j & 3] = gemm_pack16(v[2 * j], v[2 * j + 1], true);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) G[j >> 2][j & 3] = gemm_pack16(v[2 * j], v[2 * j + 1], false);
     }
     const int q = lane & 3;
 #pragma unroll
@@ -555,7 +568,7 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     VQA_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: row pitches (%lld, %lld) must be multiples of 8 bf16 elements (TMA 16-byte strides)",
                 (long long)lda, (long long)ldb);
     VQA_REQUIRE(nbatch == 1 || (a_sb % 8 == 0 && b_sb % 8 == 0), "tc_gemm: batch strides must be multiples of 8 elements");
-    VQA_REQUIRE(c_dtype == VQA_F32 || c_dtype == VQA_BF16, "tc_gemm: bad output dtype");
+    VQA_REQUIRE(c_dtype == VQA_F32 || c_dtype == VQA_BF16 || c_dtype == VQA_F16, "tc_gemm: bad output dtype");
     const bool splitk = (flags & VQA_GEMM_SPLITK) != 0;
     const bool mn = (flags & VQA_GEMM_OPERANDS_MN) != 0;
     const bool bmn = (flags & VQA_GEMM_B_MN) != 0;          // A [M,K] K-major, B stored [K,N]
@@ -615,7 +628,7 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         if (int e = make_tmap_bf16(&tb, B, 3, dimsb, strb, box)) return e;
     }
     GemmEpilogue ep{};
-    ep.out = C; ep.out_bf16 = c_dtype == VQA_BF16; ep.ldc = ldc; ep.c_sb = c_sb;
+    ep.out = C; ep.out_bf16 = c_dtype == VQA_BF16 ? 1 : (c_dtype == VQA_F16 ? 2 : 0); ep.ldc = ldc; ep.c_sb = c_sb;
     ep.bias = bias; ep.bias2 = bias2; ep.bias_sb = bias_sb;
     ep.relu = (flags & VQA_GEMM_RELU) ? 1 : 0;
     ep.atomic = splitk ? 1 : 0;

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
 
-F32, BF16, F16 = 0, 1, 2          # F16: network input only
+F32, BF16, F16 = 0, 1, 2          # F16: the network input, and v' (attention.v_conv output) on the streaming attention kernels
 ATT_ADD, ATT_MUL, ATT_CAT = 0, 1, 2
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_SPLITK, GEMM_OPERANDS_MN, GEMM_B_MN = 1, 2, 4, 8, 16
 SITE_IMAGE, SITE_ATT_V, SITE_EMBED, SITE_ATT_Q, SITE_ATT_X, SITE_CLS_IN, SITE_CLS_HID = range(7)
@@ -45,6 +45,10 @@ PROTOTYPES = {
     "vqa_attention_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "vqa_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                           _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_attention_fwd_x": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_attention_bwd_x": [_vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
+                            _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "vqa_attention_streaming_ok": [_i, _i, _i, _i, _i, _i],
     "vqa_softloss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "vqa_dropout_apply": [_vp, _i64, _vp, _i64, _i, _i64, _i, _f, _u64, _u32, _vp],
     "vqa_colsum": [_vp, _i, _i64, _vp, _vp, _i64, _i, _vp],

@@ -475,14 +475,19 @@ class VqaNet(nn.Module):
             call("vqa_dropout_apply", ptr(qf), QF, ptr(qd), QF, dt, B, QF, p_att, seed, lib.SITE_ATT_Q, st)
         qp = empty(B, A, dtype=f32)
         mm.lin_fwd(ptr(qd), dt, QF, att.q_lin.weight, ptr(qp), lib.F32, A, B, A, QF, bias=att.q_lin.bias, tag="q_lin")
-        vp = empty(B * P, A)
-        mm.lin_fwd(ptr(v_in), dt, Cimg, att.v_conv.weight, ptr(vp), dt, A, B * P, A, Cimg, tag="v_conv")
         G = self.G
+        op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
+        # v' is handed to the streaming attention kernels as FLOAT16 (written so by the v_conv GEMM): the '+' fusion rounds
+        # v' + q' to the 16-bit format, and 11 mantissa bits instead of 8 take the x_conv weight gradient from 1-2 % to
+        # ~0.3 % max-norm error (attention.cu); |v'| <= ||W_row|| is nowhere near the fp16 range and the GEMM saturates
+        vp_f16 = tc and bool(lib.load().vqa_attention_streaming_ok(dt, op, P, A, Cimg, G)) and os.environ.get("VQA_ATT_VP_F16", "1") != "0"
+        vp_dt = lib.F16 if vp_f16 else dt
+        vp = empty(B * P, A, dtype=torch.float16 if vp_f16 else adt)
+        mm.lin_fwd(ptr(v_in), dt, Cimg, att.v_conv.weight, ptr(vp), vp_dt, A, B * P, A, Cimg, tag="v_conv")
         KC = G * Cimg + QF
         comb = empty(B, KC)
         prob = empty(B, G, P, dtype=f32)
-        op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
-        call("vqa_attention_fwd", ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
+        call("vqa_attention_fwd_x", ptr(vp), vp_dt, ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
              ptr(prob), ptr(comb), KC, dt, op, B, P, A, Cimg, G, p_att, seed, st)
         # combined = cat([pooled, q])  (models/model.py:64)
         esz = comb.element_size()
@@ -804,9 +809,9 @@ class VqaNet(nn.Module):
         dwx_part = empty(B, G * AW, dtype=f32)
         dbx_part = empty(B, G, dtype=f32)
         op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
-        call("vqa_attention_bwd", ptr(dcomb), KC, ptr(vp), ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(prob),
-             ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op, B, P, A, Cimg, G,
-             p_att, seed, st)
+        call("vqa_attention_bwd_x", ptr(dcomb), KC, ptr(vp), lib.F16 if vp.dtype == torch.float16 else dt, ptr(qp), ptr(vn),
+             ptr(att.x_conv.weight), ptr(prob), ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op,
+             B, P, A, Cimg, G, p_att, seed, st)
         grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * AW, B, G * AW, "attention.x_conv.weight").view(G, AW, 1, 1)
         grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G, "attention.x_conv.bias")
         # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)

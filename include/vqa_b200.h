@@ -34,7 +34,8 @@ extern "C" {
 #define VQA_ABI_VERSION 1
 #define VQA_F32 0
 #define VQA_BF16 1
-#define VQA_F16 2    /* network INPUT only: the reference stores its pre-processed images as float16 (preprocessing/preprocess_images.py:40) */
+#define VQA_F16 2    /* the network INPUT (the reference stores its pre-processed images as float16, preprocessing/preprocess_images.py:40),
+                        the output of vqa_tc_gemm where asked for, and v' of vqa_attention_*_x */
 #define VQA_ERR_INVALID_ARGUMENT (-1)
 #define VQA_ERR_UNSUPPORTED (-2)
 #define VQA_SEED_ON_DEVICE (1ull << 63)
@@ -173,6 +174,21 @@ int vqa_attention_bwd(const void* dout, int64_t ldd, const void* vp, const float
                       float* dwx_part, float* dbx_part, int act_dtype, int op,
                       int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream);
 
+/* The same two entries with the dtype of v' explicit.  vp_dtype = act_dtype, or VQA_F16 where
+ * vqa_attention_streaming_ok(...) returns 1 (tensor-core arm at the config.yaml widths: A = 1024, C = 256, '+' / '*',
+ * G <= 2, grid small enough for shared memory): the '+' fusion of models/model.py:188-191 rounds v' + q' to the 16-bit
+ * format of v', and q' is about ten times larger than the spatial variation of v' that the x_conv weight gradient sees,
+ * so fp16 (11-bit mantissa; the v_conv GEMM writes it directly, saturating) instead of bf16 takes that gradient's error
+ * from 1-2 % to ~0.3 % of max-norm at no cost.  dvp stays act_dtype. */
+int vqa_attention_streaming_ok(int act_dtype, int op, int P, int A, int C, int G);
+int vqa_attention_fwd_x(const void* vp, int vp_dtype, const float* qp, const void* vn, const float* wx, const float* bx,
+                        float* prob, void* out, int64_t ldo, int act_dtype, int op,
+                        int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream);
+int vqa_attention_bwd_x(const void* dout, int64_t ldd, const void* vp, int vp_dtype, const float* qp, const void* vn,
+                        const float* wx, const float* prob, void* dvp, void* dvn, float* dqp,
+                        float* dwx_part, float* dbx_part, int act_dtype, int op,
+                        int B, int P, int A, int C, int G, float p_drop, uint64_t seed, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Soft-target loss + VQA score -- train.py:190-206 and utils/train_utils.py:12-25, one pass:
  *   loss = (1/B) sum_b sum_j [a_idx[b,j] != 0] * (a_val[b,j]/10) * (-log_softmax(logits[b]))[a_idx[b,j]-1]
@@ -265,7 +281,7 @@ int vqa_copy(void* dst, const void* src, int64_t bytes, void* stream);
  * staged by TMA into 128-byte-swizzled shared memory.  Same math as the entries above.
  * ============================================================================================= */
 
-/* C[z][m,n] (c_dtype, row pitch ldc) = act(sum_k A[z][m,k] * B[z][n,k] + bias[z][n] + bias2[z][n]) * dropout
+/* C[z][m,n] (c_dtype VQA_F32 / VQA_BF16 / VQA_F16 (saturating), row pitch ldc) = act(sum_k A[z][m,k] * B[z][n,k] + bias[z][n] + bias2[z][n]) * dropout
  * A [M,K] and B [N,K] are bf16, K contiguous, row pitches lda/ldb (multiples of 8 elements), 16-byte
  * aligned.  flags as vqa_gemm (VQA_GEMM_RELU, VQA_GEMM_SPLITK; ACCUMULATE unsupported).  With
  * VQA_GEMM_OPERANDS_MN the operands are stored reduction-major: A [K,M], B [K,N] (pitches lda/ldb); this is the

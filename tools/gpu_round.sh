@@ -62,4 +62,10 @@ if has sanitize; then
     echo "$tool exit $?"; tail -4 gpurun_out/${tag}_sanitizer_${tool}.log
   done
 fi
+if has scale; then            # weak scaling at N = NGPUS (the box must have been requested with gpurun --gpus N)
+  N=${NGPUS:-2}
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+    bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_scale_n$N.json 2> gpurun_out/${tag}_scale_n$N.err
+  echo "scale N=$N exit $?"; head -c 400 gpurun_out/${tag}_scale_n$N.json; echo; tail -3 gpurun_out/${tag}_scale_n$N.err
+fi
 exit 0
