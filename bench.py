@@ -477,6 +477,34 @@ def run_ours(args):
         micro_att = microbench.attention_microbench(hbm_peak_gbs=peaks["hbm_gbs"])
         micro_lstm = microbench.lstm_microbench(tflops_peak=peaks["tflops"])
 
+    # ---- the reference's own evaluated configuration (config/config_eval.yaml:52-69: stride 2, do_option '*', dropout 0.4):
+    # its convolutions are outside the direct 3x3 / stride-1 kernels and run as im2col + tcgen05 GEMM + pool (im2col.cu);
+    # the same step with those layers on the SIMT implicit-GEMM kernels (VQA_CONV_IM2COL=0) is timed beside it
+    eval_cfg_line = None
+    if world == 1 and not args.no_micro:
+        import copy
+        cfg2 = copy.deepcopy(cfg)
+        cfg2["image"]["stride"] = 2
+        cfg2["attention"]["do_option"] = "*"
+        for k in ("text", "image", "attention", "classifier"):
+            cfg2[k]["dropout"] = 0.4
+        eval_cfg_line = {"config": "config_eval.yaml train block: stride 2, do_option '*', dropout 0.4; batch 256, bf16 arm, fwd+loss+bwd+Adam"}
+        db2 = tuple(t.to(dev, non_blocking=True) for t in (hv16, hq, hai, hav, hal)) + (None, hql.to(dev, non_blocking=True))
+        for key, env in (("im2col_tcgen05", "1"), ("simt_convolutions", "0")):
+            os.environ["VQA_CONV_IM2COL"] = env
+            torch.manual_seed(1)
+            m2 = D.VqaNet(cfg2, synth.DEFAULT_TOKENS, compute_dtype=args.dtype).to(dev).train(True)
+            o2 = D.FusedAdam(m2.parameters(), lr=5e-4)
+            m2.use_gradient_arena(True)
+            g2s = D.GraphedTrainStep(m2, o2, cfg2["max_answers"], ddp=None, lr=5e-4, enabled=not args.no_graph)
+            for _ in range(3):
+                g2s(db2)
+            ms2 = timed(lambda: g2s(db2), 10) / 10
+            eval_cfg_line[key] = {"ms_per_step": ms2, "samples_per_s": B / (ms2 / 1000.0)}
+            del m2, o2, g2s
+        os.environ.pop("VQA_CONV_IM2COL", None)
+        torch.cuda.empty_cache()
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         times, cb, threads, kind = cpu_reference_steps(4, 1, batch=32)
@@ -507,7 +535,8 @@ def run_ours(args):
             "clocks": clk, "roofline": roofline, "attention_roofline": att_roof, "lstm_recurrence": lstm,
             "step_tensor_frac": (STEP_FLOP_PER_SAMPLE * B / (per_step / 1000.0) / 1e12) / peaks["tflops"],
             "roofline_frac_by_kernel": per_kernel_frac, "kernels": breakdown,
-            "exposed_comm": comm, "attention_microbench": micro_att, "lstm_microbench": micro_lstm, "cpu_baseline": cpu}
+            "exposed_comm": comm, "attention_microbench": micro_att, "lstm_microbench": micro_lstm,
+            "config_eval_yaml_step": eval_cfg_line, "cpu_baseline": cpu}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -370,7 +370,8 @@ class VqaNet(nn.Module):
 
     def _conv0_reads_fp16(self) -> bool:
         ch = self.channels
-        return (self.compute_dtype == torch.bfloat16 and ch[0] == 3 and ch[1] == 64 and self.KS == 3 and self.stride == 1)
+        direct = self.compute_dtype == torch.bfloat16 and ch[0] == 3 and ch[1] == 64 and self.KS == 3 and self.stride == 1
+        return direct or self._im2col_conv_ok(0)          # both first-layer forms of the tensor-core arm read fp16 natively
 
     # dropout probabilities in effect
     def _p(self, p: float) -> float:
@@ -488,7 +489,7 @@ class VqaNet(nn.Module):
         comb = empty(B, KC)
         prob = empty(B, G, P, dtype=f32)
         call("vqa_attention_fwd_x", ptr(vp), vp_dt, ptr(qp), ptr(vn), ptr(att.x_conv.weight), ptr(att.x_conv.bias),
-             ptr(prob), ptr(comb), KC, dt, op, B, P, A, Cimg, G, p_att, seed, st)
+             ptr(prob), ptr(comb), KC, dt, op, B, P, A, Cimg, G, p_att, seed, st, tag="vqa_attention_fwd")
         # combined = cat([pooled, q])  (models/model.py:64)
         esz = comb.element_size()
         call("vqa_dropout_apply", ptr(qf), QF, comb.data_ptr() + G * Cimg * esz, KC, dt, B, QF, 0.0, 0, 0, st)
@@ -811,7 +812,7 @@ class VqaNet(nn.Module):
         op = {"+": lib.ATT_ADD, "*": lib.ATT_MUL, "|": lib.ATT_CAT}[self.do_option]
         call("vqa_attention_bwd_x", ptr(dcomb), KC, ptr(vp), lib.F16 if vp.dtype == torch.float16 else dt, ptr(qp), ptr(vn),
              ptr(att.x_conv.weight), ptr(prob), ptr(dvp), ptr(dvn_pool), ptr(dqp), ptr(dwx_part), ptr(dbx_part), dt, op,
-             B, P, A, Cimg, G, p_att, seed, st)
+             B, P, A, Cimg, G, p_att, seed, st, tag="vqa_attention_bwd")
         grads["attention.x_conv.weight"] = colsum(dwx_part, lib.F32, G * AW, B, G * AW, "attention.x_conv.weight").view(G, AW, 1, 1)
         grads["attention.x_conv.bias"] = colsum(dbx_part, lib.F32, G, B, G, "attention.x_conv.bias")
         # ---- attention.v_conv (1x1 conv == GEMM over B*P rows)
