@@ -35,7 +35,9 @@ constexpr int HALO_BYTES = HALO_H * HALO_W * 128;            // 23040: one 64-ch
 constexpr int A_STAGE_BYTES = 23552;                          // padded to a multiple of 1024
 // Epilogue warps: 8 (two per TMEM lane quarter, alternating 32-column chunks).  (16 for the POOL epilogue measured no
 // faster once the arg-max rode in the value bits: conv1 forward is then bound by the MMAs' shared-memory reads.)
-__host__ __device__ constexpr int conv_epi_warps(int) { return 8; }
+// The UNPOOL epilogue (dgrad + max-pool backward + bias gradient of the layer below) is the longest per tile and was what
+// the MMAs waited for (tensor pipe 65 %, issue slots 27 %): 16 warps, one 32-column chunk each at BN = 128.
+__host__ __device__ constexpr int conv_epi_warps(int epi) { return epi == 2 ? 16 : 8; }
 __host__ __device__ constexpr int conv_threads(int epi) { return 64 + conv_epi_warps(epi) * 32; }
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448 - 1024;                     // 227 KB minus alignment slack
@@ -207,7 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         float dbsum[4] = {0.f, 0.f, 0.f, 0.f};          // UNPOOL: bias-gradient partials, see the epilogue for the lane -> channel map
         // UNPOOL: the pooling-mask bytes of this lane's position do not depend on the MMAs, so they are fetched one tile
         // ahead (their DRAM latency would otherwise sit on the epilogue's critical path four times per round)
-        constexpr int NMK = EPI == EPI_UNPOOL ? BN / 64 : 1;
+        constexpr int CSTEP = 32 * (conv_epi_warps(EPI) / 4);                  // columns covered by one pass of all column groups
+        constexpr int NMK = EPI == EPI_UNPOOL ? (BN + CSTEP - 1) / CSTEP : 1;
         uint32_t mnext[NMK][8];
         auto load_masks = [&](int tile) {
             const bool live = tile < ntiles;
@@ -218,9 +221,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < NMK; ++k) {
                 uint4 m0 = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u), m1 = m0;   // 4 = dead / outside
-                if (ok) {
-                    m0 = __ldcs(reinterpret_cast<const uint4*>(mp + 64 * k));
-                    m1 = __ldcs(reinterpret_cast<const uint4*>(mp + 64 * k) + 1);
+                if (ok && half * 32 + CSTEP * k < BN) {
+                    m0 = __ldcs(reinterpret_cast<const uint4*>(mp + CSTEP * k));
+                    m1 = __ldcs(reinterpret_cast<const uint4*>(mp + CSTEP * k) + 1);
                 }
                 mnext[k][0] = m0.x; mnext[k][1] = m0.y; mnext[k][2] = m0.z; mnext[k][3] = m0.w;
                 mnext[k][4] = m1.x; mnext[k][5] = m1.y; mnext[k][6] = m1.z; mnext[k][7] = m1.w;
@@ -292,7 +295,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 bf16* obase = p.udy + (((int64_t)b * 2 * p.valid_h + 2 * h) * (2 * p.valid_w) + 2 * wq) * p.N + half * 32 + 8 * q;
 #pragma unroll
                 for (int k = 0; k < NMK; ++k) {
-                    const int c0 = half * 32 + 64 * k;
+                    const int c0 = half * 32 + CSTEP * k;
+                    if (c0 >= BN) break;                                     // warp-uniform: more column groups than 32-column chunks
                     float v[32];
                     tmem_ld_32x32(taddr + c0, v);
                     uint32_t G[4][4], M[4][2];          // [piece -> position after the transpose][words]
@@ -347,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                     asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(sel) : "r"(mw[i]), "r"(want));
                                     o[i] = G[j][i] & sel;
                                 }
-                                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * p.valid_w) + 2 * j + (e & 1)) * p.N + 64 * k),
+                                __stcs(reinterpret_cast<uint4*>(obase + ((int64_t)(e >> 1) * (2 * p.valid_w) + 2 * j + (e & 1)) * p.N + CSTEP * k),
                                        make_uint4(o[0], o[1], o[2], o[3]));
                             }
                         }
@@ -450,9 +454,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (EPI == EPI_UNPOOL) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (half * 32 + 64 * k < BN)
-                    atomicAdd(p.udb + half * 32 + 64 * k + 8 * (lane & 3) + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1),
+            for (int k = 0; k < NMK; ++k)
+                if (half * 32 + CSTEP * k < BN)
+                    atomicAdd(p.udb + half * 32 + CSTEP * k + 8 * (lane & 3) + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1),
                               dbsum[k]);
         }
     }
