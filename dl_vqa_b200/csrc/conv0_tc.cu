@@ -31,10 +31,21 @@ struct Conv0Params {
     const void* x;                     // [B,3,IH,IW] NCHW, fp32 or fp16 (template parameter XHALF)
     int B, IH, IW, PH, PW, tiles_h, tiles_w;
     // forward
+    uint32_t magic_img, magic_w;       // ceil(2^32 / tiles per image), ceil(2^32 / tiles_w); 0 = divisor 1
     const float* w; const float* bias; bf16* pooled; uint8_t* mask;
     // backward
     const bf16* dpool; const uint8_t* bmask; float* dw; float* db; int tiles_per_cta;
 };
+
+// Tile index -> (image, first pooled row, first pooled column) without integer division: multiply-high by the host's
+// reciprocals, exact while tile * divisor < 2^32 (checked at launch).
+__device__ __forceinline__ void conv0_tile_pos(const Conv0Params& p, int tile, int& b, int& ph0, int& pw0) {
+    b = p.magic_img ? (int)__umulhi((uint32_t)tile, p.magic_img) : tile;
+    const int r = tile - b * (p.tiles_h * p.tiles_w);
+    const int th = p.magic_w ? (int)__umulhi((uint32_t)r, p.magic_w) : r;
+    ph0 = th * C0_WH;
+    pw0 = (r - th * p.tiles_w) * C0_WW;
+}
 
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (no wait: batch several, then tmem_ld_wait)
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
@@ -48,7 +59,27 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 3-input maximum (one FMNMX3) and saturating FMA (FFMA.SAT: result clamped to [0, 1])
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -152,24 +183,35 @@ __device__ __forceinline__ void store_patch_rows(uint8_t* tiles, int m, const fl
     }
 }
 // ------------------------------------------------------------------------------------------ forward
-// warps 0-7 epilogue (TMEM lane quarter = w & 3, channel half = w >> 2), warps 8-15 two builder groups, warp 16 MMA,
-// warp 17 TMA producer.  STAGED (image row pitch a multiple of 16 bytes): the producer streams each tile's fp32 input
-// region [3][18][36] through a 6-deep shared-memory ring with TMA (zero fill outside the image), so the builders issue
-// no global loads at all -- with direct loads they stall on the load/store-unit queue (48 scattered loads per window).
-constexpr int C0F_THREADS = 18 * 32;
+// warps 0-15 epilogue (TMEM lane quarter = w & 3, channel quarter = w >> 2), warps 16-19 builders, warp 20 MMA, warp 21
+// TMA producer.  STAGED (image row pitch a multiple of 16 bytes): the producer streams each tile's input region
+// [3][18][36] through a shared-memory ring with TMA (zero fill outside the image), so the builders issue no global loads
+// at all -- with direct loads they stall on the load/store-unit queue (48 scattered loads per window).
+//
+// Why 16 epilogue warps (r02 ncu source view of the 8-warp form): the epilogue warps were never idle -- 36 % of their
+// samples sat in the tile header (two integer divisions by run-time values, spilled addresses), 42 % in the max-pool
+// arithmetic, 22 % in the store tail, all of it dependent chains that two warps per scheduler cannot overlap -- while
+// the eight builder warps spent their time waiting for a free stage.  Now one builder group feeds four epilogue warps
+// per scheduler, tile coordinates come from multiply-high by host-computed reciprocals, and the output leaves through a
+// per-quarter staging tile so that every store instruction writes whole 128-byte lines.
+constexpr int C0F_EPI_WARPS = 16;
+constexpr int C0F_THREADS = (C0F_EPI_WARPS + 4 + 2) * 32;              // 704
 constexpr int C0F_XSTAGES = 6;
-constexpr int C0F_STAGES = 4;                      // two per builder group
+constexpr int C0F_STAGES = 3;
 constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
+constexpr int C0F_STG_QUARTER = 32 * 128 + 32 * 64;                   // pooled [32 windows][128 B] + mask [32 windows][64 B]
+constexpr int C0F_SMEM = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 4 * 2 * C0F_STG_QUARTER + 1024 + 1024;
 
 template <bool STAGED, bool XHALF>
-__global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
+__global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
     uint8_t* sa = smem + 64 * 128;                             // C0F_STAGES x 32 KB
     uint8_t* xs = sa + C0F_STAGES * C0F_STAGE_BYTES;           // C0F_XSTAGES x 8 KB staged input regions
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(xs + C0F_XSTAGES * C0_XSTAGE);
+    uint8_t* stg = xs + C0F_XSTAGES * C0_XSTAGE;               // [4 quarters][2 buffers] output staging
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(stg + 4 * 2 * C0F_STG_QUARTER);
     uint64_t* a_empty = a_full + C0F_STAGES;
     uint64_t* tmem_full = a_empty + C0F_STAGES;               // [2]
     uint64_t* tmem_empty = tmem_full + 2;                      // [2]
@@ -179,17 +221,16 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
     float* bias_s = reinterpret_cast<float*>(tmem_base_smem + 4);          // [64], read as broadcast LDS.128 by the epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = p.tiles_h * p.tiles_w;
-    const int ntiles = p.B * tiles_per_img;
+    const int ntiles = p.B * p.tiles_h * p.tiles_w;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C0F_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C0F_EPI_WARPS); }
         for (int i = 0; i < C0F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         if (STAGED) tma_prefetch_desc(&tma_x);
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc(tmem_base_smem, 512);
+    if (warp == C0F_EPI_WARPS + 4) tmem_alloc(tmem_base_smem, 512);
     pdl_wait();                                                // the weights below were written by the previous kernel (Adam)
     if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
         const int co = threadIdx.x;
@@ -211,27 +252,25 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    if (warp == 17) {
+    if (warp == C0F_EPI_WARPS + 5) {
         // ---- TMA producer of the staged input regions (one thread), tiles in consumption order
         if (STAGED && lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-                const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
+                int b, ph0, pw0;
+                conv0_tile_pos(p, tile, b, ph0, pw0);
                 const int q = it % C0F_XSTAGES;
                 mbar_wait(&x_empty[q], ((it / C0F_XSTAGES) & 1) ^ 1);
                 mbar_expect_tx(&x_full[q], XHALF ? C0_XBYTES_H : C0_XBYTES);
                 tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * pw0, 2 * ph0, 0, b);
             }
         }
-    } else if (warp >= 8 && warp < 16) {
-        // ---- builders: group g builds tiles g, g+2, ... of this CTA; thread -> window of the tile
-        const int g = (warp - 8) >> 2, t = (threadIdx.x - 256) & 127;
+    } else if (warp >= C0F_EPI_WARPS && warp < C0F_EPI_WARPS + 4) {
+        // ---- builders: thread -> window of the tile
+        const int t = threadIdx.x - C0F_EPI_WARPS * 32;
         const int wr = t >> 4, wc = t & 15;
-        uint32_t it = g;
-        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, it += 2) {
-            const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-            const int ph0 = (r / p.tiles_w) * C0_WH, pw0 = (r % p.tiles_w) * C0_WW;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = it % C0F_STAGES;
             float v[3][4][4];
             if (STAGED) {
@@ -240,6 +279,8 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
                 load_patch_staged<XHALF>(xs + q * C0_XSTAGE, wr, wc, v);
                 mbar_arrive(&x_empty[q]);                      // the values are in registers: the region can be refilled
             } else {
+                int b, ph0, pw0;
+                conv0_tile_pos(p, tile, b, ph0, pw0);
                 load_patch_global<XHALF>(p, b, ph0 + wr, pw0 + wc, v);
             }
             mbar_wait(&a_empty[s], ((it / C0F_STAGES) & 1) ^ 1);
@@ -247,7 +288,7 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
         }
-    } else if (warp == 16) {
+    } else if (warp == C0F_EPI_WARPS + 4) {
         // ---- MMA issuer: all lanes converged, one elected lane issues (see tc_common.cuh)
         constexpr uint32_t idesc = idesc_bf16(128, 64);
         const uint32_t elected = elect_one();
@@ -271,103 +312,100 @@ __global__ void __launch_bounds__(C0F_THREADS, 1) conv0_fwd_tc_kernel(const __gr
             umma_commit_issue<1>(&tmem_full[acc], elected);
         }
     } else {
-        // ---- epilogue: thread = window (TMEM lane), 2x2 max-pool = max over the four element accumulators
-        const int quarter = warp & 3, half = warp >> 2;
-        const int m = quarter * 32 + lane, wr = m >> 4, wc = m & 15;
+        // ---- epilogue: thread = window (TMEM lane) x 16 channels; 2x2 max-pool = max over the four element accumulators.
+        // Per channel two 3-input FMNMX (max of the four elements and of -bias, i.e. ReLU folded in:
+        // max(m, -b) + b == max(m + b, 0) exactly) are the only work on the half-rate ALU pipe, which the compare /
+        // select form of this epilogue kept 82 % busy (ncu, r02h).  The arg-max is ARITHMETIC on the FMA pipe:
+        // s_e = sat(2^100 (max - a_e)) is 0 for a maximal element and 1 otherwise, id = s0 (1 + s1 (1 + s2 (1 + s3))) is
+        // the first maximal element -- and 4 when no element reaches -bias, the ReLU-dead code -- in packed FMUL2 /
+        // FADD2 / FFMA2 over channel pairs, with the 2^23 magic constant folded into the last FFMA2 so that one PRMT
+        // gathers the id bytes of four channels.
+        const int quarter = warp & 3, cq = warp >> 2;
+        uint8_t* stq = stg + quarter * (2 * C0F_STG_QUARTER);
+        // staging writes: pooled piece pi (16 B = 8 channels) of window `lane` at 16-byte slot pi ^ (lane & 7) of its row;
+        // mask piece cq of the window at slot cq ^ ((lane >> 1) & 3) of its 64-byte row (conflict-free both ways)
+        const uint32_t o_wr = lane * 128, o_sw = lane & 7;
+        const uint32_t m_wr = 32 * 128 + lane * 64 + ((cq ^ ((lane >> 1) & 3)) << 4);
+        // staging reads = global stores: this warp writes the 8 windows cq*8 .. cq*8+7 of the quarter (one tile row):
+        // pooled 2 x (4 windows x 128 B), mask 1 x (8 windows x 64 B) -- whole lines, contiguous in NHWC memory
+        const int wl_m = cq * 8 + (lane >> 2);
+        const uint32_t m_rd = 32 * 128 + wl_m * 64 + (((lane & 3) ^ ((wl_m >> 1) & 3)) << 4);
+        constexpr float HUGE_ = 0x1p100f;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, use = it >> 1;
-            const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-            const int ph = (r / p.tiles_w) * C0_WH + wr, pw = (r % p.tiles_w) * C0_WW + wc;
-            const bool ok = ph < p.PH && pw < p.PW;
-            const int64_t obase = (((int64_t)b * p.PH + ph) * p.PW + pw) * 64;
+            int b, ph0, pw0;
+            conv0_tile_pos(p, tile, b, ph0, pw0);
+            uint8_t* sb = stq + (it & 1) * C0F_STG_QUARTER;
             mbar_wait(&tmem_full[acc], use & 1);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16) + half * 32;
-            uint32_t ob[4][4], mb[2][4];                       // this window's 32 channels: 64 B pooled (4 pieces), 32 B mask (2 pieces)
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16) + cq * 16;
+            uint32_t mw[4];
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float v0[16], v1[16], v2[16], v3[16];
-                tmem_ld_32x16(taddr + c0, v0);
-                tmem_ld_32x16(taddr + 64 + c0, v1);
-                tmem_ld_32x16(taddr + 128 + c0, v2);
-                tmem_ld_32x16(taddr + 192 + c0, v3);
+            for (int c0 = 0; c0 < 16; c0 += 8) {
+                float v0[8], v1[8], v2[8], v3[8];
+                tmem_ld_32x8(taddr + c0, v0);
+                tmem_ld_32x8(taddr + 64 + c0, v1);
+                tmem_ld_32x8(taddr + 128 + c0, v2);
+                tmem_ld_32x8(taddr + 192 + c0, v3);
                 tmem_ld_wait();
-                const int nb = half * 32 + c0;
-                float bb[16];                                  // (same-address global loads here cost more than the pooling)
+                uint32_t ow[4];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 q4 = *reinterpret_cast<const float4*>(bias_s + nb + j);
-                    bb[j] = q4.x; bb[j + 1] = q4.y; bb[j + 2] = q4.z; bb[j + 3] = q4.w;
-                }
+                for (int j = 0; j < 8; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + c0 + j);       // broadcast LDS.128
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    float pm[2];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float x[2]; uint32_t id[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float a0 = v0[j + u], a1 = v1[j + u], a2 = v2[j + u], a3 = v3[j + u];
-                        // first maximum in element order (ties go to the lower id, as torch max_pool2d)
-                        const float m01 = fmaxf(a0, a1), m23 = fmaxf(a2, a3);
-                        const uint32_t i01 = a1 > a0 ? 1u : 0u, i23 = a3 > a2 ? 3u : 2u;
-                        float mx = fmaxf(m01, m23);
-                        uint32_t ix = m23 > m01 ? i23 : i01;
-                        mx += bb[j + u];
-                        if (!(mx > 0.f)) { mx = 0.f; ix = 4u; }
-                        x[u] = mx; id[u] = ix;
+                    for (int u = 0; u < 4; u += 2) {
+                        const int c = j + u;
+                        const float2 bv = make_float2(bb[u], bb[u + 1]);
+                        float2 mx;                                // max over the window and -bias (ReLU folded in)
+                        mx.x = fmax3(fmax3(v0[c], v1[c], v2[c]), v3[c], -bv.x);
+                        mx.y = fmax3(fmax3(v0[c + 1], v1[c + 1], v2[c + 1]), v3[c + 1], -bv.y);
+                        const float2 mh = __fmul2_rn(mx, make_float2(HUGE_, HUGE_));
+                        const float2 s0 = make_float2(fma_sat(v0[c], -HUGE_, mh.x), fma_sat(v0[c + 1], -HUGE_, mh.y));
+                        const float2 s1 = make_float2(fma_sat(v1[c], -HUGE_, mh.x), fma_sat(v1[c + 1], -HUGE_, mh.y));
+                        const float2 s2 = make_float2(fma_sat(v2[c], -HUGE_, mh.x), fma_sat(v2[c + 1], -HUGE_, mh.y));
+                        const float2 s3 = make_float2(fma_sat(v3[c], -HUGE_, mh.x), fma_sat(v3[c + 1], -HUGE_, mh.y));
+                        const float2 one = make_float2(1.f, 1.f);
+                        float2 id = __fadd2_rn(s3, one);
+                        id = __ffma2_rn(s2, id, one);
+                        id = __ffma2_rn(s1, id, one);
+                        id = __ffma2_rn(s0, id, make_float2(8388608.f, 0.f));          // (2^23 + id_even, id_odd)
+                        pm[u >> 1] = fmaf(id.y, 256.f, id.x);                         // low bytes: id_even, id_odd
+                        const float2 x = __fadd2_rn(mx, bv);                          // exactly 0 when ReLU-dead
+                        ow[c >> 1] = pack2(x.x, x.y);
                     }
-                    ob[(c0 >> 3) + (j >> 3)][(j >> 1) & 3] = pack2(x[0], x[1]);
-                    const uint32_t pair = id[0] | (id[1] << 8);
-                    if ((j & 2) == 0) mb[c0 >> 4][j >> 2] = pair; else mb[c0 >> 4][j >> 2] |= pair << 16;
+                    mw[(c0 + j) >> 2] = __byte_perm(__float_as_uint(pm[0]), __float_as_uint(pm[1]), 0x5410);
                 }
+                *reinterpret_cast<uint4*>(sb + o_wr + (((uint32_t)(cq * 2 + (c0 >> 3)) ^ o_sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            // Coalescing transposes: inside a lane quad (4 consecutive windows of one row) lane q ends with pooled piece
-            // q of the four windows; inside a lane pair lane s ends with mask piece s of both windows.  One store
-            // instruction then writes 64 (32) contiguous bytes per window instead of 16 bytes to 32 different lines.
-            {
-                const int q = lane & 3;
-#pragma unroll
-                for (int step = 0; step < 2; ++step) {
-                    const int off = 1 << step;
-                    const bool up = (q & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int lo = step == 0 ? 2 * i : i, hi = lo + off;
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up ? ob[lo][w] : ob[hi][w], off);
-                            if (up) ob[lo][w] = rcv; else ob[hi][w] = rcv;
-                        }
-                    }
-                }
-                const bool up = (lane & 1) != 0;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up ? mb[0][w] : mb[1][w], 1);
-                    if (up) mb[0][w] = rcv; else mb[1][w] = rcv;
-                }
-                // quad / pair base windows share this lane's row ph; window columns pw - q + j and pw - (lane & 1) + j
-                if (ph < p.PH) {
-                    const int64_t qbase = obase - (int64_t)q * 64 + half * 32 + 8 * q;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (pw - q + j < p.PW)
-                            *reinterpret_cast<uint4*>(p.pooled + qbase + j * 64) = make_uint4(ob[j][0], ob[j][1], ob[j][2], ob[j][3]);
-                    const int s1 = lane & 1;
-                    const int64_t pbase = obase - (int64_t)s1 * 64 + half * 32 + 16 * s1;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (pw - s1 + j < p.PW)
-                            *reinterpret_cast<uint4*>(p.mask + pbase + j * 64) = make_uint4(mb[j][0], mb[j][1], mb[j][2], mb[j][3]);
-                }
-            }
-            tcgen05_fence_before();
+            *reinterpret_cast<uint4*>(sb + m_wr) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            tcgen05_fence_before();                                // every TMEM read of this tile has completed (wait::ld above)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);          // the accumulator may be overwritten while we store
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");      // the four warps (channel quarters) of this lane quarter
+            // (double-buffered staging: tile t+2 rewrites this buffer only after every warp passed the barrier of tile t+1)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int wl = cq * 8 + i * 4 + (lane >> 3), mm = quarter * 32 + wl;
+                const int ph = ph0 + (mm >> 4), pw = pw0 + (mm & 15);
+                const uint4 u = *reinterpret_cast<const uint4*>(sb + wl * 128 + (((lane & 7) ^ (wl & 7)) << 4));
+                if (ph < p.PH && pw < p.PW)
+                    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)b * p.PH + ph) * p.PW + pw) * 64 + (lane & 7) * 8) = u;
+            }
+            {
+                const int mm = quarter * 32 + wl_m;
+                const int ph = ph0 + (mm >> 4), pw = pw0 + (mm & 15);
+                const uint4 u = *reinterpret_cast<const uint4*>(sb + m_rd);
+                if (ph < p.PH && pw < p.PW)
+                    *reinterpret_cast<uint4*>(p.mask + (((int64_t)b * p.PH + ph) * p.PW + pw) * 64 + (lane & 3) * 16) = u;
+            }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 16) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == C0F_EPI_WARPS + 4) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ backward (weight + bias)
@@ -545,6 +583,15 @@ static int sm_count() {
     return sms;
 }
 
+static uint32_t magic_u32(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); }
+static int conv0_set_magics(Conv0Params& p) {
+    const uint64_t tpi = (uint64_t)p.tiles_h * p.tiles_w;
+    VQA_REQUIRE((uint64_t)p.B * tpi * tpi < ((uint64_t)1 << 32), "tc conv0: %d images of %llu tiles exceed the tile index range", p.B, (unsigned long long)tpi);
+    p.magic_img = magic_u32((uint32_t)tpi);
+    p.magic_w = magic_u32((uint32_t)p.tiles_w);
+    return 0;
+}
+
 // Tensor map of the NCHW network input for the staged (TMA) path; false when the layout does not allow it
 static bool conv0_input_map(CUtensorMap* tx, const void* x, bool half, int B, int IH, int IW, int* err) {
     const int esz = half ? 2 : 4;
@@ -578,8 +625,9 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd_x(const void* x, int x_dtype, const fl
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
     p.tiles_h = (p.PH + C0_WH - 1) / C0_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;
     p.w = w; p.bias = bias; p.pooled = (bf16*)out; p.mask = mask;
-    const int smem = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 1024 + 512;
+    const int smem = C0F_SMEM;
     const int ntiles = B * p.tiles_h * p.tiles_w;
+    if (int rc = conv0_set_magics(p)) return rc;
     const int sms = sm_count();
     const int grid = ntiles < sms ? ntiles : sms;
     CUtensorMap tx{};
