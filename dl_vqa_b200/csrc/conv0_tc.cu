@@ -200,7 +200,7 @@ constexpr int C0F_XSTAGES = 6;
 constexpr int C0F_STAGES = 3;
 constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 constexpr int C0F_STG_QUARTER = 32 * 128 + 32 * 64;                   // pooled [32 windows][128 B] + mask [32 windows][64 B]
-constexpr int C0F_SMEM = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 4 * 2 * C0F_STG_QUARTER + 1024 + 1024;
+constexpr int C0F_SMEM = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 2 * 4 * C0F_STG_QUARTER + 1024 + 1024;
 
 template <bool STAGED, bool XHALF>
 __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
@@ -210,7 +210,7 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
     uint8_t* sw_tile = smem;                                   // [64 co][128 B], k-range 0..31 used
     uint8_t* sa = smem + 64 * 128;                             // C0F_STAGES x 32 KB
     uint8_t* xs = sa + C0F_STAGES * C0F_STAGE_BYTES;           // C0F_XSTAGES x 8 KB staged input regions
-    uint8_t* stg = xs + C0F_XSTAGES * C0_XSTAGE;               // [4 quarters][2 buffers] output staging
+    uint8_t* stg = xs + C0F_XSTAGES * C0_XSTAGE;               // [2 sets][4 quarters] output staging
     uint64_t* a_full = reinterpret_cast<uint64_t*>(stg + 4 * 2 * C0F_STG_QUARTER);
     uint64_t* a_empty = a_full + C0F_STAGES;
     uint64_t* tmem_full = a_empty + C0F_STAGES;               // [2]
@@ -225,7 +225,7 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C0F_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C0F_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C0F_EPI_WARPS / 2); }
         for (int i = 0; i < C0F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         if (STAGED) tma_prefetch_desc(&tma_x);
         fence_barrier_init();
@@ -312,7 +312,8 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
             umma_commit_issue<1>(&tmem_full[acc], elected);
         }
     } else {
-        // ---- epilogue: thread = window (TMEM lane) x 16 channels; 2x2 max-pool = max over the four element accumulators.
+        // ---- epilogue: two SETS of eight warps take alternate tiles (set = TMEM accumulator), thread = window (TMEM lane)
+        // x 32 channels; 2x2 max-pool = max over the four element accumulators.
         // Per channel two 3-input FMNMX (max of the four elements and of -bias, i.e. ReLU folded in:
         // max(m, -b) + b == max(m + b, 0) exactly) are the only work on the half-rate ALU pipe, which the compare /
         // select form of this epilogue kept 82 % busy (ncu, r02h).  The arg-max is ARITHMETIC on the FMA pipe:
@@ -320,29 +321,34 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
         // the first maximal element -- and 4 when no element reaches -bias, the ReLU-dead code -- in packed FMUL2 /
         // FADD2 / FFMA2 over channel pairs, with the 2^23 magic constant folded into the last FFMA2 so that one PRMT
         // gathers the id bytes of four channels.
-        const int quarter = warp & 3, cq = warp >> 2;
-        uint8_t* stq = stg + quarter * (2 * C0F_STG_QUARTER);
+        const int set = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+        uint8_t* sb = stg + (set * 4 + quarter) * C0F_STG_QUARTER;
+        const uint32_t bar_id = 1 + set * 4 + quarter;            // named barrier of the two warps (channel halves) of a lane quarter
         // staging writes: pooled piece pi (16 B = 8 channels) of window `lane` at 16-byte slot pi ^ (lane & 7) of its row;
-        // mask piece cq of the window at slot cq ^ ((lane >> 1) & 3) of its 64-byte row (conflict-free both ways)
-        const uint32_t o_wr = lane * 128, o_sw = lane & 7;
-        const uint32_t m_wr = 32 * 128 + lane * 64 + ((cq ^ ((lane >> 1) & 3)) << 4);
-        // staging reads = global stores: this warp writes the 8 windows cq*8 .. cq*8+7 of the quarter (one tile row):
-        // pooled 2 x (4 windows x 128 B), mask 1 x (8 windows x 64 B) -- whole lines, contiguous in NHWC memory
-        const int wl_m = cq * 8 + (lane >> 2);
-        const uint32_t m_rd = 32 * 128 + wl_m * 64 + (((lane & 3) ^ ((wl_m >> 1) & 3)) << 4);
+        // mask piece pm (16 channels) of the window at slot pm ^ ((lane >> 1) & 3) of its 64-byte row (conflict-free both ways)
+        uint8_t* o_wr = sb + lane * 128;
+        const uint32_t o_sw = lane & 7;
+        uint8_t* m_wr = sb + 32 * 128 + lane * 64;
+        const uint32_t m_sw = (lane >> 1) & 3;
+        // staging reads = global stores: this warp writes one tile row, the 16 windows half*16 .. +15 of the quarter:
+        // pooled 4 x (4 windows x 128 B), mask 2 x (8 windows x 64 B) -- whole lines, contiguous in NHWC memory
+        const int row_in_tile = quarter * 2 + half;
+        const int col_p = lane >> 3, col_m = lane >> 2;
+        const uint8_t* o_rd = sb + (half * 16 + col_p) * 128;
+        const uint8_t* m_rd = sb + 32 * 128 + (half * 16 + col_m) * 64;
         constexpr float HUGE_ = 0x1p100f;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, use = it >> 1;
+        uint32_t it = set;
+        for (int tile = blockIdx.x + set * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, it += 2) {
+            const uint32_t use = it >> 1;                          // acc == set
             int b, ph0, pw0;
             conv0_tile_pos(p, tile, b, ph0, pw0);
-            uint8_t* sb = stq + (it & 1) * C0F_STG_QUARTER;
-            mbar_wait(&tmem_full[acc], use & 1);
+            mbar_wait_relaxed(&tmem_full[set], use & 1);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16) + cq * 16;
+            const uint32_t taddr = tmem_base + set * 256 + ((uint32_t)(quarter * 32) << 16) + half * 32;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // the partner warp has read the previous tile out of the staging tile
             uint32_t mw[4];
 #pragma unroll
-            for (int c0 = 0; c0 < 16; c0 += 8) {
+            for (int c0 = 0; c0 < 32; c0 += 8) {
                 float v0[8], v1[8], v2[8], v3[8];
                 tmem_ld_32x8(taddr + c0, v0);
                 tmem_ld_32x8(taddr + 64 + c0, v1);
@@ -352,7 +358,7 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
                 uint32_t ow[4];
 #pragma unroll
                 for (int j = 0; j < 8; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + c0 + j);       // broadcast LDS.128
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + c0 + j);       // broadcast LDS.128
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float pm[2];
 #pragma unroll
@@ -376,30 +382,33 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
                         const float2 x = __fadd2_rn(mx, bv);                          // exactly 0 when ReLU-dead
                         ow[c >> 1] = pack2(x.x, x.y);
                     }
-                    mw[(c0 + j) >> 2] = __byte_perm(__float_as_uint(pm[0]), __float_as_uint(pm[1]), 0x5410);
+                    mw[((c0 & 8) + j) >> 2] = __byte_perm(__float_as_uint(pm[0]), __float_as_uint(pm[1]), 0x5410);
                 }
-                *reinterpret_cast<uint4*>(sb + o_wr + (((uint32_t)(cq * 2 + (c0 >> 3)) ^ o_sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                *reinterpret_cast<uint4*>(o_wr + (((uint32_t)(half * 4 + (c0 >> 3)) ^ o_sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                if (c0 & 8)
+                    *reinterpret_cast<uint4*>(m_wr + (((uint32_t)(half * 2 + (c0 >> 4)) ^ m_sw) << 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
             }
-            *reinterpret_cast<uint4*>(sb + m_wr) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
             tcgen05_fence_before();                                // every TMEM read of this tile has completed (wait::ld above)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);          // the accumulator may be overwritten while we store
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");      // the four warps (channel quarters) of this lane quarter
-            // (double-buffered staging: tile t+2 rewrites this buffer only after every warp passed the barrier of tile t+1)
+            if (lane == 0) mbar_arrive(&tmem_empty[set]);          // the accumulator may be overwritten while we store
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both channel halves of the 32 windows are staged
+            const int ph = ph0 + row_in_tile;
+            if (ph < p.PH) {                                       // warp-uniform
+                const uint32_t win0 = ((uint32_t)b * p.PH + ph) * p.PW + pw0;             // first window of the row (element index fits 32 bits, checked at launch)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int wl = cq * 8 + i * 4 + (lane >> 3), mm = quarter * 32 + wl;
-                const int ph = ph0 + (mm >> 4), pw = pw0 + (mm & 15);
-                const uint4 u = *reinterpret_cast<const uint4*>(sb + wl * 128 + (((lane & 7) ^ (wl & 7)) << 4));
-                if (ph < p.PH && pw < p.PW)
-                    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)b * p.PH + ph) * p.PW + pw) * 64 + (lane & 7) * 8) = u;
-            }
-            {
-                const int mm = quarter * 32 + wl_m;
-                const int ph = ph0 + (mm >> 4), pw = pw0 + (mm & 15);
-                const uint4 u = *reinterpret_cast<const uint4*>(sb + m_rd);
-                if (ph < p.PH && pw < p.PW)
-                    *reinterpret_cast<uint4*>(p.mask + (((int64_t)b * p.PH + ph) * p.PW + pw) * 64 + (lane & 3) * 16) = u;
+                for (int i = 0; i < 4; ++i) {
+                    const int col = i * 4 + col_p;
+                    const uint4 u = *reinterpret_cast<const uint4*>(o_rd + i * 512 + (((uint32_t)(lane & 7) ^ ((uint32_t)col & 7)) << 4));
+                    if (pw0 + col < p.PW)
+                        *reinterpret_cast<uint4*>(p.pooled + (size_t)((win0 + col) * 64u + (lane & 7) * 8u)) = u;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int col = i * 8 + col_m;
+                    const uint4 u = *reinterpret_cast<const uint4*>(m_rd + i * 512 + ((((uint32_t)(lane & 3)) ^ (((uint32_t)col >> 1) & 3)) << 4));
+                    if (pw0 + col < p.PW)
+                        *reinterpret_cast<uint4*>(p.mask + (size_t)((win0 + col) * 64u + (lane & 3) * 16u)) = u;
+                }
             }
         }
     }
@@ -587,6 +596,7 @@ static uint32_t magic_u32(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((((uint6
 static int conv0_set_magics(Conv0Params& p) {
     const uint64_t tpi = (uint64_t)p.tiles_h * p.tiles_w;
     VQA_REQUIRE((uint64_t)p.B * tpi * tpi < ((uint64_t)1 << 32), "tc conv0: %d images of %llu tiles exceed the tile index range", p.B, (unsigned long long)tpi);
+    VQA_REQUIRE((uint64_t)p.B * p.PH * p.PW * 64 < ((uint64_t)1 << 32), "tc conv0: output of %d x %d x %d x 64 elements exceeds the 32-bit index range", p.B, p.PH, p.PW);
     p.magic_img = magic_u32((uint32_t)tpi);
     p.magic_w = magic_u32((uint32_t)p.tiles_w);
     return 0;
