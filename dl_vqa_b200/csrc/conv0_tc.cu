@@ -169,9 +169,10 @@ __device__ __forceinline__ void store_patch_rows(uint8_t* tiles, int m, const fl
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) k[ci * 9 + kh * 3 + kw] = v[ci][dy + kh][dx + kw];
-        k[27] = 1.f;                                   // bias-gradient column (the forward weights have a zero there)
+        k[27] = 1.f;                                   // backward: bias-gradient column; forward: the weights hold the bias there,
+        k[28] = 1.f;                                   // split into a bf16 head (k = 27) and tail (k = 28)
 #pragma unroll
-        for (int i = 28; i < 32; ++i) k[i] = 0.f;
+        for (int i = 29; i < 32; ++i) k[i] = 0.f;
         uint8_t* rowp = tiles + (e >> 1) * C0_TILE_BYTES + m * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -202,8 +203,11 @@ constexpr int C0F_STAGE_BYTES = 2 * C0_TILE_BYTES;
 constexpr int C0F_STG_QUARTER = 32 * 128 + 32 * 64;                   // pooled [32 windows][128 B] + mask [32 windows][64 B]
 constexpr int C0F_SMEM = 64 * 128 + C0F_STAGES * C0F_STAGE_BYTES + C0F_XSTAGES * C0_XSTAGE + 2 * 4 * C0F_STG_QUARTER + 1024 + 1024;
 
+struct Conv0FwdMaps { CUtensorMap x, pooled, mask; };       // input regions (load), pooled output and arg-max mask (stores)
+
 template <bool STAGED, bool XHALF>
-__global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
+__global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ Conv0FwdMaps maps, Conv0Params p) {
+    const CUtensorMap& tma_x = maps.x;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -218,7 +222,6 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
     uint64_t* x_full = tmem_empty + 2;                         // [C0F_XSTAGES]
     uint64_t* x_empty = x_full + C0F_XSTAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + C0F_XSTAGES);
-    float* bias_s = reinterpret_cast<float*>(tmem_base_smem + 4);          // [64], read as broadcast LDS.128 by the epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = p.B * p.tiles_h * p.tiles_w;
@@ -228,16 +231,20 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C0F_EPI_WARPS / 2); }
         for (int i = 0; i < C0F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         if (STAGED) tma_prefetch_desc(&tma_x);
+        tma_prefetch_desc(&maps.pooled);
+        tma_prefetch_desc(&maps.mask);
         fence_barrier_init();
     }
     if (warp == C0F_EPI_WARPS + 4) tmem_alloc(tmem_base_smem, 512);
     pdl_wait();                                                // the weights below were written by the previous kernel (Adam)
-    if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values (27 valid, rest zero)
-        const int co = threadIdx.x;
-        bias_s[co] = p.bias[co];
+    if (threadIdx.x < 64) {                                    // weight tile: row = co, 32 k-values: 27 weights, the bias as a bf16
+        const int co = threadIdx.x;                            // head + tail against the patch columns that hold 1.0, zeros
         float v[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = k < C0_K ? p.w[co * C0_K + k] : 0.f;
+        const float bias = p.bias[co];
+        v[27] = __bfloat162float(__float2bfloat16_rn(bias));   // the accumulator then carries conv + bias (error <= 2^-17 |bias|)
+        v[28] = bias - v[27];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             uint4 u = make_uint4(0, 0, 0, 0);
@@ -314,13 +321,15 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
     } else {
         // ---- epilogue: two SETS of eight warps take alternate tiles (set = TMEM accumulator), thread = window (TMEM lane)
         // x 32 channels; 2x2 max-pool = max over the four element accumulators.
-        // Per channel two 3-input FMNMX (max of the four elements and of -bias, i.e. ReLU folded in:
-        // max(m, -b) + b == max(m + b, 0) exactly) are the only work on the half-rate ALU pipe, which the compare /
-        // select form of this epilogue kept 82 % busy (ncu, r02h).  The arg-max is ARITHMETIC on the FMA pipe:
+        // The accumulators already hold conv + bias (bias columns of the weight tile).  Per channel two 3-input FMNMX
+        // (max of the four elements and of 0: ReLU folded in) are the only work on the half-rate ALU pipe, which the
+        // compare / select form of this epilogue kept 82 % busy (ncu, r02h).  The arg-max is ARITHMETIC on the FMA pipe:
         // s_e = sat(2^100 (max - a_e)) is 0 for a maximal element and 1 otherwise, id = s0 (1 + s1 (1 + s2 (1 + s3))) is
-        // the first maximal element -- and 4 when no element reaches -bias, the ReLU-dead code -- in packed FMUL2 /
-        // FADD2 / FFMA2 over channel pairs, with the 2^23 magic constant folded into the last FFMA2 so that one PRMT
-        // gathers the id bytes of four channels.
+        // the first maximal element -- and 4 when no element reaches 0, the ReLU-dead code -- in packed FMUL2 / FADD2 /
+        // FFMA2 over channel pairs, with the 2^23 magic constant folded into the last FFMA2 so that one PRMT gathers
+        // the id bytes of four channels.  The 32 windows x 64 channels of a lane quarter (two tile rows) are staged in
+        // the shared-memory layout of a 128-byte- (pooled) / 64-byte- (mask) swizzled TMA box and leave with two bulk
+        // tensor stores per quarter: no store instructions, no address arithmetic, no bounds checks (TMA clips).
         const int set = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
         uint8_t* sb = stg + (set * 4 + quarter) * C0F_STG_QUARTER;
         const uint32_t bar_id = 1 + set * 4 + quarter;            // named barrier of the two warps (channel halves) of a lane quarter
@@ -330,12 +339,7 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
         const uint32_t o_sw = lane & 7;
         uint8_t* m_wr = sb + 32 * 128 + lane * 64;
         const uint32_t m_sw = (lane >> 1) & 3;
-        // staging reads = global stores: this warp writes one tile row, the 16 windows half*16 .. +15 of the quarter:
-        // pooled 4 x (4 windows x 128 B), mask 2 x (8 windows x 64 B) -- whole lines, contiguous in NHWC memory
-        const int row_in_tile = quarter * 2 + half;
-        const int col_p = lane >> 3, col_m = lane >> 2;
-        const uint8_t* o_rd = sb + (half * 16 + col_p) * 128;
-        const uint8_t* m_rd = sb + 32 * 128 + (half * 16 + col_m) * 64;
+        const bool issuer = half == 0 && lane == 0;               // issues the quarter's two tensor stores
         constexpr float HUGE_ = 0x1p100f;
         uint32_t it = set;
         for (int tile = blockIdx.x + set * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, it += 2) {
@@ -345,7 +349,8 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
             mbar_wait_relaxed(&tmem_full[set], use & 1);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + set * 256 + ((uint32_t)(quarter * 32) << 16) + half * 32;
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // the partner warp has read the previous tile out of the staging tile
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous stores have read the staging tile
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             uint32_t mw[4];
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 8) {
@@ -358,16 +363,13 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
                 uint32_t ow[4];
 #pragma unroll
                 for (int j = 0; j < 8; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + c0 + j);       // broadcast LDS.128
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float pm[2];
 #pragma unroll
                     for (int u = 0; u < 4; u += 2) {
                         const int c = j + u;
-                        const float2 bv = make_float2(bb[u], bb[u + 1]);
-                        float2 mx;                                // max over the window and -bias (ReLU folded in)
-                        mx.x = fmax3(fmax3(v0[c], v1[c], v2[c]), v3[c], -bv.x);
-                        mx.y = fmax3(fmax3(v0[c + 1], v1[c + 1], v2[c + 1]), v3[c + 1], -bv.y);
+                        float2 mx;                                // max over the window and 0 (ReLU folded in; the bias came with the MMA)
+                        mx.x = fmax3(fmax3(v0[c], v1[c], v2[c]), v3[c], 0.f);
+                        mx.y = fmax3(fmax3(v0[c + 1], v1[c + 1], v2[c + 1]), v3[c + 1], 0.f);
                         const float2 mh = __fmul2_rn(mx, make_float2(HUGE_, HUGE_));
                         const float2 s0 = make_float2(fma_sat(v0[c], -HUGE_, mh.x), fma_sat(v0[c + 1], -HUGE_, mh.y));
                         const float2 s1 = make_float2(fma_sat(v1[c], -HUGE_, mh.x), fma_sat(v1[c + 1], -HUGE_, mh.y));
@@ -379,8 +381,7 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
                         id = __ffma2_rn(s1, id, one);
                         id = __ffma2_rn(s0, id, make_float2(8388608.f, 0.f));          // (2^23 + id_even, id_odd)
                         pm[u >> 1] = fmaf(id.y, 256.f, id.x);                         // low bytes: id_even, id_odd
-                        const float2 x = __fadd2_rn(mx, bv);                          // exactly 0 when ReLU-dead
-                        ow[c >> 1] = pack2(x.x, x.y);
+                        ow[c >> 1] = pack2(mx.x, mx.y);                               // exactly 0 when ReLU-dead
                     }
                     mw[((c0 & 8) + j) >> 2] = __byte_perm(__float_as_uint(pm[0]), __float_as_uint(pm[1]), 0x5410);
                 }
@@ -388,29 +389,18 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ CUte
                 if (c0 & 8)
                     *reinterpret_cast<uint4*>(m_wr + (((uint32_t)(half * 2 + (c0 >> 4)) ^ m_sw) << 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
             }
+            fence_proxy_async();                                   // staged bytes -> visible to the TMA (async proxy)
             tcgen05_fence_before();                                // every TMEM read of this tile has completed (wait::ld above)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[set]);          // the accumulator may be overwritten while we store
+            if (lane == 0) mbar_arrive(&tmem_empty[set]);          // the accumulator may be overwritten while the stores run
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both channel halves of the 32 windows are staged
-            const int ph = ph0 + row_in_tile;
-            if (ph < p.PH) {                                       // warp-uniform
-                const uint32_t win0 = ((uint32_t)b * p.PH + ph) * p.PW + pw0;             // first window of the row (element index fits 32 bits, checked at launch)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int col = i * 4 + col_p;
-                    const uint4 u = *reinterpret_cast<const uint4*>(o_rd + i * 512 + (((uint32_t)(lane & 7) ^ ((uint32_t)col & 7)) << 4));
-                    if (pw0 + col < p.PW)
-                        *reinterpret_cast<uint4*>(p.pooled + (size_t)((win0 + col) * 64u + (lane & 7) * 8u)) = u;
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int col = i * 8 + col_m;
-                    const uint4 u = *reinterpret_cast<const uint4*>(m_rd + i * 512 + ((((uint32_t)(lane & 3)) ^ (((uint32_t)col >> 1) & 3)) << 4));
-                    if (pw0 + col < p.PW)
-                        *reinterpret_cast<uint4*>(p.mask + (size_t)((win0 + col) * 64u + (lane & 3) * 16u)) = u;
-                }
+            if (issuer) {
+                tma_store_4d(&maps.pooled, sb, 0, pw0, ph0 + 2 * quarter, b);
+                tma_store_4d(&maps.mask, sb + 32 * 128, 0, pw0, ph0 + 2 * quarter, b);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores complete before the CTA exits
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -615,8 +605,8 @@ static bool conv0_input_map(CUtensorMap* tx, const void* x, bool half, int B, in
     return *err == 0;
 }
 
-template <void (*Kern)(const CUtensorMap, Conv0Params)>
-static int conv0_launch(int grid, int threads, int smem, cudaStream_t st, const CUtensorMap& tx, const Conv0Params& p) {
+template <typename Maps, void (*Kern)(const Maps, Conv0Params)>
+static int conv0_launch(int grid, int threads, int smem, cudaStream_t st, const Maps& tx, const Conv0Params& p) {
     static bool attr_set = false;               // one flag per kernel instantiation
     if (!attr_set) { VQA_CUDA(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
     VQA_CUDA(vqa_launch_pdl(Kern, dim3(grid), dim3(threads), smem, st, tx, p));
@@ -640,16 +630,24 @@ extern "C" int vqa_tc_conv0_relu_pool_fwd_x(const void* x, int x_dtype, const fl
     if (int rc = conv0_set_magics(p)) return rc;
     const int sms = sm_count();
     const int grid = ntiles < sms ? ntiles : sms;
-    CUtensorMap tx{};
+    Conv0FwdMaps maps{};
     int err = 0;
-    const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err);
+    const bool staged = conv0_input_map(&maps.x, x, half, B, IH, IW, &err);
     if (err) return err;
+    {   // output boxes: 64 channels x 16 windows x 2 rows = the staging tile of one lane quarter, swizzled like its rows
+        const uint64_t dims[4] = {64, (uint64_t)p.PW, (uint64_t)p.PH, (uint64_t)B};
+        const uint32_t box[4] = {64, C0_WW, 2, 1};
+        const uint64_t so[3] = {128, (uint64_t)p.PW * 128, (uint64_t)p.PH * p.PW * 128};
+        if (int e = make_tmap(&maps.pooled, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, out, 4, dims, so, box)) return e;
+        const uint64_t sm[3] = {64, (uint64_t)p.PW * 64, (uint64_t)p.PH * p.PW * 64};
+        if (int e = make_tmap(&maps.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_64B, mask, 4, dims, sm, box)) return e;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (staged) rc = half ? conv0_launch<conv0_fwd_tc_kernel<true, true>>(grid, C0F_THREADS, smem, st, tx, p)
-                          : conv0_launch<conv0_fwd_tc_kernel<true, false>>(grid, C0F_THREADS, smem, st, tx, p);
-    else rc = half ? conv0_launch<conv0_fwd_tc_kernel<false, true>>(grid, C0F_THREADS, smem, st, tx, p)
-                   : conv0_launch<conv0_fwd_tc_kernel<false, false>>(grid, C0F_THREADS, smem, st, tx, p);
+    if (staged) rc = half ? conv0_launch<Conv0FwdMaps, conv0_fwd_tc_kernel<true, true>>(grid, C0F_THREADS, smem, st, maps, p)
+                          : conv0_launch<Conv0FwdMaps, conv0_fwd_tc_kernel<true, false>>(grid, C0F_THREADS, smem, st, maps, p);
+    else rc = half ? conv0_launch<Conv0FwdMaps, conv0_fwd_tc_kernel<false, true>>(grid, C0F_THREADS, smem, st, maps, p)
+                   : conv0_launch<Conv0FwdMaps, conv0_fwd_tc_kernel<false, false>>(grid, C0F_THREADS, smem, st, maps, p);
     if (rc) return rc;
     VQA_CHECK_LAUNCH("conv0_fwd_tc");
     return 0;
@@ -687,10 +685,10 @@ extern "C" int vqa_tc_conv0_bwd_weight_bias_x(const void* x, int x_dtype, const 
     const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err);
     if (err) return err;
     int rc;
-    if (staged) rc = half ? conv0_launch<conv0_bwd_tc_kernel<true, true>>(ctas, C0B_THREADS, smem, st, tx, p)
-                          : conv0_launch<conv0_bwd_tc_kernel<true, false>>(ctas, C0B_THREADS, smem, st, tx, p);
-    else rc = half ? conv0_launch<conv0_bwd_tc_kernel<false, true>>(ctas, C0B_THREADS, smem, st, tx, p)
-                   : conv0_launch<conv0_bwd_tc_kernel<false, false>>(ctas, C0B_THREADS, smem, st, tx, p);
+    if (staged) rc = half ? conv0_launch<CUtensorMap, conv0_bwd_tc_kernel<true, true>>(ctas, C0B_THREADS, smem, st, tx, p)
+                          : conv0_launch<CUtensorMap, conv0_bwd_tc_kernel<true, false>>(ctas, C0B_THREADS, smem, st, tx, p);
+    else rc = half ? conv0_launch<CUtensorMap, conv0_bwd_tc_kernel<false, true>>(ctas, C0B_THREADS, smem, st, tx, p)
+                   : conv0_launch<CUtensorMap, conv0_bwd_tc_kernel<false, false>>(ctas, C0B_THREADS, smem, st, tx, p);
     if (rc) return rc;
     VQA_CHECK_LAUNCH("conv0_bwd_tc");
     return 0;
