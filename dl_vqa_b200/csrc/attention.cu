@@ -389,6 +389,12 @@ attention_bwd_kernel(const T* __restrict__ dout, int64_t ldd, const T* __restric
 //   softmax over the P positions per glimpse (warp shuffles), probabilities kept in shared memory and saved.
 //   phase 3 (chunk = 16 positions x 256 channels): lane = 8 channels, fp32 accumulators, one cross-warp reduction.
 // Algorithmic HBM bytes per sample as for the generic kernel; nothing is read twice.
+//
+// Sample order: both streaming kernels walk the batch from the LAST sample to the first.  The forward follows the
+// v_conv GEMM, whose persistent tiles wrote v' in ascending row order: the tail of v' (about a third of its 354 MB at
+// B = 256) is still dirty in the 126 MB L2 when this kernel starts, and reading it first turns those HBM reads into L2
+// hits instead of forcing their write-back while the head is streamed in.  The backward writes dv' last-sample-first for
+// the same reason: the v_conv data-gradient GEMM that follows reads dv' in ascending order.
 // ================================================================================================================
 namespace stream {
 
@@ -511,7 +517,8 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
         // ===== producer: one thread streams every chunk of every sample of this CTA, in consumption order =====
         if (lane == 0) {
             uint32_t c = 0;
-            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
+        const int b = B - 1 - bi;                              // last sample first: see "sample order" at the top of the streaming kernels
                 const uint8_t* src1 = reinterpret_cast<const uint8_t*>(vp + (int64_t)b * P * A_);
                 const uint8_t* src3 = reinterpret_cast<const uint8_t*>(vn + (int64_t)b * P * C_);
                 const int64_t bytes1 = (int64_t)P * A_ * 2, bytes3 = (int64_t)P * C_ * 2;
@@ -548,7 +555,8 @@ attention_fwd_stream_kernel(const bf16* __restrict__ vp, const float* __restrict
             }
 
     uint32_t c = 0;                                   // global chunk counter (same sequence as the producer)
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
+        const int b = B - 1 - bi;                              // last sample first: see "sample order" at the top of the streaming kernels
         uint32_t q2[8];                               // q' of this sample, rounded to the format of v' (packed pairs)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -746,7 +754,8 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
     if (warp == NCW) {
         if (lane == 0) {
             uint32_t c = 0;
-            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
+        const int b = B - 1 - bi;                              // last sample first: see "sample order" at the top of the streaming kernels
                 const uint8_t* srcA = reinterpret_cast<const uint8_t*>(vn + (int64_t)b * P * C_);
                 const uint8_t* srcC = reinterpret_cast<const uint8_t*>(vp + (int64_t)b * P * A_);
                 const int64_t bytesA = (int64_t)P * C_ * 2, bytesC = (int64_t)P * A_ * 2;
@@ -776,7 +785,8 @@ attention_bwd_stream_kernel(const bf16* __restrict__ dout, int64_t ldd, const bf
         for (int i = 0; i < 8; ++i) wv[g][i] = wx[g * A_ + a0 + i] * scale;
 
     uint32_t c = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
+        const int b = B - 1 - bi;                              // last sample first: see "sample order" at the top of the streaming kernels
         // per-sample inputs: probabilities, upstream gradient
         for (int i = tid; i < G * P; i += NCW * 32) { const int g = i / P, sidx = i - g * P; pr[sidx * G + g] = prob[(int64_t)b * G * P + i]; }
         for (int i = tid; i < G * C_; i += NCW * 32) dsm[i] = __bfloat162float(dout[(int64_t)b * ldd + i]);

@@ -412,7 +412,10 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ Conv
 // the staged input regions (STAGED, as in the forward)
 constexpr int C0B_THREADS = 14 * 32;
 constexpr int C0B_STAGE_BYTES = 6 * C0_TILE_BYTES;            // 4 masked-gradient tiles (A) + 2 patch tiles (B)
-constexpr int C0B_XSTAGES = 3;
+constexpr int C0B_XSTAGES = 4;                                // a multiple of the builder-group count ON PURPOSE: a slot's mbarriers then
+                                                              // always have the same consumer.  If slots alternated between the groups, a group
+                                                              // could reach a slot one full phase early (before the previous occupant's data
+                                                              // landed) and a parity wait cannot tell "phase n done" from "phase n-1 not done".
 
 template <bool STAGED, bool XHALF>
 __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {

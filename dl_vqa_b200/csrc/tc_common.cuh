@@ -36,7 +36,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) { printf("vqa_b200: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+        if (++spins > (1u << 24)) {
+            printf("vqa_b200: mbarrier timeout (block %d,%d,%d thread %d, barrier @%u, parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
     }
 }
 
