@@ -537,10 +537,11 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
             mbar_arrive(&full[g]);
         }
     } else if (warp == 12) {
-        // D[128 (co; rows 64..127 unused)][32 k] += A_e^T B_e over the 128 windows of the tile, e = 0..3.
-        // A: MN-major, 64 channels = one 128-byte block (the second M block of the instruction reads whatever follows
-        // 1 KB later: those rows only feed accumulator rows 64..127, which are never read).
-        constexpr uint32_t idesc = idesc_bf16(128, 32, 1, 1);
+        // D[64 co][32 k] += A_e^T B_e over the 128 windows of the tile, e = 0..3.  M = 64 MMAs: this kernel is bound by
+        // shared-memory bandwidth (operand stores + MMA operand reads), and an M = 128 instruction would read a second,
+        // unused 64-channel block of A with every K step.  A: MN-major, 64 channels = one 128-byte block.
+        // Accumulator layout of M = 64: row r sits in TMEM lane 32 (r / 16) + r % 16 (16 lanes of every lane quarter).
+        constexpr uint32_t idesc = idesc_bf16(64, 32, 1, 1);
         const uint32_t elected = elect_one();
         const uint64_t a_desc0 = smem_desc_mn_sw128(smem_u32(smem), 1024);
         for (int i = 0; i < nt; ++i) {
@@ -559,15 +560,17 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
             umma_commit_issue<1>(&empty[g], elected);
         }
         umma_commit_issue<1>(tmem_full, elected);
-    } else if (warp < 2 && nt > 0) {
+    } else if (warp < 4 && nt > 0) {
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
-        const int co = warp * 32 + lane;
+        if (lane < 16) {
+            const int co = warp * 16 + lane;
 #pragma unroll
-        for (int k = 0; k < C0_K; ++k) atomicAdd(p.dw + co * C0_K + k, v[k]);
-        atomicAdd(p.db + co, v[27]);
+            for (int k = 0; k < C0_K; ++k) atomicAdd(p.dw + co * C0_K + k, v[k]);
+            atomicAdd(p.db + co, v[27]);
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
