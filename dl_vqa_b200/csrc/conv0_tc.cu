@@ -39,11 +39,12 @@ struct Conv0Params {
 
 // Tile index -> (image, first pooled row, first pooled column) without integer division: multiply-high by the host's
 // reciprocals, exact while tile * divisor < 2^32 (checked at launch).
+template <int WH = C0_WH>
 __device__ __forceinline__ void conv0_tile_pos(const Conv0Params& p, int tile, int& b, int& ph0, int& pw0) {
     b = p.magic_img ? (int)__umulhi((uint32_t)tile, p.magic_img) : tile;
     const int r = tile - b * (p.tiles_h * p.tiles_w);
     const int th = p.magic_w ? (int)__umulhi((uint32_t)r, p.magic_w) : r;
-    ph0 = th * C0_WH;
+    ph0 = th * WH;
     pw0 = (r - th * p.tiles_w) * C0_WW;
 }
 
@@ -408,38 +409,120 @@ __global__ void __maxnreg__(80) conv0_fwd_tc_kernel(const __grid_constant__ Conv
 }
 
 // ------------------------------------------------------------------------------------------ backward (weight + bias)
-// warps 0-3 final epilogue, warps 4-11 two builder groups (group g owns stage g), warp 12 MMA, warp 13 TMA producer of
-// the staged input regions (STAGED, as in the forward)
+// Unit of work: a HALF tile of 4 x 16 windows.  warps 0-3 final flush, warps 4-11 two builder groups of 128 threads (group
+// g builds half tiles g, g+2, ... into its own TWO operand stages), warp 12 MMA, warp 13 TMA producer of the staged input
+// regions (STAGED, as in the forward).
+//
+// What the r02 ncu source views of the earlier forms showed, and what this form does about it:
+//  * 128-window tiles with one 96 KB stage per group: a group could not start a tile before the MMAs of its previous one
+//    had drained (29 % of the builder samples sat in that wait) and the MMA warp waited for operands 47 % of the time.
+//    Half tiles make the stage 48 KB, so every group owns two and never waits for the tensor core.
+//  * The pooled gradient and the mask arrived by global loads issued at the top of the tile that needs them: four to five
+//    long-scoreboard stall cycles per issued instruction.  They are now loaded into a second register set one whole tile
+//    ahead (two sets x 24 registers, the loop is unrolled by two so that both are plain arrays).
+//  * The kernel moves about 2 KB of shared memory per window (operand stores, MMA operand reads): M = 64 MMAs read no
+//    unused second A block, and the mask expansion is one HSET2 (ALU pipe) + one HFMA2 (FMA pipe) per channel pair and
+//    window element instead of HSET2 + LOP3 on the ALU pipe alone.
+constexpr int C0B_WH = 4;                                     // window rows of a half tile (C0_WW columns)
+constexpr int C0B_WIN = C0B_WH * C0_WW;                       // 64 windows
+constexpr int C0B_TILE = C0B_WIN * 128;                       // one operand tile: 64 windows x 128 B
 constexpr int C0B_THREADS = 14 * 32;
-constexpr int C0B_STAGE_BYTES = 6 * C0_TILE_BYTES;            // 4 masked-gradient tiles (A) + 2 patch tiles (B)
+constexpr int C0B_STAGE_BYTES = 6 * C0B_TILE;                 // 4 masked-gradient tiles (A) + 2 patch tiles (B) = 48 KB
+constexpr int C0B_NSTAGE = 4;                                 // two per builder group
 constexpr int C0B_XSTAGES = 4;                                // a multiple of the builder-group count ON PURPOSE: a slot's mbarriers then
                                                               // always have the same consumer.  If slots alternated between the groups, a group
                                                               // could reach a slot one full phase early (before the previous occupant's data
                                                               // landed) and a parity wait cannot tell "phase n done" from "phase n-1 not done".
+constexpr int C0B_XROWS = 2 * C0B_WH + 2;                     // 10 input rows
+constexpr int C0B_XBYTES = 3 * C0B_XROWS * C0_XCOLS * 4, C0B_XBYTES_H = 3 * C0B_XROWS * C0_XCOLS_H * 2;      // 4320 / 2400
+constexpr int C0B_XSLOT = 4608;
+constexpr int C0B_SMEM = C0B_NSTAGE * C0B_STAGE_BYTES + C0B_XSTAGES * C0B_XSLOT + 1024 + 256;
+
+// the three input rows dyh .. dyh+2 (+ 2*wr) of a window's patch, all channels: v[ci][r][c], from a staged region
+template <bool XHALF>
+__device__ __forceinline__ void load_rows_staged(const uint8_t* xs, int wr, int wc, int dyh, float (&v)[3][3][4]) {
+    if (XHALF) {
+        const __half* base = reinterpret_cast<const __half*>(xs) + (2 * wr + dyh) * C0_XCOLS_H + 2 * wc;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const __half2* q = reinterpret_cast<const __half2*>(base + (ci * C0B_XROWS + r) * C0_XCOLS_H);
+                const float2 a = __half22float2(q[0]), c = __half22float2(q[1]);
+                v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+            }
+        return;
+    }
+    const float* base = reinterpret_cast<const float*>(xs) + (2 * wr + dyh) * C0_XCOLS + 2 * wc;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float2* q = reinterpret_cast<const float2*>(base + (ci * C0B_XROWS + r) * C0_XCOLS);
+            const float2 a = q[0], c = q[1];
+            v[ci][r][0] = a.x; v[ci][r][1] = a.y; v[ci][r][2] = c.x; v[ci][r][3] = c.y;
+        }
+}
+// the same rows straight from global memory (image rows that TMA cannot address); coordinates clamped, the gradient of
+// an out-of-range window is zero
+template <bool XHALF>
+__device__ __forceinline__ void load_rows_global(const Conv0Params& p, int b, int ph, int pw, int dyh, float (&v)[3][3][4]) {
+    const int phc = min(ph, p.PH - 1), pwc = min(pw, p.PW - 1);
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int64_t off = (((int64_t)b * 3 + ci) * p.IH + 2 * phc + dyh + r) * p.IW + 2 * pwc;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                v[ci][r][c] = XHALF ? __half2float(__ldg(reinterpret_cast<const __half*>(p.x) + off + c))
+                                    : __ldg(reinterpret_cast<const float*>(p.x) + off + c);
+        }
+}
+
+// im2col row of element column DX from the three patch rows of its element row: k = ci*9 + kh*3 + kw <- v[ci][kh][DX + kw],
+// k = 27 holds 1.0 (bias-gradient column), the rest zero; packed to 4 x 16 bytes of bf16
+template <int DX>
+__device__ __forceinline__ void pack_patch_row(const float (&v)[3][3][4], uint4 (&u)[4]) {
+    float k[32];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) k[ci * 9 + kh * 3 + kw] = v[ci][kh][DX + kw];
+    k[27] = 1.f;
+#pragma unroll
+    for (int c = 28; c < 32; ++c) k[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        u[j].x = pack2(k[8 * j], k[8 * j + 1]); u[j].y = pack2(k[8 * j + 2], k[8 * j + 3]);
+        u[j].z = pack2(k[8 * j + 4], k[8 * j + 5]); u[j].w = pack2(k[8 * j + 6], k[8 * j + 7]);
+    }
+}
 
 template <bool STAGED, bool XHALF>
 __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x, Conv0Params p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
-    uint8_t* xs = smem + 2 * C0B_STAGE_BYTES;                  // C0B_XSTAGES x 8 KB staged input regions
-    uint64_t* full = reinterpret_cast<uint64_t*>(xs + C0B_XSTAGES * C0_XSTAGE);
-    uint64_t* empty = full + 2;
-    uint64_t* tmem_full = empty + 2;
+    uint8_t* xs = smem + C0B_NSTAGE * C0B_STAGE_BYTES;         // C0B_XSTAGES staged input regions
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs + C0B_XSTAGES * C0B_XSLOT);
+    uint64_t* empty = full + C0B_NSTAGE;
+    uint64_t* tmem_full = empty + C0B_NSTAGE;
     uint64_t* x_full = tmem_full + 1;                          // [C0B_XSTAGES]
     uint64_t* x_empty = x_full + C0B_XSTAGES;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + C0B_XSTAGES);
     constexpr uint32_t TMEM_COLS = 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = p.tiles_h * p.tiles_w;
-    const int total = p.B * tiles_per_img;
+    const int total = p.B * p.tiles_h * p.tiles_w;             // half tiles
     const int t_begin = blockIdx.x * p.tiles_per_cta;
     const int t_end = min(total, t_begin + p.tiles_per_cta);
     const int nt = max(0, t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < C0B_NSTAGE; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         for (int i = 0; i < C0B_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
         if (STAGED) tma_prefetch_desc(&tma_x);
@@ -455,109 +538,129 @@ __global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_tc_kernel(const __gr
     if (warp == 13) {
         if (STAGED && lane == 0) {
             for (int i = 0; i < nt; ++i) {
-                const int tile = t_begin + i;
-                const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+                int b, ph0, pw0;
+                conv0_tile_pos<C0B_WH>(p, t_begin + i, b, ph0, pw0);
                 const int q = i % C0B_XSTAGES;
                 mbar_wait(&x_empty[q], ((i / C0B_XSTAGES) & 1) ^ 1);
-                mbar_expect_tx(&x_full[q], XHALF ? C0_XBYTES_H : C0_XBYTES);
-                tma_load_4d(xs + q * C0_XSTAGE, &tma_x, &x_full[q], 2 * (r % p.tiles_w) * C0_WW, 2 * (r / p.tiles_w) * C0_WH, 0, b);
+                mbar_expect_tx(&x_full[q], XHALF ? C0B_XBYTES_H : C0B_XBYTES);
+                tma_load_4d(xs + q * C0B_XSLOT, &tma_x, &x_full[q], 2 * pw0, 2 * ph0, 0, b);
             }
         }
     } else if (warp >= 4 && warp < 12) {
         const int g = (warp - 4) >> 2, t = (threadIdx.x - 128) & 127;
-        const int wr = t >> 4, wc = t & 15, sw = t & 7;
-        uint8_t* stage = smem + g * C0B_STAGE_BYTES;
-        uint32_t use = 0;
-        // Pooled gradient (64 channels bf16 = 128 B per window) and arg-max mask (64 B per window), loaded COALESCED: a
-        // warp covers two window rows of the tile; in load k lane l takes 16-byte chunk c = (k & 3) * 32 + l of row
-        // 2*warp + (k >> 2), i.e. window (c >> 3), channels 8*(c & 7)..+7 -- consecutive lanes read consecutive addresses
-        // (one window per lane would touch 32 lines per instruction).  Any thread may write any (window, chunk) of the
-        // swizzled A tiles.  Branch-free: out-of-image chunks read offset 0 and are replaced at use (with if/else
-        // diamonds ptxas recycled the address registers of one load for the next and the loads ran one after the other).
-        // (A register prefetch one iteration ahead was slower: 128-register cap, and the proxy fence drains the loads.)
-        const int wg = t >> 5, jc = lane & 7;
-        uint4 d[8]; uint2 mk[8];
-        for (int i = g; i < nt; i += 2, ++use) {
-            const int tile = t_begin + i;
-            const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-            const int ph = (r / p.tiles_w) * C0_WH + wr, pw = (r % p.tiles_w) * C0_WW + wc;
-            const int ph0 = ph - wr + 2 * wg, pw0 = pw - wc + (lane >> 3);       // first of the warp's two rows / lane's first window
-            const int64_t off0 = (((int64_t)b * p.PH + ph0) * p.PW + pw0) * 64 + 8 * jc;
-            bool valid[8];
+        // gradient / mask: in load j (= window row j of the half tile) thread t takes 16-byte chunk t & 7 of window t >> 3:
+        // consecutive lanes read consecutive addresses (four windows = 512 contiguous bytes per warp and instruction) and
+        // write the eight swizzled chunks of one 128-byte operand row.
+        // patch rows: thread = (window t & 63, element row dyh = t >> 6) builds the two im2col rows e = 2 dyh, 2 dyh + 1.
+        const int uw = t >> 3, jc = t & 7;
+        const int pwin = t & 63, dyh = t >> 6;
+        const int pwr = pwin >> 4, pwc = pwin & 15;
+        // loads of half tile i into a register set; out-of-image windows read a clamped (valid) address and are zeroed at use
+        auto issue = [&](int i, uint4 (&d)[4], uint2 (&mk)[4]) {
+            int b, ph0, pw0;
+            conv0_tile_pos<C0B_WH>(p, t_begin + i, b, ph0, pw0);
+            const int pw = min(pw0 + uw, p.PW - 1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                valid[k] = ph0 + (k >> 2) < p.PH && pw0 + (k & 3) * 4 < p.PW;
-                const int64_t off = valid[k] ? off0 + ((int64_t)(k >> 2) * p.PW + (k & 3) * 4) * 64 : (int64_t)(8 * jc);
-                d[k] = __ldcs(reinterpret_cast<const uint4*>(p.dpool + off));
-                mk[k] = __ldcs(reinterpret_cast<const uint2*>(p.bmask + off));
+            for (int j = 0; j < 4; ++j) {
+                const int ph = min(ph0 + j, p.PH - 1);
+                const uint32_t off = (((uint32_t)b * p.PH + ph) * p.PW + pw) * 64u + 8u * jc;      // element index fits 32 bits (checked at launch)
+                d[j] = __ldcs(reinterpret_cast<const uint4*>(p.dpool + off));
+                mk[j] = __ldcs(reinterpret_cast<const uint2*>(p.bmask + off));
             }
-            mbar_wait(&empty[g], (use & 1) ^ 1);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (!valid[k]) { d[k] = make_uint4(0, 0, 0, 0); mk[k] = make_uint2(0x04040404u, 0x04040404u); }
-            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows per window, 128B-swizzled).  The eight mask bytes
-            // of a chunk (values 0..4) are widened ONCE to fp16 patterns 0x3C00 | id (1 + id/1024: normal numbers), so that
-            // per window element one HSET2.EQ per channel pair yields the 0xFFFF / 0 select masks on the half-precision
-            // pipe (was xor / sub / shift + two PRMT per pair on the integer pipe, the pipe this kernel saturates).
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int w = (2 * wg + (k >> 2)) * 16 + (k & 3) * 4 + (lane >> 3);      // window = row of the A tiles
-                uint8_t* chunkp = stage + w * 128 + ((jc ^ (w & 7)) << 4);
-                uint32_t mw[4];
-                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[0]) : "r"(mk[k].x), "r"(0x3C3C3C3Cu));
-                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[1]) : "r"(mk[k].x), "r"(0x3C3C3C3Cu));
-                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[2]) : "r"(mk[k].y), "r"(0x3C3C3C3Cu));
-                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[3]) : "r"(mk[k].y), "r"(0x3C3C3C3Cu));
-                const uint32_t dv[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t want = 0x3C003C00u | (0x00010001u * e);
-                    uint32_t o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t sel;
-                        asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(sel) : "r"(mw[i]), "r"(want));
-                        o[i] = dv[i] & sel;
-                    }
-                    *reinterpret_cast<uint4*>(chunkp + e * C0_TILE_BYTES) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            // the patch rows last: (d, mk) are dead by now, so the 48 patch values do not add to the register peak
-            float v[3][4][4];
+        };
+        // expansion of half tile i (the n-th of this group) from a register set into stage 2 g + (n & 1)
+        auto build = [&](int i, uint32_t n, const uint4 (&d)[4], const uint2 (&mk)[4]) {
+            const uint32_t s = 2 * g + (n & 1), use = n >> 1;
+            uint8_t* stage = smem + s * C0B_STAGE_BYTES;
+            int b, ph0, pw0;
+            conv0_tile_pos<C0B_WH>(p, t_begin + i, b, ph0, pw0);
+            float v[3][3][4];
             if (STAGED) {
                 const int q = i % C0B_XSTAGES;
                 mbar_wait(&x_full[q], (i / C0B_XSTAGES) & 1);
-                load_patch_staged<XHALF>(xs + q * C0_XSTAGE, wr, wc, v);
-                mbar_arrive(&x_empty[q]);
+                load_rows_staged<XHALF>(xs + q * C0B_XSLOT, pwr, pwc, dyh, v);
+                mbar_arrive(&x_empty[q]);                      // the values are in registers: the region can be refilled
             } else {
-                load_patch_global<XHALF>(p, b, ph, pw, v);
+                load_rows_global<XHALF>(p, b, ph0 + pwr, pw0 + pwc, dyh, v);
             }
-            store_patch_rows(stage + 4 * C0_TILE_BYTES, t, v);
+            mbar_wait(&empty[s], (use & 1) ^ 1);
+            // A_e[window][co] = mask == e ? dpool : 0   (four 128-byte rows per window, 128B-swizzled).  The mask bytes are
+            // widened to the bf16 patterns 0x3F00 | id (five distinct normal numbers), compared with the element's pattern
+            // to 1.0 / 0.0 (HSET2, ALU pipe) and multiplied into the gradient pair (HFMA2, FMA pipe).
+            const bool colok = pw0 + uw < p.PW;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = 16 * j + uw;
+                uint8_t* chunkp = stage + w * 128 + ((jc ^ (w & 7)) << 4);
+                const bool ok = colok && ph0 + j < p.PH;
+                uint32_t mw[4];
+                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[0]) : "r"(mk[j].x), "r"(0x3F3F3F3Fu));
+                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[1]) : "r"(mk[j].x), "r"(0x3F3F3F3Fu));
+                asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(mw[2]) : "r"(mk[j].y), "r"(0x3F3F3F3Fu));
+                asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(mw[3]) : "r"(mk[j].y), "r"(0x3F3F3F3Fu));
+                const uint32_t dv[4] = {ok ? d[j].x : 0u, ok ? d[j].y : 0u, ok ? d[j].z : 0u, ok ? d[j].w : 0u};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t want = 0x3F003F00u | (0x00010001u * e);
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t sel;
+                        asm("set.eq.bf16x2.bf16x2 %0, %1, %2;" : "=r"(sel) : "r"(mw[k]), "r"(want));
+                        asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o[k]) : "r"(dv[k]), "r"(sel));
+                    }
+                    *reinterpret_cast<uint4*>(chunkp + e * C0B_TILE) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            // B: the two im2col rows of (window, dyh) = one 128-byte row of patch tile dyh
+            {
+                uint8_t* rowp = stage + (4 + dyh) * C0B_TILE + pwin * 128;
+                const int sw = pwin & 7;
+                uint4 u0[4], u1[4];
+                pack_patch_row<0>(v, u0);
+                pack_patch_row<1>(v, u1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = u0[j];
+                    *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ sw) << 4)) = u1[j];
+                }
+            }
             fence_proxy_async();
-            mbar_arrive(&full[g]);
+            mbar_arrive(&full[s]);
+        };
+        uint4 dA[4], dB[4]; uint2 mkA[4], mkB[4];
+        if (g < nt) issue(g, dA, mkA);
+        if (g + 2 < nt) issue(g + 2, dB, mkB);
+        uint32_t n = 0;
+        for (int i = g; i < nt; i += 4) {
+            build(i, n, dA, mkA); ++n;
+            if (i + 4 < nt) issue(i + 4, dA, mkA);             // after the proxy fence of the tile just built: it would wait for them
+            if (i + 2 < nt) {
+                build(i + 2, n, dB, mkB); ++n;
+                if (i + 6 < nt) issue(i + 6, dB, mkB);
+            }
         }
     } else if (warp == 12) {
-        // D[64 co][32 k] += A_e^T B_e over the 128 windows of the tile, e = 0..3.  M = 64 MMAs: this kernel is bound by
-        // shared-memory bandwidth (operand stores + MMA operand reads), and an M = 128 instruction would read a second,
-        // unused 64-channel block of A with every K step.  A: MN-major, 64 channels = one 128-byte block.
-        // Accumulator layout of M = 64: row r sits in TMEM lane 32 (r / 16) + r % 16 (16 lanes of every lane quarter).
+        // D[64 co][32 k] += A_e^T B_e over the 64 windows of the half tile, e = 0..3.  M = 64 MMAs: an M = 128 instruction
+        // would read a second, unused 64-channel block of A with every K step.  A: MN-major, 64 channels = one 128-byte
+        // block.  Accumulator layout of M = 64: row r sits in TMEM lane 32 (r / 16) + r % 16 (16 lanes of every lane quarter).
         constexpr uint32_t idesc = idesc_bf16(64, 32, 1, 1);
         const uint32_t elected = elect_one();
         const uint64_t a_desc0 = smem_desc_mn_sw128(smem_u32(smem), 1024);
         for (int i = 0; i < nt; ++i) {
-            const int g = i & 1;
-            mbar_wait(&full[g], (i >> 1) & 1);
+            const uint32_t g = i & 1, n = (uint32_t)i >> 1, s = 2 * g + (n & 1);
+            mbar_wait(&full[s], (n >> 1) & 1);
             tcgen05_fence_after();
-            const uint64_t sd = a_desc0 + (uint64_t)(g * (C0B_STAGE_BYTES >> 4));
+            const uint64_t sd = a_desc0 + (uint64_t)(s * (C0B_STAGE_BYTES >> 4));
 #pragma unroll
             for (uint32_t e = 0; e < 4; ++e) {
-                const uint64_t ad = sd + (uint64_t)(e * (C0_TILE_BYTES >> 4));
-                const uint64_t bd = sd + (uint64_t)((4 + (e >> 1)) * (C0_TILE_BYTES >> 4) + (e & 1) * 4);
+                const uint64_t ad = sd + (uint64_t)(e * (C0B_TILE >> 4));
+                const uint64_t bd = sd + (uint64_t)((4 + (e >> 1)) * (C0B_TILE >> 4) + (e & 1) * 4);
 #pragma unroll
-                for (uint32_t k = 0; k < 8; ++k)            // 16 windows (rows) per MMA: 2048 bytes further
+                for (uint32_t k = 0; k < C0B_WIN / 16; ++k)       // 16 windows (rows) per MMA: 2048 bytes further
                     umma_issue<1>(tmem_base, ad + k * (2048 >> 4), bd + k * (2048 >> 4), idesc, (i > 0 || e > 0 || k > 0) ? 1u : 0u, elected);
             }
-            umma_commit_issue<1>(&empty[g], elected);
+            umma_commit_issue<1>(&empty[s], elected);
         }
         umma_commit_issue<1>(tmem_full, elected);
     } else if (warp < 4 && nt > 0) {
@@ -599,13 +702,13 @@ static int conv0_set_magics(Conv0Params& p) {
 }
 
 // Tensor map of the NCHW network input for the staged (TMA) path; false when the layout does not allow it
-static bool conv0_input_map(CUtensorMap* tx, const void* x, bool half, int B, int IH, int IW, int* err) {
+static bool conv0_input_map(CUtensorMap* tx, const void* x, bool half, int B, int IH, int IW, int* err, int box_rows = C0_XROWS) {
     const int esz = half ? 2 : 4;
     *err = 0;
     if ((IW * esz) % 16 != 0 || ((uintptr_t)x & 15) != 0) return false;      // TMA needs 16-byte aligned rows
     const uint64_t dims[4] = {(uint64_t)IW, (uint64_t)IH, 3, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)IW * esz, (uint64_t)IH * IW * esz, (uint64_t)3 * IH * IW * esz};
-    const uint32_t box[4] = {(uint32_t)(half ? C0_XCOLS_H : C0_XCOLS), C0_XROWS, 3, 1};
+    const uint32_t box[4] = {(uint32_t)(half ? C0_XCOLS_H : C0_XCOLS), (uint32_t)box_rows, 3, 1};
     *err = make_tmap(tx, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE,
                      x, 4, dims, str, box);
     return *err == 0;
@@ -678,17 +781,18 @@ extern "C" int vqa_tc_conv0_bwd_weight_bias_x(const void* x, int x_dtype, const 
     Conv0Params p{};
     p.x = x; p.B = B; p.IH = IH; p.IW = IW;
     p.PH = (IH - 2) / 2; p.PW = (IW - 2) / 2;
-    p.tiles_h = (p.PH + C0_WH - 1) / C0_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;
+    p.tiles_h = (p.PH + C0B_WH - 1) / C0B_WH; p.tiles_w = (p.PW + C0_WW - 1) / C0_WW;       // half tiles of 4 x 16 windows
     p.dpool = (const bf16*)dpool; p.bmask = mask; p.dw = dw; p.db = db;
+    if (int rc = conv0_set_magics(p)) return rc;
     const int total = B * p.tiles_h * p.tiles_w;
     const int sms = sm_count();
     int ctas = total < sms ? total : sms;
     p.tiles_per_cta = (total + ctas - 1) / ctas;
     ctas = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    const int smem = 2 * C0B_STAGE_BYTES + C0B_XSTAGES * C0_XSTAGE + 1024 + 256;
+    const int smem = C0B_SMEM;
     CUtensorMap tx{};
     int err = 0;
-    const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err);
+    const bool staged = conv0_input_map(&tx, x, half, B, IH, IW, &err, C0B_XROWS);
     if (err) return err;
     int rc;
     if (staged) rc = half ? conv0_launch<CUtensorMap, conv0_bwd_tc_kernel<true, true>>(ctas, C0B_THREADS, smem, st, tx, p)
