@@ -301,6 +301,48 @@ def test_tc_conv0_fwd_and_wgrad_match_torch(B, IH, IW):
     assert errb < 2e-3, errb
 
 
+def test_tc_conv0_argmax_arithmetic_ties_and_dead_windows():
+    """The first-layer epilogue finds the arg-max ARITHMETICALLY (saturated differences on the FMA pipe, conv0_tc.cu).
+    Pin its corner cases on inputs where every 2x2 window is an exact four-way tie: the first element must win (id 0,
+    torch's max_pool2d order), ReLU-dead windows must carry id 4 and an exactly zero output, and a window that is tied
+    in its first two elements only must still report the first."""
+    from dl_vqa_b200 import lib
+    B, IH, IW, Cin, Cout = 2, 38, 70, 3, 64
+    PH, PW = (IH - 2) // 2, (IW - 2) // 2
+    x = torch.full((B, Cin, IH, IW), 0.5, device="cuda")
+    w = torch.rand(Cout, Cin, 3, 3, device="cuda") + 0.1
+    w[Cout // 2:] *= -1.0                                        # second half of the channels: negative everywhere -> dead
+    bias = torch.zeros(Cout, device="cuda")
+    bias[:4] = torch.tensor([0.25, -0.125, 1.0, 3.0], device="cuda")
+    out = torch.empty(B, PH, PW, Cout, dtype=torch.bfloat16, device="cuda")
+    mask = torch.full((B, PH, PW, Cout), 9, dtype=torch.uint8, device="cuda")
+    lib.call("vqa_tc_conv0_relu_pool_fwd", lib.ptr(x), lib.ptr(w), lib.ptr(bias), lib.ptr(out), lib.ptr(mask),
+             B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    alive = slice(0, Cout // 2)
+    dead = slice(Cout // 2, Cout)
+    assert int((mask[..., alive] != 0).sum()) == 0               # four-way ties: first element
+    assert float(out[..., alive].float().min()) > 0
+    assert int((mask[..., dead] != 4).sum()) == 0                # all four elements negative: ReLU-dead
+    assert float(out[..., dead].float().abs().max()) == 0.0
+    want = 0.5 * w[:Cout // 2].bfloat16().float().sum(dim=(1, 2, 3)) + bias[:Cout // 2]
+    got = out[0, 0, 0, alive].float()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-2
+    # partial tie: lower the second row of every window's source pixels so that only elements 0 and 1 tie
+    x2 = x.clone()
+    x2[:, :, 1::2, :] = 0.25                                     # odd input rows smaller: elements with dy = 1 see two small rows
+    lib.call("vqa_tc_conv0_relu_pool_fwd", lib.ptr(x2), lib.ptr(w), lib.ptr(bias), lib.ptr(out), lib.ptr(mask),
+             B, IH, IW, Cin, Cout, lib.stream())
+    torch.cuda.synchronize()
+    import torch.nn.functional as F
+    pre = F.conv2d(x2.bfloat16().float(), w.bfloat16().float(), bias)
+    _, idx = F.max_pool2d(torch.relu(pre), 2, 2, return_indices=True)
+    OW = IW - 2
+    idx = idx.permute(0, 2, 3, 1)
+    e = ((idx // OW) % 2) * 2 + ((idx % OW) % 2)
+    assert torch.equal(mask[..., alive].long(), e[..., alive])
+
+
 @pytest.mark.parametrize("R,N,K", [(256, 3000, 1024), (5888, 4096, 304), (1000, 64, 72), (4, 136, 40), (20000, 1024, 256)])
 def test_tc_gemm_mn_major_weight_gradient_form(R, N, K):
     """dW[N,K] = dY[R,N]^T X[R,K] with both operands consumed row-major (reduction index = row)."""

@@ -42,7 +42,8 @@ if has launches; then
 fi
 if has full; then
   # one complete kernel-by-kernel step: skip the warm-up launches, capture the last timed step
-  timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_out/${tag}_full \
+  # NCU_K (a regex) restricts the capture to some kernels of the step: a full-set capture of all 64 costs ~10 minutes
+  timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_out/${tag}_full ${NCU_K:+-k regex:$NCU_K} \
     --profile-from-start off python bench.py --steps 1 --warmup 3 --profile-mode --no-graph > gpurun_out/${tag}_ncu_full.log 2>&1
   echo "full exit $?"
   ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
