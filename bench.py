@@ -2,7 +2,7 @@
 """Benchmark of the DL_VQA training step (BASELINE.json: "train samples/sec at 1/2/4/8 B200").
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference (oracle/_ref) on the host cores
 
 One step = forward + soft-target loss + backward + Adam on one synthetic batch of 256 samples per GPU at the
 config.yaml shapes (BASELINE.json configs[1]), dropout 0.3 active (train mode).  Prints ONE JSON line.
@@ -86,7 +86,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference step, timed on the host cores
+# CPU baseline / reference arm: the unmodified reference step (oracle/_ref; oracle port if absent), timed on the host cores
 # --------------------------------------------------------------------------------------------------
 def _use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use the host's cores."""

@@ -26,6 +26,7 @@
 //                    layer's UN-POOLED gradient (value at the arg-max element of each 2x2 window, zeros elsewhere) and
 //                    its bias gradient is reduced with a transposing butterfly -- vqa_unpool_bf16 disappears.
 #include "tc_common.cuh"
+#include <atomic>
 
 namespace tc {
 
@@ -470,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // cta_group selection: 1 = single-CTA MMAs, 2 = CTA pairs.  Changed only by vqa_tc_conv_set_cta_group (tests/bench).
-static int g_conv_cta_group = 0;        // 0 = per-shape choice (launch_conv), 1 / 2 = forced
+static std::atomic<int> g_conv_cta_group{0};   // 0 = per-shape choice (launch_conv), 1 / 2 = forced; atomic: callers may race a set against launches
 
 template <int BN, int EPI, int NCTA, bool RESIDENT, int MT = 1>
 static int launch_conv_cfg(const CUtensorMap& ta, const CUtensorMap& tb, ConvParams p, int smem_bytes, cudaStream_t st) {
@@ -513,7 +514,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb1, const CUte
     // where the weights are streamed for a 256-wide tile (conv2 forward: 0.353 -> 0.333 ms) and for the 64-wide data
     // gradient (conv1 dgrad: 0.418 -> 0.406 ms), and lose where one CTA already keeps the weights resident for a 128-wide
     // tile (conv1 forward) or shares each streamed slab between two tiles (MT = 2: conv2 dgrad).
-    const int ncta = g_conv_cta_group != 0 ? g_conv_cta_group
+    const int forced = g_conv_cta_group.load(std::memory_order_relaxed);
+    const int ncta = forced != 0 ? forced
                    : ((EPI == EPI_POOL && BN == 256) || (EPI == EPI_STORE && BN == 64)) ? 2 : 1;
     const int nkb = 9 * p.chunks;
     const int slab = (BN / ncta) * 128;
@@ -563,7 +565,7 @@ using namespace tc;
 
 extern "C" int vqa_tc_conv_set_cta_group(int cta_group) {
     VQA_REQUIRE(cta_group >= 0 && cta_group <= 2, "conv cta_group must be 0 (per-shape choice), 1 or 2");
-    g_conv_cta_group = cta_group;
+    g_conv_cta_group.store(cta_group, std::memory_order_relaxed);
     return 0;
 }
 

@@ -20,7 +20,12 @@
  *     backward entries take the same (p, seed) and regenerate the same mask.  A `seed` argument with
  *     VQA_SEED_ON_DEVICE set carries, in its low 63 bits, the DEVICE ADDRESS of a uint64 seed that is
  *     read when the kernel runs: a captured CUDA graph of the step then draws a fresh mask on every
- *     replay (vqa_step_tick advances the seed; the reference draws a new mask per call, models/model.py:84,156,185,194).
+ *     replay (vqa_step_tick advances the seed; the reference draws a new mask per call, models/model.py:84,156,185,194);
+ *   - threading: every entry may be called from any host thread on any stream; entries keep no per-call state
+ *     between calls.  Process-wide state is limited to (i) values read once and never written again (the
+ *     environment switches VQA_PDL and VQA_LSTM_CLUSTER, per-kernel "shared-memory limit already raised" flags),
+ *     (ii) the launch counter (atomic), (iii) ONE tuning knob, vqa_tc_conv_set_cta_group (atomic; every value
+ *     produces identical results).  vqa_last_error_string() is per thread.
  */
 #ifndef VQA_B200_H
 #define VQA_B200_H
