@@ -405,6 +405,56 @@ extern "C" int vqa_length_order(const int64_t* q_len, int* order, int64_t* len_s
 }
 
 // ------------------------------------------------------------------------------------------
+// Reduction-block lists for the LSTM weight gradients (vqa_tc_gemm_kblocks).  The step-indexed buffers hold rows
+// (s, r), s = 0..T-1, r = 0..B-1; the gate gradient dg[s][r] is exactly zero when s >= len[r] (question r has ended:
+// pack_padded_sequence drops those positions, models/model.py:160-164), so a 64-row block all of whose rows have ended
+// adds nothing to dW_ih = sum dg^T x or dW_hh = sum dg^T h_prev.  CTA c (c = 0, 1) lists, in ascending order, the blocks
+// of steps c..T-1 (block index relative to step c) that still hold a live row.  Works for any row order; with the rows
+// in descending length order (vqa_length_order) the live rows of a step are a prefix and about half of the blocks drop
+// out at uniformly distributed lengths.
+// ------------------------------------------------------------------------------------------
+__global__ void lstm_active_kblocks_kernel(const int64_t* __restrict__ len, int* __restrict__ list0, int* __restrict__ list1,
+                                           int B, int T_) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ int gmax[];                       // [B / 64] longest question of every 64-row group
+    const int s_begin = blockIdx.x;
+    int* list = s_begin == 0 ? list0 : list1;
+    if (list == nullptr) return;
+    const int G = B >> 6;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < G; g += nwarps) {
+        const int64_t a = len[g * 64 + lane], b = len[g * 64 + 32 + lane];
+        int m = (int)(a > b ? a : b);
+        m = m < 0 ? 0 : (m > T_ ? T_ : m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) gmax[g] = m;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int nblk = (T_ - s_begin) * G;
+    int n = 0;
+    for (int base = 0; base < nblk; base += 32) {        // ordered compaction, 32 blocks per ballot
+        const int b = base + lane;
+        const bool live = b < nblk && gmax[b % G] > s_begin + b / G;
+        const unsigned int bal = __ballot_sync(0xffffffffu, live);
+        if (live) list[1 + n + __popc(bal & ((1u << lane) - 1u))] = b;
+        n += __popc(bal);
+    }
+    if (lane == 0) list[0] = n;
+}
+
+extern "C" int vqa_lstm_active_kblocks(const int64_t* len_rows, int32_t* list0, int32_t* list1, int B, int T, void* stream) {
+    VQA_REQUIRE(len_rows && (list0 || list1) && B > 0 && T > 0, "lstm_active_kblocks: bad arguments");
+    VQA_REQUIRE(B % 64 == 0 && B <= 8192, "lstm_active_kblocks: B = %d must be a multiple of 64 (<= 8192)", B);
+    VQA_CUDA(vqa_launch_pdl(lstm_active_kblocks_kernel, dim3(2), dim3(256), (size_t)(B / 64) * sizeof(int), (cudaStream_t)stream,
+                            len_rows, (int*)list0, (int*)list1, B, T));
+    VQA_CHECK_LAUNCH("lstm_active_kblocks");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // LSTM backward, pointwise part of step s (BPTT through the cell of models/model.py:164)
 // ------------------------------------------------------------------------------------------
 template <typename T>

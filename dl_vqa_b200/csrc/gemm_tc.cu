@@ -257,7 +257,7 @@ __device__ __forceinline__ void gemm_store_chunk_bf16(const GemmEpilogue& ep, fl
 template <int BN, int MAJ, int ST, bool ATOMIC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split) {
+               GemmEpilogue ep, int M, int N, int K, int nsplit, int kblocks_per_split, const int* __restrict__ klist) {
     using S = GemmSmem<BN, ST>;
     constexpr bool AMN = MAJ == 1, BMN = MAJ >= 1;
     extern __shared__ uint8_t smem_raw[];
@@ -273,10 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int batch = blockIdx.z / nsplit, split = blockIdx.z - batch * nsplit;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int total_kb = (K + BK - 1) / BK;
-    const int kb_begin = split * kblocks_per_split;
-    const int kb_end = min(total_kb, kb_begin + kblocks_per_split);
-    const int nkb = max(0, kb_end - kb_begin);
+    int total_kb = (K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b);
@@ -291,26 +288,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_base_smem;
     pdl_wait();                                         // operands / output of the previous kernel in the stream
 
+    // Reduction-block list (vqa_tc_gemm_kblocks): klist[0] = n, klist[1..n] = the 64-row blocks of K that are not known to
+    // be all zero (written by an earlier kernel of the stream, hence read after pdl_wait).  Every role derives the same
+    // [kb_begin, kb_begin + nkb) of the LIST from klist[0]; only the producer looks at the entries.
+    if (klist != nullptr) {
+        total_kb = min(total_kb, max(0, klist[0]));
+        kblocks_per_split = (total_kb + nsplit - 1) / nsplit;
+    }
+    const int kb_begin = split * kblocks_per_split;
+    const int kb_end = min(total_kb, kb_begin + kblocks_per_split);
+    const int nkb = max(0, kb_end - kb_begin);
+
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % S::STAGES;
-                const uint32_t ph = (i / S::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
-                const int kc = (kb_begin + i) * BK;
-                if (!AMN) tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
-                else {
+        auto load_stage = [&](int i, int kb) {          // lane 0 only
+            const int s = i % S::STAGES;
+            const uint32_t ph = (i / S::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+            const int kc = kb * BK;
+            if (!AMN) tma_load_3d(sa + s * S::A_BYTES, &tma_a, &full[s], kc, m0, batch);
+            else {
 #pragma unroll
-                    for (int blk = 0; blk < BM / 64; ++blk)
-                        tma_load_3d(sa + s * S::A_BYTES + blk * 8192, &tma_a, &full[s], m0 + blk * 64, kc, batch);
-                }
-                if (!BMN) tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
-                else {
+                for (int blk = 0; blk < BM / 64; ++blk)
+                    tma_load_3d(sa + s * S::A_BYTES + blk * 8192, &tma_a, &full[s], m0 + blk * 64, kc, batch);
+            }
+            if (!BMN) tma_load_3d(sb + s * S::B_BYTES, &tma_b, &full[s], kc, n0, batch);
+            else {
 #pragma unroll
-                    for (int blk = 0; blk < BN / 64; ++blk)
-                        tma_load_3d(sb + s * S::B_BYTES + blk * 8192, &tma_b, &full[s], n0 + blk * 64, kc, batch);
+                for (int blk = 0; blk < BN / 64; ++blk)
+                    tma_load_3d(sb + s * S::B_BYTES + blk * 8192, &tma_b, &full[s], n0 + blk * 64, kc, batch);
+            }
+        };
+        if (klist == nullptr) {
+            if (lane == 0)
+                for (int i = 0; i < nkb; ++i) load_stage(i, kb_begin + i);
+        } else {
+            // 32 list entries per coalesced load (the next 32 already in flight), handed to lane 0 by shuffle: a dependent
+            // global load per k-block in a one-thread producer would cost more than the MMAs of the block
+            const int* e = klist + 1 + kb_begin;
+            int cur = lane < nkb ? e[lane] : 0;
+            for (int base = 0; base < nkb; base += 32) {
+                const int nxt = base + 32 + lane < nkb ? e[base + 32 + lane] : 0;
+                const int cnt = min(32, nkb - base);
+                for (int j = 0; j < cnt; ++j) {
+                    const int kb = __shfl_sync(0xffffffffu, cur, j);
+                    if (lane == 0) load_stage(base + j, kb);
+                    __syncwarp();
                 }
+                cur = nxt;
             }
         }
     } else if (warp == 1) {
@@ -514,28 +539,28 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
 
 template <int BN, int MAJ, int ST, bool ATOMIC>
 static int launch_gemm_sta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                           dim3 grid, int nsplit, int kbps, cudaStream_t st) {
+                           dim3 grid, int nsplit, int kbps, const int* klist, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, MAJ, ST, ATOMIC>;
     static bool attr_set = false;
     if (!attr_set) {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, ST>::BYTES));
         attr_set = true;
     }
-    VQA_CUDA(vqa_launch_pdl(kern, grid, dim3(GEMM_THREADS), GemmSmem<BN, ST>::BYTES, st, ta, tb, ep, M, N, K, nsplit, kbps));
+    VQA_CUDA(vqa_launch_pdl(kern, grid, dim3(GEMM_THREADS), GemmSmem<BN, ST>::BYTES, st, ta, tb, ep, M, N, K, nsplit, kbps, klist));
     VQA_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
 
 template <int BN, int MAJ, int ST>
 static int launch_gemm_st(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                          dim3 grid, int nsplit, int kbps, cudaStream_t st) {
-    if (ep.atomic) return launch_gemm_sta<BN, MAJ, ST, true>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
-    return launch_gemm_sta<BN, MAJ, ST, false>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+                          dim3 grid, int nsplit, int kbps, const int* klist, cudaStream_t st) {
+    if (ep.atomic) return launch_gemm_sta<BN, MAJ, ST, true>(ta, tb, ep, M, N, K, grid, nsplit, kbps, klist, st);
+    return launch_gemm_sta<BN, MAJ, ST, false>(ta, tb, ep, M, N, K, grid, nsplit, kbps, klist, st);
 }
 
 template <int BN, int MAJ>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                       int nbatch, int nsplit, cudaStream_t st) {
+                       int nbatch, int nsplit, const int* klist, cudaStream_t st) {
     const int total_kb = (K + BK - 1) / BK;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > total_kb) nsplit = total_kb > 0 ? total_kb : 1;
@@ -547,9 +572,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
     if (MAJ != 1 && nsplit == 1 && !ep.atomic && total_kb > 0 && ctas >= 4 * (int64_t)sms)
-        return launch_gemm_persistent<BN, MAJ == 2>(ta, tb, ep, M, N, K, nbatch, sms, st);
-    if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MAJ, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
-    return launch_gemm_st<BN, MAJ, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, st);
+        return launch_gemm_persistent<BN, MAJ == 2>(ta, tb, ep, M, N, K, nbatch, sms, st);     // (klist: MAJ == 1 only)
+    if (ctas >= 2 * (int64_t)sms) return launch_gemm_st<BN, MAJ, 3>(ta, tb, ep, M, N, K, grid, nsplit, kbps, klist, st);
+    return launch_gemm_st<BN, MAJ, 6>(ta, tb, ep, M, N, K, grid, nsplit, kbps, klist, st);
 }
 
 }  // namespace tc
@@ -558,11 +583,11 @@ using namespace tc;
 
 // C[z][m,n] = act(sum_k A[z][m,k] B[z][n,k] + bias) ; A [M,K] (row pitch lda), B [N,K] (row pitch ldb), bf16;
 // with VQA_GEMM_OPERANDS_MN: A stored [K,M] (row pitch lda), B stored [K,N] (row pitch ldb).
-extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
-                           void* C, int c_dtype, int64_t ldc, int64_t c_sb,
-                           const float* bias, const float* bias2, int64_t bias_sb,
-                           int M, int N, int K, int nbatch, int flags,
-                           float p_drop, uint64_t seed, uint32_t site, void* stream) {
+static int tc_gemm_impl(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
+                        void* C, int c_dtype, int64_t ldc, int64_t c_sb,
+                        const float* bias, const float* bias2, int64_t bias_sb,
+                        int M, int N, int K, int nbatch, int flags,
+                        float p_drop, uint64_t seed, uint32_t site, const int* klist, void* stream) {
     VQA_REQUIRE(M > 0 && N > 0 && K > 0 && nbatch >= 1, "tc_gemm: bad dims M=%d N=%d K=%d nbatch=%d", M, N, K, nbatch);
     VQA_REQUIRE(A && B && C, "tc_gemm: null operand");
     VQA_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: row pitches (%lld, %lld) must be multiples of 8 bf16 elements (TMA 16-byte strides)",
@@ -573,6 +598,8 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
     const bool mn = (flags & VQA_GEMM_OPERANDS_MN) != 0;
     const bool bmn = (flags & VQA_GEMM_B_MN) != 0;          // A [M,K] K-major, B stored [K,N]
     VQA_REQUIRE(!(mn && bmn), "tc_gemm: OPERANDS_MN and B_MN are mutually exclusive");
+    VQA_REQUIRE(klist == nullptr || (mn && nbatch == 1 && ((uintptr_t)klist & 3) == 0),
+                "tc_gemm_kblocks: a reduction-block list needs VQA_GEMM_OPERANDS_MN, nbatch == 1 and a 4-byte aligned list");
     if (splitk) {
         VQA_REQUIRE(c_dtype == VQA_F32 && !bias && !bias2 && !(flags & VQA_GEMM_RELU) && p_drop == 0.f,
                     "tc_gemm: split-K needs a zeroed fp32 output and no fused bias/relu/dropout");
@@ -653,15 +680,38 @@ extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void*
         return launch_gemm_persistent<256, false>(ta, tb, ep, M, N, K, nbatch, sms, st);
     }
     if (mn) {
-        if (BN == 64) return launch_gemm<64, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-        return launch_gemm<128, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        if (BN == 64) return launch_gemm<64, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, klist, st);
+        return launch_gemm<128, 1>(ta, tb, ep, M, N, K, nbatch, nsplit, klist, st);
     }
     if (bmn) {
-        if (BN == 64) return launch_gemm<64, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-        return launch_gemm<128, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+        if (BN == 64) return launch_gemm<64, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, nullptr, st);
+        return launch_gemm<128, 2>(ta, tb, ep, M, N, K, nbatch, nsplit, nullptr, st);
     }
-    if (BN == 64) return launch_gemm<64, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
-    return launch_gemm<128, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, st);
+    if (BN == 64) return launch_gemm<64, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, nullptr, st);
+    return launch_gemm<128, 0>(ta, tb, ep, M, N, K, nbatch, nsplit, nullptr, st);
+}
+
+extern "C" int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t ldb, int64_t b_sb,
+                           void* C, int c_dtype, int64_t ldc, int64_t c_sb,
+                           const float* bias, const float* bias2, int64_t bias_sb,
+                           int M, int N, int K, int nbatch, int flags,
+                           float p_drop, uint64_t seed, uint32_t site, void* stream) {
+    return tc_gemm_impl(A, lda, a_sb, B, ldb, b_sb, C, c_dtype, ldc, c_sb, bias, bias2, bias_sb, M, N, K, nbatch, flags,
+                        p_drop, seed, site, nullptr, stream);
+}
+
+// The reduction-major form (VQA_GEMM_OPERANDS_MN, nbatch = 1) restricted to the 64-row reduction blocks named by a
+// DEVICE-side list: kblocks[0] = n, kblocks[1..n] = block indices (block j = reduction rows 64j .. 64j+63), each at most
+// once.  Blocks that are not listed are not read and contribute nothing -- the caller guarantees that one operand is all
+// zero there (the LSTM gate gradients of (step, row) pairs past the end of their question: vqa_lstm_active_kblocks).
+// K is still the dense row count (tensor-map bound).  With split-K the LIST is what is divided among the splits.
+extern "C" int vqa_tc_gemm_kblocks(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                   int M, int N, int K, int flags, const int32_t* kblocks, void* stream) {
+    VQA_REQUIRE(kblocks != nullptr, "tc_gemm_kblocks: null block list");
+    VQA_REQUIRE((flags & ~(VQA_GEMM_OPERANDS_MN | VQA_GEMM_SPLITK)) == 0 && (flags & VQA_GEMM_OPERANDS_MN),
+                "tc_gemm_kblocks: flags must be VQA_GEMM_OPERANDS_MN, optionally with VQA_GEMM_SPLITK");
+    return tc_gemm_impl(A, lda, 0, B, ldb, 0, C, VQA_F32, ldc, 0, nullptr, nullptr, 0, M, N, K, 1, flags, 0.f, 0, 0,
+                        kblocks, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -6,6 +6,8 @@ _vp, _i, _i64, _u64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_
 PROTOTYPES = {
     "vqa_tc_gemm": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i, _i64, _i64, _vp, _vp, _i64,
                     _i, _i, _i, _i, _i, _f, _u64, _u32, _vp],
+    "vqa_tc_gemm_kblocks": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp],
+    "vqa_lstm_active_kblocks": [_vp, _vp, _vp, _i, _i, _vp],
     "vqa_transpose_bf16": [_vp, _i, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_relu_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vqa_tc_conv3x3_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -171,8 +171,9 @@ class _Math:
                  None, None, 0, M, K, N, 1, 0, 0.0, 0, 0, self.st, tag=tag)
 
     # ---- dW[N,K] (fp32) = dy[M,N]^T x[M,K]      (reduction over the M rows)
-    def lin_bwd_weight(self, dy_ptr, dy_dt, ldy, x_ptr, x_dt, ldx, dW, M, N, K, tag=None, zeroed=False):
-        """`zeroed`: dW already holds zeros (the gradient arena is cleared once per backward pass)."""
+    def lin_bwd_weight(self, dy_ptr, dy_dt, ldy, x_ptr, x_dt, ldx, dW, M, N, K, tag=None, zeroed=False, kblocks=None):
+        """`zeroed`: dW already holds zeros (the gradient arena is cleared once per backward pass).  `kblocks` (tensor-core
+        arm): device list of the 64-row reduction blocks that are not all zero in dy (vqa_lstm_active_kblocks)."""
         big = M >= 4096
 
         def clear():
@@ -187,6 +188,10 @@ class _Math:
             xp, ldx2, keep2 = self._as_bf16(x_ptr, x_dt, ldx, M, K)
             if big:
                 clear()
+            if kblocks is not None:
+                call("vqa_tc_gemm_kblocks", yp, ldy2, xp, ldx2, ptr(dW), K, N, K, M,
+                     lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if big else 0), ptr(kblocks), self.st, tag=tag)
+                return
             call("vqa_tc_gemm", yp, ldy2, 0, xp, ldx2, 0, ptr(dW), lib.F32, K, 0, None, None, 0,
                  N, K, M, 1, lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if big else 0), 0.0, 0, 0, self.st, tag=tag)
         else:
@@ -656,12 +661,22 @@ class VqaNet(nn.Module):
                          None, None, 0, B, H, 4 * H, dirs, 0, 0.0, 0, 0, st, tag="lstm_step_bwd")
         if after_recurrence is not None:
             after_recurrence()
+        # dg is exactly zero at (step, row) positions past the end of a question (what pack_padded_sequence drops,
+        # models/model.py:160): the weight-gradient reductions skip every 64-row block that holds only such rows -- with the
+        # rows in length order about 40 % of them at B = 256, half at B = 1024
+        kb_ih = kb_hh = None
+        if tc and T > 1 and B % 64 == 0 and B <= 8192 and os.environ.get("VQA_LSTM_KSKIP", "1") != "0":
+            kb_ih = torch.empty(1 + T * (B // 64), dtype=torch.int32, device=dev)
+            kb_hh = torch.empty(1 + (T - 1) * (B // 64), dtype=torch.int32, device=dev)
+            call("vqa_lstm_active_kblocks", ptr(len_rows if order is not None else q_len), ptr(kb_ih), ptr(kb_hh), B, T, st,
+                 tag="lstm_whh_wgrad")
         for d in range(dirs):
             dWhh = galloc(f"text.lstm.weight_hh_l0{sfx[d]}", 4 * H, H)
             mm.lin_bwd_weight(dg[d].data_ptr() + B * 4 * H * gsz, dt, 4 * H, ptr(tx["h_prev"][d]), dt, H, dWhh,
-                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad", zeroed=zeroed)
+                              (T - 1) * B, 4 * H, H, tag="lstm_whh_wgrad", zeroed=zeroed, kblocks=kb_hh)
             dWih = galloc(f"text.lstm.weight_ih_l0{sfx[d]}", 4 * H, E)
-            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad", zeroed=zeroed)
+            mm.lin_bwd_weight(ptr(dg[d]), dt, 4 * H, ptr(xs[d]), dt, ldx, dWih, T * B, 4 * H, E, tag="lstm_wih_wgrad", zeroed=zeroed,
+                              kblocks=kb_ih)
             db = colsum(dg[d], dt, 4 * H, T * B, 4 * H, f"text.lstm.bias_ih_l0{sfx[d]}")
             grads[f"text.lstm.weight_hh_l0{sfx[d]}"] = dWhh
             grads[f"text.lstm.weight_ih_l0{sfx[d]}"] = dWih

@@ -296,6 +296,20 @@ int vqa_tc_gemm(const void* A, int64_t lda, int64_t a_sb, const void* B, int64_t
                 const float* bias, const float* bias2, int64_t bias_sb,
                 int M, int N, int K, int nbatch, int flags,
                 float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* The reduction-major form of vqa_tc_gemm (VQA_GEMM_OPERANDS_MN, optionally VQA_GEMM_SPLITK into a zeroed C; nbatch = 1,
+ * fp32 C [M][ldc]) restricted to the 64-row reduction blocks named by a DEVICE-side list: kblocks[0] = n,
+ * kblocks[1..n] = block indices (block j = rows 64j..64j+63 of A [K,M] and B [K,N]), each at most once.  Blocks that are
+ * not listed are not read and contribute nothing: the caller guarantees one operand is all zero there.  Replaces what
+ * cuDNN's packed-sequence RNN backward gets from pack_padded_sequence (models/model.py:160-164): padded (step, row)
+ * positions never enter the LSTM weight gradients.  The list is read when the kernel RUNS (graph-capture safe). */
+int vqa_tc_gemm_kblocks(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                        int M, int N, int K, int flags, const int32_t* kblocks, void* stream);
+/* Block lists for the above from the row lengths of the step-indexed LSTM buffers (len_rows [B] int64 in ROW order: the
+ * len_sorted of vqa_length_order, or q_len when the rows are in sample order; B % 64 == 0): list0 = live blocks of steps
+ * 0..T-1 (capacity 1 + T*B/64: the dW_ih reduction), list1 = live blocks of steps 1..T-1, indexed from step 1 (capacity
+ * 1 + (T-1)*B/64: the dW_hh reduction, whose operands start at step 1 / h_0).  A block is live when any of its rows r has
+ * len_rows[r] > step.  Either list may be NULL. */
+int vqa_lstm_active_kblocks(const int64_t* len_rows, int32_t* list0, int32_t* list1, int B, int T, void* stream);
 /* dst[z][c, r] (bf16, row pitch ldd) = src[z][r, c] (fp32 or bf16, row pitch lds): operand re-layout for the
  * contractions whose reduction index is not contiguous in memory (weight / data gradients) */
 int vqa_transpose_bf16(const void* src, int src_dtype, int64_t lds, int64_t s_sb, void* dst, int64_t ldd,

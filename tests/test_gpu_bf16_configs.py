@@ -147,3 +147,43 @@ def test_length_ordered_question_encoder_equals_the_unordered_one(monkeypatch):
     assert torch.equal(out0, out1)
     for k in g0:
         assert _err(g1[k], g0[k]) < 2e-3, (k, _err(g1[k], g0[k]))
+
+
+@pytest.mark.parametrize("B", [256, 192, 1024])
+def test_lstm_weight_gradients_skip_ended_rows(monkeypatch, B):
+    """The LSTM weight-gradient reductions leave out the 64-row blocks whose (step, row) positions all lie past the end of
+    their question (vqa_lstm_active_kblocks + vqa_tc_gemm_kblocks; the reference never forms those positions:
+    pack_padded_sequence, models/model.py:160).  The gate gradient is exactly zero there, so nothing may change.  At
+    B = 1024 the whole text backward is free of atomics in front of the four LSTM weight gradients and the reductions are
+    not split: BIT-identical.  At B <= 256 the persistent recurrence reduces dh with split-K atomics, so two runs of the
+    SAME code already differ by bf16 rounding flips in dg: same bar as the length-order test above.  (The kernel-level
+    statement -- listed blocks only, dense result reproduced -- is tests/test_gpu_tc.py::test_tc_gemm_kblocks_*.)"""
+    import dl_vqa_b200 as D
+    cfg = O.cfg_with(O.DEFAULT_CFG)
+    V, T = 3000, 23
+    torch.manual_seed(1)
+    m = D.VqaNet(cfg, V, compute_dtype="bfloat16").cuda().train(True)
+    g = torch.Generator().manual_seed(B)
+    q_len = torch.randint(1, T + 1, (B,), generator=g)
+    q_len[5] = T
+    q = (torch.randint(1, V, (B, T), generator=g) * (torch.arange(T)[None, :] < q_len[:, None])).cuda()
+    q_len = q_len.cuda()
+    dqf = (torch.randn(B, 2048, generator=g) * 0.1).cuda().bfloat16()
+    m._next_seed = lambda: 99
+
+    def run(flag):
+        monkeypatch.setenv("VQA_LSTM_KSKIP", flag)
+        for p in m.text.parameters():
+            p.grad = None
+        out = m.text(q, q_len)
+        out.backward(dqf)
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().clone() for k, p in m.text.named_parameters()}
+
+    g0, g1 = run("0"), run("1")
+    for k in g0:
+        if B == 1024 and "lstm.weight" in k:                 # the four reductions that skip blocks
+            assert torch.equal(g0[k], g1[k]), (k, _err(g1[k], g0[k]))
+        else:
+            assert _err(g1[k], g0[k]) < 2e-3, (k, _err(g1[k], g0[k]))
+        assert float(g0[k].abs().max()) > 0

@@ -621,3 +621,102 @@ def test_tc_conv0_reads_float16_images_bit_identically(B, IH, IW):
     # fp32 atomics across CTAs: the order of the partial sums is not fixed, so compare to rounding of the sum
     assert float((a[2] - b[2]).abs().max()) <= 1e-5 * float(a[2].abs().max())
     assert float((a[3] - b[3]).abs().max()) <= 1e-5 * float(a[3].abs().max())
+
+
+def _active_kblocks_reference(lens, B, T, s_begin):
+    """numpy-free restatement of vqa_lstm_active_kblocks: 64-row blocks of steps s_begin..T-1 with any len > step."""
+    G = B // 64
+    gmax = lens.clamp(0, T).view(G, 64).max(dim=1).values.tolist()
+    return [(s - s_begin) * G + g for s in range(s_begin, T) for g in range(G) if gmax[g] > s]
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+@pytest.mark.parametrize("B,T", [(256, 23), (64, 5), (1024, 23), (128, 1), (192, 9)])
+def test_lstm_active_kblocks_lists(B, T, ordered):
+    """vqa_lstm_active_kblocks against the definition (a block is live when any of its rows has len > step), for rows in
+    sample order and in descending length order, incl. lengths outside [0, T] (clamped) and T = 1 (empty second list)."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(B * 31 + T)
+    lens = torch.randint(1, T + 1, (B,))
+    lens[0], lens[-1] = T + 5, -3
+    if B > 64:
+        lens[64:128] = torch.randint(1, max(2, T // 3 + 1), (64,))       # one short group in the middle
+    if ordered:
+        lens = torch.sort(lens, descending=True).values
+    d = lens.cuda()
+    l0 = torch.full((1 + T * (B // 64),), -7, dtype=torch.int32, device="cuda")
+    l1 = torch.full((1 + max(T - 1, 0) * (B // 64),), -7, dtype=torch.int32, device="cuda")
+    lib.call("vqa_lstm_active_kblocks", lib.ptr(d), lib.ptr(l0), lib.ptr(l1), B, T, lib.stream())
+    torch.cuda.synchronize()
+    for lst, s_begin in ((l0, 0), (l1, 1)):
+        want = _active_kblocks_reference(lens, B, T, s_begin)
+        n = int(lst[0])
+        assert n == len(want), (s_begin, n, len(want))
+        assert lst[1:1 + n].tolist() == want
+        assert bool((lst[1 + n:] == -7).all())                            # nothing written past the list
+    # one list only
+    l0b = torch.full_like(l0, -7)
+    lib.call("vqa_lstm_active_kblocks", lib.ptr(d), lib.ptr(l0b), None, B, T, lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(l0b, l0)
+    with pytest.raises(lib.VqaLibraryError):
+        lib.call("vqa_lstm_active_kblocks", lib.ptr(d), lib.ptr(l0), lib.ptr(l1), 100, T, lib.stream())
+
+
+@pytest.mark.parametrize("R,N,K,splitk", [(5888, 4096, 304, True), (5632, 1024, 1024, True), (23552, 4096, 1024, True),
+                                          (640, 256, 136, False), (4096, 128, 64, True), (8192, 200, 72, True)])
+def test_tc_gemm_kblocks_reads_listed_blocks_only(R, N, K, splitk):
+    """vqa_tc_gemm_kblocks: dW[N,K] = sum over the LISTED 64-row blocks of dY^T X.  (1) every unlisted block is zero in dY:
+    equals the dense product, bit for bit where the dense kernel does not split K either; (2) unlisted blocks hold data
+    (even NaN): they are not read; (3) empty list: dW = 0.  Covers unsplit launches (many tiles) and split-K ones (few
+    tiles: the list, not K, is divided among the splits), lists longer than one 32-entry fetch, and a one-entry list."""
+    from dl_vqa_b200 import lib
+    torch.manual_seed(R + N)
+    nb = R // 64
+    dY = torch.randn(R, N, device="cuda").bfloat16()
+    X = torch.randn(R, K, device="cuda").bfloat16()
+    flags = lib.GEMM_OPERANDS_MN | (lib.GEMM_SPLITK if splitk else 0)
+
+    def run(lst, dy=dY):
+        l = torch.tensor([len(lst)] + lst + [10 ** 6] * 3, dtype=torch.int32, device="cuda")   # junk past the end is ignored
+        dW = torch.zeros(N, K, device="cuda")
+        lib.call("vqa_tc_gemm_kblocks", lib.ptr(dy), N, lib.ptr(X), K, lib.ptr(dW), K, N, K, R, flags, lib.ptr(l), lib.stream())
+        torch.cuda.synchronize()
+        return dW
+
+    def want_of(lst, dy=dY):
+        rows = torch.tensor([b * 64 + i for b in lst for i in range(64)], dtype=torch.long, device="cuda")
+        return dy[rows].float().t() @ X[rows].float() if len(lst) else torch.zeros(N, K, device="cuda")
+
+    g = torch.Generator().manual_seed(R)
+    keep = sorted(torch.randperm(nb, generator=g)[: max(1, (nb * 3) // 5)].tolist())
+    for lst in (keep, keep[:1], list(range(nb))):
+        want = want_of(lst)
+        got = run(lst)
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < 1e-4, (len(lst), err)
+    # (2) unlisted blocks poisoned
+    poisoned = dY.clone()
+    mask = torch.ones(nb, dtype=torch.bool)
+    mask[keep] = False
+    poisoned.view(nb, 64, N)[mask.cuda()] = float("nan")
+    got = run(keep, poisoned)
+    assert bool(torch.isfinite(got).all())
+    assert float((got - want_of(keep)).abs().max() / want_of(keep).abs().max()) < 1e-4
+    # (1) zeroed blocks: same numbers as the dense entry
+    zeroed = dY.clone()
+    zeroed.view(nb, 64, N)[mask.cuda()] = 0
+    dense = torch.zeros(N, K, device="cuda")
+    lib.call("vqa_tc_gemm", lib.ptr(zeroed), N, 0, lib.ptr(X), K, 0, lib.ptr(dense), lib.F32, K, 0, None, None, 0,
+             N, K, R, 1, flags, 0.0, 0, 0, lib.stream())
+    torch.cuda.synchronize()
+    got = run(keep, zeroed)
+    assert float((got - dense).abs().max() / dense.abs().max()) < 2e-6
+    # (3) empty list
+    assert float(run([]).abs().max()) == 0.0
+    # argument checks: the list form exists for the reduction-major operands only
+    with pytest.raises(lib.VqaLibraryError):
+        lib.call("vqa_tc_gemm_kblocks", lib.ptr(dY), N, lib.ptr(X), K, lib.ptr(dense), K, N, K, R, lib.GEMM_SPLITK,
+                 lib.ptr(torch.zeros(4, dtype=torch.int32, device="cuda")), lib.stream())
+    with pytest.raises(lib.VqaLibraryError):
+        lib.call("vqa_tc_gemm_kblocks", lib.ptr(dY), N, lib.ptr(X), K, lib.ptr(dense), K, N, K, R, flags, None, lib.stream())
