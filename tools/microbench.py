@@ -142,6 +142,17 @@ def lstm_microbench(B=1024, iters=10, T=23, V=15000, tflops_peak=None):
     if tflops_peak:
         res["fwd_frac_of_tensor_peak_dense"] = round(res["fwd_TFLOPs_dense"] / tflops_peak, 4)
         res["fwd_bwd_frac_of_tensor_peak_dense"] = round(res["fwd_bwd_TFLOPs_dense"] / tflops_peak, 4)
+    # SURVEY.md section 8d's secondary, "VQA-like" length distribution: clamp(round(N(6.2, 2.0)), 1, 23), one full-length
+    # question kept so that the padded width stays T.  Same kernels, same shapes: what changes is how many (step, row)
+    # positions the length-aware parts (tile skipping in the recurrences, block skipping in the weight gradients) leave out.
+    q_len2 = torch.clamp(torch.round(torch.randn(B, generator=g) * 2.0 + 6.2), 1, T).long()
+    q_len2[0] = T
+    q2 = torch.randint(1, V, (B, T), generator=g) * (torch.arange(T)[None, :] < q_len2[:, None])
+    q, q_len = q2.cuda(), q_len2.cuda()              # fwd / fwd_bwd close over these names
+    f2, fb2 = _time(fwd, iters), _time(fwd_bwd, iters)
+    res["vqa_like_lengths"] = {"distribution": "clamp(round(N(6.2, 2.0)), 1, 23), q_len[0] = 23", "mean_len": float(q_len2.float().mean()),
+                               "fwd_ms": round(f2, 4), "fwd_bwd_ms": round(fb2, 4),
+                               "fwd_questions_per_s": round(B / f2 * 1e3, 1), "fwd_bwd_questions_per_s": round(B / fb2 * 1e3, 1)}
     return res
 
 
