@@ -120,6 +120,25 @@ def lstm_final_cell(sd, x: torch.Tensor, lengths: torch.Tensor, hidden: int,
     return torch.cat(outs, dim=1)
 
 
+def lstm_live_row_blocks(row_lengths: torch.Tensor, T: int, s_begin: int = 0, block: int = 64) -> List[int]:
+    """models/model.py:160-164: pack_padded_sequence hands nn.LSTM only the (step, row) positions with step < length,
+    so positions past the end of a question never enter the weight gradients.  For step-indexed buffers [T][B][.]
+    (row r of step s at s*B + r) this lists, in ascending order, the `block`-row blocks of steps s_begin..T-1 (indexed
+    from step s_begin) that hold at least one such position -- what dl_vqa_b200's vqa_lstm_active_kblocks computes on the
+    device.  With rows in descending length order step s keeps its first batch_sizes[s] rows (PackedSequence.batch_sizes),
+    i.e. its first ceil(batch_sizes[s] / block) blocks."""
+    B = int(row_lengths.numel())
+    assert B % block == 0
+    G = B // block
+    lens = row_lengths.clamp(0, T).view(G, block)
+    out = []
+    for s in range(s_begin, T):
+        for g in range(G):
+            if bool((lens[g] > s).any()):
+                out.append((s - s_begin) * G + g)
+    return out
+
+
 def question_encoder(sd, cfg: dict, q: torch.Tensor, q_len: torch.Tensor, rnd=_ident) -> torch.Tensor:
     """models/model.py:151-166: embedding (padding_idx 0) -> dropout(identity) -> tanh -> LSTM c_n."""
     emb = sd["text.embedding.weight"][q]                             # [B,T,E]

@@ -624,10 +624,11 @@ def test_tc_conv0_reads_float16_images_bit_identically(B, IH, IW):
 
 
 def _active_kblocks_reference(lens, B, T, s_begin):
-    """numpy-free restatement of vqa_lstm_active_kblocks: 64-row blocks of steps s_begin..T-1 with any len > step."""
-    G = B // 64
-    gmax = lens.clamp(0, T).view(G, 64).max(dim=1).values.tolist()
-    return [(s - s_begin) * G + g for s in range(s_begin, T) for g in range(G) if gmax[g] > s]
+    """The oracle's restatement (pinned on the CPU to pack_padded_sequence's batch_sizes, tests/test_oracle.py):
+    64-row blocks of steps s_begin..T-1 with any len > step."""
+    from oracle import vqa_oracle as O
+    assert lens.numel() == B
+    return O.lstm_live_row_blocks(lens, T, s_begin)
 
 
 @pytest.mark.parametrize("ordered", [False, True])
