@@ -21,6 +21,8 @@ sys.path.insert(0, ROOT)
 
 # algorithmic FLOP per sample of the contraction kernels, forward; dgrad/wgrad equal
 CONV_FLOP = {0: 0.170e9, 1: 1.752e9, 2: 1.595e9}
+WORKLOAD = ("single-B200 training step (BASELINE.json configs[1]): full VqaNet fwd + soft-target loss "
+            "+ bwd + Adam, config.yaml shapes, dropout 0.3, random init, V=15000, T=23")      # both arms name the same workload
 STEP_FLOP_PER_SAMPLE = 13.00e9          # fwd + bwd at T = 23
 
 
@@ -175,8 +177,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": steps_eff, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single-B200 training step of BASELINE.json configs[1]: full VqaNet fwd+loss+bwd+Adam "
-                                   "at config.yaml shapes, timed here on the host CPU", "batch_per_step": batch},
+            # the SAME workload as the GPU arm's line; each step is a bounded sample of it (batch 32 of the 256-sample step)
+            "config": {"workload": WORKLOAD, "batch_per_gpu": 256, "global_batch": 256 * max(1, args.gpus),
+                       "parallelism": f"dp{max(1, args.gpus)}",
+                       "sample": f"batch {batch} per step on the host CPU (rank 0 only): a bounded sample of the 256-sample step"},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -517,8 +521,7 @@ def run_ours(args):
     line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.dtype in ("bf16", "bfloat16") else "f32", "data": "synthetic",
-            "config": {"workload": "single-B200 training step (BASELINE.json configs[1]): full VqaNet fwd + soft-target loss "
-                                   "+ bwd + Adam, config.yaml shapes, dropout 0.3, random init, V=15000, T=23",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "step_launch": "one CUDA graph replay per step (GraphedTrainStep)" if not args.no_graph else "kernel by kernel",
                        "l2_policy": "inputs + activations per step (>2 GB) far exceed the 126 MB L2; no explicit flush"},
