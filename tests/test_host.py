@@ -47,6 +47,43 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared <= bound, f"declared but not bound in lib.py: {declared - bound}"
 
 
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Every entry of include/vqa_b200.h against its ctypes prototype in dl_vqa_b200/lib.py / lib_tc.py: same number of
+    parameters, same kind each (pointer, int, int64_t, uint64_t, uint32_t, float, double).  A drifted prototype would
+    otherwise only show up on the GPU as a wrong argument."""
+    from dl_vqa_b200 import lib
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vqa_b200.h")).read(), flags=re.S)
+    decls = re.findall(r"\b[A-Za-z_][A-Za-z0-9_ \*]*?\b(vqa_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(decls) >= 60
+    lib.load()
+    protos = dict(lib.PROTOTYPES)
+    protos.update(lib._optional_prototypes())
+    scalar = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32,
+              "float": ctypes.c_float, "double": ctypes.c_double}
+
+    def kind(param):
+        param = param.strip()
+        if param in ("", "void"):
+            return None
+        if "*" in param:
+            return ctypes.c_void_p
+        ctype = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", param).replace("const", "").strip()      # drop the parameter name
+        assert ctype in scalar, f"unknown C type {ctype!r} in the header"
+        return scalar[ctype]
+
+    checked = 0
+    for name, params in decls:
+        if name in ("vqa_last_error_string", "vqa_abi_version", "vqa_launch_count"):    # bound by hand in lib.load()
+            continue
+        want = [k for k in (kind(x) for x in params.split(",")) if k is not None]
+        got = list(protos[name])
+        assert len(got) == len(want), f"{name}: header has {len(want)} parameters, the prototype {len(got)}"
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g is w, f"{name}: parameter {i} is {w.__name__} in the header, {g.__name__} in the prototype"
+        checked += 1
+    assert checked >= 60
+
+
 def test_no_cpu_fallback():
     import dl_vqa_b200 as D
     from dl_vqa_b200 import lib
